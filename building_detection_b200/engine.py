@@ -1,0 +1,95 @@
+"""Model object with the two Keras methods the reference's hot path uses (predict.py:21-49,109):
+``load_weights(path)`` and ``predict(x)``.  ``predict`` runs the model's native plan -- a launch
+list of sm_100a kernels built once per batch size through the C ABI -- on the current CUDA device.
+There is no CPU execution path: without the compiled library or a GPU it raises."""
+from __future__ import annotations
+
+import os
+import zlib
+
+import numpy as np
+
+from . import graph as G
+
+MAX_PLAN_BATCH = 16  # BASELINE.json configs 2-4: batch 16 of 512x512 tiles
+
+
+class Model:
+    def __init__(self, name, build_fn, input_shape=(512, 512, 3), seed=None):
+        if tuple(input_shape) != (512, 512, 3):
+            raise ValueError("the reference tiles every scene into 512x512x3 inputs (predict.py:107)")
+        self.name = name
+        self._build = build_fn
+        net = G.Net(name, 1, None)
+        build_fn(net)
+        self.spec = net.spec
+        self.flops_per_tile = net.plan.flops
+        # a fresh Keras model carries its random initialisation (predict.py:23-24 keeps it when the
+        # checkpoint is missing); seeded per model so runs are reproducible
+        self.weights = G.init_weights(self.spec, seed=zlib.crc32(name.encode()) if seed is None else seed)
+        self._native = {}  # batch -> engine.NativePlan
+        self._version = 0
+
+    # ------------------------------------------------------------------ weights
+    def get_weights(self):
+        return dict(self.weights)
+
+    def set_weights(self, weights):
+        for k, (shape, _) in self.spec.items():
+            if k not in weights:
+                raise KeyError(f"{self.name}: missing weight {k}")
+            if tuple(np.shape(weights[k])) != shape:
+                raise ValueError(f"{self.name}: weight {k} has shape {np.shape(weights[k])}, expected {shape}")
+        self.weights = {k: np.asarray(weights[k], np.float32) for k in self.spec}
+        self._drop_native()
+
+    def load_weights(self, path):
+        """Keras raises OSError for a missing file and the reference catches exactly that
+        (predict.py:23).  Accepted container here: ``.npz`` keyed by this package's layer names
+        (the Keras-h5 reader is SURVEY section 8f item 1)."""
+        if not os.path.exists(path):
+            raise OSError(f"Unable to open file (name = '{path}')")
+        with np.load(path) as z:
+            self.set_weights({k: z[k] for k in z.files})
+
+    def save_weights(self, path):
+        np.savez(path, **self.weights)
+
+    def count_params(self):
+        return G.count_params(self.spec)
+
+    # ------------------------------------------------------------------ plans
+    def build_plan(self, batch, umma=True, keep_f32=False):
+        net = G.Net(self.name, batch, self.weights, umma=umma, keep_f32=keep_f32)
+        self._build(net)
+        return net.plan
+
+    def _drop_native(self):
+        for p in self._native.values():
+            p.close()
+        self._native = {}
+
+    def native_plan(self, batch, umma=True):
+        from .runtime import NativePlan
+        key = (batch, umma)
+        if key not in self._native:
+            self._native[key] = NativePlan(self.build_plan(batch, umma=umma))
+        return self._native[key]
+
+    # ------------------------------------------------------------------ inference
+    def predict(self, x, batch_size=None, verbose=0):
+        """x: (N,512,512,3) float in [-1,1] (predict.py:93,108).  Returns (N,512,512,2) float32 softmax
+        probabilities, like ``tf.keras.Model.predict``."""
+        x = np.asarray(x)
+        if x.ndim != 4 or x.shape[1:] != (512, 512, 3):
+            raise ValueError(f"expected input of shape (N,512,512,3), got {x.shape}")
+        x = np.ascontiguousarray(x, dtype=np.float32)  # Keras casts float64 inputs to float32
+        out = np.empty((x.shape[0], 512, 512, 2), np.float32)
+        i = 0
+        while i < x.shape[0]:
+            n = min(MAX_PLAN_BATCH, x.shape[0] - i)
+            out[i:i + n] = self.native_plan(n).run_host(x[i:i + n])
+            i += n
+        return out
+
+    __call__ = predict

@@ -1,0 +1,405 @@
+"""Host-side graph builder: lowers one of the five segmentation networks to a *plan*.
+
+A plan is plain data -- a buffer table plus an ordered list of fused ops with their
+BatchNorm-folded, bf16-quantised parameters -- that ``engine.py`` uploads once through the
+C ABI (``include/bd_b200.h``) where it becomes a native launch list of sm_100a kernels.
+Nothing in here computes activations; there is no CPU execution path in the product.
+
+Fusions decided here:
+  * Conv2D + BatchNormalization (+ReLU) (+residual add) (+ReLU)  -> one CONV op
+  * channel concat                                              -> producers write channel slices
+  * Conv2DTranspose k2/k3 stride 2                              -> 4 sub-pixel CONV ops (tap subsets)
+  * SeparableConv2D                                             -> DWCONV + 1x1 CONV (BN folded)
+  * GlobalAveragePooling of a sum                               -> sum of pooled vectors
+All feature maps are NHWC bf16 (fp32 for the network input and the 2-channel logits); pooled
+vectors and the tiny attention MLPs stay fp32.
+
+TF/Keras semantics honoured: 'same' padding incl. the asymmetric stride-2 case, BN eps 1e-3,
+nearest UpSampling2D, Conv2DTranspose crop.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+
+BN_EPS = 1e-3  # Keras BatchNormalization default
+
+# op codes shared with csrc/bd_api.cu (enum bd_op_kind in include/bd_b200.h)
+OP_CONV, OP_DWCONV, OP_MAXPOOL, OP_ADDN, OP_GAP, OP_DENSE, OP_GATE, OP_SKFUSE, OP_BCAST, OP_SOFTMAX2 = range(10)
+GATE_SE, GATE_SCSE, GATE_BAM = range(3)
+ACT_NONE, ACT_RELU, ACT_SIGMOID = range(3)
+
+
+def same_pad(size, k, s, d=1):
+    """TF 'same' padding (before, after) -- asymmetric when the total is odd."""
+    k_eff = (k - 1) * d + 1
+    out = math.ceil(size / s)
+    total = max((out - 1) * s + k_eff - size, 0)
+    return total // 2, total - total // 2
+
+
+def to_bf16(a):
+    """Round-to-nearest-even fp32 -> bf16, returned as uint16 bit patterns."""
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    u = a.view(np.uint32).astype(np.uint64)
+    r = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16).astype(np.uint16)
+    return r
+
+
+def bf16_to_f32(u16):
+    return (u16.astype(np.uint32) << 16).view(np.float32)
+
+
+@dataclass
+class Buf:
+    id: int
+    H: int
+    W: int
+    C: int
+    dtype: str = "bf16"  # 'bf16' | 'f32'
+    kind: str = "map"  # 'map' (N,H,W,C) | 'vec' (N,C) fp32
+
+
+@dataclass
+class T:
+    """Channel-slice view [c0, c0+C) of a map buffer."""
+    buf: Buf
+    c0: int
+    C: int
+
+    @property
+    def H(self):
+        return self.buf.H
+
+    @property
+    def W(self):
+        return self.buf.W
+
+    def ref(self):
+        return (self.buf.id, self.c0, self.C)
+
+
+@dataclass
+class V:
+    """fp32 (N, C) vector buffer."""
+    buf: Buf
+
+    @property
+    def C(self):
+        return self.buf.C
+
+
+@dataclass
+class Plan:
+    model: str
+    batch: int
+    bufs: list = field(default_factory=list)
+    ops: list = field(default_factory=list)
+    input: int = -1
+    logits: int = -1
+    logits_up: int = 1
+    flops: int = 0  # algorithmic 2*MAC of conv/convT/depthwise/dense per batch
+
+
+class Net:
+    """Builder.  With ``weights=None`` it only records the weight spec (name -> shape/init)."""
+
+    def __init__(self, model, batch, weights=None, umma=True, keep_f32=False):
+        self.plan = Plan(model, batch)
+        self.w = weights
+        self.spec = {}  # name -> (shape, init)
+        self.umma = umma
+        self.keep_f32 = keep_f32  # tests only: also keep the unquantised conv weights in the op
+
+    # ------------------------------------------------------------------ weights
+    def _get(self, name, shape, init):
+        shape = tuple(int(s) for s in shape)
+        assert name not in self.spec, f"duplicate weight {name}"
+        self.spec[name] = (shape, init)
+        if self.w is None:
+            return np.zeros(shape, np.float32)
+        a = np.asarray(self.w[name], dtype=np.float32)
+        if a.shape != shape:
+            raise ValueError(f"weight {name}: expected {shape}, got {a.shape}")
+        return a
+
+    def _bn(self, name, c):
+        g = self._get(name + "/gamma", (c,), "bn_gamma")
+        b = self._get(name + "/beta", (c,), "bn_beta")
+        m = self._get(name + "/mean", (c,), "bn_mean")
+        v = self._get(name + "/var", (c,), "bn_var")
+        scale = g / np.sqrt(v + BN_EPS)
+        return scale.astype(np.float32), (b - m * scale).astype(np.float32)
+
+    # ------------------------------------------------------------------ buffers
+    def buf(self, H, W, C, dtype="bf16", kind="map"):
+        b = Buf(len(self.plan.bufs), H, W, C, dtype, kind)
+        self.plan.bufs.append(b)
+        return b
+
+    def new(self, H, W, C, dtype="bf16"):
+        return T(self.buf(H, W, C, dtype), 0, C)
+
+    def vec(self, C):
+        return V(self.buf(1, 1, C, "f32", "vec"))
+
+    def input(self, H=512, W=512, C=3):
+        t = self.new(H, W, C, "f32")
+        self.plan.input = t.buf.id
+        return t
+
+    def _emit(self, **op):
+        self.plan.ops.append(op)
+
+    # ------------------------------------------------------------------ CONV
+    def _conv_op(self, x, w_tco, bias, taps, stride, Ho, Wo, act_pre, res, act_post, out,
+                 out_scale=1, out_oy=0, out_ox=0, name=""):
+        """w_tco: (ntaps, Cout, Cin) fp32 (BN already folded)."""
+        nt, cout, cin = w_tco.shape
+        assert cin == x.C and len(taps) == nt
+        assert out.C == cout and out.H == Ho * out_scale and out.W == Wo * out_scale, (name, out, Ho, Wo)
+        if res is not None:
+            assert res.C == cout and res.H == out.H and res.W == out.W and out_scale == 1
+        path = "direct"
+        if (self.umma and stride == 1 and x.buf.dtype == "bf16" and out.buf.dtype == "bf16"
+                and cin % 8 == 0 and cin >= 16 and cout % 8 == 0 and cout >= 16
+                and x.c0 % 8 == 0 and x.buf.C % 8 == 0 and out.c0 % 8 == 0 and out.buf.C % 8 == 0
+                and Wo >= 8 and (res is None or (res.c0 % 8 == 0 and res.buf.C % 8 == 0))):
+            path = "umma"
+        self.plan.flops += 2 * self.plan.batch * Ho * Wo * cout * cin * nt
+        self._emit(op=OP_CONV, name=name, path=path, x=x.ref(), y=out.ref(),
+                   res=None if res is None else res.ref(),
+                   taps=[(int(dy), int(dx)) for dy, dx in taps], stride=stride, Ho=Ho, Wo=Wo,
+                   act_pre=act_pre, act_post=act_post,
+                   out_scale=out_scale, out_oy=out_oy, out_ox=out_ox,
+                   w=to_bf16(w_tco), b=np.ascontiguousarray(bias, np.float32),
+                   w32=np.ascontiguousarray(w_tco, np.float32) if self.keep_f32 else None)
+
+    def conv(self, x, name, cout, k=1, s=1, d=1, bn=False, act=None, res=None, res_after_act=False,
+             out=None, f32_out=False, he=False):
+        """Conv2D(padding='same') [+BN] [+ReLU] [+res] [+ReLU].
+
+        act applies to conv(+BN).  With ``res`` the result is ``act(conv + res)`` or, when
+        ``res_after_act`` (res34's res_block1, res34.py:40-45), ``relu(act(conv) + res)``."""
+        kern = self._get(name + "/k", (k, k, x.C, cout), "he_normal" if he else "glorot_uniform")
+        bias = self._get(name + "/b", (cout,), "zeros")
+        w = kern.reshape(k * k, x.C, cout).transpose(0, 2, 1).copy()  # (taps, Cout, Cin)
+        if bn:
+            sc, sh = self._bn(bn if isinstance(bn, str) else name + "_bn", cout)
+            w = w * sc[None, :, None]
+            bias = bias * sc + sh
+        Ho, Wo = math.ceil(x.H / s), math.ceil(x.W / s)
+        pt, _ = same_pad(x.H, k, s, d)
+        pl, _ = same_pad(x.W, k, s, d)
+        taps = [(kh * d - pt, kw * d - pl) for kh in range(k) for kw in range(k)]
+        if out is None:
+            out = self.new(Ho, Wo, cout, "f32" if f32_out else "bf16")
+        a = ACT_RELU if act == "relu" else ACT_NONE
+        if res is None:
+            act_pre, act_post = a, ACT_NONE
+        elif res_after_act:
+            act_pre, act_post = a, ACT_RELU
+        else:
+            act_pre, act_post = ACT_NONE, a
+        self._conv_op(x, w, bias, taps, s, Ho, Wo, act_pre, res, act_post, out, name=name)
+        return out
+
+    def conv_transpose(self, x, name, cout, k, act=None, out=None):
+        """Conv2DTranspose(k in {2,3}, strides=2, padding='same') as 4 sub-pixel convs:
+        y[2m+a] = sum over kh with kh = a (mod 2) of x[m - (kh-a)/2] W[kh]."""
+        kern = self._get(name + "/k", (k, k, cout, x.C), "glorot_uniform")  # (kh,kw,Cout,Cin)
+        bias = self._get(name + "/b", (cout,), "zeros")
+        if out is None:
+            out = self.new(2 * x.H, 2 * x.W, cout)
+        a = ACT_RELU if act == "relu" else ACT_NONE
+        for py in (0, 1):
+            for px in (0, 1):
+                taps, ws = [], []
+                for kh in range(py, k, 2):
+                    for kw in range(px, k, 2):
+                        taps.append((-(kh - py) // 2, -(kw - px) // 2))
+                        ws.append(kern[kh, kw])  # (Cout, Cin)
+                self._conv_op(x, np.stack(ws), bias, taps, 1, x.H, x.W, a, None, ACT_NONE, out,
+                              out_scale=2, out_oy=py, out_ox=px, name=f"{name}[{py}{px}]")
+        return out
+
+    def sepconv(self, x, name, cout, s=1, relu_in=False, bn=True, act=None, res=None, out=None):
+        """[ReLU ->] SeparableConv2D(3x3, 'same', strides=s) [+BN] [+ReLU] [+res]."""
+        dw = self._get(name + "/dw", (3, 3, x.C, 1), "glorot_uniform")
+        pw = self._get(name + "/pw", (1, 1, x.C, cout), "glorot_uniform")
+        bias = self._get(name + "/b", (cout,), "zeros")
+        Ho, Wo = math.ceil(x.H / s), math.ceil(x.W / s)
+        mid = self.new(Ho, Wo, x.C)
+        pt, _ = same_pad(x.H, 3, s)
+        pl, _ = same_pad(x.W, 3, s)
+        self.plan.flops += 2 * self.plan.batch * Ho * Wo * x.C * 9
+        self._emit(op=OP_DWCONV, name=name + "/dw", x=x.ref(), y=mid.ref(), stride=s, pad_t=pt, pad_l=pl,
+                   relu_in=int(relu_in), w=np.ascontiguousarray(dw.reshape(9, x.C), np.float32))
+        w = pw.reshape(1, x.C, cout).transpose(0, 2, 1).copy()
+        if bn:
+            sc, sh = self._bn(name + "_bn", cout)
+            w = w * sc[None, :, None]
+            bias = bias * sc + sh
+        if out is None:
+            out = self.new(Ho, Wo, cout)
+        a = ACT_RELU if act == "relu" else ACT_NONE
+        self._conv_op(mid, w, bias, [(0, 0)], 1, Ho, Wo, ACT_NONE if res is not None else a, res,
+                      a if res is not None else ACT_NONE, out, name=name + "/pw")
+        return out
+
+    # ------------------------------------------------------------------ memory-bound ops
+    def maxpool(self, x, k, s, same=False, out=None):
+        if same:
+            Ho, Wo = math.ceil(x.H / s), math.ceil(x.W / s)
+            pt, _ = same_pad(x.H, k, s)
+            pl, _ = same_pad(x.W, k, s)
+        else:
+            Ho, Wo = (x.H - k) // s + 1, (x.W - k) // s + 1
+            pt = pl = 0
+        if out is None:
+            out = self.new(Ho, Wo, x.C)
+        assert (out.H, out.W, out.C) == (Ho, Wo, x.C)
+        self._emit(op=OP_MAXPOOL, x=x.ref(), y=out.ref(), k=k, stride=s, pad_t=pt, pad_l=pl)
+        return out
+
+    def addn(self, terms, act=None, out=None):
+        """out = act(sum_i nearest_upsample(x_i, f_i)); terms = [(T, f), ...], at most 4."""
+        x0, f0 = terms[0]
+        H, W, C = x0.H * f0, x0.W * f0, x0.C
+        for x, f in terms:
+            assert (x.H * f, x.W * f, x.C) == (H, W, C)
+        if out is None:
+            out = self.new(H, W, C)
+        assert (out.H, out.W, out.C) == (H, W, C) and len(terms) <= 4
+        self._emit(op=OP_ADDN, xs=[x.ref() for x, _ in terms], fs=[int(f) for _, f in terms], y=out.ref(),
+                   act=ACT_RELU if act == "relu" else ACT_NONE)
+        return out
+
+    def upsample(self, x, f, out=None):
+        return self.addn([(x, f)], out=out)
+
+    def copy(self, x, out):
+        return self.addn([(x, 1)], out=out)
+
+    def gap(self, x):
+        v = self.vec(x.C)
+        self._emit(op=OP_GAP, x=x.ref(), y=v.buf.id)
+        return v
+
+    def dense(self, vs, name, cout, bn=None, act=None, conv_kernel=False):
+        """y = act(BN(W . sum(vs) + b)).  conv_kernel: the reference layer is a 1x1 Conv2D on a
+        (1,1,C) map (kernel shape (1,1,in,out)) rather than a Dense layer."""
+        cin = vs[0].C
+        shape = (1, 1, cin, cout) if conv_kernel else (cin, cout)
+        kern = self._get(name + "/k", shape, "glorot_uniform").reshape(cin, cout)
+        bias = self._get(name + "/b", (cout,), "zeros")
+        w = kern.T.copy()  # (Cout, Cin)
+        if bn:
+            sc, sh = self._bn(bn, cout)
+            w = w * sc[:, None]
+            bias = bias * sc + sh
+        y = self.vec(cout)
+        self.plan.flops += 2 * self.plan.batch * cin * cout
+        self._emit(op=OP_DENSE, xs=[v.buf.id for v in vs], y=y.buf.id,
+                   act={None: ACT_NONE, "relu": ACT_RELU, "sigmoid": ACT_SIGMOID}[act],
+                   w=np.ascontiguousarray(w, np.float32), b=np.ascontiguousarray(bias, np.float32))
+        return y
+
+    def gate_se(self, x, v, out=None):
+        """x * v[n,c] (res34 attention_demo, res34.py:102-104; v already sigmoid-ed)."""
+        if out is None:
+            out = self.new(x.H, x.W, x.C)
+        self._emit(op=OP_GATE, mode=GATE_SE, x=x.ref(), y=out.ref(), v=v.buf.id, s=None, w=None, b=0.0)
+        return out
+
+    def scse(self, x, name, out=None):
+        """scSE block (scse.py:20-46, v3plus.py:141-167): x*sigmoid(conv1x1->1(x)) + x*sigmoid(W2 W1 GAP(x))."""
+        c = x.C
+        ks = self._get(name + "_s/k", (1, 1, c, 1), "glorot_uniform").reshape(c)
+        bs = self._get(name + "_s/b", (1,), "zeros")
+        g = self.gap(x)
+        h = self.dense([g], name + "_c1", c // 16, conv_kernel=True)
+        cs = self.dense([h], name + "_c2", c, act="sigmoid", conv_kernel=True)
+        if out is None:
+            out = self.new(x.H, x.W, c)
+        self.plan.flops += 2 * self.plan.batch * x.H * x.W * c
+        self._emit(op=OP_GATE, mode=GATE_SCSE, x=x.ref(), y=out.ref(), v=cs.buf.id, s=None,
+                   w=np.ascontiguousarray(ks, np.float32), b=float(bs[0]))
+        return out
+
+    def gate_bam(self, x, cg, sg, out=None):
+        """x * (1 + sigmoid(cg[n,c] + sg[n,h,w]))  (bam.py:57-71)."""
+        if out is None:
+            out = self.new(x.H, x.W, x.C)
+        assert sg.C == 1 and (sg.H, sg.W) == (x.H, x.W)
+        self._emit(op=OP_GATE, mode=GATE_BAM, x=x.ref(), y=out.ref(), v=cg.buf.id, s=sg.ref(), w=None, b=0.0)
+        return out
+
+    def skfuse(self, ds, g, logits, bn_name, out=None):
+        """Selective-kernel fusion (v3plus.py:114-136): softmax over the five 256-vectors, weighted
+        sum of the four maps and the broadcast pooled branch, then BN + ReLU."""
+        c = ds[0].C
+        sc, sh = self._bn(bn_name, c)
+        if out is None:
+            out = self.new(ds[0].H, ds[0].W, c)
+        self._emit(op=OP_SKFUSE, xs=[d.ref() for d in ds], g=g.buf.id, logits=[l.buf.id for l in logits],
+                   y=out.ref(), scale=sc, shift=sh)
+        return out
+
+    def bcast(self, v, out):
+        """UpSampling2D of a 1x1 map: broadcast v[n,c] over the slice ``out``."""
+        assert out.C == v.C
+        self._emit(op=OP_BCAST, v=v.buf.id, y=out.ref())
+        return out
+
+    def softmax_head(self, logits, up=1):
+        """2-class softmax (+ nearest upsample of the logits by ``up``, which commutes with the
+        1x1 conv + softmax head of bam.py:332-333)."""
+        assert logits.buf.dtype == "f32" and logits.C == 2 and logits.c0 == 0
+        self.plan.logits = logits.buf.id
+        self.plan.logits_up = up
+        self._emit(op=OP_SOFTMAX2, x=logits.ref(), up=up)
+
+
+# ---------------------------------------------------------------------- weight init
+def init_weights(spec, seed=0, randomize_bn=False):
+    """Keras-default initialisation of a weight spec: glorot_uniform / he_normal kernels, zero
+    biases, identity BatchNorm -- or, for parity tests, randomised BN statistics
+    (gamma~U(.5,1.5), beta~N(0,.1), mean~N(0,.1), var~U(.5,1.5))."""
+    rng = np.random.default_rng(seed)
+    out = {}
+    for name, (shape, init) in spec.items():
+        if init in ("glorot_uniform", "he_normal"):
+            if len(shape) == 4:
+                rf = shape[0] * shape[1]
+                # Conv2D kernels are (kh,kw,in,out); Conv2DTranspose (kh,kw,out,in): Keras computes
+                # fans as shape[-2]*rf and shape[-1]*rf either way.
+                fan_in, fan_out = shape[2] * rf, shape[3] * rf
+            else:
+                fan_in, fan_out = shape
+            if init == "glorot_uniform":
+                lim = math.sqrt(6.0 / (fan_in + fan_out))
+                a = rng.uniform(-lim, lim, shape)
+            else:  # he_normal: truncated normal, stddev sqrt(2/fan_in)/.8796
+                std = math.sqrt(2.0 / fan_in) / 0.87962566103423978
+                a = np.clip(rng.standard_normal(shape), -2, 2) * std
+        elif init == "zeros":
+            a = np.zeros(shape) if not randomize_bn else rng.normal(0, 0.05, shape)
+        elif init == "bn_gamma":
+            a = rng.uniform(0.5, 1.5, shape) if randomize_bn else np.ones(shape)
+        elif init == "bn_beta":
+            a = rng.normal(0, 0.1, shape) if randomize_bn else np.zeros(shape)
+        elif init == "bn_mean":
+            a = rng.normal(0, 0.1, shape) if randomize_bn else np.zeros(shape)
+        elif init == "bn_var":
+            a = rng.uniform(0.5, 1.5, shape) if randomize_bn else np.ones(shape)
+        else:
+            raise ValueError(init)
+        out[name] = a.astype(np.float32)
+    return out
+
+
+def count_params(spec, prefix=None):
+    return sum(int(np.prod(s)) for n, (s, _) in spec.items() if prefix is None or prefix(n))

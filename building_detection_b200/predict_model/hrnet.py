@@ -1,0 +1,73 @@
+"""HRNet -- B200 plan for the graph of reference predict_model/hrnet.py:20-203."""
+from ..engine import Model
+from ..graph import Net, T
+
+
+def build(g: Net):
+    x = g.input()
+
+    def cb(t, name, cout, k=3, s=1, act="relu", res=None, out=None):  # conv_bn_relu, hrnet.py:20-25
+        return g.conv(t, name, cout, k=k, s=s, bn=True, act=act, res=res, out=out)
+
+    def bottleneck(t, name, project):  # conv_block / identity_block, hrnet.py:28-49
+        c = cb(t, name + "_a", 64, k=1)
+        c = cb(c, name + "_b", 64, k=3)
+        short = cb(t, name + "_s", 256, k=1, act=None) if project else t
+        return cb(c, name + "_c", 256, k=1, act="relu", res=short)  # relu(bn(conv) + shortcut)
+
+    def branch(t, name, out=None):  # 4 x basic_block, hrnet.py:52-59,91-96
+        for i in range(4):
+            c = cb(t, f"{name}_{i}_1", t.C)
+            t = cb(c, f"{name}_{i}_2", t.C, act="relu", res=t, out=out if i == 3 else None)
+        return t
+
+    t = cb(x, "stem", 64, s=2)  # hrnet.py:168
+    t = bottleneck(t, "l1_0", True)  # layer1, hrnet.py:62-67
+    for i in range(1, 4):
+        t = bottleneck(t, f"l1_{i}", False)
+
+    # stage 1 (hrnet.py:172-178)
+    b10 = branch(cb(t, "t1_0", 32), "b1_0")
+    b11 = branch(cb(t, "t1_1", 64, s=2), "b1_1")
+    # fuse_block_1 (hrnet.py:99-111): no activation after the sums
+    u = cb(b11, "f1_up", 32, k=1, act=None)
+    f1_0 = g.addn([(b10, 1), (u, 2)])
+    f1_1 = cb(b10, "f1_down", 64, s=2, act=None, res=b11)
+
+    # stage 2 (hrnet.py:180-187)
+    b20 = branch(cb(f1_0, "t2_0", 32), "b2_0")
+    b21 = branch(cb(f1_1, "t2_1", 64), "b2_1")
+    b22 = branch(cb(f1_1, "t2_2", 128, s=2), "b2_2")
+    # fuse_block_2 (hrnet.py:114-139)
+    x12 = cb(b21, "f2_12", 32, k=1, act=None)
+    x13 = cb(b22, "f2_13", 32, k=1, act=None)
+    f2_0 = g.addn([(b20, 1), (x12, 2), (x13, 4)])
+    x21 = cb(b20, "f2_21", 64, s=2, act=None, res=b21)
+    x23 = cb(b22, "f2_23", 64, k=1, act=None)
+    f2_1 = g.addn([(x21, 1), (x23, 2)])
+    x31 = cb(b20, "f2_31a", 32, s=2)
+    x31 = cb(x31, "f2_31b", 128, s=2, act=None, res=b22)
+    f2_2 = cb(b21, "f2_32", 128, s=2, act=None, res=x31)
+
+    # stage 3 (hrnet.py:189-196); fuse_block_3 concatenates, so branch 0 lands in its slice
+    cat = g.buf(256, 256, 128)
+    branch(cb(f2_0, "t3_0", 32), "b3_0", out=T(cat, 0, 32))
+    b31 = branch(cb(f2_1, "t3_1", 64), "b3_1")
+    b32 = branch(cb(f2_2, "t3_2", 128), "b3_2")
+    b33 = branch(cb(f2_2, "t3_3", 256, s=2), "b3_3")
+    # fuse_block_3 (hrnet.py:142-162)
+    g.upsample(cb(b31, "f3_1", 32, k=1, act=None), 2, out=T(cat, 32, 32))
+    g.upsample(cb(b32, "f3_2", 32, k=1, act=None), 4, out=T(cat, 64, 32))
+    g.upsample(cb(b33, "f3_3", 32, k=1, act=None), 8, out=T(cat, 96, 32))
+
+    o = g.upsample(T(cat, 0, 128), 2)  # hrnet.py:198
+    o = cb(o, "head_conv", 64)
+    logits = g.conv(o, "head_out", 2, k=1, f32_out=True)  # hrnet.py:200
+    g.softmax_head(logits)
+
+
+def HRNet(shape=(512, 512, 3), num_classes=2):
+    """Drop-in for reference predict_model/hrnet.py:165."""
+    if num_classes != 2:
+        raise ValueError("the B200 head kernel is the reference's 2-class softmax")
+    return Model("hrnet", build, tuple(shape))

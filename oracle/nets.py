@@ -1,0 +1,495 @@
+"""ORACLE (test infrastructure only -- never imported by the product path).
+
+CPU fp32 restatement, in plain torch.nn.functional, of the five Keras graphs in the
+reference's ``predict_model/`` directory.  TensorFlow is not installable in the build
+container (no wheel, no network), so the reference graphs cannot be executed; this file
+follows them line by line instead and every function cites the lines it restates.
+
+PARITY UNPINNED for the network forwards: the reference ships no golden vectors for
+them.  The only known answer the reference holds is the res34 encoder
+parameter count 22,910,272 (predict_model/res34.py:164), checked in tests/test_oracle_nets.py.
+
+Semantics honoured: inference BatchNorm with eps=1e-3, TF 'same'
+padding (asymmetric for stride 2), nearest UpSampling2D, Conv2DTranspose 'same' crop,
+SeparableConv2D = depthwise (no bias) then pointwise (+bias), softmax heads.
+
+Weights come in as a flat ``dict[str, np.ndarray]`` in Keras layouts (HWIO conv kernels,
+(kh,kw,Cout,Cin) transposed-conv kernels, (in,out) dense kernels, BN gamma/beta/mean/var);
+the key names are the layer names the product's graph builder assigns, so a structural
+mismatch between the two transcriptions surfaces as a KeyError or a shape error.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+BN_EPS = 1e-3  # Keras BatchNormalization default epsilon
+
+
+class _W:
+    """Name-keyed weight access with use tracking (every tensor must be consumed once)."""
+
+    def __init__(self, weights):
+        self.w = weights
+        self.used = set()
+
+    def __call__(self, key):
+        self.used.add(key)
+        return torch.from_numpy(np.ascontiguousarray(self.w[key], dtype=np.float32))
+
+    def check_all_used(self):
+        missing = set(self.w) - self.used
+        if missing:
+            raise AssertionError(f"oracle did not consume weights: {sorted(missing)[:8]} ...")
+
+
+# ----------------------------------------------------------------------------- primitives
+def _same_pad(size, k, s, d):
+    """TF 'same' padding: (before, after).  SURVEY App. B #2."""
+    k_eff = (k - 1) * d + 1
+    out = math.ceil(size / s)
+    total = max((out - 1) * s + k_eff - size, 0)
+    return total // 2, total - total // 2
+
+
+def conv2d(W, x, name, k, s=1, d=1, bias=True):
+    """tf.keras.layers.Conv2D(padding='same'); x is NCHW fp32, kernel HWIO."""
+    w = W(name + "/k").permute(3, 2, 0, 1).contiguous()  # OIHW
+    assert w.shape[2] == k and w.shape[1] == x.shape[1], (name, tuple(w.shape), tuple(x.shape))
+    pt, pb = _same_pad(x.shape[2], k, s, d)
+    pl, pr = _same_pad(x.shape[3], k, s, d)
+    x = F.pad(x, (pl, pr, pt, pb))
+    b = W(name + "/b") if bias else None
+    return F.conv2d(x, w, b, stride=s, dilation=d)
+
+
+def bn(W, x, name):
+    """Inference BatchNormalization, eps 1e-3; works for NCHW maps and (N,C) vectors."""
+    g, b, m, v = W(name + "/gamma"), W(name + "/beta"), W(name + "/mean"), W(name + "/var")
+    shape = (1, -1, 1, 1) if x.dim() == 4 else (1, -1)
+    return (x - m.view(shape)) / torch.sqrt(v.view(shape) + BN_EPS) * g.view(shape) + b.view(shape)
+
+
+def sepconv(W, x, name, s=1):
+    """SeparableConv2D 3x3 'same': depthwise (3,3,Cin,1) no bias -> pointwise + bias."""
+    dw = W(name + "/dw")  # (3,3,Cin,1)
+    c = x.shape[1]
+    wd = dw.permute(2, 3, 0, 1).contiguous()  # (Cin,1,3,3)
+    pt, pb = _same_pad(x.shape[2], 3, s, 1)
+    pl, pr = _same_pad(x.shape[3], 3, s, 1)
+    x = F.conv2d(F.pad(x, (pl, pr, pt, pb)), wd, None, stride=s, groups=c)
+    pw = W(name + "/pw").permute(3, 2, 0, 1).contiguous()
+    return F.conv2d(x, pw, W(name + "/b"))
+
+
+def conv_transpose(W, x, name, k):
+    """Conv2DTranspose(k, strides=2, padding='same'): y[2i+a] += x[i] W[a], crop to 2N.
+    Keras kernel layout (kh,kw,Cout,Cin), no flip."""
+    w = W(name + "/k").permute(3, 2, 0, 1).contiguous()  # torch wants (Cin,Cout,kh,kw)
+    y = F.conv_transpose2d(x, w, W(name + "/b"), stride=2)
+    return y[:, :, : 2 * x.shape[2], : 2 * x.shape[3]]
+
+
+def dense(W, x, name):
+    return x @ W(name + "/k") + W(name + "/b")
+
+
+def maxpool(x, k, s, same=False):
+    if same:
+        pt, pb = _same_pad(x.shape[2], k, s, 1)
+        pl, pr = _same_pad(x.shape[3], k, s, 1)
+        x = F.pad(x, (pl, pr, pt, pb), value=float("-inf"))
+    return F.max_pool2d(x, k, s)
+
+
+def up(x, f):
+    """UpSampling2D(size=f), default nearest."""
+    return x.repeat_interleave(f, dim=2).repeat_interleave(f, dim=3)
+
+
+def gap(x):
+    return x.mean(dim=(2, 3))
+
+
+def softmax_head(logits):
+    return torch.softmax(logits, dim=1).permute(0, 2, 3, 1).contiguous()
+
+
+# ----------------------------------------------------------------------------- res34
+def res34_forward(weights, x_nhwc):
+    """predict_model/res34.py:27-170 (ResNetFamily.run_model('res34'))."""
+    W = _W(weights)
+    x = torch.as_tensor(x_nhwc, dtype=torch.float32).permute(0, 3, 1, 2)
+
+    def bn_conv_a(t, name, k=3):  # res34.py:32-38
+        return F.relu(bn(W, conv2d(W, t, name, k), name + "_BN"))
+
+    def res_block1(t, name):  # res34.py:40-45
+        c = bn_conv_a(t, name + "_1")
+        c = bn_conv_a(c, name + "_2")
+        return F.relu(t + c)
+
+    # res34(): res34.py:47-69
+    conv1 = bn_conv_a(x, "conv1_1")
+    conv1 = bn_conv_a(conv1, "conv1_2")
+    conv1 = bn_conv_a(conv1, "conv1_3")
+    conv2 = conv2d(W, conv1, "pool1", 1, s=2)
+    for i in range(3):
+        conv2 = res_block1(conv2, f"conv2_{i}")
+    conv3 = conv2d(W, conv2, "pool2", 1, s=2)
+    for i in range(4):
+        conv3 = res_block1(conv3, f"conv3_{i}")
+    conv4 = conv2d(W, conv3, "pool3", 1, s=2)
+    for i in range(6):
+        conv4 = res_block1(conv4, f"conv4_{i}")
+    conv5 = conv2d(W, conv4, "pool4", 1, s=2)
+    for i in range(3):
+        conv5 = res_block1(conv5, f"conv5_{i}")
+
+    def low_to_high(low, mid, high, name):  # res34.py:151-159
+        low1 = maxpool(low, 2, 2)
+        low2 = maxpool(low, 2, 4)  # MaxPool2D(strides=4): pool 2, valid
+        mid1 = maxpool(mid, 2, 2)
+        h = torch.cat([high, mid1, low2], dim=1)
+        h = F.relu(conv2d(W, h, name + "_high", 1))
+        m = torch.cat([mid, low1], dim=1)
+        m = F.relu(conv2d(W, m, name + "_mid", 1))
+        return m, h
+
+    def attention_demo(t, name):  # res34.py:90-105
+        g = gap(t)
+        f1 = F.relu(bn(W, dense(W, g, name + "_fc1"), name + "_bn1"))
+        f2 = torch.sigmoid(bn(W, dense(W, f1, name + "_fc2"), name + "_bn2"))
+        return t * f2[:, :, None, None]
+
+    def upsame(low, high, name):  # res34.py:143-149
+        hu = F.relu(conv_transpose(W, high, f"up{name}_convT", 2))
+        o = torch.cat([low, hu], dim=1)
+        o = F.relu(conv2d(W, o, f"up{name}_mix", 1))
+        return res_block1(o, f"upsame_{name}")
+
+    # feature_fusion(): res34.py:71-88
+    conv2, conv3 = low_to_high(conv1, conv2, conv3, "l2h_a")
+    conv3, conv4 = low_to_high(conv2, conv3, conv4, "l2h_b")
+    conv1 = attention_demo(conv1, "att1")
+    conv2 = attention_demo(conv2, "att2")
+    conv3 = attention_demo(conv3, "att3")
+    conv4 = attention_demo(conv4, "att4")
+    conv5 = attention_demo(conv5, "att5")
+    up4 = upsame(conv4, conv5, "4")
+    up3 = upsame(conv3, up4, "3")
+    up2 = upsame(conv2, up3, "2")
+    up1 = upsame(conv1, up2, "1")
+    o = F.relu(conv2d(W, up1, "head_conv", 3))
+    logits = conv2d(W, o, "head_out", 3)
+    W.check_all_used()
+    return softmax_head(logits).numpy()
+
+
+# ----------------------------------------------------------------------------- hrnet
+def hrnet_forward(weights, x_nhwc):
+    """predict_model/hrnet.py:20-203."""
+    W = _W(weights)
+    x = torch.as_tensor(x_nhwc, dtype=torch.float32).permute(0, 3, 1, 2)
+
+    def cbr(t, name, k=3, s=1, act=True):  # hrnet.py:20-25
+        t = bn(W, conv2d(W, t, name, k, s), name + "_bn")
+        return F.relu(t) if act else t
+
+    def conv_block(t, name, f):  # hrnet.py:28-38
+        c = cbr(t, name + "_a", 1)
+        c = cbr(c, name + "_b", 3)
+        c = cbr(c, name + "_c", 1, act=False)
+        sh = cbr(t, name + "_s", 1, act=False)
+        return F.relu(c + sh)
+
+    def identity_block(t, name):  # hrnet.py:41-49
+        c = cbr(t, name + "_a", 1)
+        c = cbr(c, name + "_b", 3)
+        c = cbr(c, name + "_c", 1, act=False)
+        return F.relu(c + t)
+
+    def basic_block(t, name):  # hrnet.py:52-59
+        c = cbr(t, name + "_1", 3)
+        c = cbr(c, name + "_2", 3, act=False)
+        return F.relu(c + t)
+
+    def branch(t, name):  # hrnet.py:91-96
+        for i in range(4):
+            t = basic_block(t, f"{name}_{i}")
+        return t
+
+    conv = cbr(x, "stem", 3, 2)  # hrnet.py:168
+    conv = conv_block(conv, "l1_0", 256)  # layer1: hrnet.py:62-67
+    for i in range(1, 4):
+        conv = identity_block(conv, f"l1_{i}")
+
+    t1 = [cbr(conv, "t1_0"), cbr(conv, "t1_1", s=2)]  # hrnet.py:70-73
+    b10 = branch(t1[0], "b1_0")
+    b11 = branch(t1[1], "b1_1")
+    # fuse_block_1: hrnet.py:99-111
+    x1 = up(cbr(b11, "f1_up", 1, act=False), 2)
+    f1_0 = b10 + x1
+    f1_1 = cbr(b10, "f1_down", 3, 2, act=False) + b11
+
+    # transition_layer2: hrnet.py:76-80
+    t2 = [cbr(f1_0, "t2_0"), cbr(f1_1, "t2_1"), cbr(f1_1, "t2_2", s=2)]
+    b20, b21, b22 = branch(t2[0], "b2_0"), branch(t2[1], "b2_1"), branch(t2[2], "b2_2")
+    # fuse_block_2: hrnet.py:114-139
+    x12 = up(cbr(b21, "f2_12", 1, act=False), 2)
+    x13 = up(cbr(b22, "f2_13", 1, act=False), 4)
+    f2_0 = b20 + x12 + x13
+    x21 = cbr(b20, "f2_21", 3, 2, act=False)
+    x23 = up(cbr(b22, "f2_23", 1, act=False), 2)
+    f2_1 = x21 + b21 + x23
+    x31 = cbr(b20, "f2_31a", 3, 2)
+    x31 = cbr(x31, "f2_31b", 3, 2, act=False)
+    x32 = cbr(b21, "f2_32", 3, 2, act=False)
+    f2_2 = x31 + x32 + b22
+
+    # transition_layer3: hrnet.py:83-88
+    t3 = [cbr(f2_0, "t3_0"), cbr(f2_1, "t3_1"), cbr(f2_2, "t3_2"), cbr(f2_2, "t3_3", s=2)]
+    b30, b31 = branch(t3[0], "b3_0"), branch(t3[1], "b3_1")
+    b32, b33 = branch(t3[2], "b3_2"), branch(t3[3], "b3_3")
+    # fuse_block_3: hrnet.py:142-162
+    y1 = up(cbr(b31, "f3_1", 1, act=False), 2)
+    y2 = up(cbr(b32, "f3_2", 1, act=False), 4)
+    y3 = up(cbr(b33, "f3_3", 1, act=False), 8)
+    f3 = torch.cat([b30, y1, y2, y3], dim=1)
+
+    o = up(f3, 2)  # hrnet.py:198-200
+    o = cbr(o, "head_conv", 3)
+    logits = conv2d(W, o, "head_out", 1)
+    W.check_all_used()
+    return softmax_head(logits).numpy()
+
+
+# ----------------------------------------------------------------------------- shared by v3plus / scse / bam
+def _sse(W, t, name):  # v3plus.py:141-146, scse.py:20-25
+    s = torch.sigmoid(conv2d(W, t, name + "_s", 1))
+    return s * t
+
+
+def _cse(W, t, name):  # v3plus.py:149-160, scse.py:28-39 -- no activation between the two 1x1 convs
+    g = gap(t)[:, :, None, None]
+    g = conv2d(W, g, name + "_c1", 1)
+    g = torch.sigmoid(conv2d(W, g, name + "_c2", 1))
+    return g * t
+
+
+def scse_block(W, t, name):  # v3plus.py:163-167, scse.py:42-46
+    return _sse(W, t, name) + _cse(W, t, name)
+
+
+def _cbr(W, t, name, k, d=1, act=True):
+    """inner conv_bn_relu of v3plus.py:288-293 / bam.py."""
+    t = bn(W, conv2d(W, t, name, k, 1, d), name + "_bn")
+    return F.relu(t) if act else t
+
+
+def sknet_block(W, t):
+    """v3plus.py:74-138 (identical in bam.py)."""
+    conv = _cbr(W, t, "sk_in", 3)
+    d1 = _cbr(W, conv, "sk_d1", 1)
+    d6 = _cbr(W, conv, "sk_d6", 3, 6)
+    d12 = _cbr(W, conv, "sk_d12", 3, 12)
+    d18 = _cbr(W, conv, "sk_d18", 3, 18)
+    g = gap(conv)[:, :, None, None]
+    g = _cbr(W, g, "sk_gap", 1)
+    g = up(g, conv.shape[2])
+    total = d1 + d6 + d12 + d18 + g
+    tf_ = gap(total)[:, :, None, None]
+    tf_ = _cbr(W, tf_, "sk_squeeze", 1)
+    ws = [conv2d(W, tf_, f"sk_w{i}", 1) for i in range(5)]  # each (B,256,1,1)
+    cat = torch.stack([w[:, :, 0, 0] for w in ws], dim=1)  # (B,5,256): axis=-2 concat
+    sm = torch.softmax(cat, dim=1)  # Softmax(axis=-2)
+    branches = [d1, d6, d12, d18, g]
+    fused = sum(b * sm[:, i, :, None, None] for i, b in enumerate(branches))
+    return F.relu(bn(W, fused, "sk_out_bn"))
+
+
+def aspp(W, t):
+    """inner ASPP, v3plus.py:295-307."""
+    c = _cbr(W, t, "aspp_1x1", 1)
+    p1 = _cbr(W, t, "aspp_d6", 3, 6)
+    p2 = _cbr(W, t, "aspp_d12", 3, 12)
+    p3 = _cbr(W, t, "aspp_d18", 3, 18)
+    a = F.avg_pool2d(t, 32)
+    a = _cbr(W, a, "aspp_pool", 1)
+    a = up(a, 32)
+    return torch.cat([c, p1, p2, p3, a], dim=1)
+
+
+def _bam_attention(W, t, name):
+    """bam.py:20-71: x * (1 + sigmoid(channel_gate(x) + spatial_gate(x)))."""
+    g = gap(t)
+    f = F.relu(bn(W, dense(W, g, name + "_cg1"), name + "_cg1_bn"))
+    f = F.relu(bn(W, dense(W, f, name + "_cg2"), name + "_cg2_bn"))
+    cg = dense(W, f, name + "_cg3")
+    s = F.relu(bn(W, conv2d(W, t, name + "_sg1", 1), name + "_sg1_bn"))
+    s = F.relu(bn(W, conv2d(W, s, name + "_sg2", 3, 1, 4), name + "_sg2_bn"))
+    s = F.relu(bn(W, conv2d(W, s, name + "_sg3", 3, 1, 4), name + "_sg3_bn"))
+    s = conv2d(W, s, name + "_sg4", 1)
+    a = torch.sigmoid(cg[:, :, None, None] + s)
+    return a * t + t
+
+
+def _xception_backbone(W, x, with_bam):
+    """v3plus.py:173-280 / bam.py:173-277.  Returns (c, c1, c2, c5)."""
+    t = F.relu(bn(W, conv2d(W, x, "entry1", 3, 2), "entry1_bn"))
+    t = F.relu(bn(W, conv2d(W, t, "entry2", 3), "entry2_bn"))
+    if with_bam:
+        t = _bam_attention(W, t, "bam1")  # bam.py:182
+    c = t
+    # block 1
+    r = bn(W, conv2d(W, t, "b1_res", 1, 2), "b1_res_bn")
+    t = F.relu(bn(W, sepconv(W, t, "b1_s1"), "b1_s1_bn"))
+    t = bn(W, sepconv(W, t, "b1_s2"), "b1_s2_bn")
+    t = maxpool(t, 3, 2, same=True)
+    t = t + r
+    c1 = t  # bam.py:194 takes c1 before BAM
+    if with_bam:
+        t = _bam_attention(W, t, "bam2")
+    # block 2
+    r = bn(W, conv2d(W, t, "b2_res", 1, 2), "b2_res_bn")
+    t = F.relu(t)
+    t = bn(W, sepconv(W, t, "b2_s1"), "b2_s1_bn")
+    t = F.relu(t)
+    t = bn(W, sepconv(W, t, "b2_s2"), "b2_s2_bn")
+    t = F.relu(t)
+    t = bn(W, sepconv(W, t, "b2_s3", 2), "b2_s3_bn")
+    t = t + r
+    c2 = t
+    if with_bam:
+        t = _bam_attention(W, t, "bam3")
+    # block 3
+    r = bn(W, conv2d(W, t, "b3_res", 1, 2), "b3_res_bn")
+    t = F.relu(t)
+    t = bn(W, sepconv(W, t, "b3_s1"), "b3_s1_bn")
+    t = F.relu(t)
+    t = bn(W, sepconv(W, t, "b3_s2"), "b3_s2_bn")
+    t = F.relu(t)
+    t = bn(W, sepconv(W, t, "b3_s3", 2), "b3_s3_bn")
+    t = t + r
+    # middle flow, 16 blocks
+    for i in range(16):
+        r = t
+        for j in range(3):
+            t = F.relu(t)
+            t = bn(W, sepconv(W, t, f"mid{i}_s{j}"), f"mid{i}_s{j}_bn")
+        t = t + r
+    if with_bam:
+        t = _bam_attention(W, t, "bam4")  # bam.py:253
+    # exit flow
+    r = bn(W, conv2d(W, t, "exit_res", 1), "exit_res_bn")
+    t = F.relu(t)
+    t = bn(W, sepconv(W, t, "exit_s1"), "exit_s1_bn")
+    t = F.relu(t)
+    t = bn(W, sepconv(W, t, "exit_s2"), "exit_s2_bn")
+    t = F.relu(t)
+    t = bn(W, sepconv(W, t, "exit_s3"), "exit_s3_bn")
+    t = t + r
+    t = F.relu(bn(W, sepconv(W, t, "exit_s4"), "exit_s4_bn"))
+    t = F.relu(bn(W, sepconv(W, t, "exit_s5"), "exit_s5_bn"))
+    t = F.relu(bn(W, sepconv(W, t, "exit_s6"), "exit_s6_bn"))
+    return c, c1, c2, t
+
+
+def _deeplab_neck(W, c5):
+    """v3plus.py:309-316 / bam.py:306-313."""
+    sk = sknet_block(W, c5)
+    a = aspp(W, c5)
+    conv1 = _cbr(W, a, "aspp_proj", 1)
+    conv1 = torch.cat([conv1, sk], dim=1)
+    conv1 = _cbr(W, conv1, "neck1", 3)
+    conv1 = _cbr(W, conv1, "neck2", 3)
+    return scse_block(W, conv1, "neck_scse")
+
+
+def v3plus_forward(weights, x_nhwc):
+    """predict_model/v3plus.py:170-350 (Xception_DeepLabV3_Plus)."""
+    W = _W(weights)
+    x = torch.as_tensor(x_nhwc, dtype=torch.float32).permute(0, 3, 1, 2)
+    c, c1, c2, c5 = _xception_backbone(W, x, with_bam=False)
+    conv1 = _deeplab_neck(W, c5)
+    up1 = up(conv1, 2)  # v3plus.py:321
+    t = torch.cat([up1, c2], dim=1)
+    t = _cbr(W, t, "dec1_a", 3)
+    t = _cbr(W, t, "dec1_b", 3)
+    t = scse_block(W, t, "dec1_scse")
+    up2 = conv_transpose(W, t, "dec2_up", 3)  # no activation (v3plus.py:328)
+    t = torch.cat([up2, c1], dim=1)
+    t = _cbr(W, t, "dec2_a", 3)
+    t = _cbr(W, t, "dec2_b", 3)
+    t = scse_block(W, t, "dec2_scse")
+    up3 = conv_transpose(W, t, "dec3_up", 3)
+    t = torch.cat([c, up3], dim=1)  # order [c, up3]: v3plus.py:336
+    t = _cbr(W, t, "dec3_a", 3)
+    t = _cbr(W, t, "dec3_b", 3)
+    t = scse_block(W, t, "dec3_scse")
+    o = up(t, 2)
+    o = _cbr(W, o, "head_a", 3)
+    o = _cbr(W, o, "head_b", 3)
+    logits = conv2d(W, o, "head_out", 1)
+    W.check_all_used()
+    return softmax_head(logits).numpy()
+
+
+def bam_forward(weights, x_nhwc):
+    """predict_model/bam.py:170-338 (Xception_DeepLabV3_Plus_bam)."""
+    W = _W(weights)
+    x = torch.as_tensor(x_nhwc, dtype=torch.float32).permute(0, 3, 1, 2)
+    _c, c1, c2, c5 = _xception_backbone(W, x, with_bam=True)
+    conv1 = _deeplab_neck(W, c5)
+    t = up(conv1, 2)  # bam.py:320-325
+    t = torch.cat([c2, t], dim=1)
+    t = _cbr(W, t, "dec1_a", 3)
+    t = _cbr(W, t, "dec1_b", 3)
+    t = scse_block(W, t, "dec1_scse")
+    t = up(t, 2)
+    t = torch.cat([c1, t], dim=1)  # bam.py:327-330
+    t = _cbr(W, t, "dec2_a", 3)
+    t = _cbr(W, t, "dec2_b", 3)
+    t = scse_block(W, t, "dec2_scse")
+    t = up(t, 4)  # bam.py:332-333
+    logits = conv2d(W, t, "head_out", 1)
+    W.check_all_used()
+    return softmax_head(logits).numpy()
+
+
+# ----------------------------------------------------------------------------- scse
+def scse_forward(weights, x_nhwc):
+    """predict_model/scse.py:49-97 (UNet): no BatchNorm, ReLU fused in every conv."""
+    W = _W(weights)
+    x = torch.as_tensor(x_nhwc, dtype=torch.float32).permute(0, 3, 1, 2)
+
+    def cr(t, name):
+        return F.relu(conv2d(W, t, name, 3))
+
+    skips = []
+    t = x
+    for lvl in range(1, 5):  # scse.py:52-66
+        t = cr(cr(t, f"enc{lvl}_a"), f"enc{lvl}_b")
+        skips.append(t)
+        t = maxpool(t, 2, 2)
+    t = cr(cr(t, "enc5_a"), "enc5_b")  # scse.py:68-69
+    for lvl, skip in zip(range(1, 5), reversed(skips)):  # scse.py:71-93
+        u = F.relu(conv_transpose(W, t, f"dec{lvl}_up", 3))
+        t = torch.cat([u, skip], dim=1)
+        t = cr(cr(t, f"dec{lvl}_a"), f"dec{lvl}_b")
+        t = scse_block(W, t, f"dec{lvl}_scse")
+    logits = conv2d(W, t, "head_out", 1)
+    W.check_all_used()
+    return softmax_head(logits).numpy()
+
+
+FORWARD = {
+    "res34": res34_forward,
+    "hrnet": hrnet_forward,
+    "v3plus": v3plus_forward,
+    "scse": scse_forward,
+    "bam": bam_forward,
+}
