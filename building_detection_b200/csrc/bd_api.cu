@@ -1,0 +1,688 @@
+// bd_api.cu -- C ABI (include/bd_b200.h): context, network plans (native launch lists), tiler/stitcher.
+// Fusion and contour entry points live in post.cu.
+#include "../../include/bd_b200.h"
+
+#include <cstdlib>
+#include <functional>
+#include <memory>
+#include <vector>
+
+#include "common.cuh"
+#include "conv_umma.cuh"
+#include "kernels.cuh"
+
+namespace bd {
+std::string& last_error() {
+  static thread_local std::string e;
+  return e;
+}
+int fail(const std::string& msg) {
+  last_error() = msg;
+  return 1;
+}
+}  // namespace bd
+
+using namespace bd;
+
+struct bd_ctx {
+  int device = 0;
+  int num_sms = 148;
+  int64_t launches = 0;
+  int umma_smem_kb = 99;    // per-CTA smem budget of the tcgen05 conv (2 CTAs / SM by default)
+  int umma_max_block_n = 256;
+  int* d_ys = nullptr;      // tile origin scratch
+  int* d_xs = nullptr;
+  int tile_cap = 0;
+};
+
+namespace {
+
+struct BufInfo {
+  int H, W, C, dtype, kind;
+  size_t bytes, offset;
+};
+
+struct Op {
+  int kclass;     // 0 conv umma, 1 conv direct, 2 other
+  double flops;
+  int launches;
+  std::function<int(cudaStream_t)> run;
+};
+
+inline int grid_for(size_t total, int num_sms) {
+  size_t b = (total + k::TPB - 1) / k::TPB;
+  size_t cap = static_cast<size_t>(num_sms) * 8;
+  return static_cast<int>(std::max<size_t>(1, std::min(b, cap)));
+}
+
+}  // namespace
+
+struct bd_plan {
+  bd_ctx* ctx = nullptr;
+  int batch = 0;
+  bool finalized = false;
+  std::vector<BufInfo> bufs;
+  std::vector<std::function<int(bd_plan*)>> builders;  // run at finalize, append to ops
+  std::vector<Op> ops;
+  std::vector<void*> dev_allocs;
+  char* arena = nullptr;
+  size_t arena_bytes = 0;
+  int input_buf = -1, logits_buf = -1, logits_up = 1;
+  float* cur_probs = nullptr;
+  uint8_t* cur_mask = nullptr;
+
+  int upload(const void* host, size_t bytes, void** out) {
+    void* d = nullptr;
+    BD_CUDA(cudaMalloc(&d, std::max<size_t>(bytes, 16)));
+    dev_allocs.push_back(d);
+    BD_CUDA(cudaMemcpy(d, host, bytes, cudaMemcpyHostToDevice));
+    *out = d;
+    return 0;
+  }
+  int scratch(size_t bytes, void** out) {
+    void* d = nullptr;
+    BD_CUDA(cudaMalloc(&d, std::max<size_t>(bytes, 16)));
+    dev_allocs.push_back(d);
+    *out = d;
+    return 0;
+  }
+  int check_ref(const bd_tref& r, bool vec8) const {
+    BD_CHECK(r.buf >= 0 && r.buf < static_cast<int>(bufs.size()), "tensor ref: bad buffer id");
+    const BufInfo& b = bufs[r.buf];
+    BD_CHECK(b.kind == BD_MAP, "tensor ref: not a map buffer");
+    BD_CHECK(r.c0 >= 0 && r.c > 0 && r.c0 + r.c <= b.C, "tensor ref: slice out of range");
+    if (vec8)
+      BD_CHECK(b.dtype == BD_BF16 && r.c % 8 == 0 && r.c0 % 8 == 0 && b.C % 8 == 0,
+               "tensor ref: op needs bf16 slices aligned to 8 channels");
+    return 0;
+  }
+  int check_vec(int id, int c) const {
+    BD_CHECK(id >= 0 && id < static_cast<int>(bufs.size()) && bufs[id].kind == BD_VEC, "bad vector buffer id");
+    BD_CHECK(c < 0 || bufs[id].C == c, "vector buffer has the wrong length");
+    return 0;
+  }
+  TView tview(const bd_tref& r) const {
+    const BufInfo& b = bufs[r.buf];
+    TView v;
+    v.base = arena + b.offset; v.N = batch; v.H = b.H; v.W = b.W; v.ctot = b.C; v.c0 = r.c0; v.c = r.c;
+    v.f32 = (b.dtype == BD_F32);
+    return v;
+  }
+  k::View kview(const bd_tref& r) const {
+    const BufInfo& b = bufs[r.buf];
+    k::View v;
+    v.base = arena + b.offset; v.H = b.H; v.W = b.W; v.ctot = b.C; v.c0 = r.c0; v.c = r.c; v.f32 = (b.dtype == BD_F32);
+    return v;
+  }
+  float* vecptr(int id) const { return reinterpret_cast<float*>(arena + bufs[id].offset); }
+};
+
+extern "C" {
+
+const char* bd_last_error(void) { return bd::last_error().c_str(); }
+const char* bd_version(void) { return "bd_b200 0.1 (sm_100a)"; }
+
+int bd_create(int device, bd_ctx** out) {
+  BD_CHECK(out != nullptr, "null out pointer");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(std::string("no CUDA device available (this library has no CPU path): ") + cudaGetErrorString(e));
+  BD_CHECK(device >= 0 && device < count, "device index out of range");
+  BD_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  BD_CUDA(cudaGetDeviceProperties(&prop, device));
+  BD_CHECK(prop.major == 10, "this library is built for sm_100a (Blackwell B200) only");
+  bd_ctx* c = new bd_ctx();
+  c->device = device;
+  c->num_sms = prop.multiProcessorCount;
+  if (const char* s = getenv("BD_UMMA_SMEM_KB")) c->umma_smem_kb = std::max(48, std::min(224, atoi(s)));
+  if (const char* s = getenv("BD_UMMA_MAX_N")) c->umma_max_block_n = std::max(16, std::min(256, atoi(s) / 16 * 16));
+  *out = c;
+  return 0;
+}
+
+void bd_destroy(bd_ctx* ctx) {
+  if (!ctx) return;
+  if (ctx->d_ys) cudaFree(ctx->d_ys);
+  if (ctx->d_xs) cudaFree(ctx->d_xs);
+  delete ctx;
+}
+
+int64_t bd_launch_count(bd_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ------------------------------------------------------------------------------------------ plans
+int bd_plan_create(bd_ctx* ctx, int batch, bd_plan** out) {
+  BD_CHECK(ctx && out, "null argument");
+  BD_CHECK(batch >= 1 && batch <= 64, "batch must be in [1,64]");
+  bd_plan* p = new bd_plan();
+  p->ctx = ctx;
+  p->batch = batch;
+  *out = p;
+  return 0;
+}
+
+void bd_plan_destroy(bd_plan* p) {
+  if (!p) return;
+  for (void* d : p->dev_allocs) cudaFree(d);
+  if (p->arena) cudaFree(p->arena);
+  delete p;
+}
+
+int bd_plan_add_buffer(bd_plan* p, int h, int w, int c, int dtype, int kind) {
+  if (!p || p->finalized || h < 1 || w < 1 || c < 1) {
+    fail("bd_plan_add_buffer: bad arguments");
+    return -1;
+  }
+  BufInfo b;
+  b.H = h; b.W = w; b.C = c; b.dtype = dtype; b.kind = kind;
+  if (kind == BD_VEC) b.bytes = static_cast<size_t>(p->batch) * c * 4;
+  else b.bytes = static_cast<size_t>(p->batch) * h * w * c * (dtype == BD_F32 ? 4 : 2);
+  b.offset = 0;
+  p->bufs.push_back(b);
+  return static_cast<int>(p->bufs.size()) - 1;
+}
+
+int bd_plan_add_conv(bd_plan* p, const bd_conv_desc* dptr) {
+  BD_CHECK(p && dptr && !p->finalized, "bad arguments");
+  bd_conv_desc d = *dptr;
+  BD_CHECK(d.ntaps >= 1 && d.ntaps <= BD_MAX_TAPS, "conv: bad tap count");
+  if (p->check_ref(d.x, false) || p->check_ref(d.y, false)) return 1;
+  const bool has_res = d.res.buf >= 0;
+  if (has_res && p->check_ref(d.res, false)) return 1;
+  const int cin = d.x.c, cout = d.y.c;
+  const BufInfo& yb = p->bufs[d.y.buf];
+  BD_CHECK(yb.H == d.ho * d.out_scale && yb.W == d.wo * d.out_scale, "conv: output geometry mismatch");
+  if (has_res) BD_CHECK(d.res.c == cout && p->bufs[d.res.buf].H == yb.H && p->bufs[d.res.buf].W == yb.W,
+                        "conv: residual geometry mismatch");
+  std::shared_ptr<std::vector<uint16_t>> w(new std::vector<uint16_t>(d.w_host, d.w_host + static_cast<size_t>(d.ntaps) * cout * cin));
+  std::shared_ptr<std::vector<float>> b(new std::vector<float>(d.bias_host, d.bias_host + cout));
+  d.w_host = nullptr; d.bias_host = nullptr;
+  p->builders.push_back([d, w, b, has_res, cin, cout](bd_plan* pl) -> int {
+    void *wd = nullptr, *bdv = nullptr;
+    if (pl->upload(w->data(), w->size() * 2, &wd) || pl->upload(b->data(), b->size() * 4, &bdv)) return 1;
+    Op op;
+    op.flops = 2.0 * pl->batch * d.ho * d.wo * static_cast<double>(cout) * cin * d.ntaps;
+    op.launches = 1;
+    bd_ctx* ctx = pl->ctx;
+    if (d.path == BD_CONV_UMMA) {
+      std::shared_ptr<umma::Launch> L(new umma::Launch());
+      TView x = pl->tview(d.x), y = pl->tview(d.y), r;
+      if (has_res) r = pl->tview(d.res);
+      if (umma::prepare(L.get(), x, y, has_res ? &r : nullptr, d.ntaps, d.dy, d.dx, d.stride, d.ho, d.wo, d.act_pre,
+                        d.act_post, d.out_scale, d.out_oy, d.out_ox, static_cast<const bf16*>(wd),
+                        static_cast<const float*>(bdv), ctx->umma_smem_kb, ctx->umma_max_block_n))
+        return 1;
+      op.kclass = 0;
+      op.run = [L, ctx](cudaStream_t s) -> int { ctx->launches++; return umma::launch(*L, s); };
+    } else {
+      k::DirectParams q;
+      memset(&q, 0, sizeof(q));
+      q.x = pl->kview(d.x); q.y = pl->kview(d.y);
+      if (has_res) q.res = pl->kview(d.res);
+      q.N = pl->batch; q.Ho = d.ho; q.Wo = d.wo; q.stride = d.stride; q.ntaps = d.ntaps;
+      for (int t = 0; t < d.ntaps; ++t) { q.dy[t] = d.dy[t]; q.dx[t] = d.dx[t]; }
+      q.act_pre = d.act_pre; q.act_post = d.act_post; q.out_scale = d.out_scale; q.out_oy = d.out_oy; q.out_ox = d.out_ox;
+      q.w = static_cast<const bf16*>(wd); q.bias = static_cast<const float*>(bdv);
+      const size_t total = static_cast<size_t>(pl->batch) * d.ho * d.wo * cdiv(cout, k::DC_CO);
+      const int grid = static_cast<int>(std::min<size_t>((total + k::TPB - 1) / k::TPB, 1u << 20));
+      op.kclass = 1;
+      op.run = [q, grid, ctx](cudaStream_t s) -> int {
+        ctx->launches++;
+        k::conv_direct_kernel<<<grid, k::TPB, 0, s>>>(q);
+        BD_CUDA(cudaGetLastError());
+        return 0;
+      };
+    }
+    pl->ops.push_back(op);
+    return 0;
+  });
+  return 0;
+}
+
+int bd_plan_add_dwconv(bd_plan* p, bd_tref x, bd_tref y, int stride, int pad_t, int pad_l, int relu_in,
+                       const float* w_host) {
+  BD_CHECK(p && !p->finalized && w_host, "bad arguments");
+  if (p->check_ref(x, true) || p->check_ref(y, true)) return 1;
+  BD_CHECK(x.c == y.c, "dwconv: channel mismatch");
+  std::shared_ptr<std::vector<float>> w(new std::vector<float>(w_host, w_host + 9 * static_cast<size_t>(x.c)));
+  p->builders.push_back([=](bd_plan* pl) -> int {
+    void* wd = nullptr;
+    if (pl->upload(w->data(), w->size() * 4, &wd)) return 1;
+    k::DwParams q;
+    q.x = pl->kview(x); q.y = pl->kview(y);
+    q.N = pl->batch; q.Ho = q.y.H; q.Wo = q.y.W; q.stride = stride; q.pad_t = pad_t; q.pad_l = pad_l; q.relu_in = relu_in;
+    q.w = static_cast<const float*>(wd);
+    const size_t total = static_cast<size_t>(pl->batch) * q.Ho * q.Wo * (x.c / 8);
+    bd_ctx* ctx = pl->ctx;
+    const int grid = grid_for(total, ctx->num_sms * 4);
+    Op op;
+    op.kclass = 2; op.launches = 1;
+    op.flops = 2.0 * pl->batch * q.Ho * q.Wo * static_cast<double>(x.c) * 9;
+    op.run = [q, grid, ctx](cudaStream_t s) -> int {
+      ctx->launches++;
+      k::dwconv3x3_kernel<<<grid, k::TPB, 0, s>>>(q);
+      BD_CUDA(cudaGetLastError());
+      return 0;
+    };
+    pl->ops.push_back(op);
+    return 0;
+  });
+  return 0;
+}
+
+int bd_plan_add_maxpool(bd_plan* p, bd_tref x, bd_tref y, int kk, int stride, int pad_t, int pad_l) {
+  BD_CHECK(p && !p->finalized, "bad arguments");
+  if (p->check_ref(x, true) || p->check_ref(y, true)) return 1;
+  BD_CHECK(x.c == y.c && kk >= 1 && kk <= 3, "maxpool: bad arguments");
+  p->builders.push_back([=](bd_plan* pl) -> int {
+    k::PoolParams q;
+    q.x = pl->kview(x); q.y = pl->kview(y);
+    q.N = pl->batch; q.Ho = q.y.H; q.Wo = q.y.W; q.k = kk; q.stride = stride; q.pad_t = pad_t; q.pad_l = pad_l;
+    const size_t total = static_cast<size_t>(pl->batch) * q.Ho * q.Wo * (x.c / 8);
+    bd_ctx* ctx = pl->ctx;
+    const int grid = grid_for(total, ctx->num_sms * 4);
+    Op op;
+    op.kclass = 2; op.launches = 1; op.flops = 0;
+    op.run = [q, grid, ctx](cudaStream_t s) -> int {
+      ctx->launches++;
+      k::maxpool_kernel<<<grid, k::TPB, 0, s>>>(q);
+      BD_CUDA(cudaGetLastError());
+      return 0;
+    };
+    pl->ops.push_back(op);
+    return 0;
+  });
+  return 0;
+}
+
+int bd_plan_add_addn(bd_plan* p, int n, const bd_tref* xs, const int32_t* fs, bd_tref y, int act) {
+  BD_CHECK(p && !p->finalized && xs && fs && n >= 1 && n <= 4, "bad arguments");
+  if (p->check_ref(y, true)) return 1;
+  std::vector<bd_tref> xv(xs, xs + n);
+  std::vector<int> fv(fs, fs + n);
+  for (int i = 0; i < n; ++i) {
+    if (p->check_ref(xv[i], true)) return 1;
+    const BufInfo& b = p->bufs[xv[i].buf];
+    BD_CHECK(xv[i].c == y.c && b.H * fv[i] == p->bufs[y.buf].H && b.W * fv[i] == p->bufs[y.buf].W,
+             "addn: geometry mismatch");
+  }
+  p->builders.push_back([=](bd_plan* pl) -> int {
+    k::AddnParams q;
+    memset(&q, 0, sizeof(q));
+    for (int i = 0; i < n; ++i) { q.x[i] = pl->kview(xv[i]); q.f[i] = fv[i]; }
+    q.y = pl->kview(y); q.n_in = n; q.N = pl->batch; q.act = act;
+    const size_t total = static_cast<size_t>(pl->batch) * q.y.H * q.y.W * (y.c / 8);
+    bd_ctx* ctx = pl->ctx;
+    const int grid = grid_for(total, ctx->num_sms * 4);
+    Op op;
+    op.kclass = 2; op.launches = 1; op.flops = 0;
+    op.run = [q, grid, ctx](cudaStream_t s) -> int {
+      ctx->launches++;
+      k::addn_kernel<<<grid, k::TPB, 0, s>>>(q);
+      BD_CUDA(cudaGetLastError());
+      return 0;
+    };
+    pl->ops.push_back(op);
+    return 0;
+  });
+  return 0;
+}
+
+int bd_plan_add_gap(bd_plan* p, bd_tref x, int y_vec) {
+  BD_CHECK(p && !p->finalized, "bad arguments");
+  if (p->check_ref(x, true) || p->check_vec(y_vec, x.c)) return 1;
+  BD_CHECK(x.c / 8 <= k::TPB, "gap: too many channels");
+  p->builders.push_back([=](bd_plan* pl) -> int {
+    k::GapParams q;
+    q.x = pl->kview(x); q.N = pl->batch;
+    const int HW = q.x.H * q.x.W;
+    q.splits = std::max(1, std::min(64, HW / 1024));
+    void* part = nullptr;
+    if (pl->scratch(static_cast<size_t>(pl->batch) * q.splits * x.c * 4, &part)) return 1;
+    q.partial = static_cast<float*>(part);
+    q.out = pl->vecptr(y_vec);
+    const int rows = k::TPB / (x.c / 8);
+    const size_t smem = static_cast<size_t>(rows) * x.c * 4;
+    bd_ctx* ctx = pl->ctx;
+    Op op;
+    op.kclass = 2; op.launches = 2; op.flops = 0;
+    op.run = [q, smem, ctx](cudaStream_t s) -> int {
+      ctx->launches += 2;
+      k::gap_partial_kernel<<<dim3(q.splits, q.N), k::TPB, smem, s>>>(q);
+      k::gap_final_kernel<<<cdiv(q.N * q.x.c, 256), 256, 0, s>>>(q);
+      BD_CUDA(cudaGetLastError());
+      return 0;
+    };
+    pl->ops.push_back(op);
+    return 0;
+  });
+  return 0;
+}
+
+int bd_plan_add_dense(bd_plan* p, int n_in, const int32_t* x_vecs, int y_vec, int cin, int cout, int act,
+                      const float* w_host, const float* b_host) {
+  BD_CHECK(p && !p->finalized && x_vecs && w_host && b_host && n_in >= 1 && n_in <= 5, "bad arguments");
+  std::vector<int> xv(x_vecs, x_vecs + n_in);
+  for (int i = 0; i < n_in; ++i)
+    if (p->check_vec(xv[i], cin)) return 1;
+  if (p->check_vec(y_vec, cout)) return 1;
+  std::shared_ptr<std::vector<float>> w(new std::vector<float>(w_host, w_host + static_cast<size_t>(cin) * cout));
+  std::shared_ptr<std::vector<float>> b(new std::vector<float>(b_host, b_host + cout));
+  p->builders.push_back([=](bd_plan* pl) -> int {
+    void *wd = nullptr, *bdv = nullptr;
+    if (pl->upload(w->data(), w->size() * 4, &wd) || pl->upload(b->data(), b->size() * 4, &bdv)) return 1;
+    k::DenseParams q;
+    memset(&q, 0, sizeof(q));
+    for (int i = 0; i < n_in; ++i) q.x[i] = pl->vecptr(xv[i]);
+    q.y = pl->vecptr(y_vec); q.w = static_cast<const float*>(wd); q.b = static_cast<const float*>(bdv);
+    q.n_in = n_in; q.N = pl->batch; q.cin = cin; q.cout = cout; q.act = act;
+    const int grid = cdiv(pl->batch * cout * 32, k::TPB);
+    bd_ctx* ctx = pl->ctx;
+    Op op;
+    op.kclass = 2; op.launches = 1; op.flops = 2.0 * pl->batch * cin * static_cast<double>(cout);
+    op.run = [q, grid, ctx](cudaStream_t s) -> int {
+      ctx->launches++;
+      k::dense_kernel<<<grid, k::TPB, 0, s>>>(q);
+      BD_CUDA(cudaGetLastError());
+      return 0;
+    };
+    pl->ops.push_back(op);
+    return 0;
+  });
+  return 0;
+}
+
+int bd_plan_add_gate(bd_plan* p, int mode, bd_tref x, bd_tref y, int v_vec, bd_tref sref, const float* w_host,
+                     float bscalar) {
+  BD_CHECK(p && !p->finalized && mode >= 0 && mode <= 2, "bad arguments");
+  if (p->check_ref(x, true) || p->check_ref(y, true) || p->check_vec(v_vec, x.c)) return 1;
+  BD_CHECK(x.c == y.c, "gate: channel mismatch");
+  if (mode == BD_GATE_BAM) {
+    if (p->check_ref(sref, false)) return 1;
+    BD_CHECK(sref.c == 1, "gate: BAM spatial logits must have one channel");
+  }
+  std::shared_ptr<std::vector<float>> w;
+  if (mode == BD_GATE_SCSE) {
+    BD_CHECK(w_host != nullptr, "gate: scSE needs spatial weights");
+    w.reset(new std::vector<float>(w_host, w_host + x.c));
+  }
+  p->builders.push_back([=](bd_plan* pl) -> int {
+    k::GateParams q;
+    memset(&q, 0, sizeof(q));
+    q.x = pl->kview(x); q.y = pl->kview(y); q.v = pl->vecptr(v_vec); q.mode = mode; q.N = pl->batch; q.b = bscalar;
+    if (mode == BD_GATE_BAM) q.s = pl->kview(sref);
+    if (mode == BD_GATE_SCSE) {
+      void* wd = nullptr;
+      if (pl->upload(w->data(), w->size() * 4, &wd)) return 1;
+      q.w = static_cast<const float*>(wd);
+    }
+    const size_t npix = static_cast<size_t>(pl->batch) * q.x.H * q.x.W;
+    bd_ctx* ctx = pl->ctx;
+    Op op;
+    op.kclass = 2; op.launches = 1;
+    op.flops = mode == BD_GATE_SCSE ? 2.0 * npix * x.c : 0.0;
+    if (mode == BD_GATE_SCSE) {
+      int lanes = 1;
+      while (lanes < 32 && lanes * 2 <= x.c / 8) lanes *= 2;
+      const size_t warps = (npix + (32 / lanes) - 1) / (32 / lanes);
+      const int grid = grid_for(warps * 32, ctx->num_sms * 4);
+      op.run = [q, grid, lanes, ctx](cudaStream_t s) -> int {
+        ctx->launches++;
+        k::gate_scse_kernel<<<grid, k::TPB, 0, s>>>(q, lanes);
+        BD_CUDA(cudaGetLastError());
+        return 0;
+      };
+    } else {
+      const int grid = grid_for(npix * (x.c / 8), ctx->num_sms * 4);
+      op.run = [q, grid, ctx](cudaStream_t s) -> int {
+        ctx->launches++;
+        k::gate_kernel<<<grid, k::TPB, 0, s>>>(q);
+        BD_CUDA(cudaGetLastError());
+        return 0;
+      };
+    }
+    pl->ops.push_back(op);
+    return 0;
+  });
+  return 0;
+}
+
+int bd_plan_add_skfuse(bd_plan* p, const bd_tref* xs4, int g_vec, const int32_t* logit_vecs5, bd_tref y,
+                       const float* scale_host, const float* shift_host) {
+  BD_CHECK(p && !p->finalized && xs4 && logit_vecs5 && scale_host && shift_host, "bad arguments");
+  if (p->check_ref(y, true) || p->check_vec(g_vec, y.c)) return 1;
+  std::vector<bd_tref> xv(xs4, xs4 + 4);
+  std::vector<int> lv(logit_vecs5, logit_vecs5 + 5);
+  for (int i = 0; i < 4; ++i) {
+    if (p->check_ref(xv[i], true)) return 1;
+    BD_CHECK(xv[i].c == y.c, "skfuse: channel mismatch");
+  }
+  for (int i = 0; i < 5; ++i)
+    if (p->check_vec(lv[i], y.c)) return 1;
+  std::shared_ptr<std::vector<float>> sc(new std::vector<float>(scale_host, scale_host + y.c));
+  std::shared_ptr<std::vector<float>> sh(new std::vector<float>(shift_host, shift_host + y.c));
+  p->builders.push_back([=](bd_plan* pl) -> int {
+    void *scd = nullptr, *shd = nullptr;
+    if (pl->upload(sc->data(), sc->size() * 4, &scd) || pl->upload(sh->data(), sh->size() * 4, &shd)) return 1;
+    k::SkParams q;
+    memset(&q, 0, sizeof(q));
+    for (int i = 0; i < 4; ++i) q.x[i] = pl->kview(xv[i]);
+    q.y = pl->kview(y); q.g = pl->vecptr(g_vec);
+    for (int i = 0; i < 5; ++i) q.lg[i] = pl->vecptr(lv[i]);
+    q.scale = static_cast<const float*>(scd); q.shift = static_cast<const float*>(shd); q.N = pl->batch;
+    const size_t total = static_cast<size_t>(pl->batch) * q.y.H * q.y.W * (y.c / 8);
+    bd_ctx* ctx = pl->ctx;
+    const int grid = grid_for(total, ctx->num_sms * 4);
+    Op op;
+    op.kclass = 2; op.launches = 1; op.flops = 0;
+    op.run = [q, grid, ctx](cudaStream_t s) -> int {
+      ctx->launches++;
+      k::skfuse_kernel<<<grid, k::TPB, 0, s>>>(q);
+      BD_CUDA(cudaGetLastError());
+      return 0;
+    };
+    pl->ops.push_back(op);
+    return 0;
+  });
+  return 0;
+}
+
+int bd_plan_add_bcast(bd_plan* p, int v_vec, bd_tref y) {
+  BD_CHECK(p && !p->finalized, "bad arguments");
+  if (p->check_ref(y, true) || p->check_vec(v_vec, y.c)) return 1;
+  p->builders.push_back([=](bd_plan* pl) -> int {
+    k::BcastParams q;
+    q.y = pl->kview(y); q.v = pl->vecptr(v_vec); q.N = pl->batch;
+    const size_t total = static_cast<size_t>(pl->batch) * q.y.H * q.y.W * (y.c / 8);
+    bd_ctx* ctx = pl->ctx;
+    const int grid = grid_for(total, ctx->num_sms * 4);
+    Op op;
+    op.kclass = 2; op.launches = 1; op.flops = 0;
+    op.run = [q, grid, ctx](cudaStream_t s) -> int {
+      ctx->launches++;
+      k::bcast_kernel<<<grid, k::TPB, 0, s>>>(q);
+      BD_CUDA(cudaGetLastError());
+      return 0;
+    };
+    pl->ops.push_back(op);
+    return 0;
+  });
+  return 0;
+}
+
+int bd_plan_finalize(bd_plan* p, int input_buf, int logits_buf, int logits_up) {
+  BD_CHECK(p && !p->finalized, "bad arguments");
+  BD_CUDA(cudaSetDevice(p->ctx->device));
+  const int nb = static_cast<int>(p->bufs.size());
+  if (input_buf >= 0) {
+    BD_CHECK(input_buf < nb && p->bufs[input_buf].dtype == BD_F32 && p->bufs[input_buf].kind == BD_MAP, "bad input buffer");
+  }
+  if (logits_buf >= 0) {
+    BD_CHECK(logits_buf < nb && p->bufs[logits_buf].dtype == BD_F32 && p->bufs[logits_buf].C == 2 && logits_up >= 1,
+             "bad logits buffer");
+  }
+  size_t off = 0;
+  for (BufInfo& b : p->bufs) {
+    b.offset = off;
+    off += (b.bytes + 1023) / 1024 * 1024;
+  }
+  p->arena_bytes = std::max<size_t>(off, 1024);
+  BD_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->arena), p->arena_bytes));
+  BD_CUDA(cudaMemset(p->arena, 0, p->arena_bytes));
+  p->input_buf = input_buf; p->logits_buf = logits_buf; p->logits_up = logits_up;
+  for (auto& b : p->builders)
+    if (b(p)) return 1;
+  p->builders.clear();
+  if (logits_buf >= 0) {
+    const BufInfo& lb = p->bufs[logits_buf];
+    const float* lg = reinterpret_cast<const float*>(p->arena + lb.offset);
+    const int H = lb.H * logits_up, W = lb.W * logits_up, N = p->batch, up = logits_up;
+    bd_ctx* ctx = p->ctx;
+    const int grid = grid_for(static_cast<size_t>(N) * H * W, ctx->num_sms * 4);
+    Op op;
+    op.kclass = 2; op.launches = 1; op.flops = 0;
+    op.run = [p, lg, N, H, W, up, grid, ctx](cudaStream_t s) -> int {
+      if (!p->cur_probs && !p->cur_mask) return 0;
+      ctx->launches++;
+      k::softmax2_kernel<<<grid, k::TPB, 0, s>>>(lg, N, H, W, up, p->cur_probs, p->cur_mask);
+      BD_CUDA(cudaGetLastError());
+      return 0;
+    };
+    p->ops.push_back(op);
+  }
+  BD_CUDA(cudaDeviceSynchronize());
+  p->finalized = true;
+  return 0;
+}
+
+int bd_plan_run(bd_plan* p, const float* x_dev, float* probs_dev, uint8_t* mask_dev, void* stream) {
+  BD_CHECK(p && p->finalized, "plan not finalized");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (x_dev) {
+    BD_CHECK(p->input_buf >= 0, "plan has no input buffer");
+    const BufInfo& ib = p->bufs[p->input_buf];
+    BD_CUDA(cudaMemcpyAsync(p->arena + ib.offset, x_dev, ib.bytes, cudaMemcpyDeviceToDevice, s));
+  }
+  p->cur_probs = probs_dev;
+  p->cur_mask = mask_dev;
+  for (Op& op : p->ops)
+    if (op.run(s)) return 1;
+  return 0;
+}
+
+int bd_plan_run_host(bd_plan* p, const float* x_host, float* probs_host, uint8_t* mask_host) {
+  BD_CHECK(p && p->finalized && p->input_buf >= 0 && p->logits_buf >= 0, "plan not runnable from host buffers");
+  const BufInfo& ib = p->bufs[p->input_buf];
+  const BufInfo& lb = p->bufs[p->logits_buf];
+  const size_t npix = static_cast<size_t>(p->batch) * lb.H * p->logits_up * lb.W * p->logits_up;
+  float* dprobs = nullptr;
+  uint8_t* dmask = nullptr;
+  if (x_host) BD_CUDA(cudaMemcpy(p->arena + ib.offset, x_host, ib.bytes, cudaMemcpyHostToDevice));
+  if (probs_host) BD_CUDA(cudaMalloc(reinterpret_cast<void**>(&dprobs), npix * 2 * 4));
+  if (mask_host) BD_CUDA(cudaMalloc(reinterpret_cast<void**>(&dmask), npix));
+  int rc = bd_plan_run(p, nullptr, dprobs, dmask, nullptr);
+  if (!rc) {
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) rc = fail(std::string("forward failed: ") + cudaGetErrorString(e));
+  }
+  if (!rc && probs_host) cudaMemcpy(probs_host, dprobs, npix * 2 * 4, cudaMemcpyDeviceToHost);
+  if (!rc && mask_host) cudaMemcpy(mask_host, dmask, npix, cudaMemcpyDeviceToHost);
+  if (dprobs) cudaFree(dprobs);
+  if (dmask) cudaFree(dmask);
+  return rc;
+}
+
+void* bd_plan_buffer_ptr(bd_plan* p, int buf) {
+  if (!p || !p->finalized || buf < 0 || buf >= static_cast<int>(p->bufs.size())) return nullptr;
+  return p->arena + p->bufs[buf].offset;
+}
+size_t bd_plan_buffer_bytes(bd_plan* p, int buf) {
+  if (!p || buf < 0 || buf >= static_cast<int>(p->bufs.size())) return 0;
+  return p->bufs[buf].bytes;
+}
+int bd_plan_read_buffer(bd_plan* p, int buf, void* host_dst, size_t bytes) {
+  BD_CHECK(p && p->finalized && buf >= 0 && buf < static_cast<int>(p->bufs.size()) && bytes <= p->bufs[buf].bytes,
+           "bad arguments");
+  BD_CUDA(cudaDeviceSynchronize());
+  BD_CUDA(cudaMemcpy(host_dst, p->arena + p->bufs[buf].offset, bytes, cudaMemcpyDeviceToHost));
+  return 0;
+}
+int bd_plan_write_buffer(bd_plan* p, int buf, const void* host_src, size_t bytes) {
+  BD_CHECK(p && p->finalized && buf >= 0 && buf < static_cast<int>(p->bufs.size()) && bytes <= p->bufs[buf].bytes,
+           "bad arguments");
+  BD_CUDA(cudaMemcpy(p->arena + p->bufs[buf].offset, host_src, bytes, cudaMemcpyHostToDevice));
+  return 0;
+}
+size_t bd_plan_arena_bytes(bd_plan* p) { return p ? p->arena_bytes : 0; }
+int bd_plan_num_launches(bd_plan* p) {
+  int n = 0;
+  if (p) for (const Op& op : p->ops) n += op.launches;
+  return n;
+}
+int bd_plan_num_ops(bd_plan* p) { return p ? static_cast<int>(p->ops.size()) : 0; }
+int bd_plan_op_info(bd_plan* p, int i, int* kind, double* flops) {
+  BD_CHECK(p && i >= 0 && i < static_cast<int>(p->ops.size()), "bad op index");
+  if (kind) *kind = p->ops[i].kclass;
+  if (flops) *flops = p->ops[i].flops;
+  return 0;
+}
+int bd_plan_time_ops(bd_plan* p, float* ms_out, void* stream) {
+  BD_CHECK(p && p->finalized && ms_out, "bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t n = p->ops.size();
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& e : ev) BD_CUDA(cudaEventCreate(&e));
+  BD_CUDA(cudaEventRecord(ev[0], s));
+  for (size_t i = 0; i < n; ++i) {
+    if (p->ops[i].run(s)) return 1;
+    BD_CUDA(cudaEventRecord(ev[i + 1], s));
+  }
+  BD_CUDA(cudaStreamSynchronize(s));
+  for (size_t i = 0; i < n; ++i) BD_CUDA(cudaEventElapsedTime(&ms_out[i], ev[i], ev[i + 1]));
+  for (auto& e : ev) cudaEventDestroy(e);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ tiler / stitcher
+static int ensure_tile_scratch(bd_ctx* ctx, int n) {
+  if (n <= ctx->tile_cap) return 0;
+  if (ctx->d_ys) cudaFree(ctx->d_ys);
+  if (ctx->d_xs) cudaFree(ctx->d_xs);
+  ctx->d_ys = ctx->d_xs = nullptr;
+  ctx->tile_cap = 0;
+  BD_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->d_ys), sizeof(int) * n));
+  BD_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->d_xs), sizeof(int) * n));
+  ctx->tile_cap = n;
+  return 0;
+}
+
+int bd_tiles_gather(bd_ctx* ctx, const uint8_t* scene_bgr_dev, int h, int w, const int32_t* ys_host,
+                    const int32_t* xs_host, int n, float* x_dev, void* stream) {
+  BD_CHECK(ctx && scene_bgr_dev && ys_host && xs_host && x_dev && n >= 1 && h >= 1 && w >= 1, "bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (ensure_tile_scratch(ctx, std::max(n, 64))) return 1;
+  BD_CUDA(cudaMemcpyAsync(ctx->d_ys, ys_host, sizeof(int) * n, cudaMemcpyHostToDevice, s));
+  BD_CUDA(cudaMemcpyAsync(ctx->d_xs, xs_host, sizeof(int) * n, cudaMemcpyHostToDevice, s));
+  ctx->launches++;
+  k::tiles_gather_kernel<<<grid_for(static_cast<size_t>(n) * 512 * 512, ctx->num_sms * 4), k::TPB, 0, s>>>(
+      scene_bgr_dev, h, w, ctx->d_ys, ctx->d_xs, n, x_dev);
+  BD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int bd_stitch_or(bd_ctx* ctx, const uint8_t* tile_masks_dev, const int32_t* ys_host, const int32_t* xs_host, int n,
+                 uint8_t* scene_mask_dev, int h, int w, void* stream) {
+  BD_CHECK(ctx && tile_masks_dev && ys_host && xs_host && scene_mask_dev && n >= 1, "bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (ensure_tile_scratch(ctx, std::max(n, 64))) return 1;
+  BD_CUDA(cudaMemcpyAsync(ctx->d_ys, ys_host, sizeof(int) * n, cudaMemcpyHostToDevice, s));
+  BD_CUDA(cudaMemcpyAsync(ctx->d_xs, xs_host, sizeof(int) * n, cudaMemcpyHostToDevice, s));
+  ctx->launches++;
+  k::stitch_or_kernel<<<grid_for(static_cast<size_t>(n) * 512 * 512, ctx->num_sms * 4), k::TPB, 0, s>>>(
+      tile_masks_dev, ctx->d_ys, ctx->d_xs, n, scene_mask_dev, h, w);
+  BD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

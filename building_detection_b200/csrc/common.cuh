@@ -1,0 +1,64 @@
+// common.cuh -- shared helpers for the sm_100a kernels of the building-detection hot path.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+namespace bd {
+
+typedef __nv_bfloat16 bf16;
+
+// thread-local last-error string behind bd_last_error()
+std::string& last_error();
+int fail(const std::string& msg);
+
+#define BD_CUDA(call)                                                                             \
+  do {                                                                                            \
+    cudaError_t e_ = (call);                                                                      \
+    if (e_ != cudaSuccess)                                                                        \
+      return ::bd::fail(std::string(#call) + ": " + cudaGetErrorString(e_) + " @" + __FILE__ +    \
+                        ":" + std::to_string(__LINE__));                                          \
+  } while (0)
+
+#define BD_CHECK(cond, msg)                                                                       \
+  do {                                                                                            \
+    if (!(cond)) return ::bd::fail(std::string(msg) + " (" #cond ") @" + __FILE__ + ":" +         \
+                                   std::to_string(__LINE__));                                     \
+  } while (0)
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// A channel-slice view of an NHWC feature map resident in the plan arena.
+struct TView {
+  void* base;      // buffer base (element 0 of channel 0)
+  int N, H, W;     // map geometry
+  int ctot;        // channels of the underlying buffer (pixel pitch in elements)
+  int c0, c;       // slice
+  int f32;         // element type: 0 bf16, 1 fp32
+};
+
+struct alignas(16) bf16x8 {
+  __nv_bfloat162 v[4];
+};
+
+__device__ __forceinline__ void unpack8(const bf16x8& p, float* f) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(p.v[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ bf16x8 pack8(const float* f) {
+  bf16x8 p;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return p;
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+}  // namespace bd

@@ -1,0 +1,451 @@
+// kernels.cuh -- CUDA-core kernels of the network forward: the memory-bound ops (depthwise 3x3,
+// pooling, nearest-upsample/add, global average pooling, attention gates, SK fusion, softmax head)
+// and the small-channel direct convolution (3-channel stems, 1/2-channel gates and heads, BAM C/16
+// convs) that is not worth a tensor-core tile.  Feature maps are NHWC; wherever channel counts are
+// multiples of 8 the access unit is one 16-byte vector of 8 bf16, with threads mapped channel-group
+// fastest so that a warp touches consecutive 16-byte vectors.
+#pragma once
+#include "common.cuh"
+
+namespace bd {
+namespace k {
+
+constexpr int TPB = 256;
+
+struct View {  // device-side channel-slice view
+  void* base;
+  int H, W, ctot, c0, c, f32;
+};
+
+__device__ __forceinline__ float ld1(const View& v, size_t pix, int ch) {
+  const size_t i = pix * v.ctot + v.c0 + ch;
+  return v.f32 ? static_cast<const float*>(v.base)[i] : __bfloat162float(static_cast<const bf16*>(v.base)[i]);
+}
+__device__ __forceinline__ void st1(const View& v, size_t pix, int ch, float x) {
+  const size_t i = pix * v.ctot + v.c0 + ch;
+  if (v.f32) static_cast<float*>(v.base)[i] = x;
+  else static_cast<bf16*>(v.base)[i] = __float2bfloat16_rn(x);
+}
+__device__ __forceinline__ void ld8(const View& v, size_t pix, int ch, float* f) {
+  unpack8(*reinterpret_cast<const bf16x8*>(static_cast<const bf16*>(v.base) + pix * v.ctot + v.c0 + ch), f);
+}
+__device__ __forceinline__ void st8(const View& v, size_t pix, int ch, const float* f) {
+  *reinterpret_cast<bf16x8*>(static_cast<bf16*>(v.base) + pix * v.ctot + v.c0 + ch) = pack8(f);
+}
+__device__ __forceinline__ float actf(float v, int act) {
+  return act == 1 ? fmaxf(v, 0.0f) : (act == 2 ? sigmoidf_(v) : v);
+}
+
+// ---------------------------------------------------------------------------------- direct conv
+struct DirectParams {
+  View x, y, res;  // res.base == nullptr: none
+  int N, Ho, Wo, stride, ntaps;
+  int dy[9], dx[9];
+  int act_pre, act_post, out_scale, out_oy, out_ox;
+  const bf16* w;  // [ntaps][Cout][Cin]
+  const float* bias;
+};
+constexpr int DC_CO = 4;  // output channels per thread
+
+// thread = (output pixel, group of DC_CO output channels); weights are warp-uniform broadcasts.
+__global__ void __launch_bounds__(TPB) conv_direct_kernel(const __grid_constant__ DirectParams p) {
+  const int cog = (p.y.c + DC_CO - 1) / DC_CO;
+  const size_t total = static_cast<size_t>(p.N) * p.Ho * p.Wo * cog;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * TPB) {
+    // pixel fastest within a warp so that the weight reads are uniform
+    const size_t pix = idx % (static_cast<size_t>(p.N) * p.Ho * p.Wo);
+    const int g = static_cast<int>(idx / (static_cast<size_t>(p.N) * p.Ho * p.Wo));
+    const int ow = static_cast<int>(pix % p.Wo), oh = static_cast<int>((pix / p.Wo) % p.Ho);
+    const int n = static_cast<int>(pix / (static_cast<size_t>(p.Wo) * p.Ho));
+    const int co0 = g * DC_CO;
+    const int Cin = p.x.c, Cout = p.y.c;
+    float acc[DC_CO];
+#pragma unroll
+    for (int j = 0; j < DC_CO; ++j) acc[j] = 0.0f;
+    for (int t = 0; t < p.ntaps; ++t) {
+      const int ih = oh * p.stride + p.dy[t], iw = ow * p.stride + p.dx[t];
+      if (ih < 0 || ih >= p.x.H || iw < 0 || iw >= p.x.W) continue;
+      const size_t ipix = (static_cast<size_t>(n) * p.x.H + ih) * p.x.W + iw;
+      const bf16* wt = p.w + (static_cast<size_t>(t) * Cout + co0) * Cin;
+      for (int ci = 0; ci < Cin; ++ci) {
+        const float xv = ld1(p.x, ipix, ci);
+#pragma unroll
+        for (int j = 0; j < DC_CO; ++j)
+          if (co0 + j < Cout) acc[j] = fmaf(xv, __bfloat162float(wt[static_cast<size_t>(j) * Cin + ci]), acc[j]);
+      }
+    }
+    const size_t opix = (static_cast<size_t>(n) * p.y.H + (oh * p.out_scale + p.out_oy)) * p.y.W +
+                        (ow * p.out_scale + p.out_ox);
+#pragma unroll
+    for (int j = 0; j < DC_CO; ++j) {
+      if (co0 + j >= Cout) break;
+      float v = actf(acc[j] + p.bias[co0 + j], p.act_pre);
+      if (p.res.base) v += ld1(p.res, opix, co0 + j);
+      st1(p.y, opix, co0 + j, actf(v, p.act_post));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------- depthwise 3x3
+struct DwParams {
+  View x, y;
+  int N, Ho, Wo, stride, pad_t, pad_l, relu_in;
+  const float* w;  // [9][C]
+};
+__global__ void __launch_bounds__(TPB) dwconv3x3_kernel(const __grid_constant__ DwParams p) {
+  const int C = p.x.c, cg = C >> 3;
+  const size_t total = static_cast<size_t>(p.N) * p.Ho * p.Wo * cg;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * TPB) {
+    const int g = static_cast<int>(idx % cg);
+    const size_t pix = idx / cg;
+    const int ow = static_cast<int>(pix % p.Wo), oh = static_cast<int>((pix / p.Wo) % p.Ho);
+    const int n = static_cast<int>(pix / (static_cast<size_t>(p.Wo) * p.Ho));
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int ih = oh * p.stride + kh - p.pad_t;
+      if (ih < 0 || ih >= p.x.H) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int iw = ow * p.stride + kw - p.pad_l;
+        if (iw < 0 || iw >= p.x.W) continue;
+        float xv[8];
+        ld8(p.x, (static_cast<size_t>(n) * p.x.H + ih) * p.x.W + iw, g * 8, xv);
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.w + (kh * 3 + kw) * C + g * 8));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.w + (kh * 3 + kw) * C + g * 8 + 4));
+        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(p.relu_in ? fmaxf(xv[j], 0.0f) : xv[j], wv[j], acc[j]);
+      }
+    }
+    st8(p.y, pix, g * 8, acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------- max pool
+struct PoolParams {
+  View x, y;
+  int N, Ho, Wo, k, stride, pad_t, pad_l;
+};
+__global__ void __launch_bounds__(TPB) maxpool_kernel(const __grid_constant__ PoolParams p) {
+  const int cg = p.x.c >> 3;
+  const size_t total = static_cast<size_t>(p.N) * p.Ho * p.Wo * cg;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * TPB) {
+    const int g = static_cast<int>(idx % cg);
+    const size_t pix = idx / cg;
+    const int ow = static_cast<int>(pix % p.Wo), oh = static_cast<int>((pix / p.Wo) % p.Ho);
+    const int n = static_cast<int>(pix / (static_cast<size_t>(p.Wo) * p.Ho));
+    float m[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+    for (int kh = 0; kh < p.k; ++kh) {
+      const int ih = oh * p.stride + kh - p.pad_t;
+      if (ih < 0 || ih >= p.x.H) continue;
+      for (int kw = 0; kw < p.k; ++kw) {
+        const int iw = ow * p.stride + kw - p.pad_l;
+        if (iw < 0 || iw >= p.x.W) continue;
+        float xv[8];
+        ld8(p.x, (static_cast<size_t>(n) * p.x.H + ih) * p.x.W + iw, g * 8, xv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], xv[j]);
+      }
+    }
+    st8(p.y, pix, g * 8, m);
+  }
+}
+
+// ---------------------------------------------------------------------------------- add-N with nearest upsample
+struct AddnParams {
+  View x[4], y;
+  int f[4];
+  int n_in, N, act;
+};
+__global__ void __launch_bounds__(TPB) addn_kernel(const __grid_constant__ AddnParams p) {
+  const int cg = p.y.c >> 3;
+  const size_t total = static_cast<size_t>(p.N) * p.y.H * p.y.W * cg;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * TPB) {
+    const int g = static_cast<int>(idx % cg);
+    const size_t pix = idx / cg;
+    const int ow = static_cast<int>(pix % p.y.W), oh = static_cast<int>((pix / p.y.W) % p.y.H);
+    const int n = static_cast<int>(pix / (static_cast<size_t>(p.y.W) * p.y.H));
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < p.n_in; ++i) {
+      float xv[8];
+      ld8(p.x[i], (static_cast<size_t>(n) * p.x[i].H + oh / p.f[i]) * p.x[i].W + ow / p.f[i], g * 8, xv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += xv[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = actf(acc[j], p.act);
+    st8(p.y, pix, g * 8, acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------- global average pool
+// pass 1: partial[n][split][c] = sum over the split's pixels; pass 2: out[n][c] = sum(partials)/(H*W).
+// Deterministic (no atomics).
+struct GapParams {
+  View x;
+  int N, splits;
+  float* partial;  // [N][splits][C]
+  float* out;      // [N][C]
+};
+__global__ void __launch_bounds__(TPB) gap_partial_kernel(const __grid_constant__ GapParams p) {
+  extern __shared__ float sh[];  // [TPB/cg rows][C]
+  const int C = p.x.c, cg = C >> 3;
+  const int n = blockIdx.y, split = blockIdx.x;
+  const int rows = TPB / cg;  // pixel lanes per block (host guarantees cg <= TPB)
+  const int g = threadIdx.x % cg, row = threadIdx.x / cg;
+  const int HW = p.x.H * p.x.W;
+  const int per = (HW + p.splits - 1) / p.splits;
+  const int beg = split * per, end = min(HW, beg + per);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (row < rows) {
+    for (int i = beg + row; i < end; i += rows) {
+      float xv[8];
+      ld8(p.x, static_cast<size_t>(n) * HW + i, g * 8, xv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += xv[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sh[row * C + g * 8 + j] = acc[j];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += TPB) {
+    float s = 0.0f;
+    for (int r2 = 0; r2 < rows; ++r2) s += sh[r2 * C + c];
+    p.partial[(static_cast<size_t>(n) * p.splits + split) * C + c] = s;
+  }
+}
+__global__ void gap_final_kernel(const __grid_constant__ GapParams p) {
+  const int C = p.x.c;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.N * C) return;
+  const int n = i / C, c = i % C;
+  float s = 0.0f;
+  for (int k2 = 0; k2 < p.splits; ++k2) s += p.partial[(static_cast<size_t>(n) * p.splits + k2) * C + c];
+  p.out[i] = s / static_cast<float>(p.x.H * p.x.W);
+}
+
+// ---------------------------------------------------------------------------------- dense on pooled vectors
+struct DenseParams {
+  const float* x[5];
+  float* y;
+  const float* w;  // [Cout][Cin]
+  const float* b;
+  int n_in, N, cin, cout, act;
+};
+// one warp per (n, output channel)
+__global__ void __launch_bounds__(TPB) dense_kernel(const __grid_constant__ DenseParams p) {
+  const int wid = (blockIdx.x * TPB + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (wid >= p.N * p.cout) return;
+  const int n = wid / p.cout, co = wid % p.cout;
+  float s = 0.0f;
+  for (int ci = lane; ci < p.cin; ci += 32) {
+    float xv = 0.0f;
+    for (int i = 0; i < p.n_in; ++i) xv += p.x[i][static_cast<size_t>(n) * p.cin + ci];
+    s = fmaf(xv, p.w[static_cast<size_t>(co) * p.cin + ci], s);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) p.y[wid] = actf(s + p.b[co], p.act);
+}
+
+// ---------------------------------------------------------------------------------- attention gates
+struct GateParams {
+  View x, y, s;    // s: 1-channel spatial logits (BAM)
+  const float* v;  // [N][C]
+  const float* w;  // [C] spatial-squeeze weights (scSE)
+  float b;
+  int mode, N;
+};
+// SE: y = x*v ; BAM: y = x*(1+sigmoid(v+s))
+__global__ void __launch_bounds__(TPB) gate_kernel(const __grid_constant__ GateParams p) {
+  const int C = p.x.c, cg = C >> 3;
+  const size_t HW = static_cast<size_t>(p.x.H) * p.x.W;
+  const size_t total = static_cast<size_t>(p.N) * HW * cg;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * TPB) {
+    const int g = static_cast<int>(idx % cg);
+    const size_t pix = idx / cg;
+    const int n = static_cast<int>(pix / HW);
+    float xv[8];
+    ld8(p.x, pix, g * 8, xv);
+    const float* vv = p.v + static_cast<size_t>(n) * C + g * 8;
+    if (p.mode == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) xv[j] *= vv[j];
+    } else {
+      const float sg = ld1(p.s, pix, 0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) xv[j] *= 1.0f + sigmoidf_(vv[j] + sg);
+    }
+    st8(p.y, pix, g * 8, xv);
+  }
+}
+// scSE: y = x*(sigmoid(w.x + b) + v): a group of min(32, C/8) lanes owns one pixel; the per-pixel dot
+// product over channels is a shuffle reduction inside the group.
+__global__ void __launch_bounds__(TPB) gate_scse_kernel(const __grid_constant__ GateParams p, int lanes_per_pix) {
+  const int C = p.x.c, cg = C >> 3;
+  const size_t HW = static_cast<size_t>(p.x.H) * p.x.W;
+  const size_t npix = static_cast<size_t>(p.N) * HW;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % lanes_per_pix;
+  const int pix_per_warp = 32 / lanes_per_pix;
+  const size_t warp_global = (blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x) >> 5;
+  const size_t nwarps = (static_cast<size_t>(gridDim.x) * TPB) >> 5;
+  for (size_t base = warp_global * pix_per_warp; base < npix; base += nwarps * pix_per_warp) {
+    const size_t pix = base + lane / lanes_per_pix;
+    const bool ok = pix < npix;
+    float dot = 0.0f;
+    if (ok) {
+      for (int g = sub; g < cg; g += lanes_per_pix) {
+        float xv[8];
+        ld8(p.x, pix, g * 8, xv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dot = fmaf(xv[j], p.w[g * 8 + j], dot);
+      }
+    }
+    for (int o = lanes_per_pix >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    if (ok) {
+      const float sp = sigmoidf_(dot + p.b);
+      const int n = static_cast<int>(pix / HW);
+      for (int g = sub; g < cg; g += lanes_per_pix) {
+        float xv[8];
+        ld8(p.x, pix, g * 8, xv);
+        const float* vv = p.v + static_cast<size_t>(n) * C + g * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) xv[j] = xv[j] * sp + xv[j] * vv[j];
+        st8(p.y, pix, g * 8, xv);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------- selective-kernel fusion
+struct SkParams {
+  View x[4], y;
+  const float* g;       // [N][C]
+  const float* lg[5];   // [N][C] each
+  const float* scale;   // [C]
+  const float* shift;
+  int N;
+};
+__global__ void __launch_bounds__(TPB) skfuse_kernel(const __grid_constant__ SkParams p) {
+  const int C = p.y.c, cg = C >> 3;
+  const size_t HW = static_cast<size_t>(p.y.H) * p.y.W;
+  const size_t total = static_cast<size_t>(p.N) * HW * cg;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * TPB) {
+    const int g = static_cast<int>(idx % cg);
+    const size_t pix = idx / cg;
+    const int n = static_cast<int>(pix / HW);
+    float xs[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ld8(p.x[i], pix, g * 8, xs[i]);
+    float out[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const size_t vi = static_cast<size_t>(n) * C + g * 8 + j;
+      float l[5], m = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 5; ++i) { l[i] = p.lg[i][vi]; m = fmaxf(m, l[i]); }
+      float den = 0.0f;
+#pragma unroll
+      for (int i = 0; i < 5; ++i) { l[i] = __expf(l[i] - m); den += l[i]; }
+      const float inv = 1.0f / den;
+      float acc = p.g[vi] * l[4] * inv;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc = fmaf(xs[i][j], l[i] * inv, acc);
+      out[j] = fmaxf(fmaf(acc, p.scale[g * 8 + j], p.shift[g * 8 + j]), 0.0f);
+    }
+    st8(p.y, pix, g * 8, out);
+  }
+}
+
+// ---------------------------------------------------------------------------------- broadcast vector over a map slice
+struct BcastParams {
+  View y;
+  const float* v;
+  int N;
+};
+__global__ void __launch_bounds__(TPB) bcast_kernel(const __grid_constant__ BcastParams p) {
+  const int C = p.y.c, cg = C >> 3;
+  const size_t HW = static_cast<size_t>(p.y.H) * p.y.W;
+  const size_t total = static_cast<size_t>(p.N) * HW * cg;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * TPB) {
+    const int g = static_cast<int>(idx % cg);
+    const size_t pix = idx / cg;
+    const int n = static_cast<int>(pix / HW);
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = p.v[static_cast<size_t>(n) * C + g * 8 + j];
+    st8(p.y, pix, g * 8, f);
+  }
+}
+
+// ---------------------------------------------------------------------------------- softmax head
+// logits fp32 (N, 512/up, 512/up, 2) -> probs fp32 (N,512,512,2) and/or mask u8 (argmax, ties -> class 0)
+__global__ void __launch_bounds__(TPB) softmax2_kernel(const float* __restrict__ logits, int N, int H, int W, int up,
+                                                       float* __restrict__ probs, uint8_t* __restrict__ mask) {
+  const size_t total = static_cast<size_t>(N) * H * W;
+  const int h2 = H / up, w2 = W / up;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * TPB) {
+    const int ow = static_cast<int>(idx % W), oh = static_cast<int>((idx / W) % H);
+    const int n = static_cast<int>(idx / (static_cast<size_t>(W) * H));
+    const float2 l = *reinterpret_cast<const float2*>(logits + ((static_cast<size_t>(n) * h2 + oh / up) * w2 + ow / up) * 2);
+    if (probs) {
+      const float m = fmaxf(l.x, l.y);
+      const float e0 = expf(l.x - m), e1 = expf(l.y - m);
+      const float inv = 1.0f / (e0 + e1);
+      *reinterpret_cast<float2*>(probs + idx * 2) = make_float2(e0 * inv, e1 * inv);
+    }
+    if (mask) mask[idx] = l.y > l.x ? 1 : 0;
+  }
+}
+
+// ---------------------------------------------------------------------------------- tiler / stitcher
+// predict.py:91-108: BGR->RGB, x/127.5-1 in float64 (then Keras casts to float32), zero pad in normalised space.
+__global__ void __launch_bounds__(TPB) tiles_gather_kernel(const uint8_t* __restrict__ scene, int H, int W,
+                                                           const int* __restrict__ ys, const int* __restrict__ xs,
+                                                           int n, float* __restrict__ out) {
+  const size_t total = static_cast<size_t>(n) * 512 * 512;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * TPB) {
+    const int tx = static_cast<int>(idx % 512), ty = static_cast<int>((idx / 512) % 512);
+    const int t = static_cast<int>(idx / (512 * 512));
+    const int y = ys[t] + ty, x = xs[t] + tx;
+    float r = 0.0f, g = 0.0f, b = 0.0f;
+    if (y < H && x < W) {
+      const uint8_t* px = scene + (static_cast<size_t>(y) * W + x) * 3;
+      b = static_cast<float>(static_cast<double>(px[0]) / 127.5 - 1.0);
+      g = static_cast<float>(static_cast<double>(px[1]) / 127.5 - 1.0);
+      r = static_cast<float>(static_cast<double>(px[2]) / 127.5 - 1.0);
+    }
+    float* o = out + idx * 3;
+    o[0] = r; o[1] = g; o[2] = b;
+  }
+}
+// predict.py:113-114: scene[y,x] = 255 where any covering tile predicts class 1 (all writers store 255).
+__global__ void __launch_bounds__(TPB) stitch_or_kernel(const uint8_t* __restrict__ tiles, const int* __restrict__ ys,
+                                                        const int* __restrict__ xs, int n, uint8_t* __restrict__ scene,
+                                                        int H, int W) {
+  const size_t total = static_cast<size_t>(n) * 512 * 512;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * TPB) {
+    if (!tiles[idx]) continue;
+    const int tx = static_cast<int>(idx % 512), ty = static_cast<int>((idx / 512) % 512);
+    const int t = static_cast<int>(idx / (512 * 512));
+    const int y = ys[t] + ty, x = xs[t] + tx;
+    if (y < H && x < W) scene[static_cast<size_t>(y) * W + x] = 255;
+  }
+}
+
+}  // namespace k
+}  // namespace bd

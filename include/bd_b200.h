@@ -1,0 +1,151 @@
+/* bd_b200.h -- C ABI of the B200 (sm_100a) implementation of the building-detection hot path.
+ *
+ * The reference (A511-1103/building-detection) has no FFI of its own: its hot path is the Python
+ * call chain predict.py:run_model -> detection -> model.predict (TensorFlow runtime) ->
+ * model_fuse.py:model_confuse (OpenCV) -> edge_3.py:_detection (OpenCV).  This header is the
+ * boundary a binding for that path targets (ctypes stub in INTEGRATION.md); every entry point
+ * names the reference interface it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; bd_last_error() gives the message
+ *     (thread-local, valid until the next call on the same thread);
+ *   - pointers named *_dev are CUDA device pointers on the context's device, *_host are host
+ *     pointers; the caller owns all of them.  The library owns only weights and workspace;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); calls are asynchronous
+ *     with respect to the host unless stated otherwise;
+ *   - feature maps are NHWC; a "tensor ref" is a channel slice [c0, c0+c) of a plan buffer;
+ *   - one bd_ctx per GPU, not thread-safe.
+ */
+#ifndef BD_B200_H
+#define BD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bd_ctx bd_ctx;
+typedef struct bd_plan bd_plan;
+
+enum bd_dtype { BD_BF16 = 0, BD_F32 = 1 };
+enum bd_buf_kind { BD_MAP = 0 /* (N,H,W,C) */, BD_VEC = 1 /* (N,C) fp32 */ };
+enum bd_act { BD_ACT_NONE = 0, BD_ACT_RELU = 1, BD_ACT_SIGMOID = 2 };
+enum bd_gate_mode { BD_GATE_SE = 0, BD_GATE_SCSE = 1, BD_GATE_BAM = 2 };
+enum bd_conv_path { BD_CONV_DIRECT = 0 /* CUDA cores */, BD_CONV_UMMA = 1 /* tcgen05 implicit GEMM */ };
+
+typedef struct bd_tref { int32_t buf, c0, c; } bd_tref;
+
+#define BD_MAX_TAPS 9
+
+/* Fused convolution: y = act_post( act_pre( sum_t W[t] . x[h*stride+dy[t], w*stride+dx[t]] + bias ) + res )
+ * written to y[(h*out_scale+out_oy), (w*out_scale+out_ox)].  Out-of-range taps read zero ('same'
+ * padding).  Replaces Conv2D / Conv2DTranspose (+BatchNormalization +Activation +Add) layer groups of
+ * predict_model/{res34,hrnet,v3plus,scse,bam}.py executed by tf.keras.Model.predict (predict.py:109).
+ * w: bf16 bit patterns, layout [ntaps][cout][cin]; bias: fp32 [cout] (BatchNorm already folded). */
+typedef struct bd_conv_desc {
+  bd_tref x, y, res;            /* res.buf < 0: no residual */
+  int32_t ntaps;
+  int32_t dy[BD_MAX_TAPS], dx[BD_MAX_TAPS];
+  int32_t stride, ho, wo;       /* logical output grid (before out_scale) */
+  int32_t act_pre, act_post;    /* bd_act (NONE or RELU) */
+  int32_t out_scale, out_oy, out_ox;
+  int32_t path;                 /* bd_conv_path */
+  const uint16_t* w_host;
+  const float* bias_host;
+} bd_conv_desc;
+
+/* ---- context ---------------------------------------------------------------------------- */
+int bd_create(int device, bd_ctx** out);
+void bd_destroy(bd_ctx* ctx);
+const char* bd_last_error(void);
+const char* bd_version(void);
+/* number of kernel launches issued by this library on this context so far */
+int64_t bd_launch_count(bd_ctx* ctx);
+
+/* ---- network plans: replace tf.keras.Model construction + Model.predict (predict.py:17-54,109) */
+int bd_plan_create(bd_ctx* ctx, int batch, bd_plan** out);
+void bd_plan_destroy(bd_plan* plan);
+/* returns the buffer id (>= 0) or a negative error */
+int bd_plan_add_buffer(bd_plan* plan, int h, int w, int c, int dtype, int kind);
+int bd_plan_add_conv(bd_plan* plan, const bd_conv_desc* d);
+/* depthwise 3x3 (first half of SeparableConv2D, v3plus.py:187-278); w fp32 [9][c], optional ReLU on load */
+int bd_plan_add_dwconv(bd_plan* plan, bd_tref x, bd_tref y, int stride, int pad_t, int pad_l, int relu_in,
+                       const float* w_host);
+/* MaxPool2D k x k (scse.py:54, res34.py:152-154, v3plus.py:192); padding reads -inf */
+int bd_plan_add_maxpool(bd_plan* plan, bd_tref x, bd_tref y, int k, int stride, int pad_t, int pad_l);
+/* y = act(sum_i nearest_upsample(x_i, f_i)), n <= 4 (UpSampling2D / tf.add / concat slices, hrnet.py:99-162) */
+int bd_plan_add_addn(bd_plan* plan, int n, const bd_tref* xs, const int32_t* fs, bd_tref y, int act);
+/* GlobalAveragePooling2D -> fp32 vector buffer */
+int bd_plan_add_gap(bd_plan* plan, bd_tref x, int y_vec);
+/* y = act(W . sum_i x_i + b); w fp32 [cout][cin] (Dense / 1x1 conv on pooled vectors, BN folded) */
+int bd_plan_add_dense(bd_plan* plan, int n_in, const int32_t* x_vecs, int y_vec, int cin, int cout, int act,
+                      const float* w_host, const float* b_host);
+/* attention gates: SE x*v (res34.py:102-104); scSE x*(sigmoid(w.x+b) + v) (scse.py:20-46);
+ * BAM x*(1+sigmoid(v + s)) (bam.py:57-71) */
+int bd_plan_add_gate(bd_plan* plan, int mode, bd_tref x, bd_tref y, int v_vec, bd_tref s, const float* w_host,
+                     float b);
+/* selective-kernel fusion (v3plus.py:114-136): softmax over 5 logit vectors, weighted sum of 4 maps and
+ * the pooled vector g, then y = relu(acc*scale + shift) */
+int bd_plan_add_skfuse(bd_plan* plan, const bd_tref* xs4, int g_vec, const int32_t* logit_vecs5, bd_tref y,
+                       const float* scale_host, const float* shift_host);
+/* broadcast a pooled vector over a map slice (UpSampling2D of a 1x1 map, v3plus.py:302-304) */
+int bd_plan_add_bcast(bd_plan* plan, int v_vec, bd_tref y);
+/* allocates the arena, uploads weights, encodes TMA tensor maps.  input_buf: fp32 (N,512,512,3) map;
+ * logits_buf: fp32 2-channel map at 512/logits_up resolution. */
+int bd_plan_finalize(bd_plan* plan, int input_buf, int logits_buf, int logits_up);
+/* One forward of the whole network.  x_dev: fp32 NHWC in [-1,1], or NULL to use what is already in the
+ * input buffer (e.g. written by bd_tiles_gather).  probs_dev: fp32 (N,512,512,2) or NULL;
+ * mask_dev: u8 (N,512,512), 1 where class 1 wins (argmax, ties -> class 0, predict.py:110) or NULL. */
+int bd_plan_run(bd_plan* plan, const float* x_dev, float* probs_dev, uint8_t* mask_dev, void* stream);
+/* host-buffer convenience (synchronous): H2D, run, D2H.  Replaces model.predict(ndarray). */
+int bd_plan_run_host(bd_plan* plan, const float* x_host, float* probs_host, uint8_t* mask_host);
+/* device pointer / byte size of a plan buffer (tests, and writing the input buffer in place) */
+void* bd_plan_buffer_ptr(bd_plan* plan, int buf);
+size_t bd_plan_buffer_bytes(bd_plan* plan, int buf);
+int bd_plan_read_buffer(bd_plan* plan, int buf, void* host_dst, size_t bytes);
+int bd_plan_write_buffer(bd_plan* plan, int buf, const void* host_src, size_t bytes);
+size_t bd_plan_arena_bytes(bd_plan* plan);
+int bd_plan_num_launches(bd_plan* plan);
+/* per-op device times of one run (CUDA events around every op; for profiling only): ms_out[num_ops] */
+int bd_plan_num_ops(bd_plan* plan);
+int bd_plan_time_ops(bd_plan* plan, float* ms_out, void* stream);
+/* kind (0=conv umma, 1=conv direct, 2=other), and algorithmic flops of op i */
+int bd_plan_op_info(bd_plan* plan, int i, int* kind, double* flops);
+
+/* ---- tiler / stitcher: replace predict.py:detection (90-116) ------------------------------- */
+/* Gather n 512x512 tiles whose top-left corners are (ys[i], xs[i]) from a BGR u8 scene (h,w,3) into
+ * fp32 RGB (n,512,512,3) = pixel/127.5-1 (computed in double like predict.py:93), zero outside the
+ * scene (predict.py:102-104 pads the *normalised* image with zeros). */
+int bd_tiles_gather(bd_ctx* ctx, const uint8_t* scene_bgr_dev, int h, int w, const int32_t* ys_host,
+                    const int32_t* xs_host, int n, float* x_dev, void* stream);
+/* OR tile masks (n,512,512) into the scene mask (h,w): scene |= 255 where the tile says class 1
+ * (predict.py:113-114: int8 accumulate then >=1 -> 255). */
+int bd_stitch_or(bd_ctx* ctx, const uint8_t* tile_masks_dev, const int32_t* ys_host, const int32_t* xs_host,
+                 int n, uint8_t* scene_mask_dev, int h, int w, void* stream);
+
+/* ---- fusion: replaces model_fuse.py:model_confuse (271-350) --------------------------------- */
+/* masks5_dev: 5 u8 masks (5,h,w) with values {0,255}; fused_dev: u8 (h,w) {0,255}.
+ * Per mask: hole fill + drop polygon-area <= 1000, directional 1x21 / 21x1 erosion split with fragment
+ * filter <= 500; vote >= 3 of 5; same clean-up again.  Synchronous. */
+int bd_fuse(bd_ctx* ctx, const uint8_t* masks5_dev, int h, int w, uint8_t* fused_dev, void* stream);
+/* the per-mask clean-up alone (fill_and_delete + eroede_dilate_process + only_plt, model_fuse.py:9-218) */
+int bd_mask_cleanup(bd_ctx* ctx, const uint8_t* mask_dev, int h, int w, uint8_t* out_dev, void* stream);
+
+/* ---- contours: replaces edge_3.py:_detection (310-387) -------------------------------------- */
+typedef struct bd_polys {
+  int32_t n_polys;
+  int32_t n_points;        /* total points over all polygons (each polygon closed: first point repeated) */
+  int32_t* offsets;        /* n_polys+1 entries into xs/ys */
+  float* xs;               /* integer-valued except minAreaRect fallbacks (edge_3.py:281-285) */
+  float* ys;
+  uint8_t* is_float;       /* per polygon: 1 if produced by the boxPoints fallback (float32 coords) */
+} bd_polys;
+int bd_contours(bd_ctx* ctx, const uint8_t* mask_dev, int h, int w, bd_polys* out, void* stream);
+void bd_polys_free(bd_polys* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BD_B200_H */

@@ -152,8 +152,19 @@ class Interp:
         bid, c0, c = op["y"]
         self._store(op["y"], self.b[op["v"]][:, None, None, :].expand(-1, self.p.bufs[bid].H, self.p.bufs[bid].W, -1))
 
-    def run(self, x_nhwc):
-        self.b[self.p.input][...] = torch.as_tensor(x_nhwc, dtype=torch.float32)
+    def set(self, buf, arr):
+        """Write a whole buffer (bf16 maps are rounded like a device store would)."""
+        t = torch.as_tensor(np.asarray(arr), dtype=torch.float32)
+        if self.emu and self.p.bufs[buf].kind == "map" and self.p.bufs[buf].dtype == "bf16":
+            t = _q(t)
+        self.b[buf] = t.clone()
+
+    def get(self, buf):
+        return self.b[buf].numpy()
+
+    def run(self, x_nhwc=None):
+        if x_nhwc is not None:
+            self.b[self.p.input][...] = torch.as_tensor(x_nhwc, dtype=torch.float32)
         disp = {G.OP_CONV: self._conv, G.OP_DWCONV: self._dwconv, G.OP_MAXPOOL: self._maxpool,
                 G.OP_ADDN: self._addn, G.OP_GAP: self._gap, G.OP_DENSE: self._dense, G.OP_GATE: self._gate,
                 G.OP_SKFUSE: self._skfuse, G.OP_BCAST: self._bcast}
@@ -167,7 +178,7 @@ class Interp:
                 probs = torch.softmax(lg, dim=-1)
             else:
                 disp[op["op"]](op)
-        return probs.numpy()
+        return None if probs is None else probs.numpy()
 
 
 def run_plan(plan, x_nhwc, emulate_bf16=True):
