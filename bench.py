@@ -1,0 +1,285 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the building-detection hot path on B200.
+
+Workload (BASELINE.json configs[4], the one the metric is quoted on; it fits one GPU): the full
+5-model ensemble over a synthetic S x S BGR scene cut into overlapping 512x512 tiles (stride 360),
+argmax masks OR-stitched per model, then 3-of-5 fusion and contour extraction.  One *step* = one
+whole scene.  Metric: ensemble tiles/s (a tile counts once after all five networks saw it).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--scene S] [--batch B] [--impl reference]
+
+value : scene already resident in HBM when the timed region starts (CUDA events, max over ranks)
+e2e   : same job through the public entry with the scene in pinned HOST memory; the H2D copy of the
+        scene (band) and the D2H read of the fused mask + polygons are inside the timed region
+N > 1 : tile rows are sharded into contiguous bands, one process per GPU (torchrun), no per-tile
+        collective; stitched band masks are gathered to rank 0 over NCCL for fusion + contours
+        (strong scaling: the scene is fixed).
+--impl reference : the CPU arm -- oracle/nets.py (fp32 torch-CPU restatement of the reference's Keras
+        graphs; TensorFlow is not installable here) on all host cores, one tile per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ensemble_tiles_per_s"
+UNIT = "tiles/s"
+GFLOP_PER_TILE = 1447.32  # 2*MAC of conv/convT/depthwise/dense, five networks
+
+
+def synthetic_scene(S, seed=4):
+    """Low-frequency BGR noise (building-sized blobs) + fine texture, u8."""
+    rng = np.random.default_rng(seed)
+    coarse = rng.random((S // 64 + 2, S // 64 + 2, 3), dtype=np.float32)
+    img = np.kron(coarse, np.ones((64, 64, 1), np.float32))[:S, :S]
+    img = img * 200.0 + rng.integers(0, 56, (S, S, 1), dtype=np.uint8)
+    return np.ascontiguousarray(img.astype(np.uint8))
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"bf16_burst": d["bf16_tflops"], "bf16_sustained": d["bf16_tflops_sustained"], "hbm": d["hbm_gbs"],
+                "source": "measured"}
+    return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm": 6650.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------- reference (CPU) arm
+def cpu_ensemble_tile_seconds(reps=1):
+    """Seconds for ONE tile through the five fp32 CPU forwards (oracle/nets.py), best of ``reps``."""
+    import torch
+    from building_detection_b200 import graph as G
+    from building_detection_b200.predict_model import CTORS, MODEL_NAMES
+    from oracle import nets
+    rng = np.random.default_rng(0)
+    x = (rng.integers(0, 256, (1, 512, 512, 3), dtype=np.uint8) / 127.5 - 1).astype(np.float32)
+    ws = {n: G.init_weights(CTORS[n]().spec, seed=1) for n in MODEL_NAMES}
+    best = float("inf")
+    with torch.no_grad():
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            for n in MODEL_NAMES:
+                nets.FORWARD[n](ws[n], x)
+            best = min(best, time.perf_counter() - t0)
+    return best, torch.get_num_threads()
+
+
+def run_reference(args):
+    """CPU arm: every step is one 512x512 tile through the five networks (a bounded sample of the scene
+    job: 1 of its tiles; fuse/contours are excluded here because the reference's own fuse is O(#objects x H x W)
+    and is reported separately in DESIGN.md)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import torch
+    from building_detection_b200 import graph as G
+    from building_detection_b200.predict_model import CTORS, MODEL_NAMES
+    from oracle import nets
+    rng = np.random.default_rng(0)
+    x = (rng.integers(0, 256, (1, 512, 512, 3), dtype=np.uint8) / 127.5 - 1).astype(np.float32)
+    ws = {n: G.init_weights(CTORS[n]().spec, seed=1) for n in MODEL_NAMES}
+
+    def step():
+        with torch.no_grad():
+            for n in MODEL_NAMES:
+                nets.FORWARD[n](ws[n], x)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    v = 1.0 / dt
+    cores = torch.get_num_threads()
+    sample = "1 tile x 5 networks per step, fp32 torch-CPU restatement of predict_model/*.py (TensorFlow absent)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"5-model ensemble forward, 512x512 tiles (sample of the {args.scene}^2 scene job)"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# --------------------------------------------------------------------------------- B200 arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--scene", type=int, default=20000, help="scene edge in px (20000 = BASELINE configs[4])")
+    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-post", action="store_true", help="skip fusion + contours (forward + stitch only)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from building_detection_b200 import post, runtime as R, scene as S
+    from building_detection_b200.predict_model import CTORS, MODEL_NAMES
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    models = [CTORS[n]() for n in MODEL_NAMES]  # seeded Keras-default random init (no checkpoints offline)
+    runner = S.SceneRunner(models, batch=args.batch, device=local)
+    Ssz = args.scene
+    origins = S.tile_origins(Ssz, Ssz)
+    mine = S.shard_rows(origins, rank, world)
+    job = post.SceneJob(runner, Ssz, Ssz, mine, rank, world, do_post=not args.no_post)
+
+    scene_host = torch.from_numpy(synthetic_scene(Ssz)).pin_memory()
+    scene_dev = scene_host.to(dev)
+    launches0 = R.lib().bd_launch_count(runner.ctx)
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(args.warmup):
+        job.run_resident(scene_dev)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = R.lib().bd_launch_count(runner.ctx)
+    ms = timed(lambda: job.run_resident(scene_dev), args.steps)
+    launches = R.lib().bd_launch_count(runner.ctx) - l0
+    clocks = sampler.stop() if rank == 0 else None
+    # end to end: pinned host scene -> H2D -> job -> D2H of the fused mask and polygons
+    job.run_e2e(scene_host)
+    ms_e2e = timed(lambda: job.run_e2e(scene_host), args.steps)
+
+    ntiles = len(origins)
+    value = ntiles * args.steps / (ms / 1e3)
+    e2e_value = ntiles * args.steps / (ms_e2e / 1e3)
+
+    # roofline of the dominant kernel (conv_umma_kernel: tcgen05 implicit-GEMM convolution), measured live
+    # with CUDA events around every op of the five batch-B plans (bd_plan_time_ops)
+    roof = None
+    if rank == 0:
+        pk = peaks()
+        tot_ms = {0: 0.0, 1: 0.0, 2: 0.0}
+        tot_fl = {0: 0.0, 1: 0.0, 2: 0.0}
+        n_umma = 0
+        for m in models:
+            plan = m.native_plan(args.batch)
+            plan.time_ops()
+            t_ms, kinds, flops = plan.time_ops()
+            for kcls in (0, 1, 2):
+                sel = kinds == kcls
+                tot_ms[kcls] += float(t_ms[sel].sum())
+                tot_fl[kcls] += float(flops[sel].sum())
+            n_umma += int((kinds == 0).sum())
+        ach = tot_fl[0] / (tot_ms[0] * 1e-3) / 1e12
+        roof = {"kernel": "conv_umma_kernel", "bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"],
+                "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"], "traffic": None,
+                "peak_source": pk["source"] + " cuBLAS 16-bit sustained (kernel timed inside a long step); burst "
+                               f"{pk['bf16_burst']}",
+                "launches_per_batch": n_umma, "avg_launch_ms": tot_ms[0] / max(n_umma, 1),
+                "share_of_forward": tot_ms[0] / sum(tot_ms.values()),
+                "forward_ms_per_batch": {"conv_umma": tot_ms[0], "conv_direct": tot_ms[1], "memory_bound": tot_ms[2]},
+                "whole_forward_tflops": sum(tot_fl.values()) / (sum(tot_ms.values()) * 1e-3) / 1e12}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sec, cores = cpu_ensemble_tile_seconds(reps=2)
+        cpu = {"value": 1.0 / sec, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "1 tile x 5 networks (best of 2), fp32 torch-CPU restatement of predict_model/*.py; "
+                         "TensorFlow is not installable offline"}
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f16", "data": "synthetic",
+            "config": {"workload": f"5-model ensemble (res34,hrnet,v3plus,scse,bam) + OR-stitch"
+                                   f"{'' if args.no_post else ' + 3-of-5 fuse + contours'} on a {Ssz}x{Ssz} px scene",
+                       "tiles": ntiles, "tile": 512, "stride": 360, "batch": args.batch,
+                       "parallelism": f"tile-row bands x{world}", "weights": "seeded Keras-default random init",
+                       "l2": "per-step working set (scene + masks + activations) >> 126 MB L2",
+                       "px_per_s": value * 360 * 360},
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": sum((b[1] - b[0]) * Ssz * 3 for b in job.bands),
+                    "d2h_bytes_per_step": job.d2h_bytes},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roof,
+            "cpu_baseline": cpu,
+            "tflops_algorithmic": value * GFLOP_PER_TILE / 1e3,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

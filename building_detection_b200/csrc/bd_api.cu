@@ -92,8 +92,8 @@ struct bd_plan {
     BD_CHECK(b.kind == BD_MAP, "tensor ref: not a map buffer");
     BD_CHECK(r.c0 >= 0 && r.c > 0 && r.c0 + r.c <= b.C, "tensor ref: slice out of range");
     if (vec8)
-      BD_CHECK(b.dtype == BD_BF16 && r.c % 8 == 0 && r.c0 % 8 == 0 && b.C % 8 == 0,
-               "tensor ref: op needs bf16 slices aligned to 8 channels");
+      BD_CHECK(b.dtype == BD_F16 && r.c % 8 == 0 && r.c0 % 8 == 0 && b.C % 8 == 0,
+               "tensor ref: op needs h16 slices aligned to 8 channels");
     return 0;
   }
   int check_vec(int id, int c) const {
@@ -210,7 +210,7 @@ int bd_plan_add_conv(bd_plan* p, const bd_conv_desc* dptr) {
       TView x = pl->tview(d.x), y = pl->tview(d.y), r;
       if (has_res) r = pl->tview(d.res);
       if (umma::prepare(L.get(), x, y, has_res ? &r : nullptr, d.ntaps, d.dy, d.dx, d.stride, d.ho, d.wo, d.act_pre,
-                        d.act_post, d.out_scale, d.out_oy, d.out_ox, static_cast<const bf16*>(wd),
+                        d.act_post, d.out_scale, d.out_oy, d.out_ox, static_cast<const h16*>(wd),
                         static_cast<const float*>(bdv), ctx->umma_smem_kb, ctx->umma_max_block_n))
         return 1;
       op.kclass = 0;
@@ -223,7 +223,7 @@ int bd_plan_add_conv(bd_plan* p, const bd_conv_desc* dptr) {
       q.N = pl->batch; q.Ho = d.ho; q.Wo = d.wo; q.stride = d.stride; q.ntaps = d.ntaps;
       for (int t = 0; t < d.ntaps; ++t) { q.dy[t] = d.dy[t]; q.dx[t] = d.dx[t]; }
       q.act_pre = d.act_pre; q.act_post = d.act_post; q.out_scale = d.out_scale; q.out_oy = d.out_oy; q.out_ox = d.out_ox;
-      q.w = static_cast<const bf16*>(wd); q.bias = static_cast<const float*>(bdv);
+      q.w = static_cast<const h16*>(wd); q.bias = static_cast<const float*>(bdv);
       const size_t total = static_cast<size_t>(pl->batch) * d.ho * d.wo * cdiv(cout, k::DC_CO);
       const int grid = static_cast<int>(std::min<size_t>((total + k::TPB - 1) / k::TPB, 1u << 20));
       op.kclass = 1;
@@ -571,6 +571,13 @@ int bd_plan_run(bd_plan* p, const float* x_dev, float* probs_dev, uint8_t* mask_
   return 0;
 }
 
+int bd_plan_run_head(bd_plan* p, float* probs_dev, uint8_t* mask_dev, void* stream) {
+  BD_CHECK(p && p->finalized && p->logits_buf >= 0, "plan has no softmax head");
+  p->cur_probs = probs_dev;
+  p->cur_mask = mask_dev;
+  return p->ops.back().run(static_cast<cudaStream_t>(stream));
+}
+
 int bd_plan_run_host(bd_plan* p, const float* x_host, float* probs_host, uint8_t* mask_host) {
   BD_CHECK(p && p->finalized && p->input_buf >= 0 && p->logits_buf >= 0, "plan not runnable from host buffers");
   const BufInfo& ib = p->bufs[p->input_buf];
@@ -588,6 +595,8 @@ int bd_plan_run_host(bd_plan* p, const float* x_host, float* probs_host, uint8_t
   }
   if (!rc && probs_host) cudaMemcpy(probs_host, dprobs, npix * 2 * 4, cudaMemcpyDeviceToHost);
   if (!rc && mask_host) cudaMemcpy(mask_host, dmask, npix, cudaMemcpyDeviceToHost);
+  p->cur_probs = nullptr;
+  p->cur_mask = nullptr;
   if (dprobs) cudaFree(dprobs);
   if (dmask) cudaFree(dmask);
   return rc;
@@ -631,6 +640,8 @@ int bd_plan_time_ops(bd_plan* p, float* ms_out, void* stream) {
   BD_CHECK(p && p->finalized && ms_out, "bad arguments");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const size_t n = p->ops.size();
+  p->cur_probs = nullptr;  // the head kernel is skipped: its outputs belong to the caller of bd_plan_run
+  p->cur_mask = nullptr;
   std::vector<cudaEvent_t> ev(n + 1);
   for (auto& e : ev) BD_CUDA(cudaEventCreate(&e));
   BD_CUDA(cudaEventRecord(ev[0], s));

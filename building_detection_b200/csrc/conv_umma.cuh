@@ -12,7 +12,7 @@
 // Roles (128 threads): warp 0 lane 0 = TMA producer, warp 1 lane 0 = MMA issuer (+ TMEM alloc by
 // warp 1), then all four warps run the epilogue: tcgen05.ld the fp32 accumulators (warp w owns TMEM
 // lanes 32w..32w+31 = tile rows), add bias (BatchNorm folded), optional ReLU / residual / ReLU, pack
-// to bf16 and store 16-byte vectors into the destination channel slice (concat elision; pixel
+// to h16 and store 16-byte vectors into the destination channel slice (concat elision; pixel
 // scatter for the sub-pixel transposed convolutions).
 #pragma once
 #include <algorithm>
@@ -25,7 +25,7 @@ namespace bd {
 namespace umma {
 
 constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 64;  // bf16 elements = one 128-byte swizzle row
+constexpr int BLOCK_K = 64;  // h16 elements = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
 constexpr int MAX_TAPS = 9;
@@ -36,9 +36,9 @@ struct Params {
   int tiles_w, tiles_h, tiles_n, n_tiles;
   int block_n, kchunks, ntaps, stages, tmem_cols;
   int tap_map[MAX_TAPS], tap_dy[MAX_TAPS], tap_dx[MAX_TAPS];
-  bf16* y;
+  h16* y;
   int y_ctot, y_c0, y_H, y_W, out_scale, out_oy, out_ox;
-  const bf16* res;
+  const h16* res;
   int res_ctot, res_c0;
   const float* bias;
   int act_pre, act_post;
@@ -94,7 +94,7 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                             uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -125,10 +125,10 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
-// kind::f16 instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7, 10), both K-major, N>>3 at [17,23), M>>4 at [24,29)
+// kind::f16 instruction descriptor: D=f32 (bit 4), A and B formats at [7,10) / [10,13) = 0 (fp16; 1 would be
+// bf16), both K-major, N>>3 at [17,23), M>>4 at [24,29)
 __device__ __forceinline__ uint32_t make_idesc(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
-         (static_cast<uint32_t>(BLOCK_M >> 4) << 24);
+  return (1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(BLOCK_M >> 4) << 24);
 }
 
 __device__ __forceinline__ float apply_act(float v, int act) { return act == 1 ? fmaxf(v, 0.0f) : v; }
@@ -206,8 +206,8 @@ __global__ void __launch_bounds__(128) conv_umma_kernel(const __grid_constant__ 
       const uint64_t adesc = make_sdesc(a_s), bdesc = make_sdesc(a_s + A_STAGE_BYTES);
 #pragma unroll
       for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-        // advance 16 bf16 = 32 bytes inside the swizzle atom: +2 in the (addr >> 4) field
-        tc_mma_bf16(tmem_base, adesc + 2u * k, bdesc + 2u * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        // advance 16 h16 = 32 bytes inside the swizzle atom: +2 in the (addr >> 4) field
+        tc_mma_f16(tmem_base, adesc + 2u * k, bdesc + 2u * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
       }
       tc_commit(empty0 + 8u * s);  // frees the smem stage once these MMAs have read it
     }
@@ -224,8 +224,8 @@ __global__ void __launch_bounds__(128) conv_umma_kernel(const __grid_constant__ 
   const bool pix_ok = (ow < p.Wo) && (oh < p.Ho) && (on < p.N);
   const size_t ypix = (static_cast<size_t>(on) * p.y_H + (oh * p.out_scale + p.out_oy)) * p.y_W +
                       (ow * p.out_scale + p.out_ox);
-  bf16* yrow = p.y + ypix * p.y_ctot + p.y_c0;
-  const bf16* rrow = p.res ? p.res + ypix * p.res_ctot + p.res_c0 : nullptr;
+  h16* yrow = p.y + ypix * p.y_ctot + p.y_c0;
+  const h16* rrow = p.res ? p.res + ypix * p.res_ctot + p.res_c0 : nullptr;
   const uint32_t trow = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
   for (int c0 = 0; c0 < p.block_n; c0 += 16) {
     uint32_t acc[16];
@@ -242,13 +242,13 @@ __global__ void __launch_bounds__(128) conv_umma_kernel(const __grid_constant__ 
           for (int j = 0; j < 8; ++j) v[j] = apply_act(__uint_as_float(acc[8 * g + j]) + __ldg(p.bias + ch + j), p.act_pre);
           if (rrow) {
             float rf[8];
-            unpack8(*reinterpret_cast<const bf16x8*>(rrow + ch), rf);
+            unpack8(*reinterpret_cast<const h16x8*>(rrow + ch), rf);
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] += rf[j];
           }
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], p.act_post);
-          *reinterpret_cast<bf16x8*>(yrow + ch) = pack8(v);
+          *reinterpret_cast<h16x8*>(yrow + ch) = pack8(v);
         }
       }
     }
@@ -277,9 +277,9 @@ inline EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// bf16 tensor map, 128-byte swizzle, zero OOB fill.  dims/strides innermost first; strides[i] is the
+// h16 tensor map, 128-byte swizzle, zero OOB fill.  dims/strides innermost first; strides[i] is the
 // byte stride of dim i+1.
-inline int encode_bf16(CUtensorMap* tm, void* base, int rank, const uint64_t* dims, const uint64_t* strides,
+inline int encode_h16(CUtensorMap* tm, void* base, int rank, const uint64_t* dims, const uint64_t* strides,
                        const uint32_t* box) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail("cuTensorMapEncodeTiled entry point not available");
@@ -291,7 +291,7 @@ inline int encode_bf16(CUtensorMap* tm, void* base, int rank, const uint64_t* di
     es[i] = 1;
   }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides[i];
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, base, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, base, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(int(r)));
   return 0;
@@ -310,12 +310,12 @@ inline int floor_pow2(int v) {
   return r;
 }
 
-// x: input view, y: output view (bf16 both).  w_dev: [ntaps][Cout][Cin] bf16.
+// x: input view, y: output view (h16 both).  w_dev: [ntaps][Cout][Cin] h16.
 inline int prepare(Launch* L, const TView& x, const TView& y, const TView* res, int ntaps, const int* dy,
                    const int* dx, int stride, int Ho, int Wo, int act_pre, int act_post, int out_scale, int out_oy,
-                   int out_ox, const bf16* w_dev, const float* bias_dev, int smem_budget_kb, int max_block_n) {
+                   int out_ox, const h16* w_dev, const float* bias_dev, int smem_budget_kb, int max_block_n) {
   const int Cin = x.c, Cout = y.c;
-  BD_CHECK(!x.f32 && !y.f32, "umma conv needs bf16 maps");
+  BD_CHECK(!x.f32 && !y.f32, "umma conv needs h16 maps");
   BD_CHECK(Cin % 8 == 0 && Cout % 8 == 0 && x.c0 % 8 == 0 && x.ctot % 8 == 0 && y.c0 % 8 == 0 && y.ctot % 8 == 0,
            "umma conv needs 16-byte aligned channel slices");
   BD_CHECK(stride == 1 || stride == 2, "umma conv stride must be 1 or 2");
@@ -362,7 +362,7 @@ inline int prepare(Launch* L, const TView& x, const TView& y, const TView* res, 
     uint64_t strides[3] = {pitch * stride, pitch * x.W * stride, pitch * x.W * x.H};
     uint32_t box[4] = {BLOCK_K, static_cast<uint32_t>(p.bw), static_cast<uint32_t>(p.bh), static_cast<uint32_t>(p.bn)};
     char* base = static_cast<char*>(x.base) + (static_cast<size_t>(py) * x.W + px) * pitch + static_cast<size_t>(x.c0) * 2;
-    if (encode_bf16(&L->tmA[m], base, 4, dims, strides, box)) return 1;
+    if (encode_h16(&L->tmA[m], base, 4, dims, strides, box)) return 1;
     if (first < 0) first = m;
   }
   for (int m = 0; m < 4; ++m)
@@ -371,14 +371,14 @@ inline int prepare(Launch* L, const TView& x, const TView& y, const TView* res, 
     uint64_t dims[3] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(Cout), static_cast<uint64_t>(ntaps)};
     uint64_t strides[2] = {static_cast<uint64_t>(Cin) * 2, static_cast<uint64_t>(Cin) * Cout * 2};
     uint32_t box[3] = {BLOCK_K, static_cast<uint32_t>(p.block_n), 1};
-    if (encode_bf16(&L->tmB, const_cast<bf16*>(w_dev), 3, dims, strides, box)) return 1;
+    if (encode_h16(&L->tmB, const_cast<h16*>(w_dev), 3, dims, strides, box)) return 1;
   }
-  p.y = static_cast<bf16*>(y.base);
+  p.y = static_cast<h16*>(y.base);
   p.y_ctot = y.ctot; p.y_c0 = y.c0; p.y_H = y.H; p.y_W = y.W;
   p.out_scale = out_scale; p.out_oy = out_oy; p.out_ox = out_ox;
   if (res) {
     BD_CHECK(!res->f32 && res->c0 % 8 == 0 && res->ctot % 8 == 0 && out_scale == 1, "bad residual view");
-    p.res = static_cast<const bf16*>(res->base); p.res_ctot = res->ctot; p.res_c0 = res->c0;
+    p.res = static_cast<const h16*>(res->base); p.res_ctot = res->ctot; p.res_c0 = res->c0;
   }
   p.bias = bias_dev; p.act_pre = act_pre; p.act_post = act_post;
   L->grid = dim3(static_cast<unsigned>(p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles));

@@ -2,7 +2,7 @@
 // pooling, nearest-upsample/add, global average pooling, attention gates, SK fusion, softmax head)
 // and the small-channel direct convolution (3-channel stems, 1/2-channel gates and heads, BAM C/16
 // convs) that is not worth a tensor-core tile.  Feature maps are NHWC; wherever channel counts are
-// multiples of 8 the access unit is one 16-byte vector of 8 bf16, with threads mapped channel-group
+// multiples of 8 the access unit is one 16-byte vector of 8 h16, with threads mapped channel-group
 // fastest so that a warp touches consecutive 16-byte vectors.
 #pragma once
 #include "common.cuh"
@@ -19,18 +19,18 @@ struct View {  // device-side channel-slice view
 
 __device__ __forceinline__ float ld1(const View& v, size_t pix, int ch) {
   const size_t i = pix * v.ctot + v.c0 + ch;
-  return v.f32 ? static_cast<const float*>(v.base)[i] : __bfloat162float(static_cast<const bf16*>(v.base)[i]);
+  return v.f32 ? static_cast<const float*>(v.base)[i] : __half2float(static_cast<const h16*>(v.base)[i]);
 }
 __device__ __forceinline__ void st1(const View& v, size_t pix, int ch, float x) {
   const size_t i = pix * v.ctot + v.c0 + ch;
   if (v.f32) static_cast<float*>(v.base)[i] = x;
-  else static_cast<bf16*>(v.base)[i] = __float2bfloat16_rn(x);
+  else static_cast<h16*>(v.base)[i] = to_h16(x);
 }
 __device__ __forceinline__ void ld8(const View& v, size_t pix, int ch, float* f) {
-  unpack8(*reinterpret_cast<const bf16x8*>(static_cast<const bf16*>(v.base) + pix * v.ctot + v.c0 + ch), f);
+  unpack8(*reinterpret_cast<const h16x8*>(static_cast<const h16*>(v.base) + pix * v.ctot + v.c0 + ch), f);
 }
 __device__ __forceinline__ void st8(const View& v, size_t pix, int ch, const float* f) {
-  *reinterpret_cast<bf16x8*>(static_cast<bf16*>(v.base) + pix * v.ctot + v.c0 + ch) = pack8(f);
+  *reinterpret_cast<h16x8*>(static_cast<h16*>(v.base) + pix * v.ctot + v.c0 + ch) = pack8(f);
 }
 __device__ __forceinline__ float actf(float v, int act) {
   return act == 1 ? fmaxf(v, 0.0f) : (act == 2 ? sigmoidf_(v) : v);
@@ -42,7 +42,7 @@ struct DirectParams {
   int N, Ho, Wo, stride, ntaps;
   int dy[9], dx[9];
   int act_pre, act_post, out_scale, out_oy, out_ox;
-  const bf16* w;  // [ntaps][Cout][Cin]
+  const h16* w;  // [ntaps][Cout][Cin]
   const float* bias;
 };
 constexpr int DC_CO = 4;  // output channels per thread
@@ -67,12 +67,12 @@ __global__ void __launch_bounds__(TPB) conv_direct_kernel(const __grid_constant_
       const int ih = oh * p.stride + p.dy[t], iw = ow * p.stride + p.dx[t];
       if (ih < 0 || ih >= p.x.H || iw < 0 || iw >= p.x.W) continue;
       const size_t ipix = (static_cast<size_t>(n) * p.x.H + ih) * p.x.W + iw;
-      const bf16* wt = p.w + (static_cast<size_t>(t) * Cout + co0) * Cin;
+      const h16* wt = p.w + (static_cast<size_t>(t) * Cout + co0) * Cin;
       for (int ci = 0; ci < Cin; ++ci) {
         const float xv = ld1(p.x, ipix, ci);
 #pragma unroll
         for (int j = 0; j < DC_CO; ++j)
-          if (co0 + j < Cout) acc[j] = fmaf(xv, __bfloat162float(wt[static_cast<size_t>(j) * Cin + ci]), acc[j]);
+          if (co0 + j < Cout) acc[j] = fmaf(xv, __half2float(wt[static_cast<size_t>(j) * Cin + ci]), acc[j]);
       }
     }
     const size_t opix = (static_cast<size_t>(n) * p.y.H + (oh * p.out_scale + p.out_oy)) * p.y.W +

@@ -1,7 +1,7 @@
 """Host-side graph builder: lowers one of the five segmentation networks to a *plan*.
 
 A plan is plain data -- a buffer table plus an ordered list of fused ops with their
-BatchNorm-folded, bf16-quantised parameters -- that ``engine.py`` uploads once through the
+BatchNorm-folded, fp16-quantised parameters -- that ``engine.py`` uploads once through the
 C ABI (``include/bd_b200.h``) where it becomes a native launch list of sm_100a kernels.
 Nothing in here computes activations; there is no CPU execution path in the product.
 
@@ -11,7 +11,7 @@ Fusions decided here:
   * Conv2DTranspose k2/k3 stride 2                              -> 4 sub-pixel CONV ops (tap subsets)
   * SeparableConv2D                                             -> DWCONV + 1x1 CONV (BN folded)
   * GlobalAveragePooling of a sum                               -> sum of pooled vectors
-All feature maps are NHWC bf16 (fp32 for the network input and the 2-channel logits); pooled
+All feature maps are NHWC fp16 (fp32 for the network input and the 2-channel logits); pooled
 vectors and the tiny attention MLPs stay fp32.
 
 TF/Keras semantics honoured: 'same' padding incl. the asymmetric stride-2 case, BN eps 1e-3,
@@ -40,16 +40,17 @@ def same_pad(size, k, s, d=1):
     return total // 2, total - total // 2
 
 
-def to_bf16(a):
-    """Round-to-nearest-even fp32 -> bf16, returned as uint16 bit patterns."""
-    a = np.ascontiguousarray(a, dtype=np.float32)
-    u = a.view(np.uint32).astype(np.uint64)
-    r = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16).astype(np.uint16)
-    return r
+H16_MAX = 65504.0
 
 
-def bf16_to_f32(u16):
-    return (u16.astype(np.uint32) << 16).view(np.float32)
+def to_h16(a):
+    """fp32 -> IEEE fp16 (round to nearest even, saturating like the device stores), as uint16 bits."""
+    a = np.clip(np.ascontiguousarray(a, dtype=np.float32), -H16_MAX, H16_MAX)
+    return a.astype(np.float16).view(np.uint16)
+
+
+def h16_to_f32(u16):
+    return np.ascontiguousarray(u16, dtype=np.uint16).view(np.float16).astype(np.float32)
 
 
 @dataclass
@@ -58,7 +59,7 @@ class Buf:
     H: int
     W: int
     C: int
-    dtype: str = "bf16"  # 'bf16' | 'f32'
+    dtype: str = "f16"  # 'f16' | 'f32'
     kind: str = "map"  # 'map' (N,H,W,C) | 'vec' (N,C) fp32
 
 
@@ -134,12 +135,12 @@ class Net:
         return scale.astype(np.float32), (b - m * scale).astype(np.float32)
 
     # ------------------------------------------------------------------ buffers
-    def buf(self, H, W, C, dtype="bf16", kind="map"):
+    def buf(self, H, W, C, dtype="f16", kind="map"):
         b = Buf(len(self.plan.bufs), H, W, C, dtype, kind)
         self.plan.bufs.append(b)
         return b
 
-    def new(self, H, W, C, dtype="bf16"):
+    def new(self, H, W, C, dtype="f16"):
         return T(self.buf(H, W, C, dtype), 0, C)
 
     def vec(self, C):
@@ -163,7 +164,7 @@ class Net:
         if res is not None:
             assert res.C == cout and res.H == out.H and res.W == out.W and out_scale == 1
         path = "direct"
-        if (self.umma and stride == 1 and x.buf.dtype == "bf16" and out.buf.dtype == "bf16"
+        if (self.umma and stride in (1, 2) and x.buf.dtype == "f16" and out.buf.dtype == "f16"
                 and cin % 8 == 0 and cin >= 16 and cout % 8 == 0 and cout >= 16
                 and x.c0 % 8 == 0 and x.buf.C % 8 == 0 and out.c0 % 8 == 0 and out.buf.C % 8 == 0
                 and Wo >= 8 and (res is None or (res.c0 % 8 == 0 and res.buf.C % 8 == 0))):
@@ -174,7 +175,7 @@ class Net:
                    taps=[(int(dy), int(dx)) for dy, dx in taps], stride=stride, Ho=Ho, Wo=Wo,
                    act_pre=act_pre, act_post=act_post,
                    out_scale=out_scale, out_oy=out_oy, out_ox=out_ox,
-                   w=to_bf16(w_tco), b=np.ascontiguousarray(bias, np.float32),
+                   w=to_h16(w_tco), b=np.ascontiguousarray(bias, np.float32),
                    w32=np.ascontiguousarray(w_tco, np.float32) if self.keep_f32 else None)
 
     def conv(self, x, name, cout, k=1, s=1, d=1, bn=False, act=None, res=None, res_after_act=False,
@@ -195,7 +196,7 @@ class Net:
         pl, _ = same_pad(x.W, k, s, d)
         taps = [(kh * d - pt, kw * d - pl) for kh in range(k) for kw in range(k)]
         if out is None:
-            out = self.new(Ho, Wo, cout, "f32" if f32_out else "bf16")
+            out = self.new(Ho, Wo, cout, "f32" if f32_out else "f16")
         a = ACT_RELU if act == "relu" else ACT_NONE
         if res is None:
             act_pre, act_post = a, ACT_NONE

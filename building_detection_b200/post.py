@@ -1,0 +1,105 @@
+"""Whole-scene job: tiles -> five stitched masks (sharded over GPUs) -> gather to rank 0 -> 3-of-5 fusion
+-> contours.  This is run_model + model_confuse + _detection of the reference (predict.py:148-152) as one
+device-resident pipeline; bench.py and predict.predict() drive it.
+
+Multi-GPU: every rank owns a contiguous band of tile rows and all five models' weights;
+no collective per tile.  Band masks (5 x rows x W u8) are sent to rank 0 over NCCL and OR-ed into its scene
+masks (adjacent bands overlap by 152 rows; OR is idempotent), then fusion and contour extraction -- which
+need whole connected components -- run on rank 0.
+"""
+from __future__ import annotations
+
+from . import scene as S
+
+
+class SceneJob:
+    def __init__(self, runner, h, w, origins, rank=0, world=1, do_post=True):
+        import torch
+        self.t = torch
+        self.runner, self.h, self.w = runner, h, w
+        self.origins, self.rank, self.world, self.do_post = origins, rank, world, do_post
+        dev = runner.device
+        self.masks = torch.zeros((len(runner.models), h, w), dtype=torch.uint8, device=dev)
+        self.all_origins = S.tile_origins(h, w)
+        self.bands = [self._band(S.shard_rows(self.all_origins, r, world)) for r in range(world)]
+        self.scene_dev = None
+        self.stage = None
+        if world > 1 and rank == 0:
+            rows = max(b[1] - b[0] for b in self.bands[1:])
+            self.stage = torch.empty((len(runner.models), rows, w), dtype=torch.uint8, device=dev)
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+        self.host_mask = None
+        self.result = None
+
+    def _band(self, origins):
+        if not origins:
+            return (0, 0)
+        r0 = min(o[0] for o in origins)
+        r1 = min(self.h, max(o[0] for o in origins) + S.TILE)
+        return (r0, r1)
+
+    # ------------------------------------------------------------------ stages
+    def _forward(self, scene_dev):
+        self.masks.zero_()
+        self.runner.run(scene_dev, origins=self.origins, out=self.masks)
+
+    def _gather(self):
+        """Band masks -> rank 0 (NCCL send/recv), OR-ed into rank 0's scene masks."""
+        if self.world == 1:
+            return
+        import torch.distributed as dist
+        t = self.t
+        if self.rank == 0:
+            for r in range(1, self.world):
+                r0, r1 = self.bands[r]
+                if r1 <= r0:
+                    continue
+                buf = self.stage[:, :r1 - r0]
+                buf = buf if buf.is_contiguous() else None
+                if buf is None:
+                    buf = t.empty((self.masks.shape[0], r1 - r0, self.w), dtype=t.uint8, device=self.masks.device)
+                dist.recv(buf, src=r)
+                self.masks[:, r0:r1].bitwise_or_(buf)
+        else:
+            r0, r1 = self.bands[self.rank]
+            if r1 > r0:
+                dist.send(self.masks[:, r0:r1].contiguous(), dst=0)
+
+    def _post(self):
+        if not self.do_post or self.rank != 0:
+            return None
+        from . import edge_3, model_fuse
+        fused = model_fuse.fuse_device(self.masks)
+        polys = edge_3.contours_device(fused)
+        return fused, polys
+
+    # ------------------------------------------------------------------ entry points
+    def run_resident(self, scene_dev):
+        """Scene already in HBM.  Returns (fused mask tensor, polygons) on rank 0 (None elsewhere / without post)."""
+        self._forward(scene_dev)
+        self._gather()
+        self.result = self._post()
+        return self.result
+
+    def run_e2e(self, scene_host):
+        """Scene in pinned host memory: every rank uploads the rows its band needs, rank 0 reads the fused mask
+        (or, without post-processing, the five stitched masks) back to the host."""
+        t = self.t
+        dev = self.runner.device
+        if self.scene_dev is None:
+            self.scene_dev = t.empty((self.h, self.w, 3), dtype=t.uint8, device=dev)
+        r0, r1 = self.bands[self.rank]
+        self.scene_dev[r0:r1].copy_(scene_host[r0:r1], non_blocking=True)
+        self.h2d_bytes = (r1 - r0) * self.w * 3
+        res = self.run_resident(self.scene_dev)
+        if self.rank == 0:
+            src = res[0] if res is not None else self.masks
+            if self.host_mask is None or self.host_mask.shape != src.shape:
+                self.host_mask = t.empty(src.shape, dtype=t.uint8).pin_memory()
+            self.host_mask.copy_(src, non_blocking=True)
+            self.d2h_bytes = src.numel()
+            if res is not None:
+                self.d2h_bytes += res[1].nbytes if hasattr(res[1], "nbytes") else 0
+        t.cuda.current_stream(dev).synchronize()
+        return self.host_mask, (res[1] if res is not None else None)

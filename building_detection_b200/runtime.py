@@ -57,6 +57,7 @@ _SIGS = {
     "bd_plan_add_bcast": (C.c_int, [C.c_void_p, C.c_int, TRef]),
     "bd_plan_finalize": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "bd_plan_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bd_plan_run_head": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bd_plan_run_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bd_plan_buffer_ptr": (C.c_void_p, [C.c_void_p, C.c_int]),
     "bd_plan_buffer_bytes": (C.c_size_t, [C.c_void_p, C.c_int]),
@@ -232,7 +233,7 @@ class NativePlan:
         return lib().bd_plan_buffer_ptr(self.h, buf)
 
     def read_buffer(self, buf):
-        """Whole plan buffer as float32 numpy (bf16 maps are widened)."""
+        """Whole plan buffer as float32 numpy (fp16 maps are widened)."""
         b = self.plan.bufs[buf]
         n = self.plan.batch
         if b.kind == "vec":
@@ -245,14 +246,14 @@ class NativePlan:
             return out
         raw = np.empty((n, b.H, b.W, b.C), np.uint16)
         check(lib().bd_plan_read_buffer(self.h, buf, _ptr(raw), raw.nbytes))
-        return G.bf16_to_f32(raw)
+        return G.h16_to_f32(raw)
 
     def write_buffer(self, buf, arr):
         b = self.plan.bufs[buf]
         if b.kind == "vec" or b.dtype == "f32":
             a = np.ascontiguousarray(arr, np.float32)
         else:
-            a = G.to_bf16(arr)
+            a = G.to_h16(arr)
         check(lib().bd_plan_write_buffer(self.h, buf, _ptr(a), a.nbytes))
 
     def time_ops(self, stream=0):

@@ -1,0 +1,97 @@
+"""Device-resident scene pipeline: the reference's tiler (predict.py:90-116) driven through the C ABI.
+
+A scene (H,W,3 BGR u8) is uploaded once; tiles are gathered on the device (normalise + zero pad fused
+into the gather), pushed through a model's native plan in batches, and the per-tile argmax masks are
+OR-stitched into a u8 scene mask that never leaves the GPU until fusion / contour extraction are done.
+torch is used only for device memory and streams.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from . import runtime as R
+
+TILE, STRIDE, OVERLAP = 512, 360, 152  # predict.py:98-107
+
+
+def tile_origins(h, w, bug_compatible=True):
+    """Top-left corners of the 512x512 tiles in the reference's order (predict.py:98-106).
+
+    The reference iterates the *column* loop over ``new_h`` as well; with
+    ``bug_compatible`` that is reproduced, and a scene for which it would slice a tile narrower than
+    512 px (Keras rejects the shape) raises ValueError.  ``bug_compatible=False`` tiles the columns
+    over ``new_w``."""
+    h_num = math.ceil((h - OVERLAP) / STRIDE)
+    w_num = math.ceil((w - OVERLAP) / STRIDE)
+    new_h, new_w = h_num * STRIDE + OVERLAP, w_num * STRIDE + OVERLAP
+    pad_h, pad_w = max(new_h, TILE), max(new_w, TILE)
+    col_extent = new_h if bug_compatible else new_w
+    out = []
+    for i in range(0, new_h - OVERLAP, STRIDE):
+        for j in range(0, col_extent - OVERLAP, STRIDE):
+            if i + TILE > pad_h or j + TILE > pad_w:
+                raise ValueError(f"tile at ({i},{j}) leaves the padded {pad_h}x{pad_w} scene: the reference slices a "
+                                 "short tile there and model.predict rejects it (predict.py:106 iterates columns "
+                                 "over new_h); pass bug_compatible=False for non-square scenes")
+            out.append((i, j))
+    return out
+
+
+def shard_rows(origins, rank, world):
+    """Contiguous row-band shard of the tile list for ``rank`` of ``world``: whole
+    tile rows stay on one GPU so that each rank's writes cover a contiguous band of the scene mask."""
+    rows = sorted({i for i, _ in origins})
+    per = math.ceil(len(rows) / world) if rows else 0
+    mine = set(rows[rank * per:(rank + 1) * per])
+    return [o for o in origins if o[0] in mine]
+
+
+class SceneRunner:
+    """Runs models over one scene on one GPU.  ``models``: engine.Model objects."""
+
+    def __init__(self, models, batch=16, device=None):
+        import torch
+        if not torch.cuda.is_available():
+            raise R.NativeError("building_detection_b200 needs a CUDA device (B200); there is no CPU path")
+        self.torch = torch
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        self.models = list(models)
+        self.batch = batch
+        self.ctx = R.context(self.device.index)
+        self.lib = R.lib()
+        self.tile_masks = torch.empty((batch, TILE, TILE), dtype=torch.uint8, device=self.device)
+
+    def upload(self, scene_bgr):
+        """numpy (H,W,3) u8 BGR (what cv.imread returns) -> device tensor."""
+        t = self.torch
+        a = np.ascontiguousarray(scene_bgr, dtype=np.uint8)
+        if a.ndim != 3 or a.shape[2] != 3:
+            raise ValueError(f"expected (H,W,3) uint8 BGR, got {a.shape}")
+        return t.from_numpy(a).to(self.device, non_blocking=True)
+
+    def run(self, scene_dev, origins=None, out=None, bug_compatible=True):
+        """scene_dev: (H,W,3) u8 cuda tensor.  Returns masks (len(models),H,W) u8 {0,255} on the device
+        (predict.py:113-114).  ``origins`` restricts the work to a shard of the tile list."""
+        t = self.torch
+        h, w = int(scene_dev.shape[0]), int(scene_dev.shape[1])
+        if origins is None:
+            origins = tile_origins(h, w, bug_compatible)
+        if out is None:
+            out = t.zeros((len(self.models), h, w), dtype=t.uint8, device=self.device)
+        stream = t.cuda.current_stream(self.device).cuda_stream
+        L, C = self.lib, R.C
+        for b0 in range(0, len(origins), self.batch):
+            chunk = origins[b0:b0 + self.batch]
+            n = len(chunk)
+            ys = np.asarray([o[0] for o in chunk], np.int32)
+            xs = np.asarray([o[1] for o in chunk], np.int32)
+            for mi, m in enumerate(self.models):
+                plan = m.native_plan(n)
+                x_ptr = plan.buffer_ptr(plan.plan.input)
+                R.check(L.bd_tiles_gather(self.ctx, scene_dev.data_ptr(), h, w, R._ptr(ys), R._ptr(xs), n, x_ptr, stream))
+                plan.run_device(0, 0, self.tile_masks.data_ptr(), stream)
+                R.check(L.bd_stitch_or(self.ctx, self.tile_masks.data_ptr(), R._ptr(ys), R._ptr(xs), n,
+                                       out[mi].data_ptr(), h, w, stream))
+        return out

@@ -29,7 +29,7 @@ extern "C" {
 typedef struct bd_ctx bd_ctx;
 typedef struct bd_plan bd_plan;
 
-enum bd_dtype { BD_BF16 = 0, BD_F32 = 1 };
+enum bd_dtype { BD_F16 = 0, BD_F32 = 1 };
 enum bd_buf_kind { BD_MAP = 0 /* (N,H,W,C) */, BD_VEC = 1 /* (N,C) fp32 */ };
 enum bd_act { BD_ACT_NONE = 0, BD_ACT_RELU = 1, BD_ACT_SIGMOID = 2 };
 enum bd_gate_mode { BD_GATE_SE = 0, BD_GATE_SCSE = 1, BD_GATE_BAM = 2 };
@@ -43,7 +43,7 @@ typedef struct bd_tref { int32_t buf, c0, c; } bd_tref;
  * written to y[(h*out_scale+out_oy), (w*out_scale+out_ox)].  Out-of-range taps read zero ('same'
  * padding).  Replaces Conv2D / Conv2DTranspose (+BatchNormalization +Activation +Add) layer groups of
  * predict_model/{res34,hrnet,v3plus,scse,bam}.py executed by tf.keras.Model.predict (predict.py:109).
- * w: bf16 bit patterns, layout [ntaps][cout][cin]; bias: fp32 [cout] (BatchNorm already folded). */
+ * w: fp16 bit patterns, layout [ntaps][cout][cin]; bias: fp32 [cout] (BatchNorm already folded). */
 typedef struct bd_conv_desc {
   bd_tref x, y, res;            /* res.buf < 0: no residual */
   int32_t ntaps;
@@ -99,6 +99,8 @@ int bd_plan_finalize(bd_plan* plan, int input_buf, int logits_buf, int logits_up
  * input buffer (e.g. written by bd_tiles_gather).  probs_dev: fp32 (N,512,512,2) or NULL;
  * mask_dev: u8 (N,512,512), 1 where class 1 wins (argmax, ties -> class 0, predict.py:110) or NULL. */
 int bd_plan_run(bd_plan* plan, const float* x_dev, float* probs_dev, uint8_t* mask_dev, void* stream);
+/* only the softmax / argmax head (last op) on whatever the logits buffer currently holds */
+int bd_plan_run_head(bd_plan* plan, float* probs_dev, uint8_t* mask_dev, void* stream);
 /* host-buffer convenience (synchronous): H2D, run, D2H.  Replaces model.predict(ndarray). */
 int bd_plan_run_host(bd_plan* plan, const float* x_host, float* probs_host, uint8_t* mask_host);
 /* device pointer / byte size of a plan buffer (tests, and writing the input buffer in place) */

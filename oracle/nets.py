@@ -32,9 +32,13 @@ BN_EPS = 1e-3  # Keras BatchNormalization default epsilon
 class _W:
     """Name-keyed weight access with use tracking (every tensor must be consumed once)."""
 
-    def __init__(self, weights):
+    def __init__(self, weights, calibrate=False):
         self.w = weights
         self.used = set()
+        # calibrate=True: every BatchNormalization over a feature map first overwrites its moving
+        # mean/variance in ``weights`` with the statistics of its actual input (what training leaves
+        # behind), so that a random-init network is as well conditioned as a trained one.
+        self.calibrate = calibrate
 
     def __call__(self, key):
         self.used.add(key)
@@ -68,6 +72,13 @@ def conv2d(W, x, name, k, s=1, d=1, bias=True):
 
 def bn(W, x, name):
     """Inference BatchNormalization, eps 1e-3; works for NCHW maps and (N,C) vectors."""
+    if W.calibrate and x.dim() == 4 and x.shape[0] * x.shape[2] * x.shape[3] >= 64:
+        if W.calibrate == "rms":  # scale only: keeps every layer's output at unit rms, no re-centring
+            W.w[name + "/mean"] = np.zeros(x.shape[1], np.float32)
+            W.w[name + "/var"] = (x * x).mean(dim=(0, 2, 3)).numpy().astype(np.float32)
+        else:
+            W.w[name + "/mean"] = x.mean(dim=(0, 2, 3)).numpy().astype(np.float32)
+            W.w[name + "/var"] = x.var(dim=(0, 2, 3), unbiased=False).numpy().astype(np.float32)
     g, b, m, v = W(name + "/gamma"), W(name + "/beta"), W(name + "/mean"), W(name + "/var")
     shape = (1, -1, 1, 1) if x.dim() == 4 else (1, -1)
     return (x - m.view(shape)) / torch.sqrt(v.view(shape) + BN_EPS) * g.view(shape) + b.view(shape)
@@ -119,9 +130,9 @@ def softmax_head(logits):
 
 
 # ----------------------------------------------------------------------------- res34
-def res34_forward(weights, x_nhwc):
+def res34_forward(weights, x_nhwc, calibrate=False):
     """predict_model/res34.py:27-170 (ResNetFamily.run_model('res34'))."""
-    W = _W(weights)
+    W = _W(weights, calibrate)
     x = torch.as_tensor(x_nhwc, dtype=torch.float32).permute(0, 3, 1, 2)
 
     def bn_conv_a(t, name, k=3):  # res34.py:32-38
@@ -190,9 +201,9 @@ def res34_forward(weights, x_nhwc):
 
 
 # ----------------------------------------------------------------------------- hrnet
-def hrnet_forward(weights, x_nhwc):
+def hrnet_forward(weights, x_nhwc, calibrate=False):
     """predict_model/hrnet.py:20-203."""
-    W = _W(weights)
+    W = _W(weights, calibrate)
     x = torch.as_tensor(x_nhwc, dtype=torch.float32).permute(0, 3, 1, 2)
 
     def cbr(t, name, k=3, s=1, act=True):  # hrnet.py:20-25
@@ -409,9 +420,9 @@ def _deeplab_neck(W, c5):
     return scse_block(W, conv1, "neck_scse")
 
 
-def v3plus_forward(weights, x_nhwc):
+def v3plus_forward(weights, x_nhwc, calibrate=False):
     """predict_model/v3plus.py:170-350 (Xception_DeepLabV3_Plus)."""
-    W = _W(weights)
+    W = _W(weights, calibrate)
     x = torch.as_tensor(x_nhwc, dtype=torch.float32).permute(0, 3, 1, 2)
     c, c1, c2, c5 = _xception_backbone(W, x, with_bam=False)
     conv1 = _deeplab_neck(W, c5)
@@ -438,9 +449,9 @@ def v3plus_forward(weights, x_nhwc):
     return softmax_head(logits).numpy()
 
 
-def bam_forward(weights, x_nhwc):
+def bam_forward(weights, x_nhwc, calibrate=False):
     """predict_model/bam.py:170-338 (Xception_DeepLabV3_Plus_bam)."""
-    W = _W(weights)
+    W = _W(weights, calibrate)
     x = torch.as_tensor(x_nhwc, dtype=torch.float32).permute(0, 3, 1, 2)
     _c, c1, c2, c5 = _xception_backbone(W, x, with_bam=True)
     conv1 = _deeplab_neck(W, c5)
@@ -461,9 +472,9 @@ def bam_forward(weights, x_nhwc):
 
 
 # ----------------------------------------------------------------------------- scse
-def scse_forward(weights, x_nhwc):
+def scse_forward(weights, x_nhwc, calibrate=False):
     """predict_model/scse.py:49-97 (UNet): no BatchNorm, ReLU fused in every conv."""
-    W = _W(weights)
+    W = _W(weights, calibrate)
     x = torch.as_tensor(x_nhwc, dtype=torch.float32).permute(0, 3, 1, 2)
 
     def cr(t, name):
@@ -493,3 +504,14 @@ FORWARD = {
     "scse": scse_forward,
     "bam": bam_forward,
 }
+
+
+def calibrated_weights(model, spec, seed, x_nhwc, mode="rms"):
+    """Seeded Keras-default initialisation with randomised BN gamma/beta, then one calibration pass
+    over ``x_nhwc`` that sets every feature-map BatchNormalization's moving statistics to those of
+    its input.  Returns the weight dict used on both sides of a parity test."""
+    from building_detection_b200 import graph as G
+    w = G.init_weights(spec, seed=seed, randomize_bn=True)
+    with torch.no_grad():
+        FORWARD[model](w, x_nhwc, calibrate=mode)
+    return w

@@ -1,11 +1,11 @@
 """ORACLE (test infrastructure only): CPU interpreter for the product's *plan* ops.
 
 It executes a ``graph.Plan`` with torch on the CPU, reproducing what each sm_100a kernel is
-specified to compute -- bf16 storage of feature maps, bf16 conv weights, fp32 accumulation,
+specified to compute -- fp16 storage of feature maps, fp16 conv weights, fp32 accumulation,
 fp32 vectors -- so that
   (1) the host-side lowering (fusions, concat slices, sub-pixel transposed convs, TF padding)
       can be checked against oracle/nets.py without a GPU, and
-  (2) GPU kernels can be checked against a bf16-faithful expectation with a tight tolerance.
+  (2) GPU kernels can be checked against a fp16-faithful expectation with a tight tolerance.
 It mirrors the op semantics documented in include/bd_b200.h; it is never used by the product.
 """
 from __future__ import annotations
@@ -17,8 +17,8 @@ import torch.nn.functional as F
 from building_detection_b200 import graph as G
 
 
-def _q(t):  # bf16 storage round trip
-    return t.to(torch.bfloat16).to(torch.float32)
+def _q(t):  # fp16 storage round trip (saturating, like the device stores)
+    return t.clamp(-G.H16_MAX, G.H16_MAX).to(torch.float16).to(torch.float32)
 
 
 def _act(t, a):
@@ -30,9 +30,9 @@ def _act(t, a):
 
 
 class Interp:
-    def __init__(self, plan, emulate_bf16=True):
+    def __init__(self, plan, emulate_h16=True):
         self.p = plan
-        self.emu = emulate_bf16
+        self.emu = emulate_h16
         n = plan.batch
         self.b = []
         for b in plan.bufs:
@@ -43,7 +43,7 @@ class Interp:
 
     def _store(self, ref, val):
         bid, c0, c = ref
-        if self.emu and self.p.bufs[bid].dtype == "bf16":
+        if self.emu and self.p.bufs[bid].dtype == "f16":
             val = _q(val)
         self.b[bid][..., c0:c0 + c] = val
 
@@ -58,7 +58,7 @@ class Interp:
         if not self.emu and op.get("w32") is not None:
             w = torch.from_numpy(op["w32"])
         else:
-            w = torch.from_numpy(G.bf16_to_f32(op["w"]).copy())  # (taps, Cout, Cin)
+            w = torch.from_numpy(G.h16_to_f32(op["w"]).copy())  # (taps, Cout, Cin)
         s, Ho, Wo = op["stride"], op["Ho"], op["Wo"]
         acc = torch.zeros(n, w.shape[1], Ho, Wo)
         for t, (dy, dx) in enumerate(op["taps"]):
@@ -80,7 +80,7 @@ class Interp:
             self._store(op["y"], acc)
         else:
             bid, c0, c = op["y"]
-            if self.emu and self.p.bufs[bid].dtype == "bf16":
+            if self.emu and self.p.bufs[bid].dtype == "f16":
                 acc = _q(acc)
             self.b[bid][:, op["out_oy"]::sc, op["out_ox"]::sc, c0:c0 + c] = acc
 
@@ -153,9 +153,9 @@ class Interp:
         self._store(op["y"], self.b[op["v"]][:, None, None, :].expand(-1, self.p.bufs[bid].H, self.p.bufs[bid].W, -1))
 
     def set(self, buf, arr):
-        """Write a whole buffer (bf16 maps are rounded like a device store would)."""
+        """Write a whole buffer (fp16 maps are rounded like a device store would)."""
         t = torch.as_tensor(np.asarray(arr), dtype=torch.float32)
-        if self.emu and self.p.bufs[buf].kind == "map" and self.p.bufs[buf].dtype == "bf16":
+        if self.emu and self.p.bufs[buf].kind == "map" and self.p.bufs[buf].dtype == "f16":
             t = _q(t)
         self.b[buf] = t.clone()
 
@@ -181,6 +181,6 @@ class Interp:
         return None if probs is None else probs.numpy()
 
 
-def run_plan(plan, x_nhwc, emulate_bf16=True):
+def run_plan(plan, x_nhwc, emulate_h16=True):
     with torch.no_grad():
-        return Interp(plan, emulate_bf16).run(x_nhwc)
+        return Interp(plan, emulate_h16).run(x_nhwc)

@@ -23,8 +23,8 @@ def rand_map(rng, plan, buf, scale=1.0):
     return (rng.standard_normal((plan.batch, b.H, b.W, b.C)) * scale).astype(np.float32)
 
 
-def run_interp(plan, inputs, emulate_bf16=True):
-    it = plan_interp.Interp(plan, emulate_bf16)
+def run_interp(plan, inputs, emulate_h16=True):
+    it = plan_interp.Interp(plan, emulate_h16)
     for k, v in inputs.items():
         it.set(k, v)
     with torch.no_grad():
@@ -41,7 +41,7 @@ def run_native(plan, inputs):
     return npn
 
 
-def bf16_ulp(x):
-    """Size of one bf16 ulp at |x| (8 significant bits)."""
-    x = np.maximum(np.abs(x), 1e-30)
-    return 2.0 ** (np.floor(np.log2(x)) - 7)
+def h16_ulp(x):
+    """Size of one fp16 ulp at |x| (11 significant bits; subnormal spacing 2^-24 below 2^-14)."""
+    x = np.maximum(np.abs(x), 2.0 ** -14)
+    return 2.0 ** (np.floor(np.log2(x)) - 10)

@@ -15,7 +15,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 from building_detection_b200 import graph as G  # noqa: E402
-from util import build_two_pass, rand_map, run_interp, run_native, bf16_ulp  # noqa: E402
+from util import build_two_pass, rand_map, run_interp, run_native, h16_ulp  # noqa: E402
 
 
 if os.environ.get("BD_DRY"):  # CPU dry run of the harness itself: "native" = a second interpreter run
@@ -32,7 +32,7 @@ if os.environ.get("BD_DRY"):  # CPU dry run of the harness itself: "native" = a 
 
 def report(tag, got, ref):
     err = np.abs(got - ref)
-    ulp = bf16_ulp(ref)
+    ulp = h16_ulp(ref)
     rel = (err / np.maximum(ulp, 1e-6)).max()
     bad = int((err > 2 * ulp + 1e-5).sum())
     status = "OK " if bad == 0 else "BAD"
