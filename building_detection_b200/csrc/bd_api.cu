@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "conv_umma.cuh"
 #include "kernels.cuh"
+#include "post_ws.cuh"
 
 namespace bd {
 std::string& last_error() {
@@ -24,16 +25,6 @@ int fail(const std::string& msg) {
 
 using namespace bd;
 
-struct bd_ctx {
-  int device = 0;
-  int num_sms = 148;
-  int64_t launches = 0;
-  int umma_smem_kb = 99;    // per-CTA smem budget of the tcgen05 conv (2 CTAs / SM by default)
-  int umma_max_block_n = 256;
-  int* d_ys = nullptr;      // tile origin scratch
-  int* d_xs = nullptr;
-  int tile_cap = 0;
-};
 
 namespace {
 
@@ -146,6 +137,7 @@ void bd_destroy(bd_ctx* ctx) {
   if (!ctx) return;
   if (ctx->d_ys) cudaFree(ctx->d_ys);
   if (ctx->d_xs) cudaFree(ctx->d_xs);
+  ctx->post_ws.release();
   delete ctx;
 }
 

@@ -6,5 +6,6 @@ NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall --expt-relaxed-constexpr -cudart static"
 $NVCC $FLAGS ${PTXAS_V:+-Xptxas -v} -c bd_api.cu -o bd_api.o
 $NVCC $FLAGS ${PTXAS_V:+-Xptxas -v} -c post.cu -o post.o
-$NVCC $FLAGS -shared bd_api.o post.o -o ../libbd_b200.so
+$NVCC $FLAGS -fmad=false ${PTXAS_V:+-Xptxas -v} -c contours.cu -o contours.o
+$NVCC $FLAGS -shared bd_api.o post.o contours.o -o ../libbd_b200.so
 echo "built $(cd .. && pwd)/libbd_b200.so"

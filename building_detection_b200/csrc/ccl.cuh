@@ -1,0 +1,161 @@
+// ccl.cuh -- connected-component labelling and the mask primitives shared by the fusion (model_fuse.py)
+// and contour (edge_3.py) stages.  All kernels are HBM-bound integer/byte work: one thread per pixel,
+// consecutive threads on consecutive pixels of a row (coalesced), grid-stride loops.
+//
+// Labels: int32 per pixel, -1 = not in the set, otherwise the raster index of the component's FIRST pixel in
+// raster order (union-find with atomicMin links the larger root under the smaller).  That root is exactly the
+// pixel cv::findContours starts a contour from, and reverse root order is the order it returns them in.
+#pragma once
+#include "common.cuh"
+
+namespace bd {
+namespace ccl {
+
+constexpr int TPB = 256;
+
+__device__ __forceinline__ int find_root(const int* __restrict__ L, int i) {
+  int p = L[i];
+  while (p != i) {
+    i = p;
+    p = L[i];
+  }
+  return i;
+}
+__device__ __forceinline__ void unite(int* L, int a, int b) {
+  while (true) {
+    a = find_root(L, a);
+    b = find_root(L, b);
+    if (a == b) return;
+    if (a < b) { const int t = a; a = b; b = t; }  // a > b: hang a under b
+    const int old = atomicMin(&L[a], b);
+    if (old == a) return;
+    a = old;
+  }
+}
+
+// L[p] = p where the predicate holds, else -1.  fg != 0: label the set pixels; fg == 0: label the zero pixels.
+__global__ void __launch_bounds__(TPB) init_labels(const uint8_t* __restrict__ m, int* __restrict__ L, size_t n, int fg) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * TPB)
+    L[i] = ((m[i] != 0) == (fg != 0)) ? static_cast<int>(i) : -1;
+}
+// 8-connectivity: neighbours already visited in raster order are W, NW, N, NE; N subsumes NW/NE/W (they are
+// 4-adjacent to it or joined through it by their own unions).
+__global__ void __launch_bounds__(TPB) merge8(int* L, int H, int W) {
+  const size_t n = static_cast<size_t>(H) * W;
+  for (size_t i = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * TPB) {
+    if (L[i] < 0) continue;
+    const int x = static_cast<int>(i % W), y = static_cast<int>(i / W);
+    const int p = static_cast<int>(i);
+    if (y > 0 && L[i - W] >= 0) { unite(L, p, p - W); continue; }
+    if (x > 0 && L[i - 1] >= 0) unite(L, p, p - 1);
+    else if (y > 0 && x > 0 && L[i - W - 1] >= 0) unite(L, p, p - W - 1);
+    if (y > 0 && x + 1 < W && L[i - W + 1] >= 0) unite(L, p, p - W + 1);
+  }
+}
+// 4-connectivity (background regions)
+__global__ void __launch_bounds__(TPB) merge4(int* L, int H, int W) {
+  const size_t n = static_cast<size_t>(H) * W;
+  for (size_t i = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * TPB) {
+    if (L[i] < 0) continue;
+    const int x = static_cast<int>(i % W), y = static_cast<int>(i / W);
+    const int p = static_cast<int>(i);
+    if (y > 0 && L[i - W] >= 0) unite(L, p, p - W);
+    if (x > 0 && L[i - 1] >= 0) unite(L, p, p - 1);
+  }
+}
+__global__ void __launch_bounds__(TPB) flatten(int* L, size_t n) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * TPB)
+    if (L[i] >= 0) L[i] = find_root(L, static_cast<int>(i));
+}
+
+// ---- hole filling: cv::fillPoly / drawContours(FILLED) of an external contour = the component plus every pixel
+// it encloses = complement of the background that is 4-connected to the outside of the image.
+// Pass 1 (after flatten of the background labels): every background pixel on the image frame marks its root as
+// outside by overwriting the root's own label with OUTSIDE.
+constexpr int OUTSIDE = -2;
+__global__ void __launch_bounds__(TPB) mark_outside(int* L, int H, int W) {
+  const int per = 2 * (H + W);
+  for (int t = blockIdx.x * TPB + threadIdx.x; t < per; t += gridDim.x * TPB) {
+    int x, y;
+    if (t < W) { x = t; y = 0; }
+    else if (t < 2 * W) { x = t - W; y = H - 1; }
+    else if (t < 2 * W + H) { x = 0; y = t - 2 * W; }
+    else { x = W - 1; y = t - 2 * W - H; }
+    const size_t i = static_cast<size_t>(y) * W + x;
+    const int r = L[i];
+    if (r >= 0) L[r] = OUTSIDE;  // benign race: all writers store the same value; non-root frame pixels keep r
+  }
+}
+// out = 255 for set pixels and for background pixels whose region is not outside
+__global__ void __launch_bounds__(TPB) fill_holes(const uint8_t* __restrict__ m, const int* __restrict__ L,
+                                                  uint8_t* __restrict__ out, size_t n) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * TPB) {
+    uint8_t v = 255;
+    if (m[i] == 0) {
+      const int r = L[i];  // r == OUTSIDE: this pixel is an outside root; else look at the root's label
+      v = (r == OUTSIDE || L[r] == OUTSIDE) ? 0 : 255;
+    }
+    out[i] = v;
+  }
+}
+
+// ---- polygon area of every component's external contour (cv::contourArea = |shoelace| / 2 over the boundary
+// pixel centres) without tracing: the border following of a hole-free component walks the pixel cracks with the
+// component on one side, and the step it takes at a grid vertex is determined by the 2x2 pixels around that
+// vertex.  Summing cross(p, q) of those steps per component gives twice the signed area; vertices with one, four
+// or two diagonal set pixels contribute nothing (same pixel / no crack / out-and-back).  Verified against
+// cv2.contourArea in tests/test_post_cpu.py (numpy twin of this kernel).  area2 must be zero at the roots.
+__global__ void __launch_bounds__(TPB) polygon_area2(const int* __restrict__ L, int H, int W,
+                                                     long long* __restrict__ area2) {
+  const size_t nv = static_cast<size_t>(H + 1) * (W + 1);
+  for (size_t t = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; t < nv; t += static_cast<size_t>(gridDim.x) * TPB) {
+    const int x = static_cast<int>(t % (W + 1)), y = static_cast<int>(t / (W + 1));
+    // a=(x-1,y-1) b=(x,y-1) c=(x-1,y) d=(x,y)
+    const int la = (x > 0 && y > 0) ? L[static_cast<size_t>(y - 1) * W + x - 1] : -1;
+    const int lb = (x < W && y > 0) ? L[static_cast<size_t>(y - 1) * W + x] : -1;
+    const int lc = (x > 0 && y < H) ? L[static_cast<size_t>(y) * W + x - 1] : -1;
+    const int ld = (x < W && y < H) ? L[static_cast<size_t>(y) * W + x] : -1;
+    const int code = (la >= 0) | ((lb >= 0) << 1) | ((lc >= 0) << 2) | ((ld >= 0) << 3);
+    // step p -> q with p, q in {a,b,c,d}: encoded as (p index << 2 | q index), 0xFF = none
+    int p, q, lab;
+    switch (code) {
+      case 0x3: p = 0; q = 1; lab = la; break;  // a,b   : a -> b
+      case 0xC: p = 3; q = 2; lab = lc; break;  // c,d   : d -> c
+      case 0x5: p = 2; q = 0; lab = la; break;  // a,c   : c -> a
+      case 0xA: p = 1; q = 3; lab = lb; break;  // b,d   : b -> d
+      case 0x7: p = 2; q = 1; lab = la; break;  // a,b,c : c -> b
+      case 0xB: p = 0; q = 3; lab = la; break;  // a,b,d : a -> d
+      case 0xD: p = 3; q = 0; lab = la; break;  // a,c,d : d -> a
+      case 0xE: p = 1; q = 2; lab = lb; break;  // b,c,d : b -> c
+      default: continue;
+    }
+    const long long px = x - 1 + (p & 1), py = y - 1 + (p >> 1);
+    const long long qx = x - 1 + (q & 1), qy = y - 1 + (q >> 1);
+    atomicAdd(reinterpret_cast<unsigned long long*>(area2 + lab), static_cast<unsigned long long>(px * qy - qx * py));
+  }
+}
+
+// ---- 1 x K / K x 1 erosion (K odd) of a binary mask; pixels outside the image count as set (cv::erode's default
+// border value), so a component touching the frame is not eroded from that side.
+__global__ void __launch_bounds__(TPB) erode_line(const uint8_t* __restrict__ m, uint8_t* __restrict__ out, int H,
+                                                  int W, int half, int vertical) {
+  const size_t n = static_cast<size_t>(H) * W;
+  for (size_t i = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * TPB) {
+    uint8_t v = m[i];
+    if (v) {
+      const int x = static_cast<int>(i % W), y = static_cast<int>(i / W);
+      if (vertical) {
+        const int y0 = max(0, y - half), y1 = min(H - 1, y + half);
+        for (int yy = y0; yy <= y1 && v; ++yy) v = m[static_cast<size_t>(yy) * W + x] ? 255 : 0;
+      } else {
+        const int x0 = max(0, x - half), x1 = min(W - 1, x + half);
+        const uint8_t* row = m + static_cast<size_t>(y) * W;
+        for (int xx = x0; xx <= x1 && v; ++xx) v = row[xx] ? 255 : 0;
+      }
+    }
+    out[i] = v ? 255 : 0;
+  }
+}
+
+}  // namespace ccl
+}  // namespace bd

@@ -1,0 +1,62 @@
+// post_ws.cuh -- bd_ctx (shared by bd_api.cu / post.cu / contours.cu) and the scene-sized workspace of the
+// fusion and contour stages.  The workspace grows on demand and is reused across calls.
+#pragma once
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace bd {
+namespace post {
+struct Workspace {
+  size_t cap = 0;            // pixels
+  int *L = nullptr, *Lh = nullptr, *Lv = nullptr;              // parent / fragment labels
+  long long *a2 = nullptr, *a2h = nullptr, *a2v = nullptr;    // 2 x signed polygon area, indexed by root pixel
+  int *cntH = nullptr, *survH = nullptr, *cntV = nullptr, *survV = nullptr;
+  uint8_t *filled = nullptr, *keep = nullptr, *er = nullptr, *voted = nullptr, *cleaned = nullptr;  // cleaned: 5 masks
+  void release() {
+    void* ptrs[] = {L, Lh, Lv, a2, a2h, a2v, cntH, survH, cntV, survV, filled, keep, er, voted, cleaned};
+    for (void* p : ptrs)
+      if (p) cudaFree(p);
+    *this = Workspace();
+  }
+};
+}  // namespace post
+}  // namespace bd
+
+struct bd_ctx {
+  int device = 0;
+  int num_sms = 148;
+  int64_t launches = 0;
+  int umma_smem_kb = 99;    // per-CTA smem budget of the tcgen05 conv (2 CTAs / SM by default)
+  int umma_max_block_n = 256;
+  int* d_ys = nullptr;      // tile origin scratch
+  int* d_xs = nullptr;
+  int tile_cap = 0;
+  bd::post::Workspace post_ws;
+};
+
+namespace bd {
+namespace post {
+inline int ctx_sms(bd_ctx* c) { return c->num_sms; }
+inline void ctx_count(bd_ctx* c, int n) { c->launches += n; }
+
+inline int workspace(bd_ctx* ctx, int H, int W, Workspace** out) {
+  Workspace& w = ctx->post_ws;
+  const size_t n = static_cast<size_t>(H) * W;
+  if (n > w.cap) {
+    w.release();
+    const size_t cap = n + 64;
+#define BD_WS_ALLOC(field, type, count) BD_CUDA(cudaMalloc(reinterpret_cast<void**>(&w.field), sizeof(type) * (count)))
+    BD_WS_ALLOC(L, int, cap); BD_WS_ALLOC(Lh, int, cap); BD_WS_ALLOC(Lv, int, cap);
+    BD_WS_ALLOC(a2, long long, cap); BD_WS_ALLOC(a2h, long long, cap); BD_WS_ALLOC(a2v, long long, cap);
+    BD_WS_ALLOC(cntH, int, cap); BD_WS_ALLOC(survH, int, cap); BD_WS_ALLOC(cntV, int, cap); BD_WS_ALLOC(survV, int, cap);
+    BD_WS_ALLOC(filled, uint8_t, cap); BD_WS_ALLOC(keep, uint8_t, cap); BD_WS_ALLOC(er, uint8_t, cap);
+    BD_WS_ALLOC(voted, uint8_t, cap); BD_WS_ALLOC(cleaned, uint8_t, 5 * cap);
+#undef BD_WS_ALLOC
+    w.cap = n;
+  }
+  *out = &w;
+  return 0;
+}
+}  // namespace post
+}  // namespace bd
