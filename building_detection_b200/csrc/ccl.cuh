@@ -34,13 +34,13 @@ __device__ __forceinline__ void unite(int* L, int a, int b) {
 }
 
 // L[p] = p where the predicate holds, else -1.  fg != 0: label the set pixels; fg == 0: label the zero pixels.
-__global__ void __launch_bounds__(TPB) init_labels(const uint8_t* __restrict__ m, int* __restrict__ L, size_t n, int fg) {
+static __global__ void __launch_bounds__(TPB) init_labels(const uint8_t* __restrict__ m, int* __restrict__ L, size_t n, int fg) {
   for (size_t i = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * TPB)
     L[i] = ((m[i] != 0) == (fg != 0)) ? static_cast<int>(i) : -1;
 }
 // 8-connectivity: neighbours already visited in raster order are W, NW, N, NE; N subsumes NW/NE/W (they are
 // 4-adjacent to it or joined through it by their own unions).
-__global__ void __launch_bounds__(TPB) merge8(int* L, int H, int W) {
+static __global__ void __launch_bounds__(TPB) merge8(int* L, int H, int W) {
   const size_t n = static_cast<size_t>(H) * W;
   for (size_t i = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * TPB) {
     if (L[i] < 0) continue;
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(TPB) merge8(int* L, int H, int W) {
   }
 }
 // 4-connectivity (background regions)
-__global__ void __launch_bounds__(TPB) merge4(int* L, int H, int W) {
+static __global__ void __launch_bounds__(TPB) merge4(int* L, int H, int W) {
   const size_t n = static_cast<size_t>(H) * W;
   for (size_t i = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * TPB) {
     if (L[i] < 0) continue;
@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(TPB) merge4(int* L, int H, int W) {
     if (x > 0 && L[i - 1] >= 0) unite(L, p, p - 1);
   }
 }
-__global__ void __launch_bounds__(TPB) flatten(int* L, size_t n) {
+static __global__ void __launch_bounds__(TPB) flatten(int* L, size_t n) {
   for (size_t i = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * TPB)
     if (L[i] >= 0) L[i] = find_root(L, static_cast<int>(i));
 }
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(TPB) flatten(int* L, size_t n) {
 // Pass 1 (after flatten of the background labels): every background pixel on the image frame marks its root as
 // outside by overwriting the root's own label with OUTSIDE.
 constexpr int OUTSIDE = -2;
-__global__ void __launch_bounds__(TPB) mark_outside(int* L, int H, int W) {
+static __global__ void __launch_bounds__(TPB) mark_outside(int* L, int H, int W) {
   const int per = 2 * (H + W);
   for (int t = blockIdx.x * TPB + threadIdx.x; t < per; t += gridDim.x * TPB) {
     int x, y;
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(TPB) mark_outside(int* L, int H, int W) {
   }
 }
 // out = 255 for set pixels and for background pixels whose region is not outside
-__global__ void __launch_bounds__(TPB) fill_holes(const uint8_t* __restrict__ m, const int* __restrict__ L,
+static __global__ void __launch_bounds__(TPB) fill_holes(const uint8_t* __restrict__ m, const int* __restrict__ L,
                                                   uint8_t* __restrict__ out, size_t n) {
   for (size_t i = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * TPB) {
     uint8_t v = 255;
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(TPB) fill_holes(const uint8_t* __restrict__ m,
 // vertex.  Summing cross(p, q) of those steps per component gives twice the signed area; vertices with one, four
 // or two diagonal set pixels contribute nothing (same pixel / no crack / out-and-back).  Verified against
 // cv2.contourArea in tests/test_post_cpu.py (numpy twin of this kernel).  area2 must be zero at the roots.
-__global__ void __launch_bounds__(TPB) polygon_area2(const int* __restrict__ L, int H, int W,
+static __global__ void __launch_bounds__(TPB) polygon_area2(const int* __restrict__ L, int H, int W,
                                                      long long* __restrict__ area2) {
   const size_t nv = static_cast<size_t>(H + 1) * (W + 1);
   for (size_t t = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; t < nv; t += static_cast<size_t>(gridDim.x) * TPB) {
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(TPB) polygon_area2(const int* __restrict__ L, 
 
 // ---- 1 x K / K x 1 erosion (K odd) of a binary mask; pixels outside the image count as set (cv::erode's default
 // border value), so a component touching the frame is not eroded from that side.
-__global__ void __launch_bounds__(TPB) erode_line(const uint8_t* __restrict__ m, uint8_t* __restrict__ out, int H,
+static __global__ void __launch_bounds__(TPB) erode_line(const uint8_t* __restrict__ m, uint8_t* __restrict__ out, int H,
                                                   int W, int half, int vertical) {
   const size_t n = static_cast<size_t>(H) * W;
   for (size_t i = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * TPB) {
@@ -154,6 +154,32 @@ __global__ void __launch_bounds__(TPB) erode_line(const uint8_t* __restrict__ m,
       }
     }
     out[i] = v ? 255 : 0;
+  }
+}
+
+// roots get their accumulators zeroed (cheaper than a memset of the scene-sized arrays)
+static __global__ void __launch_bounds__(TPB) zero_at_roots(const int* __restrict__ L, size_t n, long long* a0, int* c0,
+                                                            int* c1, int* c2, int* c3) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * TPB)
+    if (L[i] == static_cast<int>(i)) {
+      if (a0) a0[i] = 0;
+      if (c0) c0[i] = 0;
+      if (c1) c1[i] = 0;
+      if (c2) c2[i] = 0;
+      if (c3) c3[i] = 0;
+    }
+}
+// keep[p] = 255 for set pixels whose component's polygon area exceeds thr2/2 (strict: is at least thr2/2)
+static __global__ void __launch_bounds__(TPB) drop_small(const int* __restrict__ L, const long long* __restrict__ area2,
+                                                         long long thr2, uint8_t* __restrict__ keep, size_t n, int strict) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * TPB) {
+    const int r = L[i];
+    uint8_t v = 0;
+    if (r >= 0) {
+      const long long a = llabs(area2[r]);
+      v = (strict ? a >= thr2 : a > thr2) ? 255 : 0;
+    }
+    keep[i] = v;
   }
 }
 

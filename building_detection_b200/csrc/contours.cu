@@ -1,8 +1,541 @@
-// contours.cu -- contour extraction (reference edge_3.py) entry points.
+// contours.cu -- contour extraction and polygon simplification (reference edge_3.py:_detection, 310-387).
+//
+// Device side (pixel work, O(H*W)): hole fill, 8-connected labelling, polygon-area filter (<= 100), 1x7 and 7x1
+// erosions with their fragment filter (< 50), border following of every kept component (one thread per
+// contour; the traced sequence is the one cv::findContours(RETR_EXTERNAL, CHAIN_APPROX_NONE) returns: start at
+// the component's first raster pixel, first step down/left, contours listed by descending start pixel), and the
+// all-pairs bounding-box IoU matching of process_td / process_rl.
+// Host side (O(#boundary points), double precision, compiled without FMA contraction so that it rounds like
+// OpenCV's scalar code): the list surgery of detction_overlap_building and the area-tiered Douglas-Peucker
+// simplification (restatement of cv::approxPolyDP / arcLength / contourArea for integer contours).
 #include "../../include/bd_b200.h"
-#include "common.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "ccl.cuh"
+#include "post_ws.cuh"
+
 using namespace bd;
-extern "C" {
-int bd_contours(bd_ctx*, const uint8_t*, int, int, bd_polys*, void*) { return fail("bd_contours: not implemented yet"); }
-void bd_polys_free(bd_polys*) {}
+
+namespace bd {
+namespace cont {
+
+constexpr int TPB = 256;
+
+// roots of the components to trace: L[i] == i and |area2| passes the threshold (strict: >= thr2, else > thr2)
+static __global__ void __launch_bounds__(TPB) collect_roots(const int* __restrict__ L, const long long* __restrict__ a2,
+                                                     long long thr2, int strict, size_t n, int* __restrict__ list,
+                                                     int* __restrict__ count, int cap) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * TPB)
+    if (L[i] == static_cast<int>(i)) {
+      const long long a = llabs(a2[i]);
+      if (strict ? a >= thr2 : a > thr2) {
+        const int k = atomicAdd(count, 1);
+        if (k < cap) list[k] = static_cast<int>(i);
+      }
+    }
 }
+
+__constant__ int c_dx[8] = {1, 1, 0, -1, -1, -1, 0, 1};
+__constant__ int c_dy[8] = {0, -1, -1, -1, 0, 1, 1, 1};
+
+// Border following of one component (Suzuki-Abe outer border as implemented by cv::findContours): returns the
+// number of points; writes them when out != nullptr; accumulates the bounding box.
+template <bool WRITE>
+__device__ int trace_one(const uint8_t* __restrict__ img, int H, int W, int root, int2* out, int* bb) {
+  auto at = [&](int x, int y) { return x >= 0 && x < W && y >= 0 && y < H && img[static_cast<size_t>(y) * W + x] != 0; };
+  const int x0 = root % W, y0 = root / W;
+  int minx = x0, maxx = x0, miny = y0, maxy = y0;
+  int s = 4, x1, y1;
+  bool found;
+  do {
+    s = (s - 1) & 7;
+    x1 = x0 + c_dx[s];
+    y1 = y0 + c_dy[s];
+    found = at(x1, y1);
+  } while (!found && s != 4);
+  int n = 0;
+  if (!found) {
+    if (WRITE) out[0] = make_int2(x0, y0);
+    n = 1;
+  } else {
+    int x3 = x0, y3 = y0;
+    const long long limit = 8ll * H * W + 16;
+    for (long long it = 0; it < limit; ++it) {
+      int x4, y4;
+      for (;;) {
+        ++s;
+        x4 = x3 + c_dx[s & 7];
+        y4 = y3 + c_dy[s & 7];
+        if (at(x4, y4)) break;
+      }
+      s &= 7;
+      if (WRITE) out[n] = make_int2(x3, y3);
+      ++n;
+      minx = min(minx, x3); maxx = max(maxx, x3); miny = min(miny, y3); maxy = max(maxy, y3);
+      if (x4 == x0 && y4 == y0 && x3 == x1 && y3 == y1) break;
+      x3 = x4; y3 = y4;
+      s = (s + 4) & 7;
+    }
+  }
+  if (!WRITE) { bb[0] = minx; bb[1] = miny; bb[2] = maxx + 1; bb[3] = maxy + 1; }  // x, y, x+w, y+h of cv::boundingRect
+  return n;
+}
+static __global__ void trace_count(const uint8_t* __restrict__ img, int H, int W, const int* __restrict__ roots, int n,
+                            int* __restrict__ npts, int* __restrict__ bbox) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) npts[i] = trace_one<false>(img, H, W, roots[i], nullptr, bbox + 4 * i);
+}
+static __global__ void trace_write(const uint8_t* __restrict__ img, int H, int W, const int* __restrict__ roots, int n,
+                            const long long* __restrict__ off, int2* __restrict__ pts) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) trace_one<true>(img, H, W, roots[i], pts + off[i], nullptr);
+}
+
+// edge_3.py:26-47 for every initial box against all eroded boxes: index of the first maximum IoU if any IoU
+// exceeds 0.5, else -1.  Boxes are (x0, y0, x1, y1); IoU in float64 exactly like numpy's int64 / int64.
+static __global__ void __launch_bounds__(TPB) match_boxes(const int* __restrict__ a, int na, const int* __restrict__ b, int nb,
+                                                   int* __restrict__ res) {
+  __shared__ int sb[TPB * 4];
+  const int i = blockIdx.x * TPB + threadIdx.x;
+  int ax0 = 0, ay0 = 0, ax1 = 0, ay1 = 0;
+  if (i < na) { ax0 = a[4 * i]; ay0 = a[4 * i + 1]; ax1 = a[4 * i + 2]; ay1 = a[4 * i + 3]; }
+  const long long aarea = static_cast<long long>(ax1 - ax0) * (ay1 - ay0);
+  double best = -1.0;
+  int besti = 0;
+  bool any = false;
+  for (int j0 = 0; j0 < nb; j0 += TPB) {
+    const int m = min(TPB, nb - j0);
+    __syncthreads();
+    for (int t = threadIdx.x; t < m * 4; t += TPB) sb[t] = b[4 * j0 + t];
+    __syncthreads();
+    if (i < na)
+      for (int j = 0; j < m; ++j) {
+        const int bx0 = sb[4 * j], by0 = sb[4 * j + 1], bx1 = sb[4 * j + 2], by1 = sb[4 * j + 3];
+        const long long iw = max(min(ax1, bx1) - max(ax0, bx0), 0), ih = max(min(ay1, by1) - max(ay0, by0), 0);
+        const long long inter = iw * ih;
+        const long long uni = aarea + static_cast<long long>(bx1 - bx0) * (by1 - by0) - inter;
+        const double v = static_cast<double>(inter) / static_cast<double>(uni);
+        if (v > best) { best = v; besti = j0 + j; }
+        any |= v > 0.5;
+      }
+  }
+  if (i < na) res[i] = any ? besti : -1;
+}
+
+// ------------------------------------------------------------------------------------------ host geometry
+struct Pt { int x, y; };
+
+// cv::contourArea for integer points: |sum(x_{i-1} y_i - x_i y_{i-1})| / 2 (exact in double)
+static double contour_area(const Pt* p, int n) {
+  if (n == 0) return 0.0;
+  double a = 0;
+  Pt prev = p[n - 1];
+  for (int i = 0; i < n; ++i) {
+    a += static_cast<double>(prev.x) * p[i].y - static_cast<double>(prev.y) * p[i].x;
+    prev = p[i];
+  }
+  return std::fabs(a * 0.5);
+}
+// cv::arcLength(closed): float32 segment lengths summed in double
+static double arc_length_closed(const Pt* p, int n) {
+  if (n <= 1) return 0.0;
+  double per = 0;
+  float px = static_cast<float>(p[n - 1].x), py = static_cast<float>(p[n - 1].y);
+  for (int i = 0; i < n; ++i) {
+    const float x = static_cast<float>(p[i].x), y = static_cast<float>(p[i].y);
+    const float dx = x - px, dy = y - py;
+    const float d2 = dx * dx + dy * dy;
+    per += static_cast<double>(std::sqrt(d2));
+    px = x; py = y;
+  }
+  return per;
+}
+// cv::approxPolyDP(closed=true) for integer contours (Douglas-Peucker with OpenCV's start-point search and its
+// final collinear clean-up).
+static void approx_poly_closed(const Pt* src, int count, double eps, std::vector<Pt>& dst) {
+  dst.clear();
+  if (count == 0) return;
+  struct Range { int start, end; };
+  std::vector<Range> stack;
+  eps *= eps;
+  Range slice{0, 0}, right{0, 0};
+  Pt start_pt{-1000000, -1000000}, end_pt{0, 0}, pt{0, 0};
+  int pos = 0;
+  bool le_eps = false;
+  auto read = [&](Pt& q, int& ps) { q = src[ps]; if (++ps >= count) ps = 0; };
+  // 1. approximately the two farthest points
+  right.start = 0;
+  for (int i = 0; i < 3; ++i) {
+    double max_dist = 0;
+    pos = (pos + right.start) % count;
+    read(start_pt, pos);
+    for (int j = 1; j < count; ++j) {
+      read(pt, pos);
+      const double dx = pt.x - start_pt.x, dy = pt.y - start_pt.y;
+      const double dist = dx * dx + dy * dy;
+      if (dist > max_dist) { max_dist = dist; right.start = j; }
+    }
+    le_eps = max_dist <= eps;
+  }
+  // 2. initial two slices
+  if (!le_eps) {
+    right.end = slice.start = pos % count;
+    slice.end = right.start = (right.start + slice.start) % count;
+    stack.push_back(right);
+    stack.push_back(slice);
+  } else {
+    dst.push_back(start_pt);
+  }
+  // 3. recursive subdivision
+  while (!stack.empty()) {
+    slice = stack.back();
+    stack.pop_back();
+    end_pt = src[slice.end];
+    pos = slice.start;
+    read(start_pt, pos);
+    if (pos != slice.end) {
+      // distance to the SEGMENT start-end (cv2 >= 4.10 measures points that project beyond an end point to that
+      // end point; pinned by the differential test against cv2 4.13 in tests/test_post_cpu.py)
+      double max_dist = 0;
+      const double dx = end_pt.x - start_pt.x, dy = end_pt.y - start_pt.y;
+      const double len2 = dx * dx + dy * dy;
+      while (pos != slice.end) {
+        read(pt, pos);
+        const double px = pt.x - start_pt.x, py = pt.y - start_pt.y;
+        const double dot = px * dx + py * dy;
+        double dist;
+        if (len2 == 0 || dot < 0) dist = std::sqrt(px * px + py * py);
+        else if (dot > len2) {
+          const double qx = pt.x - end_pt.x, qy = pt.y - end_pt.y;
+          dist = std::sqrt(qx * qx + qy * qy);
+        } else dist = std::fabs(py * dx - px * dy) / std::sqrt(len2);
+        if (dist > max_dist) { max_dist = dist; right.start = (pos + count - 1) % count; }
+      }
+      le_eps = max_dist * max_dist <= eps;
+    } else {
+      le_eps = true;
+      start_pt = src[slice.start];
+    }
+    if (le_eps) {
+      dst.push_back(start_pt);
+    } else {
+      right.end = slice.end;
+      slice.end = right.start;
+      stack.push_back(right);
+      stack.push_back(slice);
+    }
+  }
+  // 4. remove points on (almost) straight lines
+  int new_count = static_cast<int>(dst.size());
+  count = new_count;
+  auto read_dst = [&](Pt& q, int& ps) { q = dst[ps]; if (++ps >= count) ps = 0; };
+  pos = count - 1;
+  read_dst(start_pt, pos);
+  int wpos = pos;
+  read_dst(pt, pos);
+  for (int i = 0; i < count && new_count > 2; ++i) {
+    read_dst(end_pt, pos);
+    const double dx = end_pt.x - start_pt.x, dy = end_pt.y - start_pt.y;
+    const double dist = std::fabs((pt.x - start_pt.x) * dy - (pt.y - start_pt.y) * dx);
+    const double sip = static_cast<double>(pt.x - start_pt.x) * (end_pt.x - pt.x) +
+                       static_cast<double>(pt.y - start_pt.y) * (end_pt.y - pt.y);
+    if (dist * dist <= 0.5 * eps * (dx * dx + dy * dy) && dx != 0 && dy != 0 && sip >= 0) {
+      new_count--;
+      dst[wpos] = start_pt = end_pt;
+      if (++wpos >= count) wpos = 0;
+      read_dst(pt, pos);
+      i++;
+      continue;
+    }
+    dst[wpos] = start_pt = pt;
+    if (++wpos >= count) wpos = 0;
+    pt = end_pt;
+  }
+  dst.resize(new_count);
+}
+
+// edge_3.py:351-378.  Returns 0 = skip (m00 <= 10), 1 = polygon in `out`, 2 = the 4-vertex search failed: the
+// caller must take cv::boxPoints(cv::minAreaRect(contour)) (float32 libm trigonometry, kept on the host side).
+static int simplify(const Pt* c, int n, std::vector<Pt>& out) {
+  const double area = contour_area(c, n);
+  const double per = arc_length_closed(c, n);
+  double eps = 0.01 * per;
+  if (area <= 10) return 0;  // cv::moments(contour)["m00"] equals contourArea for a closed integer contour
+  if (area < 150) {          // small_target, edge_3.py:265-286
+    approx_poly_closed(c, n, eps, out);
+    double rate = 0.002;
+    int tries = 0;
+    while (out.size() != 4) {
+      eps = rate * per;
+      rate = rate + 0.002;
+      approx_poly_closed(c, n, eps, out);
+      if (++tries > 10) break;
+    }
+    return out.size() == 4 ? 1 : 2;
+  }
+  if (150 < area && area < 300) eps = 5 * eps;
+  else if (3000 < area && area < 8000) eps = 0.005 * per;
+  else if (8000 < area && area <= 15000) eps = 0.004 * per;
+  else if (area > 15000) eps = 0.002 * per;
+  approx_poly_closed(c, n, eps, out);
+  return 1;
+}
+
+struct HostSet {           // one traced contour list, in cv::findContours order
+  int n = 0;
+  std::vector<int> bbox;   // 4 per contour
+  std::vector<long long> off;  // n + 1
+  std::vector<Pt> pts;
+  int* d_bbox = nullptr;   // device copy (matching kernel)
+};
+
+static int grid_for(size_t n, int sms) {
+  return static_cast<int>(std::max<size_t>(1, std::min<size_t>((n + TPB - 1) / TPB, static_cast<size_t>(sms) * 16)));
+}
+
+// trace every component of `img` whose root passes the area threshold
+static int trace_set(bd_ctx* ctx, const uint8_t* img, const int* L, const long long* a2, long long thr2, int strict, int H,
+                     int W, cudaStream_t s, HostSet* out, std::vector<void*>& frees) {
+  const size_t n = static_cast<size_t>(H) * W;
+  int* d_count = nullptr;
+  BD_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_count), sizeof(int)));
+  frees.push_back(d_count);
+  BD_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int), s));
+  int cap = static_cast<int>(std::min<size_t>(n, 1u << 22));
+  int* d_list = nullptr;
+  BD_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_list), sizeof(int) * cap));
+  frees.push_back(d_list);
+  collect_roots<<<grid_for(n, ctx->num_sms), TPB, 0, s>>>(L, a2, thr2, strict, n, d_list, d_count, cap);
+  ctx->launches++;
+  int cnt = 0;
+  BD_CUDA(cudaMemcpyAsync(&cnt, d_count, sizeof(int), cudaMemcpyDeviceToHost, s));
+  BD_CUDA(cudaStreamSynchronize(s));
+  BD_CHECK(cnt <= cap, "too many components for the contour stage");
+  out->n = cnt;
+  out->off.assign(cnt + 1, 0);
+  out->bbox.assign(static_cast<size_t>(cnt) * 4, 0);
+  if (cnt == 0) return 0;
+  std::vector<int> roots(cnt);
+  BD_CUDA(cudaMemcpy(roots.data(), d_list, sizeof(int) * cnt, cudaMemcpyDeviceToHost));
+  std::sort(roots.begin(), roots.end(), [](int a, int b) { return a > b; });  // findContours lists the last-found first
+  BD_CUDA(cudaMemcpyAsync(d_list, roots.data(), sizeof(int) * cnt, cudaMemcpyHostToDevice, s));
+  int *d_npts = nullptr, *d_bbox = nullptr;
+  BD_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_npts), sizeof(int) * cnt));
+  frees.push_back(d_npts);
+  BD_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_bbox), sizeof(int) * 4 * cnt));
+  frees.push_back(d_bbox);
+  trace_count<<<(cnt + 63) / 64, 64, 0, s>>>(img, H, W, d_list, cnt, d_npts, d_bbox);
+  ctx->launches++;
+  std::vector<int> npts(cnt);
+  BD_CUDA(cudaMemcpyAsync(npts.data(), d_npts, sizeof(int) * cnt, cudaMemcpyDeviceToHost, s));
+  BD_CUDA(cudaMemcpyAsync(out->bbox.data(), d_bbox, sizeof(int) * 4 * cnt, cudaMemcpyDeviceToHost, s));
+  BD_CUDA(cudaStreamSynchronize(s));
+  for (int i = 0; i < cnt; ++i) out->off[i + 1] = out->off[i] + npts[i];
+  const long long total = out->off[cnt];
+  long long* d_off = nullptr;
+  int2* d_pts = nullptr;
+  BD_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_off), sizeof(long long) * (cnt + 1)));
+  frees.push_back(d_off);
+  BD_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_pts), sizeof(int2) * std::max<long long>(total, 1)));
+  frees.push_back(d_pts);
+  BD_CUDA(cudaMemcpyAsync(d_off, out->off.data(), sizeof(long long) * (cnt + 1), cudaMemcpyHostToDevice, s));
+  trace_write<<<(cnt + 63) / 64, 64, 0, s>>>(img, H, W, d_list, cnt, d_off, d_pts);
+  ctx->launches++;
+  out->pts.resize(total);
+  BD_CUDA(cudaMemcpyAsync(out->pts.data(), d_pts, sizeof(int2) * total, cudaMemcpyDeviceToHost, s));
+  BD_CUDA(cudaStreamSynchronize(s));
+  out->d_bbox = d_bbox;
+  return 0;
+}
+
+// _match of the oracle (edge_3.py process_td / process_rl): lost = initial contours without counterpart,
+// fresh = eroded contours nobody claimed (ascending index)
+static int match_sets(bd_ctx* ctx, const HostSet& ini, const HostSet& ero, cudaStream_t s, std::vector<int>* lost,
+                      std::vector<int>* fresh, std::vector<void*>& frees) {
+  lost->clear();
+  fresh->clear();
+  if (ini.n == 0) {
+    for (int j = 0; j < ero.n; ++j) fresh->push_back(j);
+    return 0;
+  }
+  if (ero.n == 0) {
+    last_error() = "IndexError: too many indices for array (edge_3.py:33 with no eroded contours)";
+    return 2;
+  }
+  int* d_res = nullptr;
+  BD_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_res), sizeof(int) * ini.n));
+  frees.push_back(d_res);
+  match_boxes<<<(ini.n + TPB - 1) / TPB, TPB, 0, s>>>(ini.d_bbox, ini.n, ero.d_bbox, ero.n, d_res);
+  ctx->launches++;
+  std::vector<int> res(ini.n);
+  BD_CUDA(cudaMemcpyAsync(res.data(), d_res, sizeof(int) * ini.n, cudaMemcpyDeviceToHost, s));
+  BD_CUDA(cudaStreamSynchronize(s));
+  std::vector<char> claimed(ero.n, 0);
+  for (int i = 0; i < ini.n; ++i) {
+    if (res[i] < 0) lost->push_back(i);
+    else claimed[res[i]] = 1;
+  }
+  for (int j = 0; j < ero.n; ++j)
+    if (!claimed[j]) fresh->push_back(j);
+  return 0;
+}
+
+static int best_iou_host(const int* box, const std::vector<const int*>& others) {  // edge_3.py:26-47 on small lists
+  double best = -1;
+  int besti = 0;
+  bool any = false;
+  const long long aarea = static_cast<long long>(box[2] - box[0]) * (box[3] - box[1]);
+  for (size_t j = 0; j < others.size(); ++j) {
+    const int* o = others[j];
+    const long long iw = std::max(std::min(box[2], o[2]) - std::max(box[0], o[0]), 0);
+    const long long ih = std::max(std::min(box[3], o[3]) - std::max(box[1], o[1]), 0);
+    const long long inter = iw * ih;
+    const long long uni = aarea + static_cast<long long>(o[2] - o[0]) * (o[3] - o[1]) - inter;
+    const double v = static_cast<double>(inter) / static_cast<double>(uni);
+    if (v > best) { best = v; besti = static_cast<int>(j); }
+    any |= v > 0.5;
+  }
+  return any ? besti : -1;
+}
+
+}  // namespace cont
+}  // namespace bd
+
+extern "C" {
+
+void bd_polys_free(bd_polys* p) {
+  if (!p) return;
+  free(p->offsets); free(p->xs); free(p->ys); free(p->is_float);
+  memset(p, 0, sizeof(*p));
+}
+
+int bd_contours(bd_ctx* ctx, const uint8_t* mask_dev, int h, int w, bd_polys* out, void* stream) {
+  BD_CHECK(ctx && mask_dev && out && h >= 1 && w >= 1, "bad arguments");
+  BD_CHECK(static_cast<size_t>(h) * w < (1ull << 31), "scene too large for int32 pixel labels");
+  using namespace bd::cont;
+  memset(out, 0, sizeof(*out));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  post::Workspace* ws = nullptr;
+  if (post::workspace(ctx, h, w, &ws)) return 1;
+  const size_t n = static_cast<size_t>(h) * w;
+  const int g = grid_for(n, ctx->num_sms);
+  const int gv = grid_for(static_cast<size_t>(h + 1) * (w + 1), ctx->num_sms);
+  std::vector<void*> frees;
+  struct Guard { std::vector<void*>& f; ~Guard() { for (void* p : f) cudaFree(p); } } guard{frees};
+
+  // edge_3.py:317-329: fill every external contour, erase polygon area <= 100 -> initial_img (ws->keep)
+  if (post::fill(ctx, mask_dev, ws->Lh, ws->filled, h, w, s)) return 1;
+  if (post::label8(ctx, ws->filled, ws->L, h, w, s)) return 1;
+  ccl::zero_at_roots<<<g, ccl::TPB, 0, s>>>(ws->L, n, ws->a2, nullptr, nullptr, nullptr, nullptr);
+  ccl::polygon_area2<<<gv, ccl::TPB, 0, s>>>(ws->L, h, w, ws->a2);
+  ccl::drop_small<<<g, ccl::TPB, 0, s>>>(ws->L, ws->a2, 2 * 100, ws->keep, n, 0);
+  // :172-199: 1x7 and 7x1 erosion (one iteration), fragments of area < 50 erased
+  uint8_t* er_h = ws->er;
+  uint8_t* er_v = ws->filled;  // free again once L is built
+  ccl::erode_line<<<g, ccl::TPB, 0, s>>>(ws->keep, er_h, h, w, 3, 0);
+  ccl::erode_line<<<g, ccl::TPB, 0, s>>>(ws->keep, er_v, h, w, 3, 1);
+  ctx->launches += 5;
+  if (post::label8(ctx, er_h, ws->Lh, h, w, s) || post::label8(ctx, er_v, ws->Lv, h, w, s)) return 1;
+  ccl::zero_at_roots<<<g, ccl::TPB, 0, s>>>(ws->Lh, n, ws->a2h, nullptr, nullptr, nullptr, nullptr);
+  ccl::zero_at_roots<<<g, ccl::TPB, 0, s>>>(ws->Lv, n, ws->a2v, nullptr, nullptr, nullptr, nullptr);
+  ccl::polygon_area2<<<gv, ccl::TPB, 0, s>>>(ws->Lh, h, w, ws->a2h);
+  ccl::polygon_area2<<<gv, ccl::TPB, 0, s>>>(ws->Lv, h, w, ws->a2v);
+  ctx->launches += 4;
+  BD_CUDA(cudaGetLastError());
+
+  HostSet ini, td, rl;
+  if (trace_set(ctx, ws->keep, ws->L, ws->a2, 2 * 100, 0, h, w, s, &ini, frees)) return 1;
+  if (trace_set(ctx, er_h, ws->Lh, ws->a2h, 2 * 50, 1, h, w, s, &td, frees)) return 1;
+  if (trace_set(ctx, er_v, ws->Lv, ws->a2v, 2 * 50, 1, h, w, s, &rl, frees)) return 1;
+
+  // detction_overlap_building (:159-262): final list of (set, index); set < 0 marks None
+  struct Ref { const HostSet* set; int idx; };
+  std::vector<Ref> finals;
+  for (int i = 0; i < ini.n; ++i) finals.push_back({&ini, i});
+  if (!(td.n == ini.n && rl.n == ini.n)) {
+    std::vector<int> lost_td, new_td, lost_rl, new_rl;
+    const bool do_td = td.n != ini.n, do_rl = rl.n != ini.n;
+    if (do_td) { int rc = match_sets(ctx, ini, td, s, &lost_td, &new_td, frees); if (rc) return rc; }
+    if (do_rl) { int rc = match_sets(ctx, ini, rl, s, &lost_rl, &new_rl, frees); if (rc) return rc; }
+    for (int i : lost_td) finals[i].set = nullptr;
+    for (int i : lost_rl) finals[i].set = nullptr;
+    if (do_td && do_rl) {
+      if (!new_td.empty() && !new_rl.empty()) {
+        std::vector<const int*> rl_boxes;
+        for (int j : new_rl) rl_boxes.push_back(&rl.bbox[4 * static_cast<size_t>(j)]);
+        std::vector<char> dup(new_rl.size(), 0);
+        for (int j : new_td) {
+          const int r = best_iou_host(&td.bbox[4 * static_cast<size_t>(j)], rl_boxes);
+          finals.push_back({&td, j});
+          if (r >= 0) dup[r] = 1;
+        }
+        for (size_t i = 0; i < new_rl.size(); ++i)
+          if (!dup[i]) finals.push_back({&rl, new_rl[i]});
+      } else if (!new_td.empty()) {
+        for (int j : new_td) finals.push_back({&td, j});
+      } else {
+        for (int j : new_rl) finals.push_back({&rl, j});
+      }
+    } else if (do_td) {
+      for (int j : new_td) finals.push_back({&td, j});
+    } else {
+      for (int j : new_rl) finals.push_back({&rl, j});
+    }
+  }
+
+  // :351-385 per contour
+  std::vector<int> offsets{0};
+  std::vector<float> xs, ys;
+  std::vector<uint8_t> kinds;
+  std::vector<Pt> poly;
+  for (const Ref& r : finals) {
+    if (!r.set) continue;
+    const Pt* c = r.set->pts.data() + r.set->off[r.idx];
+    const int cn = static_cast<int>(r.set->off[r.idx + 1] - r.set->off[r.idx]);
+    const int kind = simplify(c, cn, poly);
+    if (kind == 0) continue;
+    if (kind == 1) {
+      for (const Pt& p : poly) { xs.push_back(static_cast<float>(p.x)); ys.push_back(static_cast<float>(p.y)); }
+      xs.push_back(static_cast<float>(poly[0].x)); ys.push_back(static_cast<float>(poly[0].y));  // closed (:379-384)
+    } else {
+      for (int i = 0; i < cn; ++i) { xs.push_back(static_cast<float>(c[i].x)); ys.push_back(static_cast<float>(c[i].y)); }
+    }
+    kinds.push_back(kind == 1 ? 0 : 2);
+    offsets.push_back(static_cast<int>(xs.size()));
+  }
+  out->n_polys = static_cast<int>(kinds.size());
+  out->n_points = static_cast<int>(xs.size());
+  out->offsets = static_cast<int32_t*>(malloc(sizeof(int32_t) * offsets.size()));
+  out->xs = static_cast<float*>(malloc(sizeof(float) * std::max<size_t>(xs.size(), 1)));
+  out->ys = static_cast<float*>(malloc(sizeof(float) * std::max<size_t>(ys.size(), 1)));
+  out->is_float = static_cast<uint8_t*>(malloc(std::max<size_t>(kinds.size(), 1)));
+  BD_CHECK(out->offsets && out->xs && out->ys && out->is_float, "out of host memory");
+  memcpy(out->offsets, offsets.data(), sizeof(int32_t) * offsets.size());
+  if (!xs.empty()) { memcpy(out->xs, xs.data(), sizeof(float) * xs.size()); memcpy(out->ys, ys.data(), sizeof(float) * ys.size()); }
+  if (!kinds.empty()) memcpy(out->is_float, kinds.data(), kinds.size());
+  return 0;
+}
+
+// host-side geometry exposed for CPU differential tests against cv2 (no GPU involved)
+double bd_host_contour_area(const int32_t* xy, int n) { return cont::contour_area(reinterpret_cast<const cont::Pt*>(xy), n); }
+double bd_host_arc_length(const int32_t* xy, int n) { return cont::arc_length_closed(reinterpret_cast<const cont::Pt*>(xy), n); }
+int bd_host_approx_poly(const int32_t* xy, int n, double eps, int32_t* out_xy) {
+  std::vector<cont::Pt> dst;
+  cont::approx_poly_closed(reinterpret_cast<const cont::Pt*>(xy), n, eps, dst);
+  memcpy(out_xy, dst.data(), sizeof(cont::Pt) * dst.size());
+  return static_cast<int>(dst.size());
+}
+int bd_host_simplify(const int32_t* xy, int n, int32_t* out_xy, int* out_n) {
+  std::vector<cont::Pt> dst;
+  const int kind = cont::simplify(reinterpret_cast<const cont::Pt*>(xy), n, dst);
+  *out_n = kind == 1 ? static_cast<int>(dst.size()) : 0;
+  if (kind == 1) memcpy(out_xy, dst.data(), sizeof(cont::Pt) * dst.size());
+  return kind;
+}
+
+}  // extern "C"

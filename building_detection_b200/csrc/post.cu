@@ -18,33 +18,8 @@ namespace post {
 
 constexpr int TPB = ccl::TPB;
 
-// roots get their accumulators zeroed (cheaper than memset of the whole scene-sized arrays)
-__global__ void __launch_bounds__(TPB) zero_at_roots(const int* __restrict__ L, size_t n, long long* a0, int* c0, int* c1,
-                                                     int* c2, int* c3) {
-  for (size_t i = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * TPB)
-    if (L[i] == static_cast<int>(i)) {
-      if (a0) a0[i] = 0;
-      if (c0) c0[i] = 0;
-      if (c1) c1[i] = 0;
-      if (c2) c2[i] = 0;
-      if (c3) c3[i] = 0;
-    }
-}
-// keep[p] = 255 for set pixels whose component's polygon area exceeds thr2/2 (strict: is at least thr2/2)
-__global__ void __launch_bounds__(TPB) drop_small(int* __restrict__ L, const long long* __restrict__ area2, long long thr2,
-                                                  uint8_t* __restrict__ keep, size_t n, int strict) {
-  for (size_t i = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * TPB) {
-    const int r = L[i];
-    uint8_t v = 0;
-    if (r >= 0) {
-      const long long a = llabs(area2[r]);
-      v = (strict ? a >= thr2 : a > thr2) ? 255 : 0;
-    }
-    keep[i] = v;
-  }
-}
 // For every fragment root f: parent = L[f]; cnt[parent]++; surv[parent]++ when the fragment's polygon area > 500.
-__global__ void __launch_bounds__(TPB) count_fragments(const int* __restrict__ Lf, const long long* __restrict__ area2f,
+static __global__ void __launch_bounds__(TPB) count_fragments(const int* __restrict__ Lf, const long long* __restrict__ area2f,
                                                        const int* __restrict__ L, int* cnt, int* surv, size_t n,
                                                        long long thr2) {
   for (size_t i = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * TPB)
@@ -55,7 +30,7 @@ __global__ void __launch_bounds__(TPB) count_fragments(const int* __restrict__ L
     }
 }
 // eroede_dilate_process decision + only_plt rasterisation (model_fuse.py:173-218, 265-268) per pixel of a kept object
-__global__ void __launch_bounds__(TPB) rasterise_objects(const uint8_t* __restrict__ keep, const int* __restrict__ L,
+static __global__ void __launch_bounds__(TPB) rasterise_objects(const uint8_t* __restrict__ keep, const int* __restrict__ L,
                                                          const int* __restrict__ Lh, const int* __restrict__ Lv,
                                                          const long long* __restrict__ a2h, const long long* __restrict__ a2v,
                                                          const int* __restrict__ cntH, const int* __restrict__ survH,
@@ -94,7 +69,7 @@ __global__ void __launch_bounds__(TPB) rasterise_objects(const uint8_t* __restri
     out[i] = v;
   }
 }
-__global__ void __launch_bounds__(TPB) vote3of5(const uint8_t* __restrict__ m, size_t n, uint8_t* __restrict__ out) {
+static __global__ void __launch_bounds__(TPB) vote3of5(const uint8_t* __restrict__ m, size_t n, uint8_t* __restrict__ out) {
   // 16 pixels per thread (128-bit loads) when the five planes stay 16-byte aligned; l_k // 255 summed, >= 3 -> 255
   // (model_fuse.py:315-324)
   const size_t nv = (n % 16 == 0) ? n / 16 : 0;
@@ -160,20 +135,20 @@ int cleanup(bd_ctx* ctx, const uint8_t* mask, int H, int W, uint8_t* out, cudaSt
   // fill_and_delete: fill, label, polygon area, drop <= 1000
   if (fill(ctx, mask, ws->Lh, ws->filled, H, W, s)) return 1;
   if (label8(ctx, ws->filled, ws->L, H, W, s)) return 1;
-  zero_at_roots<<<g, TPB, 0, s>>>(ws->L, n, ws->a2, ws->cntH, ws->survH, ws->cntV, ws->survV);
+  ccl::zero_at_roots<<<g, TPB, 0, s>>>(ws->L, n, ws->a2, ws->cntH, ws->survH, ws->cntV, ws->survV);
   ccl::polygon_area2<<<gv, TPB, 0, s>>>(ws->L, H, W, ws->a2);
-  drop_small<<<g, TPB, 0, s>>>(ws->L, ws->a2, 2 * 1000, ws->keep, n, 0);
+  ccl::drop_small<<<g, TPB, 0, s>>>(ws->L, ws->a2, 2 * 1000, ws->keep, n, 0);
   // eroede_dilate_process: 1x5 / 5x1 kernels, 5 iterations == one 1x21 / 21x1 erosion
   ccl::erode_line<<<g, TPB, 0, s>>>(ws->keep, ws->er, H, W, 10, 0);
   ctx_count(ctx, 4);
   if (label8(ctx, ws->er, ws->Lh, H, W, s)) return 1;
-  zero_at_roots<<<g, TPB, 0, s>>>(ws->Lh, n, ws->a2h, nullptr, nullptr, nullptr, nullptr);
+  ccl::zero_at_roots<<<g, TPB, 0, s>>>(ws->Lh, n, ws->a2h, nullptr, nullptr, nullptr, nullptr);
   ccl::polygon_area2<<<gv, TPB, 0, s>>>(ws->Lh, H, W, ws->a2h);
   count_fragments<<<g, TPB, 0, s>>>(ws->Lh, ws->a2h, ws->L, ws->cntH, ws->survH, n, 2 * 500);
   ccl::erode_line<<<g, TPB, 0, s>>>(ws->keep, ws->er, H, W, 10, 1);
   ctx_count(ctx, 4);
   if (label8(ctx, ws->er, ws->Lv, H, W, s)) return 1;
-  zero_at_roots<<<g, TPB, 0, s>>>(ws->Lv, n, ws->a2v, nullptr, nullptr, nullptr, nullptr);
+  ccl::zero_at_roots<<<g, TPB, 0, s>>>(ws->Lv, n, ws->a2v, nullptr, nullptr, nullptr, nullptr);
   ccl::polygon_area2<<<gv, TPB, 0, s>>>(ws->Lv, H, W, ws->a2v);
   count_fragments<<<g, TPB, 0, s>>>(ws->Lv, ws->a2v, ws->L, ws->cntV, ws->survV, n, 2 * 500);
   rasterise_objects<<<g, TPB, 0, s>>>(ws->keep, ws->L, ws->Lh, ws->Lv, ws->a2h, ws->a2v, ws->cntH, ws->survH, ws->cntV,

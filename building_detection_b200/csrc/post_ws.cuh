@@ -37,6 +37,9 @@ struct bd_ctx {
 
 namespace bd {
 namespace post {
+// defined in post.cu
+int label8(bd_ctx* ctx, const uint8_t* m, int* L, int H, int W, cudaStream_t s);                 // 8-connected labels of m
+int fill(bd_ctx* ctx, const uint8_t* m, int* Lbg, uint8_t* out, int H, int W, cudaStream_t s);  // hole fill
 inline int ctx_sms(bd_ctx* c) { return c->num_sms; }
 inline void ctx_count(bd_ctx* c, int n) { c->launches += n; }
 

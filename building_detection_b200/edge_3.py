@@ -1,0 +1,72 @@
+"""Drop-in for the reference's edge_3.py: ``_detection(label_path) -> (all_coner, height)`` (edge_3.py:310-387)
+plus the device-resident entry ``contours_device``.  The pixel work (hole fill, labelling, erosions, border
+following, box matching) runs in bd_contours (csrc/contours.cu); the polygon simplification is the library's
+restatement of cv::approxPolyDP.  The one piece delegated to OpenCV is the minimum-area-rectangle fallback of
+small_target (edge_3.py:281-285) for the few tiny contours whose 4-vertex search fails: its float32 result depends
+on libm's atan2 / cos / sin, which only the host can reproduce bit for bit."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import runtime as R
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise R.NativeError("building_detection_b200 needs a CUDA device (B200); there is no CPU path")
+    return torch
+
+
+def contours_device(mask):
+    """mask: (H,W) u8 cuda tensor -> (polygons, H) with polygons[i] = [xs, ys] (closed; np.int32 coordinates, or
+    np.float32 for the minAreaRect fallback), exactly what edge_3._detection returns."""
+    t = _torch()
+    assert mask.is_cuda and mask.dtype == t.uint8 and mask.dim() == 2
+    mask = mask.contiguous()
+    h, w = mask.shape
+    polys = R.Polys()
+    stream = t.cuda.current_stream(mask.device).cuda_stream
+    rc = R.lib().bd_contours(R.context(mask.device.index), mask.data_ptr(), h, w, C.byref(polys), stream)
+    if rc != 0:
+        msg = R.lib().bd_last_error().decode(errors="replace")
+        if msg.startswith("IndexError"):
+            raise IndexError(msg)  # the reference fails the same way (edge_3.py:33 on an empty eroded list)
+        raise R.NativeError(msg)
+    try:
+        n = polys.n_polys
+        off = np.ctypeslib.as_array(polys.offsets, shape=(n + 1,)).copy()
+        tot = int(off[-1])
+        xs = np.ctypeslib.as_array(polys.xs, shape=(max(tot, 1),))[:tot].copy()
+        ys = np.ctypeslib.as_array(polys.ys, shape=(max(tot, 1),))[:tot].copy()
+        kinds = np.ctypeslib.as_array(polys.is_float, shape=(max(n, 1),))[:n].copy()
+    finally:
+        R.lib().bd_polys_free(C.byref(polys))
+    out = []
+    for i in range(n):
+        px, py = xs[off[i]:off[i + 1]], ys[off[i]:off[i + 1]]
+        if kinds[i] == 2:
+            import cv2 as cv
+            c = np.stack([px, py], axis=1).astype(np.int32).reshape(-1, 1, 2)
+            pts = cv.boxPoints(cv.minAreaRect(c))
+            out.append([list(pts[:, 0]) + [pts[0, 0]], list(pts[:, 1]) + [pts[0, 1]]])
+        else:
+            out.append([list(px.astype(np.int32)), list(py.astype(np.int32))])
+    return out, h
+
+
+def detect(mask):
+    """Host array in: (H,W) u8 mask -> (polygons, H)."""
+    t = _torch()
+    return contours_device(t.from_numpy(np.ascontiguousarray(mask, np.uint8)).cuda())
+
+
+def _detection(label_path):
+    """edge_3.py:310-387: read the fused-mask PNG, return (all_coner, img_height)."""
+    import cv2 as cv
+    img = cv.imread(label_path)
+    if img is None:
+        raise AttributeError("'NoneType' object has no attribute 'copy'")  # what edge_3.py:313 raises for a bad path
+    return detect(cv.cvtColor(img, cv.COLOR_BGR2GRAY))

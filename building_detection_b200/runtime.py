@@ -76,6 +76,10 @@ _SIGS = {
     "bd_mask_cleanup": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "bd_contours": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(Polys), C.c_void_p]),
     "bd_polys_free": (None, [C.POINTER(Polys)]),
+    "bd_host_contour_area": (C.c_double, [C.c_void_p, C.c_int]),
+    "bd_host_arc_length": (C.c_double, [C.c_void_p, C.c_int]),
+    "bd_host_approx_poly": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_void_p]),
+    "bd_host_simplify": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
 }
 
 _lib = None

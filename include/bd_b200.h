@@ -142,10 +142,21 @@ typedef struct bd_polys {
   int32_t* offsets;        /* n_polys+1 entries into xs/ys */
   float* xs;               /* integer-valued except minAreaRect fallbacks (edge_3.py:281-285) */
   float* ys;
-  uint8_t* is_float;       /* per polygon: 1 if produced by the boxPoints fallback (float32 coords) */
+  uint8_t* is_float;       /* per polygon: 0 = closed integer polygon; 2 = the 4-vertex search of small_target
+                              (edge_3.py:265-286) failed and xs/ys hold the RAW contour: the caller applies
+                              cv::boxPoints(cv::minAreaRect(.)), whose float32 libm trigonometry stays on the host */
 } bd_polys;
 int bd_contours(bd_ctx* ctx, const uint8_t* mask_dev, int h, int w, bd_polys* out, void* stream);
 void bd_polys_free(bd_polys* p);
+
+/* host-side restatements of the OpenCV primitives edge_3.py applies per contour (integer (x,y) pairs, closed
+ * curves), exposed so that they can be checked against cv2 without a GPU: cv::contourArea, cv::arcLength,
+ * cv::approxPolyDP (returns the vertex count, writes out_xy[2*count]) and the area-tiered choice of
+ * edge_3.py:351-378 (returns 0 = skipped, 1 = polygon written, 2 = needs minAreaRect). */
+double bd_host_contour_area(const int32_t* xy, int n);
+double bd_host_arc_length(const int32_t* xy, int n);
+int bd_host_approx_poly(const int32_t* xy, int n, double eps, int32_t* out_xy);
+int bd_host_simplify(const int32_t* xy, int n, int32_t* out_xy, int* out_n);
 
 #ifdef __cplusplus
 }

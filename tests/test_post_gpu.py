@@ -74,3 +74,66 @@ def test_fuse_idempotent_at_scale(gpu):
     crop = c1[1000:1700, 2000:2700].cpu().numpy()
     np.testing.assert_array_equal(model_fuse.cleanup_device(torch.from_numpy(crop).cuda()).cpu().numpy(),
                                   post_ref.clean_mask(crop))
+
+
+# ------------------------------------------------------------------------------------------ contours (edge_3.py)
+def _same(polys, want):
+    assert len(polys) == len(want), (len(polys), len(want))
+    for p, q in zip(polys, want):
+        assert type(p[0][0]) is type(q[0][0])
+        assert np.array_equal(np.asarray(p[0]), np.asarray(q[0])) and np.array_equal(np.asarray(p[1]), np.asarray(q[1]))
+
+
+def _golden_polys(prefix):
+    off, xs, ys, isf = (GOLD[prefix + k] for k in ("off", "xs", "ys", "isf"))
+    return [[list(xs[off[i]:off[i + 1]].astype(np.float32 if isf[i] else np.int32)),
+             list(ys[off[i]:off[i + 1]].astype(np.float32 if isf[i] else np.int32))] for i in range(len(off) - 1)]
+
+
+@pytest.mark.parametrize("name,size,seed", PS.CONTOUR_CASES)
+def test_contours_match_reference_golden(gpu, name, size, seed):
+    """bit-exact polygons vs the reference's own edge_3._detection (golden)."""
+    from building_detection_b200 import edge_3
+    polys, h = edge_3.detect(PS.contour_case_mask(name, size, seed))
+    assert h == size
+    _same(polys, _golden_polys(name + "_"))
+
+
+@pytest.mark.parametrize("name,size,seed", PS.FUSE_CASES)
+def test_fuse_then_contours_match_reference_golden(gpu, name, size, seed):
+    """the real hand-off: fused mask (device) -> polygons, both against the reference's outputs."""
+    import torch
+    from building_detection_b200 import edge_3, model_fuse
+    masks = torch.from_numpy(np.stack(PS.five_masks(size, seed))).cuda()
+    polys, _ = edge_3.contours_device(model_fuse.fuse_device(masks))
+    _same(polys, _golden_polys(name + "_poly_"))
+
+
+@pytest.mark.parametrize("size,seed,kind", [(300, 301, "base"), (512, 302, "base"), (900, 303, "base"), (1400, 304, "base"),
+                                            (256, 305, "noise"), (384, 306, "noise"), (200, 307, "noise5")])
+def test_contours_match_oracle(gpu, size, seed, kind):
+    from building_detection_b200 import edge_3
+    m = PS.base_mask(size, seed) if kind == "base" else PS.noise_mask(size, seed, 0.35 if kind == "noise" else 0.5, 9 if kind == "noise" else 5)
+    try:
+        want, _ = post_ref.detection(m)
+    except IndexError:
+        with pytest.raises(IndexError):
+            edge_3.detect(m)
+        return
+    polys, _ = edge_3.detect(m)
+    _same(polys, want)
+
+
+def test_contours_edge_cases(gpu):
+    from building_detection_b200 import edge_3
+    assert edge_3.detect(np.zeros((40, 50), np.uint8)) == ([], 40)
+    one = np.zeros((64, 64), np.uint8)
+    one[10:40, 12:50] = 255
+    _same(edge_3.detect(one)[0], post_ref.detection(one)[0])
+    full = np.full((64, 64), 255, np.uint8)
+    _same(edge_3.detect(full)[0], post_ref.detection(full)[0])
+    # two squares joined only through a corner: the 7-px erosion splits them (edge_3.py:159-262)
+    m = np.zeros((200, 200), np.uint8)
+    m[20:80, 20:80] = 255
+    m[79:140, 79:140] = 255
+    _same(edge_3.detect(m)[0], post_ref.detection(m)[0])
