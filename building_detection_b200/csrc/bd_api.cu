@@ -143,6 +143,15 @@ void bd_destroy(bd_ctx* ctx) {
 
 int64_t bd_launch_count(bd_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+int bd_debug_read_trace(bd_ctx* ctx, long long* host_dst, int max_events) {
+  BD_CHECK(ctx && ctx->trace_buf && host_dst, "no trace buffer (set BD_UMMA_TRACE=1 before building the plan)");
+  BD_CUDA(cudaDeviceSynchronize());
+  (void)max_events;
+  BD_CUDA(cudaMemcpy(host_dst, ctx->trace_buf, sizeof(long long) * 4 * 4096, cudaMemcpyDeviceToHost));
+  BD_CUDA(cudaMemset(ctx->trace_buf, 0, sizeof(long long) * 4 * 4096));
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------ plans
 int bd_plan_create(bd_ctx* ctx, int batch, bd_plan** out) {
   BD_CHECK(ctx && out, "null argument");
@@ -203,8 +212,16 @@ int bd_plan_add_conv(bd_plan* p, const bd_conv_desc* dptr) {
       if (has_res) r = pl->tview(d.res);
       if (umma::prepare(L.get(), x, y, has_res ? &r : nullptr, d.ntaps, d.dy, d.dx, d.stride, d.ho, d.wo, d.act_pre,
                         d.act_post, d.out_scale, d.out_oy, d.out_ox, static_cast<const h16*>(wd),
-                        static_cast<const float*>(bdv), ctx->umma_smem_kb, ctx->umma_max_block_n))
+                        static_cast<const float*>(bdv), ctx->umma_smem_kb, ctx->umma_max_block_n, ctx->num_sms))
         return 1;
+      if (const char* tr = getenv("BD_UMMA_TRACE")) {  // debug: event trace of CTA 0 (tools/umma_trace.py)
+        void* tbuf = nullptr;
+        if (pl->scratch(sizeof(long long) * 4 * 4096, &tbuf)) return 1;
+        cudaMemset(tbuf, 0, sizeof(long long) * 4 * 4096);
+        L->p.trace = static_cast<long long*>(tbuf);
+        ctx->trace_buf = tbuf;
+        (void)tr;
+      }
       op.kclass = 0;
       op.run = [L, ctx](cudaStream_t s) -> int { ctx->launches++; return umma::launch(*L, s); };
     } else {
@@ -508,7 +525,8 @@ int bd_plan_finalize(bd_plan* p, int input_buf, int logits_buf, int logits_up) {
   BD_CUDA(cudaSetDevice(p->ctx->device));
   const int nb = static_cast<int>(p->bufs.size());
   if (input_buf >= 0) {
-    BD_CHECK(input_buf < nb && p->bufs[input_buf].dtype == BD_F32 && p->bufs[input_buf].kind == BD_MAP, "bad input buffer");
+    BD_CHECK(input_buf < nb && p->bufs[input_buf].dtype == BD_F16 && p->bufs[input_buf].C == 8 &&
+                 p->bufs[input_buf].kind == BD_MAP, "bad input buffer (expected an fp16 map with 8 channels)");
   }
   if (logits_buf >= 0) {
     BD_CHECK(logits_buf < nb && p->bufs[logits_buf].dtype == BD_F32 && p->bufs[logits_buf].C == 2 && logits_up >= 1,
@@ -554,7 +572,11 @@ int bd_plan_run(bd_plan* p, const float* x_dev, float* probs_dev, uint8_t* mask_
   if (x_dev) {
     BD_CHECK(p->input_buf >= 0, "plan has no input buffer");
     const BufInfo& ib = p->bufs[p->input_buf];
-    BD_CUDA(cudaMemcpyAsync(p->arena + ib.offset, x_dev, ib.bytes, cudaMemcpyDeviceToDevice, s));
+    const size_t npix = static_cast<size_t>(p->batch) * ib.H * ib.W;
+    p->ctx->launches++;
+    k::input_convert_kernel<<<grid_for(npix, p->ctx->num_sms * 4), k::TPB, 0, s>>>(
+        x_dev, npix, reinterpret_cast<h16*>(p->arena + ib.offset));
+    BD_CUDA(cudaGetLastError());
   }
   p->cur_probs = probs_dev;
   p->cur_mask = mask_dev;
@@ -577,10 +599,15 @@ int bd_plan_run_host(bd_plan* p, const float* x_host, float* probs_host, uint8_t
   const size_t npix = static_cast<size_t>(p->batch) * lb.H * p->logits_up * lb.W * p->logits_up;
   float* dprobs = nullptr;
   uint8_t* dmask = nullptr;
-  if (x_host) BD_CUDA(cudaMemcpy(p->arena + ib.offset, x_host, ib.bytes, cudaMemcpyHostToDevice));
+  float* dx = nullptr;
+  if (x_host) {
+    const size_t xbytes = static_cast<size_t>(p->batch) * ib.H * ib.W * 3 * sizeof(float);
+    BD_CUDA(cudaMalloc(reinterpret_cast<void**>(&dx), xbytes));
+    BD_CUDA(cudaMemcpy(dx, x_host, xbytes, cudaMemcpyHostToDevice));
+  }
   if (probs_host) BD_CUDA(cudaMalloc(reinterpret_cast<void**>(&dprobs), npix * 2 * 4));
   if (mask_host) BD_CUDA(cudaMalloc(reinterpret_cast<void**>(&dmask), npix));
-  int rc = bd_plan_run(p, nullptr, dprobs, dmask, nullptr);
+  int rc = bd_plan_run(p, dx, dprobs, dmask, nullptr);
   if (!rc) {
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) rc = fail(std::string("forward failed: ") + cudaGetErrorString(e));
@@ -589,6 +616,7 @@ int bd_plan_run_host(bd_plan* p, const float* x_host, float* probs_host, uint8_t
   if (!rc && mask_host) cudaMemcpy(mask_host, dmask, npix, cudaMemcpyDeviceToHost);
   p->cur_probs = nullptr;
   p->cur_mask = nullptr;
+  if (dx) cudaFree(dx);
   if (dprobs) cudaFree(dprobs);
   if (dmask) cudaFree(dmask);
   return rc;
@@ -661,7 +689,7 @@ static int ensure_tile_scratch(bd_ctx* ctx, int n) {
 }
 
 int bd_tiles_gather(bd_ctx* ctx, const uint8_t* scene_bgr_dev, int h, int w, const int32_t* ys_host,
-                    const int32_t* xs_host, int n, float* x_dev, void* stream) {
+                    const int32_t* xs_host, int n, void* x_dev, void* stream) {
   BD_CHECK(ctx && scene_bgr_dev && ys_host && xs_host && x_dev && n >= 1 && h >= 1 && w >= 1, "bad arguments");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (ensure_tile_scratch(ctx, std::max(n, 64))) return 1;
@@ -669,7 +697,7 @@ int bd_tiles_gather(bd_ctx* ctx, const uint8_t* scene_bgr_dev, int h, int w, con
   BD_CUDA(cudaMemcpyAsync(ctx->d_xs, xs_host, sizeof(int) * n, cudaMemcpyHostToDevice, s));
   ctx->launches++;
   k::tiles_gather_kernel<<<grid_for(static_cast<size_t>(n) * 512 * 512, ctx->num_sms * 4), k::TPB, 0, s>>>(
-      scene_bgr_dev, h, w, ctx->d_ys, ctx->d_xs, n, x_dev);
+      scene_bgr_dev, h, w, ctx->d_ys, ctx->d_xs, n, static_cast<h16*>(x_dev));
   BD_CUDA(cudaGetLastError());
   return 0;
 }

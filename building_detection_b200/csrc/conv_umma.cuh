@@ -1,19 +1,24 @@
 // conv_umma.cuh -- implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05 / TMEM / TMA).
 //
-// One CTA computes a 128-pixel x BLOCK_N-channel output tile.  GEMM view of the convolution:
-//   D[m, n] = sum_{tap, c} A_tap[m, c] * W[tap][n][c]
-// where m runs over a (bn x bh x bw) box of output pixels (bn*bh*bw = 128) and A_tap is the NHWC
-// input box shifted by the tap offset (dy, dx).  The im2col matrix is never materialised: for every
-// (tap, 64-channel chunk) the TMA engine loads the shifted 4-D box straight from the activation
-// tensor into shared memory in the 128-byte-swizzled K-major layout tcgen05.mma consumes, and its
-// out-of-bounds zero fill IS the 'same' padding.  Stride-2 convolutions use up to four parity views
-// of the input (one tensor map per (row parity, column parity)), each again a plain tiled map.
+// GEMM view of the convolution:  D[m, n] = sum_{tap, c} A_tap[m, c] * W[tap][n][c]
+// where m runs over a (bn x bh x bw) box of output pixels (bn*bh*bw = 128) and A_tap is the NHWC input box
+// shifted by the tap offset (dy, dx).  The im2col matrix is never materialised: for every (tap, 64-channel
+// chunk) the TMA engine loads the shifted 4-D box straight from the activation tensor into shared memory in
+// the 128-byte-swizzled K-major layout tcgen05.mma consumes, and its out-of-bounds zero fill IS the 'same'
+// padding (and the channel padding when Cin is not a multiple of 64).  Stride-2 convolutions use up to four
+// parity views of the input (one tensor map per (row parity, column parity)), each again a plain tiled map.
 //
-// Roles (128 threads): warp 0 lane 0 = TMA producer, warp 1 lane 0 = MMA issuer (+ TMEM alloc by
-// warp 1), then all four warps run the epilogue: tcgen05.ld the fp32 accumulators (warp w owns TMEM
-// lanes 32w..32w+31 = tile rows), add bias (BatchNorm folded), optional ReLU / residual / ReLU, pack
-// to h16 and store 16-byte vectors into the destination channel slice (concat elision; pixel
-// scatter for the sub-pixel transposed convolutions).
+// Persistent kernel, one CTA per SM, 192 threads, warp-specialised:
+//   warp 0 (one lane)  TMA producer: A box + W tile per k-block into a ring of shared-memory stages
+//   warp 1 (one lane)  MMA issuer: tcgen05.mma kind::f16 (fp16 x fp16 -> fp32) into one of TWO TMEM accumulator
+//                      stages; tcgen05.commit releases the smem stage / publishes the accumulator
+//   warps 2-5          epilogue: tcgen05.ld the finished accumulator (warp w owns TMEM lanes 32*(w%4)..+31 =
+//                      tile rows), + bias (BatchNorm folded) / ReLU / residual / ReLU, pack to fp16 into a
+//                      swizzled staging tile and hand it to a TMA STORE (full-line writes, ragged tiles and the
+//                      destination channel slice clipped by the tensor map; the sub-pixel scatter of the
+//                      transposed convolutions is a strided output map).  fp32 outputs (2-channel logits,
+//                      1-channel gates) are stored directly.
+// so the epilogue of tile i overlaps the main loop of tile i+1.
 #pragma once
 #include <algorithm>
 #include <cstdio>
@@ -25,24 +30,38 @@ namespace bd {
 namespace umma {
 
 constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 64;  // h16 elements = one 128-byte swizzle row
+constexpr int BLOCK_K = 64;  // fp16 elements = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
-constexpr int MAX_TAPS = 9;
+constexpr int OUT_CHUNK = 64;                             // channels per staging tile / TMA store
+constexpr int OUT_STAGE_BYTES = BLOCK_M * OUT_CHUNK * 2;  // 16 KB
+constexpr int MAX_TAPS = 18;
+constexpr int THREADS = 192;
 
 struct Params {
-  int N, Ho, Wo, Cout;
+  int N, Ho, Wo, Cout, Cin;
   int bw, bh, bn;
-  int tiles_w, tiles_h, tiles_n, n_tiles;
+  int tiles_w, tiles_h, tiles_n, n_tiles, total_tiles;
   int block_n, kchunks, ntaps, stages, tmem_cols;
   int tap_map[MAX_TAPS], tap_dy[MAX_TAPS], tap_dx[MAX_TAPS];
-  h16* y;
+  float* y32;  // fp32 output path (Cout <= 16): direct stores
   int y_ctot, y_c0, y_H, y_W, out_scale, out_oy, out_ox;
   const h16* res;
   int res_ctot, res_c0;
   const float* bias;
   int act_pre, act_post;
+  long long* trace;  // optional (debug): per-event clock64 of CTA 0, see tools/umma_trace.py
 };
+
+// event record (debug): role r owns trace[r*4096 ...]: [count, (a, b, clock) triples]; plain stores, no atomics
+constexpr int TRACE_PER_ROLE = 4096;
+__device__ __forceinline__ void trace_ev(const Params& p, int role, int& idx, int a, int b) {
+  if (p.trace && blockIdx.x == 0 && idx < 1300) {
+    long long* e = p.trace + role * TRACE_PER_ROLE + 1 + 3 * idx;
+    e[0] = a; e[1] = b; e[2] = clock64();
+    p.trace[role * TRACE_PER_ROLE] = ++idx;
+  }
+}
 
 // ------------------------------------------------------------------------------------------ PTX
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -54,11 +73,14 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// Bounded wait: a tile finishes in microseconds, so ~2^24 polls mean a protocol bug -> trap instead of
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a tile finishes in microseconds, so ~2^26 polls mean a protocol bug -> trap instead of
 // hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
-  for (uint32_t it = 0; it < (1u << 24); ++it) {
+  for (uint32_t it = 0; it < (1u << 26); ++it) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -86,8 +108,26 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm,
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -95,7 +135,7 @@ __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                            uint32_t accumulate) {
+                                           uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
@@ -133,37 +173,44 @@ __device__ __forceinline__ uint32_t make_idesc(int n) {
 
 __device__ __forceinline__ float apply_act(float v, int act) { return act == 1 ? fmaxf(v, 0.0f) : v; }
 
+// all tensor maps of one launch as a single kernel parameter: the producer selects the input parity view by
+// pointer arithmetic instead of a chain of selects
+struct alignas(64) Maps {
+  CUtensorMap a[4];
+  CUtensorMap b;
+  CUtensorMap y;
+};
+
 // ------------------------------------------------------------------------------------------ kernel
-__global__ void __launch_bounds__(128) conv_umma_kernel(const __grid_constant__ CUtensorMap tmA0,
-                                                        const __grid_constant__ CUtensorMap tmA1,
-                                                        const __grid_constant__ CUtensorMap tmA2,
-                                                        const __grid_constant__ CUtensorMap tmA3,
-                                                        const __grid_constant__ CUtensorMap tmB,
-                                                        const __grid_constant__ Params p) {
+// The producer and the MMA issuer are single threads executing dependent scalar code: every instruction in
+// their per-k-block loops costs several cycles of latency (a k-block's four N=64 MMAs take only 128 cycles), so
+// those loops keep their ring position incrementally and contain no integer division.
+__global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_constant__ Maps maps,
+                                                               const __grid_constant__ Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t b_bytes = static_cast<uint32_t>(p.block_n) * 128u;
   const uint32_t stage_bytes = A_STAGE_BYTES + b_bytes;
-  const uint32_t bar_base = smem_base + static_cast<uint32_t>(p.stages) * stage_bytes;  // 8-byte slots
-  const uint32_t full0 = bar_base, empty0 = bar_base + 8u * p.stages, accum_bar = bar_base + 16u * p.stages;
-  const uint32_t holder = accum_bar + 8u;
-  uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t out0 = smem_base + static_cast<uint32_t>(p.stages) * stage_bytes;  // 2 staging tiles
+  const uint32_t bar_base = out0 + 2u * OUT_STAGE_BYTES;                             // 8-byte slots
+  const uint32_t full0 = bar_base, empty0 = bar_base + 8u * p.stages;
+  const uint32_t tfull0 = bar_base + 16u * p.stages, tempty0 = tfull0 + 16u;
+  const uint32_t holder = tempty0 + 16u;
   volatile uint32_t* holder_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (holder - smem_base));
-
-  const int nt = blockIdx.x % p.n_tiles;
-  const int mt = blockIdx.x / p.n_tiles;
-  const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
-  const int n_base = nt * p.block_n;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(full0 + 8u * s, 1);
       mbar_init(empty0 + 8u * s, 1);
     }
-    mbar_init(accum_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull0 + 8u * a, 1);
+      mbar_init(tempty0 + 8u * a, 4);  // one arrival per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    fence_async_smem();
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(holder), "r"(p.tmem_cols)
@@ -175,83 +222,161 @@ __global__ void __launch_bounds__(128) conv_umma_kernel(const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *holder_ptr;
 
-  const int num_kb = p.ntaps * p.kchunks;
-  if (warp == 0 && lane == 0) {
-    // ---------------- TMA producer
-    prefetch_tmap(&tmA0);
-    prefetch_tmap(&tmB);
-    const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
-    for (int kb = 0; kb < num_kb; ++kb) {
-      const int s = kb % p.stages;
-      const uint32_t ph = (kb / p.stages) & 1;
-      mbar_wait(empty0 + 8u * s, ph ^ 1u);
-      const uint32_t fb = full0 + 8u * s;
-      mbar_expect_tx(fb, stage_bytes);
-      const int tap = kb / p.kchunks, kc = kb - tap * p.kchunks;
-      const int m = p.tap_map[tap];
-      const CUtensorMap* tm = (m == 0) ? &tmA0 : (m == 1) ? &tmA1 : (m == 2) ? &tmA2 : &tmA3;
-      const uint32_t a_s = smem_base + s * stage_bytes;
-      tma_load_4d(a_s, tm, fb, kc * BLOCK_K, w0 + p.tap_dx[tap], h0 + p.tap_dy[tap], n0);
-      tma_load_3d(a_s + A_STAGE_BYTES, &tmB, fb, kc * BLOCK_K, n_base, tap);
-    }
-  } else if (warp == 1 && lane == 0) {
-    // ---------------- MMA issuer
-    const uint32_t idesc = make_idesc(p.block_n);
-    for (int kb = 0; kb < num_kb; ++kb) {
-      const int s = kb % p.stages;
-      const uint32_t ph = (kb / p.stages) & 1;
-      mbar_wait(full0 + 8u * s, ph);
-      tc_fence_after();
-      const uint32_t a_s = smem_base + s * stage_bytes;
-      const uint64_t adesc = make_sdesc(a_s), bdesc = make_sdesc(a_s + A_STAGE_BYTES);
-#pragma unroll
-      for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-        // advance 16 h16 = 32 bytes inside the swizzle atom: +2 in the (addr >> 4) field
-        tc_mma_f16(tmem_base, adesc + 2u * k, bdesc + 2u * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-      }
-      tc_commit(empty0 + 8u * s);  // frees the smem stage once these MMAs have read it
-    }
-    tc_commit(accum_bar);  // accumulators complete
-  }
-  __syncwarp();
+  int tr_i = 0, tr_j = 0;  // debug trace cursors
 
-  // ---------------- epilogue (all 4 warps)
-  mbar_wait(accum_bar, 0);
-  tc_fence_after();
-  const int r = warp * 32 + lane;  // tile row = TMEM lane
-  const int wl = r % p.bw, hl = (r / p.bw) % p.bh, nl = r / (p.bw * p.bh);
-  const int ow = tw * p.bw + wl, oh = th * p.bh + hl, on = tn * p.bn + nl;
-  const bool pix_ok = (ow < p.Wo) && (oh < p.Ho) && (on < p.N);
-  const size_t ypix = (static_cast<size_t>(on) * p.y_H + (oh * p.out_scale + p.out_oy)) * p.y_W +
-                      (ow * p.out_scale + p.out_ox);
-  h16* yrow = p.y + ypix * p.y_ctot + p.y_c0;
-  const h16* rrow = p.res ? p.res + ypix * p.res_ctot + p.res_c0 : nullptr;
-  const uint32_t trow = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-  for (int c0 = 0; c0 < p.block_n; c0 += 16) {
-    uint32_t acc[16];
-    tmem_ld16(trow + c0, acc);
-    tmem_ld_wait();
-    const int ch0 = n_base + c0;
-    if (pix_ok && ch0 < p.Cout) {
-#pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        const int ch = ch0 + 8 * g;
-        if (ch < p.Cout) {
-          float v[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = apply_act(__uint_as_float(acc[8 * g + j]) + __ldg(p.bias + ch + j), p.act_pre);
-          if (rrow) {
-            float rf[8];
-            unpack8(*reinterpret_cast<const h16x8*>(rrow + ch), rf);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] += rf[j];
+  // Warps 0 and 1 run their loops with all 32 lanes (every value is warp-uniform, so the compiler keeps the ring
+  // state in uniform registers next to the UTMALDG / UTCHMMA operands); one elected lane issues.
+  if (warp == 0) {
+    // ---------------- TMA producer
+    uint32_t s = 0, ph = 0, a_s = smem_base, fb = full0, eb = empty0;  // ring position, kept incrementally
+    const char* maps_a = reinterpret_cast<const char*>(&maps.a[0]);
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      int nt = 0, mt = tile;
+      if (p.n_tiles > 1) { nt = tile % p.n_tiles; mt = tile / p.n_tiles; }
+      const int tw = mt % p.tiles_w, t2 = mt / p.tiles_w;
+      const int th = t2 % p.tiles_h, tn = t2 / p.tiles_h;
+      const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn, n_base = nt * p.block_n;
+      for (int tap = 0; tap < p.ntaps; ++tap) {
+        const CUtensorMap* tm = reinterpret_cast<const CUtensorMap*>(maps_a + p.tap_map[tap] * sizeof(CUtensorMap));
+        const int cx = w0 + p.tap_dx[tap], cy = h0 + p.tap_dy[tap];
+        for (int c = 0; c < p.Cin; c += BLOCK_K) {
+          mbar_wait(eb, ph ^ 1u);
+          if (elect_one()) {
+            trace_ev(p, 0, tr_i, tile, tap);
+            mbar_expect_tx(fb, stage_bytes);
+            tma_load_4d(a_s, tm, fb, c, cx, cy, n0);
+            tma_load_3d(a_s + A_STAGE_BYTES, &maps.b, fb, c, n_base, tap);
           }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], p.act_post);
-          *reinterpret_cast<h16x8*>(yrow + ch) = pack8(v);
+          __syncwarp();
+          if (++s == static_cast<uint32_t>(p.stages)) { s = 0; ph ^= 1u; a_s = smem_base; fb = full0; eb = empty0; }
+          else { a_s += stage_bytes; fb += 8u; eb += 8u; }
         }
       }
     }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer
+    const uint32_t idesc = make_idesc(p.block_n);
+    const uint64_t desc0 = make_sdesc(smem_base);
+    const uint32_t dstage = stage_bytes >> 4;  // descriptor start-address field counts 16-byte units
+    uint32_t s = 0, ph = 0, doff = 0, fb = full0, eb = empty0, ti = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
+      const uint32_t a = ti & 1u, aph = (ti >> 1) & 1u;
+      mbar_wait(tempty0 + 8u * a, aph ^ 1u);  // epilogue has drained this accumulator stage
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + a * static_cast<uint32_t>(p.block_n);
+      uint32_t accum = 0;
+      for (int tap = 0; tap < p.ntaps; ++tap) {
+        for (int c = p.Cin; c > 0; c -= BLOCK_K) {  // c = channels left in this tap
+          mbar_wait(fb, ph);
+          tc_fence_after();
+          if (elect_one()) {
+            trace_ev(p, 1, tr_i, tile, tap);
+            const uint64_t adesc = desc0 + doff, bdesc = adesc + (A_STAGE_BYTES >> 4);
+            // 16 fp16 = 32 bytes inside the swizzle atom per MMA: +2 in the (addr >> 4) field
+            tc_mma_f16(tacc, adesc, bdesc, idesc, accum);
+            if (c > 16) tc_mma_f16(tacc, adesc + 2u, bdesc + 2u, idesc, 1u);
+            if (c > 32) tc_mma_f16(tacc, adesc + 4u, bdesc + 4u, idesc, 1u);
+            if (c > 48) tc_mma_f16(tacc, adesc + 6u, bdesc + 6u, idesc, 1u);
+            tc_commit(eb);  // frees the smem stage once these MMAs have read it
+          }
+          __syncwarp();
+          accum = 1u;
+          if (++s == static_cast<uint32_t>(p.stages)) { s = 0; ph ^= 1u; doff = 0; fb = full0; eb = empty0; }
+          else { doff += dstage; fb += 8u; eb += 8u; }
+        }
+      }
+      if (elect_one()) tc_commit(tfull0 + 8u * a);  // accumulator complete
+      __syncwarp();
+    }
+  } else {
+    // ---------------- epilogue warps 2..5
+    const int q = warp & 3;             // TMEM lane quadrant this warp may access
+    const int r = q * 32 + lane;        // tile row = TMEM lane
+    const int et = threadIdx.x - 64;    // 0..127
+    const int wl = r % p.bw, hl = (r / p.bw) % p.bh, nl = r / (p.bw * p.bh);
+    uint32_t ti = 0, ob = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
+      const uint32_t a = ti & 1u, aph = (ti >> 1) & 1u;
+      const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+      const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
+      const int n_base = nt * p.block_n;
+      const int ow = tw * p.bw + wl, oh = th * p.bh + hl, on = tn * p.bn + nl;
+      const bool pix_ok = (ow < p.Wo) && (oh < p.Ho) && (on < p.N);
+      const size_t ypix = (static_cast<size_t>(on) * p.y_H + (oh * p.out_scale + p.out_oy)) * p.y_W +
+                          (ow * p.out_scale + p.out_ox);
+      const h16* rrow = (p.res && pix_ok) ? p.res + ypix * p.res_ctot + p.res_c0 : nullptr;
+      mbar_wait(tfull0 + 8u * a, aph);
+      tc_fence_after();
+      if (et == 0) trace_ev(p, 2, tr_i, tile, 0);
+      const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * static_cast<uint32_t>(p.block_n);
+      if (p.y32) {
+        // fp32 output (logits / gate maps, Cout <= 16): one 16-column read, direct coalesced stores
+        uint32_t acc[16];
+        tmem_ld16(trow, acc);
+        tmem_ld_wait();
+        if (pix_ok) {
+          float* yrow = p.y32 + ypix * p.y_ctot + p.y_c0;
+#pragma unroll
+          for (int c = 0; c < 16; ++c)
+            if (c < p.Cout) {
+              const float v = apply_act(__uint_as_float(acc[c]) + __ldg(p.bias + c), p.act_pre);
+              yrow[c] = apply_act(v, p.act_post);
+            }
+        }
+      } else {
+        for (int c0 = 0; c0 < p.block_n; c0 += OUT_CHUNK, ob ^= 1u) {
+          const int cw = min(OUT_CHUNK, p.block_n - c0);
+          // the TMA store that last read this staging tile must have finished reading it
+          if (et == 0) tma_store_wait_read<1>();
+          epi_bar_sync();
+          uint8_t* srow = gen_base + (out0 - smem_base) + ob * OUT_STAGE_BYTES + r * 128;
+          for (int cc = 0; cc < cw; cc += 16) {
+            uint32_t acc[16];
+            tmem_ld16(trow + c0 + cc, acc);
+            tmem_ld_wait();
+            const int ch0 = n_base + c0 + cc;
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              const int ch = ch0 + 8 * g;
+              float v[8];
+              if (ch < p.Cout) {  // Cout is a multiple of 8 on this path
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + ch));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + ch + 4));
+                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = apply_act(__uint_as_float(acc[8 * g + j]) + bb[j], p.act_pre);
+                if (rrow) {
+                  float rf[8];
+                  unpack8(*reinterpret_cast<const h16x8*>(rrow + ch), rf);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) v[j] += rf[j];
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], p.act_post);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = 0.0f;
+              }
+              // 128-byte-swizzled staging row: 16-byte chunk index XOR (row % 8)
+              const int chunk = ((cc >> 3) + g) ^ (r & 7);
+              *reinterpret_cast<h16x8*>(srow + chunk * 16) = pack8(v);
+            }
+          }
+          fence_async_smem();
+          epi_bar_sync();
+          if (et == 0) {
+            tma_store_4d(&maps.y, out0 + ob * OUT_STAGE_BYTES, n_base + c0, tw * p.bw, th * p.bh, tn * p.bn);
+            tma_store_commit();
+          }
+        }
+      }
+      if (et == 0) trace_ev(p, 3, tr_j, tile, 0);
+      // accumulator stage drained: let the MMA warp reuse it
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty0 + 8u * a);
+    }
+    if (et == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -277,10 +402,10 @@ inline EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// h16 tensor map, 128-byte swizzle, zero OOB fill.  dims/strides innermost first; strides[i] is the
+// fp16 tensor map, 128-byte swizzle, zero OOB fill.  dims/strides innermost first; strides[i] is the
 // byte stride of dim i+1.
 inline int encode_h16(CUtensorMap* tm, void* base, int rank, const uint64_t* dims, const uint64_t* strides,
-                       const uint32_t* box) {
+                      const uint32_t* box) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail("cuTensorMapEncodeTiled entry point not available");
   cuuint64_t gd[5], gs[5];
@@ -298,7 +423,7 @@ inline int encode_h16(CUtensorMap* tm, void* base, int rank, const uint64_t* dim
 }
 
 struct Launch {
-  CUtensorMap tmA[4], tmB;
+  Maps maps;
   Params p;
   dim3 grid;
   int smem_bytes;
@@ -310,35 +435,44 @@ inline int floor_pow2(int v) {
   return r;
 }
 
-// x: input view, y: output view (h16 both).  w_dev: [ntaps][Cout][Cin] h16.
+// x: input view (fp16), y: output view (fp16, or fp32 with at most 16 channels).  w_dev: [ntaps][Cout][Cin] fp16.
 inline int prepare(Launch* L, const TView& x, const TView& y, const TView* res, int ntaps, const int* dy,
                    const int* dx, int stride, int Ho, int Wo, int act_pre, int act_post, int out_scale, int out_oy,
-                   int out_ox, const h16* w_dev, const float* bias_dev, int smem_budget_kb, int max_block_n) {
+                   int out_ox, const h16* w_dev, const float* bias_dev, int smem_budget_kb, int max_block_n,
+                   int num_sms) {
   const int Cin = x.c, Cout = y.c;
-  BD_CHECK(!x.f32 && !y.f32, "umma conv needs h16 maps");
-  BD_CHECK(Cin % 8 == 0 && Cout % 8 == 0 && x.c0 % 8 == 0 && x.ctot % 8 == 0 && y.c0 % 8 == 0 && y.ctot % 8 == 0,
-           "umma conv needs 16-byte aligned channel slices");
+  BD_CHECK(!x.f32, "umma conv needs an fp16 input map");
+  BD_CHECK(Cin % 8 == 0 && x.c0 % 8 == 0 && x.ctot % 8 == 0, "umma conv needs 16-byte aligned input channel slices");
+  if (y.f32) BD_CHECK(Cout <= 16 && res == nullptr && out_scale == 1, "fp32 umma output: at most 16 channels, no residual");
+  else BD_CHECK(Cout % 8 == 0 && y.c0 % 8 == 0 && y.ctot % 8 == 0, "umma conv needs 16-byte aligned output channel slices");
   BD_CHECK(stride == 1 || stride == 2, "umma conv stride must be 1 or 2");
   BD_CHECK(ntaps >= 1 && ntaps <= MAX_TAPS, "bad tap count");
   Params& p = L->p;
   memset(&p, 0, sizeof(p));
-  p.N = x.N; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout;
+  p.N = x.N; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout; p.Cin = Cin;
   p.bw = std::min(16, floor_pow2(Wo));
   p.bh = std::min(BLOCK_M / p.bw, floor_pow2(Ho));
   p.bn = BLOCK_M / (p.bw * p.bh);
   p.tiles_w = cdiv(Wo, p.bw); p.tiles_h = cdiv(Ho, p.bh); p.tiles_n = cdiv(x.N, p.bn);
   const int cout16 = cdiv(Cout, 16) * 16;
-  const int ntile = cdiv(cout16, max_block_n);
-  p.block_n = cdiv(cdiv(cout16, ntile), 16) * 16;
+  if (cout16 <= max_block_n) {
+    p.block_n = cout16;  // a single N tile; staging chunks that overhang Cout are clipped by the output map
+  } else {
+    // several N tiles: multiples of 64 so that no staging chunk spills into the next tile's channels
+    const int cap = std::max(64, max_block_n / 64 * 64);
+    const int ntile = cdiv(cout16, cap);
+    p.block_n = std::min(cap, cdiv(cdiv(cout16, ntile), 64) * 64);
+  }
   p.n_tiles = cdiv(Cout, p.block_n);
   p.kchunks = cdiv(Cin, BLOCK_K);
   p.ntaps = ntaps;
   p.tmem_cols = 32;
-  while (p.tmem_cols < p.block_n) p.tmem_cols *= 2;
+  while (p.tmem_cols < 2 * p.block_n) p.tmem_cols *= 2;
   const int stage_bytes = A_STAGE_BYTES + p.block_n * 128;
-  p.stages = std::max(2, std::min(8, (smem_budget_kb * 1024 - 2048) / stage_bytes));
-  p.stages = std::min(p.stages, std::max(2, ntaps * p.kchunks));
-  L->smem_bytes = p.stages * stage_bytes + 1024 + 256;
+  const int fixed = 2 * OUT_STAGE_BYTES + 1024 + 1024;  // staging tiles, alignment slack, barriers + tap table
+  p.stages = std::max(2, std::min(12, (smem_budget_kb * 1024 - fixed) / stage_bytes));
+  p.stages = std::min(p.stages, std::max(2, 2 * ntaps * p.kchunks));
+  L->smem_bytes = p.stages * stage_bytes + fixed;
   BD_CHECK(L->smem_bytes <= 227 * 1024, "umma conv smem budget exceeded");
 
   // parity views of the input for stride 2 (a single plain view for stride 1)
@@ -362,26 +496,40 @@ inline int prepare(Launch* L, const TView& x, const TView& y, const TView* res, 
     uint64_t strides[3] = {pitch * stride, pitch * x.W * stride, pitch * x.W * x.H};
     uint32_t box[4] = {BLOCK_K, static_cast<uint32_t>(p.bw), static_cast<uint32_t>(p.bh), static_cast<uint32_t>(p.bn)};
     char* base = static_cast<char*>(x.base) + (static_cast<size_t>(py) * x.W + px) * pitch + static_cast<size_t>(x.c0) * 2;
-    if (encode_h16(&L->tmA[m], base, 4, dims, strides, box)) return 1;
+    if (encode_h16(&L->maps.a[m], base, 4, dims, strides, box)) return 1;
     if (first < 0) first = m;
   }
   for (int m = 0; m < 4; ++m)
-    if (!used[m]) L->tmA[m] = L->tmA[first];
+    if (!used[m]) L->maps.a[m] = L->maps.a[first];
   {
     uint64_t dims[3] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(Cout), static_cast<uint64_t>(ntaps)};
     uint64_t strides[2] = {static_cast<uint64_t>(Cin) * 2, static_cast<uint64_t>(Cin) * Cout * 2};
     uint32_t box[3] = {BLOCK_K, static_cast<uint32_t>(p.block_n), 1};
-    if (encode_h16(&L->tmB, const_cast<h16*>(w_dev), 3, dims, strides, box)) return 1;
+    if (encode_h16(&L->maps.b, const_cast<h16*>(w_dev), 3, dims, strides, box)) return 1;
   }
-  p.y = static_cast<h16*>(y.base);
   p.y_ctot = y.ctot; p.y_c0 = y.c0; p.y_H = y.H; p.y_W = y.W;
   p.out_scale = out_scale; p.out_oy = out_oy; p.out_ox = out_ox;
+  if (y.f32) {
+    p.y32 = static_cast<float*>(y.base);
+    L->maps.y = L->maps.b;  // unused
+  } else {
+    // output map over the destination channel slice; the sub-pixel phases of a transposed convolution are a
+    // strided view (every out_scale-th pixel starting at (out_oy, out_ox))
+    const uint64_t ypitch = static_cast<uint64_t>(y.ctot) * 2;
+    uint64_t dims[4] = {static_cast<uint64_t>(Cout), static_cast<uint64_t>(Wo), static_cast<uint64_t>(Ho),
+                        static_cast<uint64_t>(x.N)};
+    uint64_t strides[3] = {ypitch * out_scale, ypitch * y.W * out_scale, ypitch * y.W * y.H};
+    uint32_t box[4] = {OUT_CHUNK, static_cast<uint32_t>(p.bw), static_cast<uint32_t>(p.bh), static_cast<uint32_t>(p.bn)};
+    char* base = static_cast<char*>(y.base) + (static_cast<size_t>(out_oy) * y.W + out_ox) * ypitch + static_cast<size_t>(y.c0) * 2;
+    if (encode_h16(&L->maps.y, base, 4, dims, strides, box)) return 1;
+  }
   if (res) {
     BD_CHECK(!res->f32 && res->c0 % 8 == 0 && res->ctot % 8 == 0 && out_scale == 1, "bad residual view");
     p.res = static_cast<const h16*>(res->base); p.res_ctot = res->ctot; p.res_c0 = res->c0;
   }
   p.bias = bias_dev; p.act_pre = act_pre; p.act_post = act_post;
-  L->grid = dim3(static_cast<unsigned>(p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles));
+  p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
+  L->grid = dim3(static_cast<unsigned>(std::min(p.total_tiles, num_sms)));
   return 0;
 }
 
@@ -391,7 +539,7 @@ inline int launch(const Launch& L, cudaStream_t stream) {
     BD_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  conv_umma_kernel<<<L.grid, 128, L.smem_bytes, stream>>>(L.tmA[0], L.tmA[1], L.tmA[2], L.tmA[3], L.tmB, L.p);
+  conv_umma_kernel<<<L.grid, THREADS, L.smem_bytes, stream>>>(L.maps, L.p);
   BD_CUDA(cudaGetLastError());
   return 0;
 }

@@ -411,25 +411,36 @@ __global__ void __launch_bounds__(TPB) softmax2_kernel(const float* __restrict__
 }
 
 // ---------------------------------------------------------------------------------- tiler / stitcher
-// predict.py:91-108: BGR->RGB, x/127.5-1 in float64 (then Keras casts to float32), zero pad in normalised space.
+// Network input layout: fp16, 8 channels per pixel (one 16-byte vector): [255*r, 255*g, 255*b, 0, 0, 0, 0, 0].
+// predict.py:91-108 computes x = pixel/127.5 - 1 (float64, cast to float32 by Keras) and zero-pads in normalised
+// space; 255*x = 2*pixel - 255 is an integer in [-255, 255], exact in fp16, and the first convolution of every
+// network carries the 1/255 in its weights.
 __global__ void __launch_bounds__(TPB) tiles_gather_kernel(const uint8_t* __restrict__ scene, int H, int W,
                                                            const int* __restrict__ ys, const int* __restrict__ xs,
-                                                           int n, float* __restrict__ out) {
+                                                           int n, h16* __restrict__ out) {
   const size_t total = static_cast<size_t>(n) * 512 * 512;
   for (size_t idx = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; idx < total;
        idx += static_cast<size_t>(gridDim.x) * TPB) {
     const int tx = static_cast<int>(idx % 512), ty = static_cast<int>((idx / 512) % 512);
     const int t = static_cast<int>(idx / (512 * 512));
     const int y = ys[t] + ty, x = xs[t] + tx;
-    float r = 0.0f, g = 0.0f, b = 0.0f;
+    float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (y < H && x < W) {
-      const uint8_t* px = scene + (static_cast<size_t>(y) * W + x) * 3;
-      b = static_cast<float>(static_cast<double>(px[0]) / 127.5 - 1.0);
-      g = static_cast<float>(static_cast<double>(px[1]) / 127.5 - 1.0);
-      r = static_cast<float>(static_cast<double>(px[2]) / 127.5 - 1.0);
+      const uint8_t* px = scene + (static_cast<size_t>(y) * W + x) * 3;  // BGR -> RGB
+      f[0] = static_cast<float>(2 * static_cast<int>(px[2]) - 255);
+      f[1] = static_cast<float>(2 * static_cast<int>(px[1]) - 255);
+      f[2] = static_cast<float>(2 * static_cast<int>(px[0]) - 255);
     }
-    float* o = out + idx * 3;
-    o[0] = r; o[1] = g; o[2] = b;
+    *reinterpret_cast<h16x8*>(out + idx * 8) = pack8(f);
+  }
+}
+// model.predict(x) path: fp32 (N,H,W,3) in [-1,1] -> the layout above (255*x rounded to fp16)
+__global__ void __launch_bounds__(TPB) input_convert_kernel(const float* __restrict__ x, size_t npix, h16* __restrict__ out) {
+  for (size_t idx = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; idx < npix;
+       idx += static_cast<size_t>(gridDim.x) * TPB) {
+    float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    f[0] = x[idx * 3] * 255.0f; f[1] = x[idx * 3 + 1] * 255.0f; f[2] = x[idx * 3 + 2] * 255.0f;
+    *reinterpret_cast<h16x8*>(out + idx * 8) = pack8(f);
   }
 }
 // predict.py:113-114: scene[y,x] = 255 where any covering tile predicts class 1 (all writers store 255).

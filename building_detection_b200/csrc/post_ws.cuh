@@ -27,12 +27,13 @@ struct bd_ctx {
   int device = 0;
   int num_sms = 148;
   int64_t launches = 0;
-  int umma_smem_kb = 99;    // per-CTA smem budget of the tcgen05 conv (2 CTAs / SM by default)
+  int umma_smem_kb = 200;   // per-CTA smem budget of the persistent tcgen05 conv (1 CTA / SM)
   int umma_max_block_n = 256;
   int* d_ys = nullptr;      // tile origin scratch
   int* d_xs = nullptr;
   int tile_cap = 0;
   bd::post::Workspace post_ws;
+  void* trace_buf = nullptr;  // BD_UMMA_TRACE debug buffer of the most recently built conv
 };
 
 namespace bd {

@@ -25,6 +25,8 @@ from dataclasses import dataclass, field
 import numpy as np
 
 BN_EPS = 1e-3  # Keras BatchNormalization default
+INPUT_C = 8          # the 3-channel network input is stored as 8 fp16 channels (one 16-byte vector per pixel)
+INPUT_SCALE = 255.0  # ... holding 255 * x
 
 # op codes shared with csrc/bd_api.cu (enum bd_op_kind in include/bd_b200.h)
 OP_CONV, OP_DWCONV, OP_MAXPOOL, OP_ADDN, OP_GAP, OP_DENSE, OP_GATE, OP_SKFUSE, OP_BCAST, OP_SOFTMAX2 = range(10)
@@ -65,10 +67,19 @@ class Buf:
 
 @dataclass
 class T:
-    """Channel-slice view [c0, c0+C) of a map buffer."""
+    """Channel-slice view [c0, c0+C) of a map buffer.  ``ctrue`` < C marks zero-padded channels (the network
+    input is stored as 8 channels, BAM's C/16-channel maps as multiples of 16, so that every convolution is a
+    tensor-core tile); ``wscale`` is folded into the weights of whatever convolution consumes the tensor (the
+    input buffer holds 255*x, exact integers for 8-bit imagery)."""
     buf: Buf
     c0: int
     C: int
+    ctrue: int = -1
+    wscale: float = 1.0
+
+    @property
+    def cin(self):
+        return self.C if self.ctrue < 0 else self.ctrue
 
     @property
     def H(self):
@@ -147,7 +158,10 @@ class Net:
         return V(self.buf(1, 1, C, "f32", "vec"))
 
     def input(self, H=512, W=512, C=3):
-        t = self.new(H, W, C, "f32")
+        """Network input: fp16, padded to 8 channels, holding 255 * x for x in [-1, 1] (= 2*pixel - 255 exactly for
+        8-bit imagery normalised as predict.py:93 does); the first convolution's weights carry the 1/255."""
+        assert C <= INPUT_C
+        t = T(self.buf(H, W, INPUT_C, "f16"), 0, INPUT_C, ctrue=C, wscale=1.0 / INPUT_SCALE)
         self.plan.input = t.buf.id
         return t
 
@@ -156,7 +170,7 @@ class Net:
 
     # ------------------------------------------------------------------ CONV
     def _conv_op(self, x, w_tco, bias, taps, stride, Ho, Wo, act_pre, res, act_post, out,
-                 out_scale=1, out_oy=0, out_ox=0, name=""):
+                 out_scale=1, out_oy=0, out_ox=0, name="", macs_per_pixel=None):
         """w_tco: (ntaps, Cout, Cin) fp32 (BN already folded)."""
         nt, cout, cin = w_tco.shape
         assert cin == x.C and len(taps) == nt
@@ -164,12 +178,16 @@ class Net:
         if res is not None:
             assert res.C == cout and res.H == out.H and res.W == out.W and out_scale == 1
         path = "direct"
-        if (self.umma and stride in (1, 2) and x.buf.dtype == "f16" and out.buf.dtype == "f16"
-                and cin % 8 == 0 and cin >= 16 and cout % 8 == 0 and cout >= 16
-                and x.c0 % 8 == 0 and x.buf.C % 8 == 0 and out.c0 % 8 == 0 and out.buf.C % 8 == 0
-                and Wo >= 8 and (res is None or (res.c0 % 8 == 0 and res.buf.C % 8 == 0))):
-            path = "umma"
-        self.plan.flops += 2 * self.plan.batch * Ho * Wo * cout * cin * nt
+        if (self.umma and stride in (1, 2) and x.buf.dtype == "f16" and cin % 8 == 0 and x.c0 % 8 == 0
+                and x.buf.C % 8 == 0 and Wo >= 8):
+            if out.buf.dtype == "f16":
+                if (cout % 8 == 0 and out.c0 % 8 == 0 and out.buf.C % 8 == 0
+                        and (res is None or (res.c0 % 8 == 0 and res.buf.C % 8 == 0))):
+                    path = "umma"
+            elif cout <= 16 and res is None and out_scale == 1:
+                path = "umma"  # fp32 logits / gate maps: one 16-column tile, direct stores
+        # algorithmic work: true (unpadded) channel counts
+        self.plan.flops += 2 * self.plan.batch * Ho * Wo * (cout * cin * nt if macs_per_pixel is None else macs_per_pixel)
         self._emit(op=OP_CONV, name=name, path=path, x=x.ref(), y=out.ref(),
                    res=None if res is None else res.ref(),
                    taps=[(int(dy), int(dx)) for dy, dx in taps], stride=stride, Ho=Ho, Wo=Wo,
@@ -179,18 +197,26 @@ class Net:
                    w32=np.ascontiguousarray(w_tco, np.float32) if self.keep_f32 else None)
 
     def conv(self, x, name, cout, k=1, s=1, d=1, bn=False, act=None, res=None, res_after_act=False,
-             out=None, f32_out=False, he=False):
+             out=None, f32_out=False, he=False, cout_pad=None):
         """Conv2D(padding='same') [+BN] [+ReLU] [+res] [+ReLU].
 
         act applies to conv(+BN).  With ``res`` the result is ``act(conv + res)`` or, when
         ``res_after_act`` (res34's res_block1, res34.py:40-45), ``relu(act(conv) + res)``."""
-        kern = self._get(name + "/k", (k, k, x.C, cout), "he_normal" if he else "glorot_uniform")
+        kern = self._get(name + "/k", (k, k, x.cin, cout), "he_normal" if he else "glorot_uniform")
         bias = self._get(name + "/b", (cout,), "zeros")
-        w = kern.reshape(k * k, x.C, cout).transpose(0, 2, 1).copy()  # (taps, Cout, Cin)
+        w = kern.reshape(k * k, x.cin, cout).transpose(0, 2, 1).copy()  # (taps, Cout, Cin)
         if bn:
             sc, sh = self._bn(bn if isinstance(bn, str) else name + "_bn", cout)
             w = w * sc[None, :, None]
             bias = bias * sc + sh
+        w = w * np.float32(x.wscale)
+        cout_true = cout
+        if x.cin != x.C or cout_pad:  # zero weights for padded input channels / padded output channels
+            cout = max(cout, cout_pad or 0)
+            wp = np.zeros((k * k, cout, x.C), np.float32)
+            wp[:, :cout_true, :x.cin] = w
+            w = wp
+            bias = np.concatenate([bias, np.zeros(cout - cout_true, np.float32)])
         Ho, Wo = math.ceil(x.H / s), math.ceil(x.W / s)
         pt, _ = same_pad(x.H, k, s, d)
         pl, _ = same_pad(x.W, k, s, d)
@@ -204,7 +230,10 @@ class Net:
             act_pre, act_post = a, ACT_RELU
         else:
             act_pre, act_post = ACT_NONE, a
-        self._conv_op(x, w, bias, taps, s, Ho, Wo, act_pre, res, act_post, out, name=name)
+        self._conv_op(x, w, bias, taps, s, Ho, Wo, act_pre, res, act_post, out, name=name,
+                      macs_per_pixel=cout_true * x.cin * k * k)
+        if cout != cout_true:
+            out = T(out.buf, out.c0, out.C, ctrue=cout_true)
         return out
 
     def conv_transpose(self, x, name, cout, k, act=None, out=None):

@@ -6,16 +6,18 @@ from ..graph import Net, T
 
 def bam_attention(g: Net, x, name):
     """BAM block, bam.py:20-71: x * (1 + sigmoid(channel_gate(x) + spatial_gate(x))).
-    The C/16-channel spatial-gate convs (4..45 channels, dilation 4) are CUDA-core direct convs."""
+    The C/16-channel maps of the spatial gate (4..45 channels, dilation 4) are zero-padded to a multiple of 16
+    channels so that these convolutions are tensor-core tiles too; the 1-channel gate logits stay fp32."""
     r = x.C // 16
+    rp = -(-r // 16) * 16
     v = g.gap(x)
     v = g.dense([v], name + "_cg1", r, bn=name + "_cg1_bn", act="relu")
     v = g.dense([v], name + "_cg2", r, bn=name + "_cg2_bn", act="relu")
     cg = g.dense([v], name + "_cg3", x.C)
-    s = g.conv(x, name + "_sg1", r, k=1, bn=True, act="relu")
-    s = g.conv(s, name + "_sg2", r, k=3, d=4, bn=True, act="relu")
-    s = g.conv(s, name + "_sg3", r, k=3, d=4, bn=True, act="relu")
-    s = g.conv(s, name + "_sg4", 1, k=1)
+    s = g.conv(x, name + "_sg1", r, k=1, bn=True, act="relu", cout_pad=rp)
+    s = g.conv(s, name + "_sg2", r, k=3, d=4, bn=True, act="relu", cout_pad=rp)
+    s = g.conv(s, name + "_sg3", r, k=3, d=4, bn=True, act="relu", cout_pad=rp)
+    s = g.conv(s, name + "_sg4", 1, k=1, f32_out=True)
     return g.gate_bam(x, cg, s)
 
 

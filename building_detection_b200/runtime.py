@@ -41,6 +41,7 @@ _SIGS = {
     "bd_last_error": (C.c_char_p, []),
     "bd_version": (C.c_char_p, []),
     "bd_launch_count": (C.c_int64, [C.c_void_p]),
+    "bd_debug_read_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "bd_plan_create": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
     "bd_plan_destroy": (None, [C.c_void_p]),
     "bd_plan_add_buffer": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),

@@ -64,6 +64,11 @@ const char* bd_version(void);
 /* number of kernel launches issued by this library on this context so far */
 int64_t bd_launch_count(bd_ctx* ctx);
 
+/* debug: with BD_UMMA_TRACE=1 in the environment when a plan is finalized, CTA 0 of the most recently built
+ * tcgen05 conv records (tile, k-block, clock64) events per role; host_dst receives 4 x 4096 int64 (per role:
+ * count, then triples) */
+int bd_debug_read_trace(bd_ctx* ctx, long long* host_dst, int max_events);
+
 /* ---- network plans: replace tf.keras.Model construction + Model.predict (predict.py:17-54,109) */
 int bd_plan_create(bd_ctx* ctx, int batch, bd_plan** out);
 void bd_plan_destroy(bd_plan* plan);
@@ -92,11 +97,13 @@ int bd_plan_add_skfuse(bd_plan* plan, const bd_tref* xs4, int g_vec, const int32
                        const float* scale_host, const float* shift_host);
 /* broadcast a pooled vector over a map slice (UpSampling2D of a 1x1 map, v3plus.py:302-304) */
 int bd_plan_add_bcast(bd_plan* plan, int v_vec, bd_tref y);
-/* allocates the arena, uploads weights, encodes TMA tensor maps.  input_buf: fp32 (N,512,512,3) map;
+/* allocates the arena, uploads weights, encodes TMA tensor maps.  input_buf: fp16 (N,512,512,8) map holding
+ * [255*r, 255*g, 255*b, 0 x5] (what bd_tiles_gather writes; the first convolution's weights carry the 1/255);
  * logits_buf: fp32 2-channel map at 512/logits_up resolution. */
 int bd_plan_finalize(bd_plan* plan, int input_buf, int logits_buf, int logits_up);
-/* One forward of the whole network.  x_dev: fp32 NHWC in [-1,1], or NULL to use what is already in the
- * input buffer (e.g. written by bd_tiles_gather).  probs_dev: fp32 (N,512,512,2) or NULL;
+/* One forward of the whole network.  x_dev: fp32 (N,512,512,3) NHWC in [-1,1] as handed to model.predict
+ * (converted on the device into the input buffer), or NULL to use what is already in the input buffer (e.g.
+ * written by bd_tiles_gather).  probs_dev: fp32 (N,512,512,2) or NULL;
  * mask_dev: u8 (N,512,512), 1 where class 1 wins (argmax, ties -> class 0, predict.py:110) or NULL. */
 int bd_plan_run(bd_plan* plan, const float* x_dev, float* probs_dev, uint8_t* mask_dev, void* stream);
 /* only the softmax / argmax head (last op) on whatever the logits buffer currently holds */
@@ -117,11 +124,11 @@ int bd_plan_time_ops(bd_plan* plan, float* ms_out, void* stream);
 int bd_plan_op_info(bd_plan* plan, int i, int* kind, double* flops);
 
 /* ---- tiler / stitcher: replace predict.py:detection (90-116) ------------------------------- */
-/* Gather n 512x512 tiles whose top-left corners are (ys[i], xs[i]) from a BGR u8 scene (h,w,3) into
- * fp32 RGB (n,512,512,3) = pixel/127.5-1 (computed in double like predict.py:93), zero outside the
- * scene (predict.py:102-104 pads the *normalised* image with zeros). */
+/* Gather n 512x512 tiles whose top-left corners are (ys[i], xs[i]) from a BGR u8 scene (h,w,3) into the plan
+ * input layout: fp16 (n,512,512,8), channels [2r-255, 2g-255, 2b-255, 0 x5] = 255 * (pixel/127.5 - 1) exactly
+ * (predict.py:93), zero outside the scene (predict.py:102-104 pads the *normalised* image with zeros). */
 int bd_tiles_gather(bd_ctx* ctx, const uint8_t* scene_bgr_dev, int h, int w, const int32_t* ys_host,
-                    const int32_t* xs_host, int n, float* x_dev, void* stream);
+                    const int32_t* xs_host, int n, void* x_dev, void* stream);
 /* OR tile masks (n,512,512) into the scene mask (h,w): scene |= 255 where the tile says class 1
  * (predict.py:113-114: int8 accumulate then >=1 -> 255). */
 int bd_stitch_or(bd_ctx* ctx, const uint8_t* tile_masks_dev, const int32_t* ys_host, const int32_t* xs_host,

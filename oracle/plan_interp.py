@@ -164,7 +164,10 @@ class Interp:
 
     def run(self, x_nhwc=None):
         if x_nhwc is not None:
-            self.b[self.p.input][...] = torch.as_tensor(x_nhwc, dtype=torch.float32)
+            # the product stores the network input as 255 * x in fp16, zero-padded to graph.INPUT_C channels
+            xin = torch.as_tensor(np.asarray(x_nhwc), dtype=torch.float32) * G.INPUT_SCALE
+            self.b[self.p.input].zero_()
+            self.b[self.p.input][..., :xin.shape[-1]] = _q(xin) if self.emu else xin
         disp = {G.OP_CONV: self._conv, G.OP_DWCONV: self._dwconv, G.OP_MAXPOOL: self._maxpool,
                 G.OP_ADDN: self._addn, G.OP_GAP: self._gap, G.OP_DENSE: self._dense, G.OP_GATE: self._gate,
                 G.OP_SKFUSE: self._skfuse, G.OP_BCAST: self._bcast}

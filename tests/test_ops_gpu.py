@@ -84,6 +84,7 @@ DIRECT_CASES = {
     "3x3_d4_c4": dict(N=1, H=32, W=32, Cin=4, Cout=4, d=4),
     "3x3_d4_c45": dict(N=1, H=32, W=32, Cin=45, Cout=45, d=4),
     "1x1_to_1": dict(N=2, H=32, W=32, Cin=45, Cout=1, k=1, act=None, bn=False),
+    "3x3_tiny_map_4x4": dict(N=2, H=4, W=4, Cin=32, Cout=32),
     "3x3_res_after_act": dict(N=1, H=16, W=16, Cin=16, Cout=16, res=True, res_after_act=True),
 }
 
@@ -94,18 +95,39 @@ def test_conv_direct(gpu, case):
 
 
 def test_stem_conv_f32_input(gpu):
-    """3-channel fp32 network input -> 64 channels (res34.py:50, hrnet.py:168 stride 2)."""
+    """3-channel network input (stored as 8 fp16 channels holding 2*pixel-255) -> 64 channels on the tensor cores
+    (res34.py:50, hrnet.py:168 stride 2)."""
     for s in (1, 2):
         def builder(g):
             x = g.input(64, 64, 3)
             return x, g.conv(x, "stem", 64, k=3, s=s, bn=True, act="relu")
         plan, (x, y), _ = build_two_pass(builder, 2)
+        assert plan.ops[0]["path"] == "umma"
         rng = np.random.default_rng(3)
-        inputs = {x.buf.id: rng.uniform(-1, 1, (2, 64, 64, 3)).astype(np.float32)}
+        xin = np.zeros((2, 64, 64, 8), np.float32)
+        xin[..., :3] = 2.0 * rng.integers(0, 256, (2, 64, 64, 3)) - 255.0
+        inputs = {x.buf.id: xin}
         ref = run_interp(plan, inputs).get(y.buf.id)
         nat = run_native(plan, inputs)
         assert_close(nat.read_buffer(y.buf.id), ref)
         nat.close()
+
+
+@pytest.mark.parametrize("cout,k", [(2, 3), (2, 1), (1, 1)])
+def test_fp32_head_conv(gpu, cout, k):
+    """2-channel logits / 1-channel gate maps: one 16-column tensor-core tile, fp32 direct stores (res34.py:87)."""
+    def builder(g):
+        x = g.new(64, 64, 64)
+        return x, g.conv(x, "head", cout, k=k, f32_out=True)
+    plan, (x, y), _ = build_two_pass(builder, 2)
+    assert plan.ops[0]["path"] == "umma"
+    rng = np.random.default_rng(4)
+    inputs = {x.buf.id: rand_map(rng, plan, x.buf.id)}
+    ref = run_interp(plan, inputs).get(y.buf.id)
+    nat = run_native(plan, inputs)
+    got = nat.read_buffer(y.buf.id)
+    nat.close()
+    assert np.abs(got - ref).max() < 2e-4 * max(1.0, np.abs(ref).max())
 
 
 @pytest.mark.parametrize("k,umma", [(2, True), (3, True), (2, False), (3, False)])

@@ -57,15 +57,17 @@ def test_device_gather_and_stitch_match_reference(gpu, case):
         n = len(chunk)
         ys = np.asarray([c[0] for c in chunk], np.int32)
         xs = np.asarray([c[1] for c in chunk], np.int32)
-        x = torch.empty((n, 512, 512, 3), dtype=torch.float32, device="cuda")
+        x = torch.empty((n, 512, 512, 8), dtype=torch.float16, device="cuda")
         R.check(L.bd_tiles_gather(ctx, scene.data_ptr(), h, w, R._ptr(ys), R._ptr(xs), n, x.data_ptr(), None))
         torch.cuda.synchronize()
-        xh = x.cpu().numpy()
-        # the gather is bit-identical to predict.py:91-104 (BGR->RGB, /127.5-1 in float64, zero pad, float32 cast)
+        x8 = x.cpu().numpy().astype(np.float64)
+        # plan input layout: 255 * (predict.py:91-104's BGR->RGB, /127.5-1, zero pad) = 2*pixel-255, exact in fp16
         pad = np.zeros((n, 512, 512, 3))
         for k, (i, j) in enumerate(chunk):
             sub = img[i:i + 512, j:j + 512, ::-1] / 127.5 - 1
             pad[k, :sub.shape[0], :sub.shape[1]] = sub
+        assert np.array_equal(x8, np.round(x8)) and not x8[..., 3:].any()
+        xh = (x8[..., :3] / 255.0).astype(np.float32)
         np.testing.assert_array_equal(xh, pad.astype(np.float32))
         tile_mask = torch.from_numpy(fake_probs(xh).argmax(-1).astype(np.uint8)).cuda()
         R.check(L.bd_stitch_or(ctx, tile_mask.data_ptr(), R._ptr(ys), R._ptr(xs), n, out.data_ptr(), h, w, None))
