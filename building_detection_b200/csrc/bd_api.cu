@@ -128,6 +128,7 @@ int bd_create(int device, bd_ctx** out) {
   c->device = device;
   c->num_sms = prop.multiProcessorCount;
   if (const char* s = getenv("BD_UMMA_SMEM_KB")) c->umma_smem_kb = std::max(48, std::min(224, atoi(s)));
+  if (const char* s = getenv("BD_UMMA_GROUP")) c->umma_group = std::max(0, std::min(9, atoi(s)));
   if (const char* s = getenv("BD_UMMA_MAX_N")) c->umma_max_block_n = std::max(16, std::min(256, atoi(s) / 16 * 16));
   *out = c;
   return 0;
@@ -212,7 +213,7 @@ int bd_plan_add_conv(bd_plan* p, const bd_conv_desc* dptr) {
       if (has_res) r = pl->tview(d.res);
       if (umma::prepare(L.get(), x, y, has_res ? &r : nullptr, d.ntaps, d.dy, d.dx, d.stride, d.ho, d.wo, d.act_pre,
                         d.act_post, d.out_scale, d.out_oy, d.out_ox, static_cast<const h16*>(wd),
-                        static_cast<const float*>(bdv), ctx->umma_smem_kb, ctx->umma_max_block_n, ctx->num_sms))
+                        static_cast<const float*>(bdv), ctx->umma_smem_kb, ctx->umma_max_block_n, ctx->num_sms, ctx->umma_group))
         return 1;
       if (const char* tr = getenv("BD_UMMA_TRACE")) {  // debug: event trace of CTA 0 (tools/umma_trace.py)
         void* tbuf = nullptr;
@@ -262,15 +263,17 @@ int bd_plan_add_dwconv(bd_plan* p, bd_tref x, bd_tref y, int stride, int pad_t, 
     q.x = pl->kview(x); q.y = pl->kview(y);
     q.N = pl->batch; q.Ho = q.y.H; q.Wo = q.y.W; q.stride = stride; q.pad_t = pad_t; q.pad_l = pad_l; q.relu_in = relu_in;
     q.w = static_cast<const float*>(wd);
-    const size_t total = static_cast<size_t>(pl->batch) * q.Ho * q.Wo * (x.c / 8);
+    BD_CHECK(stride == 1 || stride == 2, "dwconv: stride must be 1 or 2");
+    const size_t total = static_cast<size_t>(pl->batch) * cdiv(q.Ho, k::DW_ROWS) * q.Wo * (x.c / 8);
     bd_ctx* ctx = pl->ctx;
     const int grid = grid_for(total, ctx->num_sms * 4);
     Op op;
     op.kclass = 2; op.launches = 1;
     op.flops = 2.0 * pl->batch * q.Ho * q.Wo * static_cast<double>(x.c) * 9;
-    op.run = [q, grid, ctx](cudaStream_t s) -> int {
+    op.run = [q, grid, ctx, stride](cudaStream_t s) -> int {
       ctx->launches++;
-      k::dwconv3x3_kernel<<<grid, k::TPB, 0, s>>>(q);
+      if (stride == 1) k::dwconv3x3_kernel<1><<<grid, k::TPB, 0, s>>>(q);
+      else k::dwconv3x3_kernel<2><<<grid, k::TPB, 0, s>>>(q);
       BD_CUDA(cudaGetLastError());
       return 0;
     };

@@ -8,11 +8,11 @@
 // padding (and the channel padding when Cin is not a multiple of 64).  Stride-2 convolutions use up to four
 // parity views of the input (one tensor map per (row parity, column parity)), each again a plain tiled map.
 //
-// Persistent kernel, one CTA per SM, 192 threads, warp-specialised:
+// Persistent kernel, one CTA per SM, 320 threads, warp-specialised:
 //   warp 0 (one lane)  TMA producer: A box + W tile per k-block into a ring of shared-memory stages
 //   warp 1 (one lane)  MMA issuer: tcgen05.mma kind::f16 (fp16 x fp16 -> fp32) into one of TWO TMEM accumulator
 //                      stages; tcgen05.commit releases the smem stage / publishes the accumulator
-//   warps 2-5          epilogue: tcgen05.ld the finished accumulator (warp w owns TMEM lanes 32*(w%4)..+31 =
+//   warps 2-9          epilogue (two warps per TMEM lane quadrant): tcgen05.ld the finished accumulator (warp w owns TMEM lanes 32*(w%4)..+31 =
 //                      tile rows), + bias (BatchNorm folded) / ReLU / residual / ReLU, pack to fp16 into a
 //                      swizzled staging tile and hand it to a TMA STORE (full-line writes, ragged tiles and the
 //                      destination channel slice clipped by the tensor map; the sub-pixel scatter of the
@@ -36,13 +36,14 @@ constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
 constexpr int OUT_CHUNK = 64;                             // channels per staging tile / TMA store
 constexpr int OUT_STAGE_BYTES = BLOCK_M * OUT_CHUNK * 2;  // 16 KB
 constexpr int MAX_TAPS = 18;
-constexpr int THREADS = 192;
+constexpr int EPI_WARPS = 8;                 // two warps per TMEM lane quadrant, each takes half of a column chunk
+constexpr int THREADS = 64 + 32 * EPI_WARPS;
 
 struct Params {
   int N, Ho, Wo, Cout, Cin;
   int bw, bh, bn;
   int tiles_w, tiles_h, tiles_n, n_tiles, total_tiles;
-  int block_n, kchunks, ntaps, stages, tmem_cols;
+  int block_n, kchunks, ntaps, stages, group, tmem_cols;  // group: k-blocks per shared-memory stage
   int tap_map[MAX_TAPS], tap_dy[MAX_TAPS], tap_dx[MAX_TAPS];
   float* y32;  // fp32 output path (Cout <= 16): direct stores
   int y_ctot, y_c0, y_H, y_W, out_scale, out_oy, out_ox;
@@ -120,7 +121,7 @@ __device__ __forceinline__ void tma_store_wait_read() {
 }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory"); }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
 }
@@ -151,6 +152,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, 128-byte-swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
@@ -179,6 +190,7 @@ struct alignas(64) Maps {
   CUtensorMap a[4];
   CUtensorMap b;
   CUtensorMap y;
+  CUtensorMap r;  // residual (same boxes as y), only valid when Params::res != nullptr
 };
 
 // ------------------------------------------------------------------------------------------ kernel
@@ -192,12 +204,15 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
   uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t b_bytes = static_cast<uint32_t>(p.block_n) * 128u;
-  const uint32_t stage_bytes = A_STAGE_BYTES + b_bytes;
+  const uint32_t sub_bytes = A_STAGE_BYTES + b_bytes;                       // one k-block: A box + W tile
+  const uint32_t stage_bytes = sub_bytes * static_cast<uint32_t>(p.group);  // a stage holds `group` k-blocks
   const uint32_t out0 = smem_base + static_cast<uint32_t>(p.stages) * stage_bytes;  // 2 staging tiles
-  const uint32_t bar_base = out0 + 2u * OUT_STAGE_BYTES;                             // 8-byte slots
+  const uint32_t res0 = out0 + 2u * OUT_STAGE_BYTES;                                 // 2 residual tiles (if any)
+  const uint32_t bar_base = res0 + (p.res ? 2u * OUT_STAGE_BYTES : 0u);              // 8-byte slots
   const uint32_t full0 = bar_base, empty0 = bar_base + 8u * p.stages;
   const uint32_t tfull0 = bar_base + 16u * p.stages, tempty0 = tfull0 + 16u;
-  const uint32_t holder = tempty0 + 16u;
+  const uint32_t rbar0 = tempty0 + 16u;
+  const uint32_t holder = rbar0 + 16u;
   volatile uint32_t* holder_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (holder - smem_base));
 
   if (threadIdx.x == 0) {
@@ -207,7 +222,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull0 + 8u * a, 1);
-      mbar_init(tempty0 + 8u * a, 4);  // one arrival per epilogue warp
+      mbar_init(tempty0 + 8u * a, EPI_WARPS);  // one arrival per epilogue warp
+      mbar_init(rbar0 + 8u * a, 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_async_smem();
@@ -228,7 +244,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
   // state in uniform registers next to the UTMALDG / UTCHMMA operands); one elected lane issues.
   if (warp == 0) {
     // ---------------- TMA producer
-    uint32_t s = 0, ph = 0, a_s = smem_base, fb = full0, eb = empty0;  // ring position, kept incrementally
+    uint32_t s = 0, sub = 0, ph = 0, a_s = smem_base, fb = full0, eb = empty0;  // ring position, kept incrementally
     const char* maps_a = reinterpret_cast<const char*>(&maps.a[0]);
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       int nt = 0, mt = tile;
@@ -240,16 +256,20 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
         const CUtensorMap* tm = reinterpret_cast<const CUtensorMap*>(maps_a + p.tap_map[tap] * sizeof(CUtensorMap));
         const int cx = w0 + p.tap_dx[tap], cy = h0 + p.tap_dy[tap];
         for (int c = 0; c < p.Cin; c += BLOCK_K) {
-          mbar_wait(eb, ph ^ 1u);
+          if (sub == 0) mbar_wait(eb, ph ^ 1u);
           if (elect_one()) {
             trace_ev(p, 0, tr_i, tile, tap);
-            mbar_expect_tx(fb, stage_bytes);
+            if (sub == 0) mbar_expect_tx(fb, stage_bytes);
             tma_load_4d(a_s, tm, fb, c, cx, cy, n0);
             tma_load_3d(a_s + A_STAGE_BYTES, &maps.b, fb, c, n_base, tap);
           }
           __syncwarp();
-          if (++s == static_cast<uint32_t>(p.stages)) { s = 0; ph ^= 1u; a_s = smem_base; fb = full0; eb = empty0; }
-          else { a_s += stage_bytes; fb += 8u; eb += 8u; }
+          a_s += sub_bytes;
+          if (++sub == static_cast<uint32_t>(p.group)) {
+            sub = 0;
+            if (++s == static_cast<uint32_t>(p.stages)) { s = 0; ph ^= 1u; a_s = smem_base; fb = full0; eb = empty0; }
+            else { fb += 8u; eb += 8u; }
+          }
         }
       }
     }
@@ -257,8 +277,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
     // ---------------- MMA issuer
     const uint32_t idesc = make_idesc(p.block_n);
     const uint64_t desc0 = make_sdesc(smem_base);
-    const uint32_t dstage = stage_bytes >> 4;  // descriptor start-address field counts 16-byte units
-    uint32_t s = 0, ph = 0, doff = 0, fb = full0, eb = empty0, ti = 0;
+    const uint32_t dsub = sub_bytes >> 4;  // descriptor start-address field counts 16-byte units
+    uint32_t s = 0, sub = 0, ph = 0, doff = 0, fb = full0, eb = empty0, ti = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
       const uint32_t a = ti & 1u, aph = (ti >> 1) & 1u;
       mbar_wait(tempty0 + 8u * a, aph ^ 1u);  // epilogue has drained this accumulator stage
@@ -267,8 +287,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
       uint32_t accum = 0;
       for (int tap = 0; tap < p.ntaps; ++tap) {
         for (int c = p.Cin; c > 0; c -= BLOCK_K) {  // c = channels left in this tap
-          mbar_wait(fb, ph);
-          tc_fence_after();
+          if (sub == 0) {
+            mbar_wait(fb, ph);
+            tc_fence_after();
+          }
           if (elect_one()) {
             trace_ev(p, 1, tr_i, tile, tap);
             const uint64_t adesc = desc0 + doff, bdesc = adesc + (A_STAGE_BYTES >> 4);
@@ -277,67 +299,95 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
             if (c > 16) tc_mma_f16(tacc, adesc + 2u, bdesc + 2u, idesc, 1u);
             if (c > 32) tc_mma_f16(tacc, adesc + 4u, bdesc + 4u, idesc, 1u);
             if (c > 48) tc_mma_f16(tacc, adesc + 6u, bdesc + 6u, idesc, 1u);
-            tc_commit(eb);  // frees the smem stage once these MMAs have read it
+            if (sub + 1 == static_cast<uint32_t>(p.group)) tc_commit(eb);  // frees the stage once these MMAs have read it
           }
           __syncwarp();
           accum = 1u;
-          if (++s == static_cast<uint32_t>(p.stages)) { s = 0; ph ^= 1u; doff = 0; fb = full0; eb = empty0; }
-          else { doff += dstage; fb += 8u; eb += 8u; }
+          doff += dsub;
+          if (++sub == static_cast<uint32_t>(p.group)) {
+            sub = 0;
+            if (++s == static_cast<uint32_t>(p.stages)) { s = 0; ph ^= 1u; doff = 0; fb = full0; eb = empty0; }
+            else { fb += 8u; eb += 8u; }
+          }
         }
       }
       if (elect_one()) tc_commit(tfull0 + 8u * a);  // accumulator complete
       __syncwarp();
     }
   } else {
-    // ---------------- epilogue warps 2..5
+    // ---------------- epilogue warps 2..9: warp w reads TMEM lane quadrant w % 4 (hardware rule); warps 2-5 take
+    // the first 32 columns of every 64-column chunk, warps 6-9 the second 32
     const int q = warp & 3;             // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;   // 0 / 1: which 32 columns of a chunk
     const int r = q * 32 + lane;        // tile row = TMEM lane
-    const int et = threadIdx.x - 64;    // 0..127
+    const int et = threadIdx.x - 64;    // 0 .. 32*EPI_WARPS-1
     const int wl = r % p.bw, hl = (r / p.bw) % p.bh, nl = r / (p.bw * p.bh);
-    uint32_t ti = 0, ob = 0;
+    uint32_t ti = 0, ob = 0, gc = 0;  // gc: running chunk counter (residual buffer / barrier parity)
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
       const uint32_t a = ti & 1u, aph = (ti >> 1) & 1u;
-      const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
-      const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
+      int nt = 0, mt = tile;
+      if (p.n_tiles > 1) { nt = tile % p.n_tiles; mt = tile / p.n_tiles; }
+      const int tw = mt % p.tiles_w, t2 = mt / p.tiles_w;
+      const int th = t2 % p.tiles_h, tn = t2 / p.tiles_h;
       const int n_base = nt * p.block_n;
       const int ow = tw * p.bw + wl, oh = th * p.bh + hl, on = tn * p.bn + nl;
       const bool pix_ok = (ow < p.Wo) && (oh < p.Ho) && (on < p.N);
       const size_t ypix = (static_cast<size_t>(on) * p.y_H + (oh * p.out_scale + p.out_oy)) * p.y_W +
                           (ow * p.out_scale + p.out_ox);
-      const h16* rrow = (p.res && pix_ok) ? p.res + ypix * p.res_ctot + p.res_c0 : nullptr;
+      const bool has_res = p.res != nullptr;
+      // residual tile of the first chunk: fetched by TMA while the main loop of this tile is still running
+      if (has_res && et == 0) {
+        mbar_expect_tx(rbar0 + 8u * (gc & 1u), OUT_STAGE_BYTES);
+        tma_load_4d(res0 + (gc & 1u) * OUT_STAGE_BYTES, &maps.r, rbar0 + 8u * (gc & 1u), n_base, tw * p.bw, th * p.bh,
+                    tn * p.bn);
+      }
       mbar_wait(tfull0 + 8u * a, aph);
       tc_fence_after();
       if (et == 0) trace_ev(p, 2, tr_i, tile, 0);
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * static_cast<uint32_t>(p.block_n);
       if (p.y32) {
         // fp32 output (logits / gate maps, Cout <= 16): one 16-column read, direct coalesced stores
-        uint32_t acc[16];
-        tmem_ld16(trow, acc);
-        tmem_ld_wait();
-        if (pix_ok) {
-          float* yrow = p.y32 + ypix * p.y_ctot + p.y_c0;
+        if (half == 0) {
+          uint32_t acc[16];
+          tmem_ld16(trow, acc);
+          tmem_ld_wait();
+          if (pix_ok) {
+            float* yrow = p.y32 + ypix * p.y_ctot + p.y_c0;
 #pragma unroll
-          for (int c = 0; c < 16; ++c)
-            if (c < p.Cout) {
-              const float v = apply_act(__uint_as_float(acc[c]) + __ldg(p.bias + c), p.act_pre);
-              yrow[c] = apply_act(v, p.act_post);
-            }
+            for (int c = 0; c < 16; ++c)
+              if (c < p.Cout) {
+                const float v = apply_act(__uint_as_float(acc[c]) + __ldg(p.bias + c), p.act_pre);
+                yrow[c] = apply_act(v, p.act_post);
+              }
+          }
         }
       } else {
-        for (int c0 = 0; c0 < p.block_n; c0 += OUT_CHUNK, ob ^= 1u) {
-          const int cw = min(OUT_CHUNK, p.block_n - c0);
+        for (int c0 = 0; c0 < p.block_n; c0 += OUT_CHUNK, ob ^= 1u, ++gc) {
           // the TMA store that last read this staging tile must have finished reading it
           if (et == 0) tma_store_wait_read<1>();
           epi_bar_sync();
+          if (has_res) {
+            if (et == 0 && c0 + OUT_CHUNK < p.block_n) {  // prefetch the next chunk's residual tile
+              const uint32_t nb = (gc + 1u) & 1u;
+              mbar_expect_tx(rbar0 + 8u * nb, OUT_STAGE_BYTES);
+              tma_load_4d(res0 + nb * OUT_STAGE_BYTES, &maps.r, rbar0 + 8u * nb, n_base + c0 + OUT_CHUNK, tw * p.bw,
+                          th * p.bh, tn * p.bn);
+            }
+            mbar_wait(rbar0 + 8u * (gc & 1u), (gc >> 1) & 1u);
+          }
+          const uint8_t* rsrow = gen_base + (res0 - smem_base) + (gc & 1u) * OUT_STAGE_BYTES + r * 128;
           uint8_t* srow = gen_base + (out0 - smem_base) + ob * OUT_STAGE_BYTES + r * 128;
-          for (int cc = 0; cc < cw; cc += 16) {
-            uint32_t acc[16];
-            tmem_ld16(trow + c0 + cc, acc);
+          const int cc = c0 + 32 * half;  // this warp's 32 columns (block_n is a multiple of 16)
+          if (cc < p.block_n) {
+            uint32_t acc[32];
+            if (cc + 32 <= p.block_n) tmem_ld32(trow + cc, acc);
+            else tmem_ld16(trow + cc, acc);
             tmem_ld_wait();
-            const int ch0 = n_base + c0 + cc;
+            const int ngrp = (cc + 32 <= p.block_n) ? 4 : 2;
 #pragma unroll
-            for (int g = 0; g < 2; ++g) {
-              const int ch = ch0 + 8 * g;
+            for (int g = 0; g < 4; ++g) {
+              if (g >= ngrp) break;
+              const int ch = n_base + cc + 8 * g;
               float v[8];
               if (ch < p.Cout) {  // Cout is a multiple of 8 on this path
                 const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + ch));
@@ -345,9 +395,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
                 const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] = apply_act(__uint_as_float(acc[8 * g + j]) + bb[j], p.act_pre);
-                if (rrow) {
+                if (has_res) {  // same swizzled position in the residual tile as in the staging tile
                   float rf[8];
-                  unpack8(*reinterpret_cast<const h16x8*>(rrow + ch), rf);
+                  unpack8(*reinterpret_cast<const h16x8*>(rsrow + (((4 * half + g) ^ (r & 7)) * 16)), rf);
 #pragma unroll
                   for (int j = 0; j < 8; ++j) v[j] += rf[j];
                 }
@@ -358,7 +408,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
                 for (int j = 0; j < 8; ++j) v[j] = 0.0f;
               }
               // 128-byte-swizzled staging row: 16-byte chunk index XOR (row % 8)
-              const int chunk = ((cc >> 3) + g) ^ (r & 7);
+              const int chunk = (4 * half + g) ^ (r & 7);
               *reinterpret_cast<h16x8*>(srow + chunk * 16) = pack8(v);
             }
           }
@@ -439,7 +489,7 @@ inline int floor_pow2(int v) {
 inline int prepare(Launch* L, const TView& x, const TView& y, const TView* res, int ntaps, const int* dy,
                    const int* dx, int stride, int Ho, int Wo, int act_pre, int act_post, int out_scale, int out_oy,
                    int out_ox, const h16* w_dev, const float* bias_dev, int smem_budget_kb, int max_block_n,
-                   int num_sms) {
+                   int num_sms, int group_hint = 0) {
   const int Cin = x.c, Cout = y.c;
   BD_CHECK(!x.f32, "umma conv needs an fp16 input map");
   BD_CHECK(Cin % 8 == 0 && x.c0 % 8 == 0 && x.ctot % 8 == 0, "umma conv needs 16-byte aligned input channel slices");
@@ -468,10 +518,20 @@ inline int prepare(Launch* L, const TView& x, const TView& y, const TView* res, 
   p.ntaps = ntaps;
   p.tmem_cols = 32;
   while (p.tmem_cols < 2 * p.block_n) p.tmem_cols *= 2;
-  const int stage_bytes = A_STAGE_BYTES + p.block_n * 128;
-  const int fixed = 2 * OUT_STAGE_BYTES + 1024 + 1024;  // staging tiles, alignment slack, barriers + tap table
-  p.stages = std::max(2, std::min(12, (smem_budget_kb * 1024 - fixed) / stage_bytes));
-  p.stages = std::min(p.stages, std::max(2, 2 * ntaps * p.kchunks));
+  const int sub_bytes = A_STAGE_BYTES + p.block_n * 128;
+  const int fixed = (res ? 4 : 2) * OUT_STAGE_BYTES + 1024 + 1024;  // staging (+ residual) tiles, alignment slack, barriers
+  const int avail = smem_budget_kb * 1024 - fixed;
+  // Small-N layers are bound by the fixed cost of a barrier round in the single-thread producer / MMA loops, so
+  // several k-blocks share one stage (one wait + one expect_tx + one commit per `group` k-blocks) whenever the
+  // k-block count divides evenly and at least two such stages fit.
+  const int num_kb = ntaps * p.kchunks;
+  p.group = 1;
+  for (int g : {4, 3, 2})
+    if (group_hint != 1 && num_kb % g == 0 && 2 * g * sub_bytes <= avail && p.block_n <= 128) { p.group = g; break; }
+  if (group_hint > 1 && num_kb % group_hint == 0 && 2 * group_hint * sub_bytes <= avail) p.group = group_hint;
+  const int stage_bytes = sub_bytes * p.group;
+  p.stages = std::max(2, std::min(12, avail / stage_bytes));
+  p.stages = std::min(p.stages, std::max(2, 2 * num_kb / p.group));
   L->smem_bytes = p.stages * stage_bytes + fixed;
   BD_CHECK(L->smem_bytes <= 227 * 1024, "umma conv smem budget exceeded");
 
@@ -523,9 +583,17 @@ inline int prepare(Launch* L, const TView& x, const TView& y, const TView* res, 
     char* base = static_cast<char*>(y.base) + (static_cast<size_t>(out_oy) * y.W + out_ox) * ypitch + static_cast<size_t>(y.c0) * 2;
     if (encode_h16(&L->maps.y, base, 4, dims, strides, box)) return 1;
   }
+  L->maps.r = L->maps.y;
   if (res) {
     BD_CHECK(!res->f32 && res->c0 % 8 == 0 && res->ctot % 8 == 0 && out_scale == 1, "bad residual view");
     p.res = static_cast<const h16*>(res->base); p.res_ctot = res->ctot; p.res_c0 = res->c0;
+    const uint64_t rpitch = static_cast<uint64_t>(res->ctot) * 2;
+    uint64_t dims[4] = {static_cast<uint64_t>(Cout), static_cast<uint64_t>(Wo), static_cast<uint64_t>(Ho),
+                        static_cast<uint64_t>(x.N)};
+    uint64_t strides[3] = {rpitch, rpitch * res->W, rpitch * res->W * res->H};
+    uint32_t box[4] = {OUT_CHUNK, static_cast<uint32_t>(p.bw), static_cast<uint32_t>(p.bh), static_cast<uint32_t>(p.bn)};
+    char* base = static_cast<char*>(res->base) + static_cast<size_t>(res->c0) * 2;
+    if (encode_h16(&L->maps.r, base, 4, dims, strides, box)) return 1;
   }
   p.bias = bias_dev; p.act_pre = act_pre; p.act_post = act_post;
   p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;

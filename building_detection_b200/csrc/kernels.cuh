@@ -93,34 +93,75 @@ struct DwParams {
   int N, Ho, Wo, stride, pad_t, pad_l, relu_in;
   const float* w;  // [9][C]
 };
+// thread = (8-channel group, output column, block of DW_ROWS output rows, image): the 9x8 weights stay in
+// registers and the 3-row input window slides down, so an output costs 3 (stride 1) new 16-byte loads instead of 9
+// plus 18 weight loads; consecutive threads are consecutive channel groups (coalesced 16-byte vectors).
+constexpr int DW_ROWS = 4;
+template <int STRIDE>
 __global__ void __launch_bounds__(TPB) dwconv3x3_kernel(const __grid_constant__ DwParams p) {
   const int C = p.x.c, cg = C >> 3;
-  const size_t total = static_cast<size_t>(p.N) * p.Ho * p.Wo * cg;
+  const int rb = (p.Ho + DW_ROWS - 1) / DW_ROWS;
+  const size_t total = static_cast<size_t>(p.N) * rb * p.Wo * cg;
   for (size_t idx = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; idx < total;
        idx += static_cast<size_t>(gridDim.x) * TPB) {
     const int g = static_cast<int>(idx % cg);
-    const size_t pix = idx / cg;
-    const int ow = static_cast<int>(pix % p.Wo), oh = static_cast<int>((pix / p.Wo) % p.Ho);
-    const int n = static_cast<int>(pix / (static_cast<size_t>(p.Wo) * p.Ho));
-    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    size_t t = idx / cg;
+    const int ow = static_cast<int>(t % p.Wo);
+    t /= p.Wo;
+    const int ob = static_cast<int>(t % rb), n = static_cast<int>(t / rb);
+    float w[9][8];
 #pragma unroll
-    for (int kh = 0; kh < 3; ++kh) {
-      const int ih = oh * p.stride + kh - p.pad_t;
-      if (ih < 0 || ih >= p.x.H) continue;
+    for (int k = 0; k < 9; ++k) {
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.w + k * C + g * 8));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.w + k * C + g * 8 + 4));
+      w[k][0] = w0.x; w[k][1] = w0.y; w[k][2] = w0.z; w[k][3] = w0.w;
+      w[k][4] = w1.x; w[k][5] = w1.y; w[k][6] = w1.z; w[k][7] = w1.w;
+    }
+    const int iw0 = ow * STRIDE - p.pad_l;
+    const h16* xb = static_cast<const h16*>(p.x.base) + p.x.c0 + g * 8;
+    const size_t img = static_cast<size_t>(n) * p.x.H;
+    auto load_row = [&](int ih, h16x8* row) {  // 3 taps of input row ih (zero outside the map)
+      const bool rok = ih >= 0 && ih < p.x.H;
 #pragma unroll
       for (int kw = 0; kw < 3; ++kw) {
-        const int iw = ow * p.stride + kw - p.pad_l;
-        if (iw < 0 || iw >= p.x.W) continue;
-        float xv[8];
-        ld8(p.x, (static_cast<size_t>(n) * p.x.H + ih) * p.x.W + iw, g * 8, xv);
-        const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.w + (kh * 3 + kw) * C + g * 8));
-        const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.w + (kh * 3 + kw) * C + g * 8 + 4));
-        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        const int iw = iw0 + kw;
+        if (rok && iw >= 0 && iw < p.x.W)
+          row[kw] = *reinterpret_cast<const h16x8*>(xb + ((img + ih) * p.x.W + iw) * p.x.ctot);
+        else
+          row[kw] = h16x8{};
+      }
+    };
+    h16x8 win[3][3];  // input rows ih0 .. ih0+2 of the current output row
+    const int oh0 = ob * DW_ROWS;
+    const int ih0 = oh0 * STRIDE - p.pad_t;
+    load_row(ih0, win[0]);
+    load_row(ih0 + 1, win[1]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = fmaf(p.relu_in ? fmaxf(xv[j], 0.0f) : xv[j], wv[j], acc[j]);
+    for (int r = 0; r < DW_ROWS; ++r) {
+      const int oh = oh0 + r;
+      if (oh >= p.Ho) break;
+      const int ih = oh * STRIDE - p.pad_t;
+      if (STRIDE == 2 && r > 0) load_row(ih + 1, win[1]);
+      load_row(ih + 2, win[2]);
+      float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          float xv[8];
+          unpack8(win[kh][kw], xv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(p.relu_in ? fmaxf(xv[j], 0.0f) : xv[j], w[kh * 3 + kw][j], acc[j]);
+        }
+      st8(p.y, (static_cast<size_t>(n) * p.Ho + oh) * p.Wo + ow, g * 8, acc);
+      if (STRIDE == 1) {
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) { win[0][kw] = win[1][kw]; win[1][kw] = win[2][kw]; }
+      } else {
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) win[0][kw] = win[2][kw];
       }
     }
-    st8(p.y, pix, g * 8, acc);
   }
 }
 

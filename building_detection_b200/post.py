@@ -12,6 +12,39 @@ from __future__ import annotations
 from . import scene as S
 
 
+def band_of(origins, h):
+    """Rows [r0, r1) of the scene that a shard of tile origins can write."""
+    if not origins:
+        return (0, 0)
+    return (min(o[0] for o in origins), min(h, max(o[0] for o in origins) + S.TILE))
+
+
+def gather_bands(masks, bands, rank, world, stage=None):
+    """Band masks -> rank 0 (send/recv on the default process group: NCCL on GPUs, gloo in the CPU tests), OR-ed
+    into rank 0's scene masks.  ``masks``: (M,H,W) u8 tensor on every rank; ``bands[r]`` = rows rank r owns."""
+    if world == 1:
+        return masks
+    import torch
+    import torch.distributed as dist
+    if rank == 0:
+        for r in range(1, world):
+            r0, r1 = bands[r]
+            if r1 <= r0:
+                continue
+            if stage is not None and stage.shape[1] >= r1 - r0:
+                buf = stage[:, :r1 - r0]
+                buf = buf if buf.is_contiguous() else torch.empty_like(masks[:, r0:r1])
+            else:
+                buf = torch.empty_like(masks[:, r0:r1])
+            dist.recv(buf, src=r)
+            masks[:, r0:r1].bitwise_or_(buf)
+    else:
+        r0, r1 = bands[rank]
+        if r1 > r0:
+            dist.send(masks[:, r0:r1].contiguous(), dst=0)
+    return masks
+
+
 class SceneJob:
     def __init__(self, runner, h, w, origins, rank=0, world=1, do_post=True):
         import torch
@@ -21,7 +54,7 @@ class SceneJob:
         dev = runner.device
         self.masks = torch.zeros((len(runner.models), h, w), dtype=torch.uint8, device=dev)
         self.all_origins = S.tile_origins(h, w)
-        self.bands = [self._band(S.shard_rows(self.all_origins, r, world)) for r in range(world)]
+        self.bands = [band_of(S.shard_rows(self.all_origins, r, world), h) for r in range(world)]
         self.scene_dev = None
         self.stage = None
         if world > 1 and rank == 0:
@@ -32,39 +65,13 @@ class SceneJob:
         self.host_mask = None
         self.result = None
 
-    def _band(self, origins):
-        if not origins:
-            return (0, 0)
-        r0 = min(o[0] for o in origins)
-        r1 = min(self.h, max(o[0] for o in origins) + S.TILE)
-        return (r0, r1)
-
     # ------------------------------------------------------------------ stages
     def _forward(self, scene_dev):
         self.masks.zero_()
         self.runner.run(scene_dev, origins=self.origins, out=self.masks)
 
     def _gather(self):
-        """Band masks -> rank 0 (NCCL send/recv), OR-ed into rank 0's scene masks."""
-        if self.world == 1:
-            return
-        import torch.distributed as dist
-        t = self.t
-        if self.rank == 0:
-            for r in range(1, self.world):
-                r0, r1 = self.bands[r]
-                if r1 <= r0:
-                    continue
-                buf = self.stage[:, :r1 - r0]
-                buf = buf if buf.is_contiguous() else None
-                if buf is None:
-                    buf = t.empty((self.masks.shape[0], r1 - r0, self.w), dtype=t.uint8, device=self.masks.device)
-                dist.recv(buf, src=r)
-                self.masks[:, r0:r1].bitwise_or_(buf)
-        else:
-            r0, r1 = self.bands[self.rank]
-            if r1 > r0:
-                dist.send(self.masks[:, r0:r1].contiguous(), dst=0)
+        gather_bands(self.masks, self.bands, self.rank, self.world, self.stage)
 
     def _post(self):
         if not self.do_post or self.rank != 0:
