@@ -255,14 +255,19 @@ int bd_plan_add_dwconv(bd_plan* p, bd_tref x, bd_tref y, int stride, int pad_t, 
   BD_CHECK(p && !p->finalized && w_host, "bad arguments");
   if (p->check_ref(x, true) || p->check_ref(y, true)) return 1;
   BD_CHECK(x.c == y.c, "dwconv: channel mismatch");
-  std::shared_ptr<std::vector<float>> w(new std::vector<float>(w_host, w_host + 9 * static_cast<size_t>(x.c)));
+  // depthwise weights are stored as fp16 on the device (the host passes fp16-representable values)
+  std::shared_ptr<std::vector<uint16_t>> w(new std::vector<uint16_t>(9 * static_cast<size_t>(x.c)));
+  for (size_t i = 0; i < w->size(); ++i) {
+    const __half hv = __float2half_rn(std::max(-65504.0f, std::min(65504.0f, w_host[i])));
+    memcpy(&(*w)[i], &hv, 2);
+  }
   p->builders.push_back([=](bd_plan* pl) -> int {
     void* wd = nullptr;
-    if (pl->upload(w->data(), w->size() * 4, &wd)) return 1;
+    if (pl->upload(w->data(), w->size() * 2, &wd)) return 1;
     k::DwParams q;
     q.x = pl->kview(x); q.y = pl->kview(y);
     q.N = pl->batch; q.Ho = q.y.H; q.Wo = q.y.W; q.stride = stride; q.pad_t = pad_t; q.pad_l = pad_l; q.relu_in = relu_in;
-    q.w = static_cast<const float*>(wd);
+    q.w = static_cast<const h16*>(wd);
     BD_CHECK(stride == 1 || stride == 2, "dwconv: stride must be 1 or 2");
     const size_t total = static_cast<size_t>(pl->batch) * cdiv(q.Ho, k::DW_ROWS) * q.Wo * (x.c / 8);
     bd_ctx* ctx = pl->ctx;
@@ -528,8 +533,10 @@ int bd_plan_finalize(bd_plan* p, int input_buf, int logits_buf, int logits_up) {
   BD_CUDA(cudaSetDevice(p->ctx->device));
   const int nb = static_cast<int>(p->bufs.size());
   if (input_buf >= 0) {
-    BD_CHECK(input_buf < nb && p->bufs[input_buf].dtype == BD_F16 && p->bufs[input_buf].C == 8 &&
-                 p->bufs[input_buf].kind == BD_MAP, "bad input buffer (expected an fp16 map with 8 channels)");
+    const BufInfo& ib = p->bufs[input_buf];
+    BD_CHECK(input_buf < nb && ib.dtype == BD_F16 && ib.C == 32 && ib.kind == BD_MAP && ib.H == ib.W &&
+                 (ib.H == 512 || ib.H == 256),
+             "bad input buffer (expected the im2col'ed stem input: fp16, 32 channels, 512x512 or 256x256)");
   }
   if (logits_buf >= 0) {
     BD_CHECK(logits_buf < nb && p->bufs[logits_buf].dtype == BD_F32 && p->bufs[logits_buf].C == 2 && logits_up >= 1,
@@ -575,10 +582,11 @@ int bd_plan_run(bd_plan* p, const float* x_dev, float* probs_dev, uint8_t* mask_
   if (x_dev) {
     BD_CHECK(p->input_buf >= 0, "plan has no input buffer");
     const BufInfo& ib = p->bufs[p->input_buf];
-    const size_t npix = static_cast<size_t>(p->batch) * ib.H * ib.W;
+    const size_t work = static_cast<size_t>(p->batch) * ib.H * ib.W * 4;
     p->ctx->launches++;
-    k::input_convert_kernel<<<grid_for(npix, p->ctx->num_sms * 4), k::TPB, 0, s>>>(
-        x_dev, npix, reinterpret_cast<h16*>(p->arena + ib.offset));
+    h16* dst = reinterpret_cast<h16*>(p->arena + ib.offset);
+    if (ib.H == 512) k::input_convert_kernel<1><<<grid_for(work, p->ctx->num_sms * 4), k::TPB, 0, s>>>(x_dev, p->batch, dst);
+    else k::input_convert_kernel<2><<<grid_for(work, p->ctx->num_sms * 4), k::TPB, 0, s>>>(x_dev, p->batch, dst);
     BD_CUDA(cudaGetLastError());
   }
   p->cur_probs = probs_dev;
@@ -604,7 +612,7 @@ int bd_plan_run_host(bd_plan* p, const float* x_host, float* probs_host, uint8_t
   uint8_t* dmask = nullptr;
   float* dx = nullptr;
   if (x_host) {
-    const size_t xbytes = static_cast<size_t>(p->batch) * ib.H * ib.W * 3 * sizeof(float);
+    const size_t xbytes = static_cast<size_t>(p->batch) * 512 * 512 * 3 * sizeof(float);
     BD_CUDA(cudaMalloc(reinterpret_cast<void**>(&dx), xbytes));
     BD_CUDA(cudaMemcpy(dx, x_host, xbytes, cudaMemcpyHostToDevice));
   }
@@ -692,15 +700,21 @@ static int ensure_tile_scratch(bd_ctx* ctx, int n) {
 }
 
 int bd_tiles_gather(bd_ctx* ctx, const uint8_t* scene_bgr_dev, int h, int w, const int32_t* ys_host,
-                    const int32_t* xs_host, int n, void* x_dev, void* stream) {
+                    const int32_t* xs_host, int n, void* x_dev, int stem_stride, void* stream) {
   BD_CHECK(ctx && scene_bgr_dev && ys_host && xs_host && x_dev && n >= 1 && h >= 1 && w >= 1, "bad arguments");
+  BD_CHECK(stem_stride == 1 || stem_stride == 2, "stem stride must be 1 or 2");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (ensure_tile_scratch(ctx, std::max(n, 64))) return 1;
   BD_CUDA(cudaMemcpyAsync(ctx->d_ys, ys_host, sizeof(int) * n, cudaMemcpyHostToDevice, s));
   BD_CUDA(cudaMemcpyAsync(ctx->d_xs, xs_host, sizeof(int) * n, cudaMemcpyHostToDevice, s));
   ctx->launches++;
-  k::tiles_gather_kernel<<<grid_for(static_cast<size_t>(n) * 512 * 512, ctx->num_sms * 4), k::TPB, 0, s>>>(
-      scene_bgr_dev, h, w, ctx->d_ys, ctx->d_xs, n, static_cast<h16*>(x_dev));
+  const size_t work = static_cast<size_t>(n) * (512 / stem_stride) * (512 / stem_stride) * 4;
+  if (stem_stride == 1)
+    k::tiles_gather_kernel<1><<<grid_for(work, ctx->num_sms * 4), k::TPB, 0, s>>>(scene_bgr_dev, h, w, ctx->d_ys, ctx->d_xs, n,
+                                                                                static_cast<h16*>(x_dev));
+  else
+    k::tiles_gather_kernel<2><<<grid_for(work, ctx->num_sms * 4), k::TPB, 0, s>>>(scene_bgr_dev, h, w, ctx->d_ys, ctx->d_xs, n,
+                                                                                static_cast<h16*>(x_dev));
   BD_CUDA(cudaGetLastError());
   return 0;
 }

@@ -44,6 +44,7 @@ struct Params {
   int bw, bh, bn;
   int tiles_w, tiles_h, tiles_n, n_tiles, total_tiles;
   int block_n, kchunks, ntaps, stages, group, tmem_cols;  // group: k-blocks per shared-memory stage
+  int spec;  // 0 generic loops; 1 = 9 taps x 1 chunk, group 3; 2 = 9 taps x 2 chunks, group 2 (fully unrolled loops)
   int tap_map[MAX_TAPS], tap_dy[MAX_TAPS], tap_dx[MAX_TAPS];
   float* y32;  // fp32 output path (Cout <= 16): direct stores
   int y_ctot, y_c0, y_H, y_W, out_scale, out_oy, out_ox;
@@ -193,6 +194,74 @@ struct alignas(64) Maps {
   CUtensorMap r;  // residual (same boxes as y), only valid when Params::res != nullptr
 };
 
+// ------------------------------------------------------------------------------------------ unrolled loops
+// The small-channel 3x3 convolutions (Cin <= 128: most of res34 / scse / hrnet's time) have k-blocks whose MMAs take
+// 100-300 cycles, so the per-k-block bookkeeping of the generic loops below dominates.  For them one tile's whole
+// main loop is unrolled at compile time: tap offsets come straight from the constant bank, descriptor offsets are
+// immediates, and a barrier round covers G k-blocks.
+struct Ring {
+  uint32_t s, ph, off, fb, eb;  // stage index, phase, byte offset of the stage, full / empty barrier addresses
+};
+__device__ __forceinline__ void ring_advance(Ring& r, const Params& p, uint32_t stage_bytes, uint32_t full0, uint32_t empty0) {
+  if (++r.s == static_cast<uint32_t>(p.stages)) { r.s = 0; r.ph ^= 1u; r.off = 0; r.fb = full0; r.eb = empty0; }
+  else { r.off += stage_bytes; r.fb += 8u; r.eb += 8u; }
+}
+template <int NTAPS, int KCH, int G>
+__device__ __forceinline__ void produce_tile(const Maps& maps, const Params& p, Ring& r, uint32_t smem_base, uint32_t sub_bytes,
+                                             uint32_t full0, uint32_t empty0, int w0, int h0, int n0, int n_base) {
+  static_assert((NTAPS * KCH) % G == 0, "group must divide the k-block count");
+  const char* maps_a = reinterpret_cast<const char*>(&maps.a[0]);
+#pragma unroll
+  for (int grp = 0; grp < NTAPS * KCH / G; ++grp) {
+    mbar_wait(r.eb, r.ph ^ 1u);
+    if (elect_one()) {
+      mbar_expect_tx(r.fb, sub_bytes * G);
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const int kb = grp * G + g, tap = kb / KCH, kc = kb % KCH;  // compile-time
+        const CUtensorMap* tm = reinterpret_cast<const CUtensorMap*>(maps_a + p.tap_map[tap] * sizeof(CUtensorMap));
+        const uint32_t dst = smem_base + r.off + g * sub_bytes;
+        tma_load_4d(dst, tm, r.fb, kc * BLOCK_K, w0 + p.tap_dx[tap], h0 + p.tap_dy[tap], n0);
+        tma_load_3d(dst + A_STAGE_BYTES, &maps.b, r.fb, kc * BLOCK_K, n_base, tap);
+      }
+    }
+    __syncwarp();
+    ring_advance(r, p, sub_bytes * G, full0, empty0);
+  }
+}
+template <int NTAPS, int KCH, int G>
+__device__ __forceinline__ void mma_tile(const Params& p, Ring& r, uint64_t desc0, uint32_t sub_bytes, uint32_t full0,
+                                         uint32_t empty0, uint32_t tacc, uint32_t idesc, uint32_t tfull_bar) {
+  const int last_c = p.Cin - (KCH - 1) * BLOCK_K;  // channels in the last chunk of a tap (runtime, 8..64)
+#pragma unroll
+  for (int grp = 0; grp < NTAPS * KCH / G; ++grp) {
+    mbar_wait(r.fb, r.ph);
+    tc_fence_after();
+    if (elect_one()) {
+      const uint64_t d = desc0 + (r.off >> 4);
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const int kb = grp * G + g, kc = kb % KCH;
+        const uint64_t adesc = d + g * (sub_bytes >> 4), bdesc = adesc + (A_STAGE_BYTES >> 4);
+        tc_mma_f16(tacc, adesc, bdesc, idesc, kb > 0 ? 1u : 0u);
+        if (kc < KCH - 1) {
+          tc_mma_f16(tacc, adesc + 2u, bdesc + 2u, idesc, 1u);
+          tc_mma_f16(tacc, adesc + 4u, bdesc + 4u, idesc, 1u);
+          tc_mma_f16(tacc, adesc + 6u, bdesc + 6u, idesc, 1u);
+        } else {
+          if (last_c > 16) tc_mma_f16(tacc, adesc + 2u, bdesc + 2u, idesc, 1u);
+          if (last_c > 32) tc_mma_f16(tacc, adesc + 4u, bdesc + 4u, idesc, 1u);
+          if (last_c > 48) tc_mma_f16(tacc, adesc + 6u, bdesc + 6u, idesc, 1u);
+        }
+      }
+      tc_commit(r.eb);
+      if (grp == NTAPS * KCH / G - 1) tc_commit(tfull_bar);
+    }
+    __syncwarp();
+    ring_advance(r, p, sub_bytes * G, full0, empty0);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ kernel
 // The producer and the MMA issuer are single threads executing dependent scalar code: every instruction in
 // their per-k-block loops costs several cycles of latency (a k-block's four N=64 MMAs take only 128 cycles), so
@@ -246,12 +315,15 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
     // ---------------- TMA producer
     uint32_t s = 0, sub = 0, ph = 0, a_s = smem_base, fb = full0, eb = empty0;  // ring position, kept incrementally
     const char* maps_a = reinterpret_cast<const char*>(&maps.a[0]);
+    Ring ring{0u, 0u, 0u, full0, empty0};
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       int nt = 0, mt = tile;
       if (p.n_tiles > 1) { nt = tile % p.n_tiles; mt = tile / p.n_tiles; }
       const int tw = mt % p.tiles_w, t2 = mt / p.tiles_w;
       const int th = t2 % p.tiles_h, tn = t2 / p.tiles_h;
       const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn, n_base = nt * p.block_n;
+      if (p.spec == 1) { produce_tile<9, 1, 3>(maps, p, ring, smem_base, sub_bytes, full0, empty0, w0, h0, n0, n_base); continue; }
+      if (p.spec == 2) { produce_tile<9, 2, 2>(maps, p, ring, smem_base, sub_bytes, full0, empty0, w0, h0, n0, n_base); continue; }
       for (int tap = 0; tap < p.ntaps; ++tap) {
         const CUtensorMap* tm = reinterpret_cast<const CUtensorMap*>(maps_a + p.tap_map[tap] * sizeof(CUtensorMap));
         const int cx = w0 + p.tap_dx[tap], cy = h0 + p.tap_dy[tap];
@@ -279,11 +351,14 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
     const uint64_t desc0 = make_sdesc(smem_base);
     const uint32_t dsub = sub_bytes >> 4;  // descriptor start-address field counts 16-byte units
     uint32_t s = 0, sub = 0, ph = 0, doff = 0, fb = full0, eb = empty0, ti = 0;
+    Ring ring{0u, 0u, 0u, full0, empty0};
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
       const uint32_t a = ti & 1u, aph = (ti >> 1) & 1u;
       mbar_wait(tempty0 + 8u * a, aph ^ 1u);  // epilogue has drained this accumulator stage
       tc_fence_after();
       const uint32_t tacc = tmem_base + a * static_cast<uint32_t>(p.block_n);
+      if (p.spec == 1) { mma_tile<9, 1, 3>(p, ring, desc0, sub_bytes, full0, empty0, tacc, idesc, tfull0 + 8u * a); continue; }
+      if (p.spec == 2) { mma_tile<9, 2, 2>(p, ring, desc0, sub_bytes, full0, empty0, tacc, idesc, tfull0 + 8u * a); continue; }
       uint32_t accum = 0;
       for (int tap = 0; tap < p.ntaps; ++tap) {
         for (int c = p.Cin; c > 0; c -= BLOCK_K) {  // c = channels left in this tap
@@ -529,6 +604,9 @@ inline int prepare(Launch* L, const TView& x, const TView& y, const TView* res, 
   for (int g : {4, 3, 2})
     if (group_hint != 1 && num_kb % g == 0 && 2 * g * sub_bytes <= avail && p.block_n <= 128) { p.group = g; break; }
   if (group_hint > 1 && num_kb % group_hint == 0 && 2 * group_hint * sub_bytes <= avail) p.group = group_hint;
+  p.spec = 0;
+  if (group_hint == 0 && ntaps == 9 && p.kchunks == 1 && 2 * 3 * sub_bytes <= avail) { p.spec = 1; p.group = 3; }
+  else if (group_hint == 0 && ntaps == 9 && p.kchunks == 2 && 2 * 2 * sub_bytes <= avail) { p.spec = 2; p.group = 2; }
   const int stage_bytes = sub_bytes * p.group;
   p.stages = std::max(2, std::min(12, avail / stage_bytes));
   p.stages = std::min(p.stages, std::max(2, 2 * num_kb / p.group));

@@ -91,14 +91,14 @@ __global__ void __launch_bounds__(TPB) conv_direct_kernel(const __grid_constant_
 struct DwParams {
   View x, y;
   int N, Ho, Wo, stride, pad_t, pad_l, relu_in;
-  const float* w;  // [9][C]
+  const h16* w;  // [9][C] fp16
 };
 // thread = (8-channel group, output column, block of DW_ROWS output rows, image): the 9x8 weights stay in
 // registers and the 3-row input window slides down, so an output costs 3 (stride 1) new 16-byte loads instead of 9
 // plus 18 weight loads; consecutive threads are consecutive channel groups (coalesced 16-byte vectors).
 constexpr int DW_ROWS = 4;
 template <int STRIDE>
-__global__ void __launch_bounds__(TPB) dwconv3x3_kernel(const __grid_constant__ DwParams p) {
+__global__ void __launch_bounds__(TPB, 2) dwconv3x3_kernel(const __grid_constant__ DwParams p) {
   const int C = p.x.c, cg = C >> 3;
   const int rb = (p.Ho + DW_ROWS - 1) / DW_ROWS;
   const size_t total = static_cast<size_t>(p.N) * rb * p.Wo * cg;
@@ -109,14 +109,9 @@ __global__ void __launch_bounds__(TPB) dwconv3x3_kernel(const __grid_constant__ 
     const int ow = static_cast<int>(t % p.Wo);
     t /= p.Wo;
     const int ob = static_cast<int>(t % rb), n = static_cast<int>(t / rb);
-    float w[9][8];
+    h16x8 wp[9];  // packed fp16 weights of this channel group (36 registers), widened at use
 #pragma unroll
-    for (int k = 0; k < 9; ++k) {
-      const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.w + k * C + g * 8));
-      const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.w + k * C + g * 8 + 4));
-      w[k][0] = w0.x; w[k][1] = w0.y; w[k][2] = w0.z; w[k][3] = w0.w;
-      w[k][4] = w1.x; w[k][5] = w1.y; w[k][6] = w1.z; w[k][7] = w1.w;
-    }
+    for (int k = 0; k < 9; ++k) wp[k] = *reinterpret_cast<const h16x8*>(p.w + k * C + g * 8);
     const int iw0 = ow * STRIDE - p.pad_l;
     const h16* xb = static_cast<const h16*>(p.x.base) + p.x.c0 + g * 8;
     const size_t img = static_cast<size_t>(n) * p.x.H;
@@ -148,10 +143,11 @@ __global__ void __launch_bounds__(TPB) dwconv3x3_kernel(const __grid_constant__ 
       for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw) {
-          float xv[8];
+          float xv[8], wv[8];
           unpack8(win[kh][kw], xv);
+          unpack8(wp[kh * 3 + kw], wv);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] = fmaf(p.relu_in ? fmaxf(xv[j], 0.0f) : xv[j], w[kh * 3 + kw][j], acc[j]);
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(p.relu_in ? fmaxf(xv[j], 0.0f) : xv[j], wv[j], acc[j]);
         }
       st8(p.y, (static_cast<size_t>(n) * p.Ho + oh) * p.Wo + ow, g * 8, acc);
       if (STRIDE == 1) {
@@ -452,35 +448,62 @@ __global__ void __launch_bounds__(TPB) softmax2_kernel(const float* __restrict__
 }
 
 // ---------------------------------------------------------------------------------- tiler / stitcher
-// Network input layout: fp16, 8 channels per pixel (one 16-byte vector): [255*r, 255*g, 255*b, 0, 0, 0, 0, 0].
-// predict.py:91-108 computes x = pixel/127.5 - 1 (float64, cast to float32 by Keras) and zero-pads in normalised
-// space; 255*x = 2*pixel - 255 is an integer in [-255, 255], exact in fp16, and the first convolution of every
-// network carries the 1/255 in its weights.
+// Network input layout (graph.Net.input): fp16, 32 channels per pixel of the STEM OUTPUT grid, channel
+// (kh*3+kw)*3+c = 255 * x[oy*S+kh-PAD, ox*S+kw-PAD, c] for the 3x3 stem conv of stride S with TF 'same' padding
+// (PAD = 1 for S = 1, 0 for S = 2), zero outside the 512x512 tile.  predict.py:91-108 computes x = pixel/127.5 - 1
+// (float64, cast to float32 by Keras) and zero-pads in normalised space; 255*x = 2*pixel - 255 is an integer in
+// [-255, 255], exact in fp16; the stem weights carry the 1/255.  thread = (output pixel, 8-channel quarter).
+template <int S>
 __global__ void __launch_bounds__(TPB) tiles_gather_kernel(const uint8_t* __restrict__ scene, int H, int W,
                                                            const int* __restrict__ ys, const int* __restrict__ xs,
                                                            int n, h16* __restrict__ out) {
-  const size_t total = static_cast<size_t>(n) * 512 * 512;
+  constexpr int O = 512 / S, PAD = S == 1 ? 1 : 0;
+  const size_t total = static_cast<size_t>(n) * O * O * 4;
   for (size_t idx = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; idx < total;
        idx += static_cast<size_t>(gridDim.x) * TPB) {
-    const int tx = static_cast<int>(idx % 512), ty = static_cast<int>((idx / 512) % 512);
-    const int t = static_cast<int>(idx / (512 * 512));
-    const int y = ys[t] + ty, x = xs[t] + tx;
-    float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (y < H && x < W) {
-      const uint8_t* px = scene + (static_cast<size_t>(y) * W + x) * 3;  // BGR -> RGB
-      f[0] = static_cast<float>(2 * static_cast<int>(px[2]) - 255);
-      f[1] = static_cast<float>(2 * static_cast<int>(px[1]) - 255);
-      f[2] = static_cast<float>(2 * static_cast<int>(px[0]) - 255);
+    const int q = static_cast<int>(idx & 3);
+    const size_t pix = idx >> 2;
+    const int ox = static_cast<int>(pix % O), oy = static_cast<int>((pix / O) % O);
+    const int t = static_cast<int>(pix / (static_cast<size_t>(O) * O));
+    const int y0 = ys[t], x0 = xs[t];
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = q * 8 + j, tap = k / 3, c = k - tap * 3;
+      float v = 0.0f;
+      if (k < 27) {
+        const int ty = oy * S + tap / 3 - PAD, tx = ox * S + tap % 3 - PAD;  // position inside the tile
+        const int y = y0 + ty, x = x0 + tx;
+        if (ty >= 0 && ty < 512 && tx >= 0 && tx < 512 && y < H && x < W)
+          v = static_cast<float>(2 * static_cast<int>(scene[(static_cast<size_t>(y) * W + x) * 3 + (2 - c)]) - 255);  // BGR -> RGB
+      }
+      f[j] = v;
     }
     *reinterpret_cast<h16x8*>(out + idx * 8) = pack8(f);
   }
 }
-// model.predict(x) path: fp32 (N,H,W,3) in [-1,1] -> the layout above (255*x rounded to fp16)
-__global__ void __launch_bounds__(TPB) input_convert_kernel(const float* __restrict__ x, size_t npix, h16* __restrict__ out) {
-  for (size_t idx = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; idx < npix;
+// model.predict(x) path: fp32 (N,512,512,3) in [-1,1] -> the same layout (255*x rounded to fp16)
+template <int S>
+__global__ void __launch_bounds__(TPB) input_convert_kernel(const float* __restrict__ x, int n, h16* __restrict__ out) {
+  constexpr int O = 512 / S, PAD = S == 1 ? 1 : 0;
+  const size_t total = static_cast<size_t>(n) * O * O * 4;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; idx < total;
        idx += static_cast<size_t>(gridDim.x) * TPB) {
-    float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    f[0] = x[idx * 3] * 255.0f; f[1] = x[idx * 3 + 1] * 255.0f; f[2] = x[idx * 3 + 2] * 255.0f;
+    const int q = static_cast<int>(idx & 3);
+    const size_t pix = idx >> 2;
+    const int ox = static_cast<int>(pix % O), oy = static_cast<int>((pix / O) % O);
+    const size_t t = pix / (static_cast<size_t>(O) * O);
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = q * 8 + j, tap = k / 3, c = k - tap * 3;
+      float v = 0.0f;
+      if (k < 27) {
+        const int ty = oy * S + tap / 3 - PAD, tx = ox * S + tap % 3 - PAD;
+        if (ty >= 0 && ty < 512 && tx >= 0 && tx < 512) v = x[((t * 512 + ty) * 512 + tx) * 3 + c] * 255.0f;
+      }
+      f[j] = v;
+    }
     *reinterpret_cast<h16x8*>(out + idx * 8) = pack8(f);
   }
 }

@@ -25,8 +25,8 @@ from dataclasses import dataclass, field
 import numpy as np
 
 BN_EPS = 1e-3  # Keras BatchNormalization default
-INPUT_C = 8          # the 3-channel network input is stored as 8 fp16 channels (one 16-byte vector per pixel)
-INPUT_SCALE = 255.0  # ... holding 255 * x
+INPUT_C = 32         # the network input is stored im2col'ed for its 3x3 stem conv: 27 = 9 taps x RGB, padded to 32
+INPUT_SCALE = 255.0  # ... holding 255 * x (exact integers for 8-bit imagery)
 
 # op codes shared with csrc/bd_api.cu (enum bd_op_kind in include/bd_b200.h)
 OP_CONV, OP_DWCONV, OP_MAXPOOL, OP_ADDN, OP_GAP, OP_DENSE, OP_GATE, OP_SKFUSE, OP_BCAST, OP_SOFTMAX2 = range(10)
@@ -110,6 +110,7 @@ class Plan:
     bufs: list = field(default_factory=list)
     ops: list = field(default_factory=list)
     input: int = -1
+    input_stride: int = 1  # stride of the stem conv the im2col'ed input buffer was laid out for
     logits: int = -1
     logits_up: int = 1
     flops: int = 0  # algorithmic 2*MAC of conv/convT/depthwise/dense per batch
@@ -158,12 +159,42 @@ class Net:
         return V(self.buf(1, 1, C, "f32", "vec"))
 
     def input(self, H=512, W=512, C=3):
-        """Network input: fp16, padded to 8 channels, holding 255 * x for x in [-1, 1] (= 2*pixel - 255 exactly for
-        8-bit imagery normalised as predict.py:93 does); the first convolution's weights carry the 1/255."""
-        assert C <= INPUT_C
-        t = T(self.buf(H, W, INPUT_C, "f16"), 0, INPUT_C, ctrue=C, wscale=1.0 / INPUT_SCALE)
+        """Network input.  All five networks start with a 3x3 convolution on the RGB tile (res34.py:50, scse.py:52
+        stride 1; hrnet.py:168, v3plus.py:173 stride 2), so the input buffer holds the tile already im2col'ed for
+        that convolution: fp16, at the stem's OUTPUT resolution, channel (kh*3+kw)*3+c = 255 * x[oy*s+kh-pt,
+        ox*s+kw-pl, c] (zero outside the tile: TF 'same' padding), 27 channels padded to 32.  255*x = 2*pixel-255
+        is exact in fp16 for 8-bit imagery normalised as predict.py:93 does; the stem weights carry the 1/255.
+        The stem then is a 1x1 tensor-core convolution with K = 32.  The buffer is laid out when the stem conv is
+        built (``conv`` sees it is fed by the plan input)."""
+        assert C == 3
+        t = T(self.buf(H, W, INPUT_C, "f16"), 0, INPUT_C, ctrue=27, wscale=1.0 / INPUT_SCALE)
         self.plan.input = t.buf.id
+        self._input_hw = (H, W)
+        self._input_used = False
         return t
+
+    def _stem(self, x, name, cout, s, bn, act, out, he):
+        """3x3 stem conv on the plan input, lowered to a 1x1 conv over the im2col'ed input buffer."""
+        assert not self._input_used, "the plan input feeds exactly one (stem) convolution"
+        self._input_used = True
+        H, W = self._input_hw
+        kern = self._get(name + "/k", (3, 3, 3, cout), "he_normal" if he else "glorot_uniform")
+        bias = self._get(name + "/b", (cout,), "zeros")
+        w = kern.reshape(27, cout).T.copy()[None]  # (1, Cout, 27): column (kh*3+kw)*3+c
+        if bn:
+            sc, sh = self._bn(bn if isinstance(bn, str) else name + "_bn", cout)
+            w = w * sc[None, :, None]
+            bias = bias * sc + sh
+        wp = np.zeros((1, cout, INPUT_C), np.float32)
+        wp[:, :, :27] = w * np.float32(x.wscale)
+        Ho, Wo = math.ceil(H / s), math.ceil(W / s)
+        x.buf.H, x.buf.W = Ho, Wo  # the gather writes the input at the stem's output resolution
+        self.plan.input_stride = s
+        if out is None:
+            out = self.new(Ho, Wo, cout)
+        a = ACT_RELU if act == "relu" else ACT_NONE
+        self._conv_op(x, wp, bias, [(0, 0)], 1, Ho, Wo, a, None, ACT_NONE, out, name=name, macs_per_pixel=cout * 27)
+        return out
 
     def _emit(self, **op):
         self.plan.ops.append(op)
@@ -202,6 +233,9 @@ class Net:
 
         act applies to conv(+BN).  With ``res`` the result is ``act(conv + res)`` or, when
         ``res_after_act`` (res34's res_block1, res34.py:40-45), ``relu(act(conv) + res)``."""
+        if x.buf.id == self.plan.input:
+            assert k == 3 and d == 1 and res is None and not f32_out and not cout_pad
+            return self._stem(x, name, cout, s, bn, act, out, he)
         kern = self._get(name + "/k", (k, k, x.cin, cout), "he_normal" if he else "glorot_uniform")
         bias = self._get(name + "/b", (cout,), "zeros")
         w = kern.reshape(k * k, x.cin, cout).transpose(0, 2, 1).copy()  # (taps, Cout, Cin)
@@ -266,7 +300,8 @@ class Net:
         pl, _ = same_pad(x.W, 3, s)
         self.plan.flops += 2 * self.plan.batch * Ho * Wo * x.C * 9
         self._emit(op=OP_DWCONV, name=name + "/dw", x=x.ref(), y=mid.ref(), stride=s, pad_t=pt, pad_l=pl,
-                   relu_in=int(relu_in), w=np.ascontiguousarray(dw.reshape(9, x.C), np.float32))
+                   relu_in=int(relu_in), w=h16_to_f32(to_h16(dw.reshape(9, x.C))),  # fp16 weights like every conv
+                   w32=np.ascontiguousarray(dw.reshape(9, x.C), np.float32) if self.keep_f32 else None)
         w = pw.reshape(1, x.C, cout).transpose(0, 2, 1).copy()
         if bn:
             sc, sh = self._bn(name + "_bn", cout)

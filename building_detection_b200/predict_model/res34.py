@@ -14,7 +14,7 @@ def build(g: Net):
     x = g.input()
 
     def cbr(t, name, out=None):  # bn_conv_a, res34.py:32-38 (he_normal, BN named '<name>_BN')
-        return g.conv(t, name, 64 if t.cin == 3 else t.C, k=3, bn=name + "_BN", act="relu", he=True, out=out)
+        return g.conv(t, name, 64 if t.buf.id == g.plan.input else t.C, k=3, bn=name + "_BN", act="relu", he=True, out=out)
 
     def res_block(t, name, out=None):  # res_block1, res34.py:40-45: relu(x + relu(bn(conv(relu(bn(conv x))))))
         a = cbr(t, name + "_1")

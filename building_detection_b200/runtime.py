@@ -70,7 +70,7 @@ _SIGS = {
     "bd_plan_time_ops": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "bd_plan_op_info": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]),
     "bd_tiles_gather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
-                                  C.c_void_p, C.c_void_p]),
+                                  C.c_void_p, C.c_int, C.c_void_p]),
     "bd_stitch_or": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                C.c_void_p]),
     "bd_fuse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),

@@ -90,7 +90,8 @@ class SceneRunner:
             for mi, m in enumerate(self.models):
                 plan = m.native_plan(n)
                 x_ptr = plan.buffer_ptr(plan.plan.input)
-                R.check(L.bd_tiles_gather(self.ctx, scene_dev.data_ptr(), h, w, R._ptr(ys), R._ptr(xs), n, x_ptr, stream))
+                R.check(L.bd_tiles_gather(self.ctx, scene_dev.data_ptr(), h, w, R._ptr(ys), R._ptr(xs), n, x_ptr,
+                                          plan.plan.input_stride, stream))
                 plan.run_device(0, 0, self.tile_masks.data_ptr(), stream)
                 R.check(L.bd_stitch_or(self.ctx, self.tile_masks.data_ptr(), R._ptr(ys), R._ptr(xs), n,
                                        out[mi].data_ptr(), h, w, stream))

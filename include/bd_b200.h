@@ -97,9 +97,11 @@ int bd_plan_add_skfuse(bd_plan* plan, const bd_tref* xs4, int g_vec, const int32
                        const float* scale_host, const float* shift_host);
 /* broadcast a pooled vector over a map slice (UpSampling2D of a 1x1 map, v3plus.py:302-304) */
 int bd_plan_add_bcast(bd_plan* plan, int v_vec, bd_tref y);
-/* allocates the arena, uploads weights, encodes TMA tensor maps.  input_buf: fp16 (N,512,512,8) map holding
- * [255*r, 255*g, 255*b, 0 x5] (what bd_tiles_gather writes; the first convolution's weights carry the 1/255);
- * logits_buf: fp32 2-channel map at 512/logits_up resolution. */
+/* allocates the arena, uploads weights, encodes TMA tensor maps.  input_buf: the network input im2col'ed for its
+ * 3x3 stem convolution of stride s (1 or 2): fp16 (N, 512/s, 512/s, 32), channel (kh*3+kw)*3+c = 255 * x at
+ * input pixel (oy*s+kh-pad, ox*s+kw-pad) with TF 'same' padding, zero outside the tile, 27 channels padded to 32
+ * (what bd_tiles_gather writes; the stem weights carry the 1/255); logits_buf: fp32 2-channel map at
+ * 512/logits_up resolution. */
 int bd_plan_finalize(bd_plan* plan, int input_buf, int logits_buf, int logits_up);
 /* One forward of the whole network.  x_dev: fp32 (N,512,512,3) NHWC in [-1,1] as handed to model.predict
  * (converted on the device into the input buffer), or NULL to use what is already in the input buffer (e.g.
@@ -125,10 +127,11 @@ int bd_plan_op_info(bd_plan* plan, int i, int* kind, double* flops);
 
 /* ---- tiler / stitcher: replace predict.py:detection (90-116) ------------------------------- */
 /* Gather n 512x512 tiles whose top-left corners are (ys[i], xs[i]) from a BGR u8 scene (h,w,3) into the plan
- * input layout: fp16 (n,512,512,8), channels [2r-255, 2g-255, 2b-255, 0 x5] = 255 * (pixel/127.5 - 1) exactly
- * (predict.py:93), zero outside the scene (predict.py:102-104 pads the *normalised* image with zeros). */
+ * input layout for a stem of stride stem_stride (see bd_plan_finalize): values 2*pixel-255 = 255 * (pixel/127.5 - 1)
+ * exactly (predict.py:93), zero outside the scene (predict.py:102-104 pads the *normalised* image with zeros) and
+ * outside the tile ('same' padding of the stem). */
 int bd_tiles_gather(bd_ctx* ctx, const uint8_t* scene_bgr_dev, int h, int w, const int32_t* ys_host,
-                    const int32_t* xs_host, int n, void* x_dev, void* stream);
+                    const int32_t* xs_host, int n, void* x_dev, int stem_stride, void* stream);
 /* OR tile masks (n,512,512) into the scene mask (h,w): scene |= 255 where the tile says class 1
  * (predict.py:113-114: int8 accumulate then >=1 -> 255). */
 int bd_stitch_or(bd_ctx* ctx, const uint8_t* tile_masks_dev, const int32_t* ys_host, const int32_t* xs_host,

@@ -95,7 +95,8 @@ class Interp:
         pt, pl = op["pad_t"], op["pad_l"]
         pb = max(0, (Ho - 1) * s + 3 - pt - H)
         pr = max(0, (Wo - 1) * s + 3 - pl - W)
-        w = torch.from_numpy(op["w"]).view(3, 3, c).permute(2, 0, 1).unsqueeze(1).contiguous()
+        wsrc = op["w32"] if (not self.emu and op.get("w32") is not None) else op["w"]
+        w = torch.from_numpy(np.ascontiguousarray(wsrc)).view(3, 3, c).permute(2, 0, 1).unsqueeze(1).contiguous()
         y = F.conv2d(F.pad(x, (pl, pr, pt, pb)), w, None, stride=s, groups=c)
         self._store(op["y"], y.permute(0, 2, 3, 1))
 
@@ -164,10 +165,7 @@ class Interp:
 
     def run(self, x_nhwc=None):
         if x_nhwc is not None:
-            # the product stores the network input as 255 * x in fp16, zero-padded to graph.INPUT_C channels
-            xin = torch.as_tensor(np.asarray(x_nhwc), dtype=torch.float32) * G.INPUT_SCALE
-            self.b[self.p.input].zero_()
-            self.b[self.p.input][..., :xin.shape[-1]] = _q(xin) if self.emu else xin
+            self.b[self.p.input] = im2col_input(x_nhwc, self.p.input_stride, self.emu)
         disp = {G.OP_CONV: self._conv, G.OP_DWCONV: self._dwconv, G.OP_MAXPOOL: self._maxpool,
                 G.OP_ADDN: self._addn, G.OP_GAP: self._gap, G.OP_DENSE: self._dense, G.OP_GATE: self._gate,
                 G.OP_SKFUSE: self._skfuse, G.OP_BCAST: self._bcast}
@@ -182,6 +180,22 @@ class Interp:
             else:
                 disp[op["op"]](op)
         return None if probs is None else probs.numpy()
+
+
+def im2col_input(x_nhwc, stride, emulate_h16=True):
+    """The product's network-input layout (graph.Net.input): 255 * x, im2col'ed for the 3x3 stem conv with TF
+    'same' padding at the stem's output resolution, channel (kh*3+kw)*3+c, padded to graph.INPUT_C channels."""
+    x = torch.as_tensor(np.asarray(x_nhwc), dtype=torch.float32) * G.INPUT_SCALE
+    n, H, W, _ = x.shape
+    pt, pb = G.same_pad(H, 3, stride)
+    pl, pr = G.same_pad(W, 3, stride)
+    xp = F.pad(x.permute(0, 3, 1, 2), (pl, pr, pt, pb)).permute(0, 2, 3, 1)
+    Ho, Wo = -(-H // stride), -(-W // stride)
+    cols = [xp[:, kh:kh + (Ho - 1) * stride + 1:stride, kw:kw + (Wo - 1) * stride + 1:stride, :]
+            for kh in range(3) for kw in range(3)]
+    out = torch.zeros(n, Ho, Wo, G.INPUT_C)
+    out[..., :27] = torch.cat(cols, dim=-1)
+    return _q(out) if emulate_h16 else out
 
 
 def run_plan(plan, x_nhwc, emulate_h16=True):

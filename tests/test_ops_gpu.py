@@ -94,22 +94,28 @@ def test_conv_direct(gpu, case):
     conv_case(umma=False, expect="direct", **DIRECT_CASES[case])
 
 
-def test_stem_conv_f32_input(gpu):
-    """3-channel network input (stored as 8 fp16 channels holding 2*pixel-255) -> 64 channels on the tensor cores
-    (res34.py:50, hrnet.py:168 stride 2)."""
+def test_stem_conv(gpu):
+    """3x3 stem on the RGB tile, lowered to a K=32 tensor-core 1x1 conv over the im2col'ed input buffer that
+    bd_plan_run builds from the float tile (res34.py:50 stride 1, hrnet.py:168 stride 2)."""
+    from building_detection_b200.runtime import NativePlan
+    from oracle import plan_interp
+    import torch
     for s in (1, 2):
         def builder(g):
-            x = g.input(64, 64, 3)
+            x = g.input()
             return x, g.conv(x, "stem", 64, k=3, s=s, bn=True, act="relu")
         plan, (x, y), _ = build_two_pass(builder, 2)
-        assert plan.ops[0]["path"] == "umma"
+        assert plan.ops[0]["path"] == "umma" and plan.input_stride == s
         rng = np.random.default_rng(3)
-        xin = np.zeros((2, 64, 64, 8), np.float32)
-        xin[..., :3] = 2.0 * rng.integers(0, 256, (2, 64, 64, 3)) - 255.0
-        inputs = {x.buf.id: xin}
-        ref = run_interp(plan, inputs).get(y.buf.id)
-        nat = run_native(plan, inputs)
-        assert_close(nat.read_buffer(y.buf.id), ref)
+        xin = (rng.integers(0, 256, (2, 512, 512, 3)) / 127.5 - 1).astype(np.float32)
+        it = plan_interp.Interp(plan, True)
+        with torch.no_grad():
+            it.run(xin)
+        nat = NativePlan(plan)
+        xd = torch.from_numpy(xin).cuda()
+        nat.run_device(xd.data_ptr(), 0, 0)
+        assert_close(nat.read_buffer(x.buf.id), it.get(x.buf.id), ulps=0.0, rel_rms=0.0)  # the im2col'ed input, exact
+        assert_close(nat.read_buffer(y.buf.id), it.get(y.buf.id))
         nat.close()
 
 

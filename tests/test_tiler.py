@@ -52,23 +52,26 @@ def test_device_gather_and_stitch_match_reference(gpu, case):
     L, ctx = R.lib(), R.context(0)
     scene = torch.from_numpy(img).cuda()
     out = torch.zeros((h, w), dtype=torch.uint8, device="cuda")
+    from oracle import plan_interp
     for b0 in range(0, len(origins), 5):
         chunk = origins[b0:b0 + 5]
         n = len(chunk)
         ys = np.asarray([c[0] for c in chunk], np.int32)
         xs = np.asarray([c[1] for c in chunk], np.int32)
-        x = torch.empty((n, 512, 512, 8), dtype=torch.float16, device="cuda")
-        R.check(L.bd_tiles_gather(ctx, scene.data_ptr(), h, w, R._ptr(ys), R._ptr(xs), n, x.data_ptr(), None))
-        torch.cuda.synchronize()
-        x8 = x.cpu().numpy().astype(np.float64)
-        # plan input layout: 255 * (predict.py:91-104's BGR->RGB, /127.5-1, zero pad) = 2*pixel-255, exact in fp16
+        # what predict.py:91-104 feeds the model: BGR->RGB, /127.5-1 in float64, zero pad, float32 cast
         pad = np.zeros((n, 512, 512, 3))
         for k, (i, j) in enumerate(chunk):
             sub = img[i:i + 512, j:j + 512, ::-1] / 127.5 - 1
             pad[k, :sub.shape[0], :sub.shape[1]] = sub
-        assert np.array_equal(x8, np.round(x8)) and not x8[..., 3:].any()
-        xh = (x8[..., :3] / 255.0).astype(np.float32)
-        np.testing.assert_array_equal(xh, pad.astype(np.float32))
+        xh = pad.astype(np.float32)
+        for stride in (1, 2):  # plan input layout: the tile im2col'ed for the 3x3 stem, 255*x exact in fp16
+            o = 512 // stride
+            x = torch.empty((n, o, o, 32), dtype=torch.float16, device="cuda")
+            R.check(L.bd_tiles_gather(ctx, scene.data_ptr(), h, w, R._ptr(ys), R._ptr(xs), n, x.data_ptr(), stride, None))
+            torch.cuda.synchronize()
+            want_x = plan_interp.im2col_input(xh, stride, emulate_h16=False).numpy()
+            np.testing.assert_array_equal(x.cpu().numpy().astype(np.float32), np.round(want_x))
+            assert np.abs(want_x - np.round(want_x)).max() < 1e-4  # 255*x is an integer up to float32 rounding
         tile_mask = torch.from_numpy(fake_probs(xh).argmax(-1).astype(np.uint8)).cuda()
         R.check(L.bd_stitch_or(ctx, tile_mask.data_ptr(), R._ptr(ys), R._ptr(xs), n, out.data_ptr(), h, w, None))
     torch.cuda.synchronize()
