@@ -93,15 +93,18 @@ struct DwParams {
   int N, Ho, Wo, stride, pad_t, pad_l, relu_in;
   const h16* w;  // [9][C] fp16
 };
-// thread = (8-channel group, output column, block of DW_ROWS output rows, image): the 9x8 weights stay in
-// registers and the 3-row input window slides down, so an output costs 3 (stride 1) new 16-byte loads instead of 9
-// plus 18 weight loads; consecutive threads are consecutive channel groups (coalesced 16-byte vectors).
+// thread = (8-channel group, output column, block of DW_ROWS output rows, image): the 9x8 fp16 weights stay packed
+// in registers and the 3-row input window slides down (3 new 16-byte loads per output at stride 1).  The 9-tap sum
+// runs on packed half2 FMAs (fp16 accumulate, one rounding per tap, tap order kh-major): 36 instructions per 8
+// output channels instead of ~290 with fp32 conversion; oracle/plan_interp.py mirrors this rounding sequence
+// exactly.  Consecutive threads are consecutive channel groups (coalesced 16-byte vectors).
 constexpr int DW_ROWS = 4;
 template <int STRIDE>
-__global__ void __launch_bounds__(TPB, 2) dwconv3x3_kernel(const __grid_constant__ DwParams p) {
+__global__ void __launch_bounds__(TPB) dwconv3x3_kernel(const __grid_constant__ DwParams p) {
   const int C = p.x.c, cg = C >> 3;
   const int rb = (p.Ho + DW_ROWS - 1) / DW_ROWS;
   const size_t total = static_cast<size_t>(p.N) * rb * p.Wo * cg;
+  const __half2 zero2 = __float2half2_rn(0.0f);
   for (size_t idx = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; idx < total;
        idx += static_cast<size_t>(gridDim.x) * TPB) {
     const int g = static_cast<int>(idx % cg);
@@ -109,21 +112,26 @@ __global__ void __launch_bounds__(TPB, 2) dwconv3x3_kernel(const __grid_constant
     const int ow = static_cast<int>(t % p.Wo);
     t /= p.Wo;
     const int ob = static_cast<int>(t % rb), n = static_cast<int>(t / rb);
-    h16x8 wp[9];  // packed fp16 weights of this channel group (36 registers), widened at use
+    h16x8 wp[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) wp[k] = *reinterpret_cast<const h16x8*>(p.w + k * C + g * 8);
     const int iw0 = ow * STRIDE - p.pad_l;
     const h16* xb = static_cast<const h16*>(p.x.base) + p.x.c0 + g * 8;
     const size_t img = static_cast<size_t>(n) * p.x.H;
-    auto load_row = [&](int ih, h16x8* row) {  // 3 taps of input row ih (zero outside the map)
+    auto load_row = [&](int ih, h16x8* row) {  // 3 taps of input row ih (zero outside the map), ReLU applied once
       const bool rok = ih >= 0 && ih < p.x.H;
 #pragma unroll
       for (int kw = 0; kw < 3; ++kw) {
         const int iw = iw0 + kw;
-        if (rok && iw >= 0 && iw < p.x.W)
-          row[kw] = *reinterpret_cast<const h16x8*>(xb + ((img + ih) * p.x.W + iw) * p.x.ctot);
-        else
-          row[kw] = h16x8{};
+        h16x8 v{};
+        if (rok && iw >= 0 && iw < p.x.W) {
+          v = *reinterpret_cast<const h16x8*>(xb + ((img + ih) * p.x.W + iw) * p.x.ctot);
+          if (p.relu_in) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v.v[j] = __hmax2(v.v[j], zero2);
+          }
+        }
+        row[kw] = v;
       }
     };
     h16x8 win[3][3];  // input rows ih0 .. ih0+2 of the current output row
@@ -138,18 +146,15 @@ __global__ void __launch_bounds__(TPB, 2) dwconv3x3_kernel(const __grid_constant
       const int ih = oh * STRIDE - p.pad_t;
       if (STRIDE == 2 && r > 0) load_row(ih + 1, win[1]);
       load_row(ih + 2, win[2]);
-      float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      h16x8 acc{};
 #pragma unroll
       for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-          float xv[8], wv[8];
-          unpack8(win[kh][kw], xv);
-          unpack8(wp[kh * 3 + kw], wv);
+        for (int kw = 0; kw < 3; ++kw)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] = fmaf(p.relu_in ? fmaxf(xv[j], 0.0f) : xv[j], wv[j], acc[j]);
-        }
-      st8(p.y, (static_cast<size_t>(n) * p.Ho + oh) * p.Wo + ow, g * 8, acc);
+          for (int j = 0; j < 4; ++j) acc.v[j] = __hfma2(win[kh][kw].v[j], wp[kh * 3 + kw].v[j], acc.v[j]);
+      *reinterpret_cast<h16x8*>(static_cast<h16*>(p.y.base) +
+                                ((static_cast<size_t>(n) * p.Ho + oh) * p.Wo + ow) * p.y.ctot + p.y.c0 + g * 8) = acc;
       if (STRIDE == 1) {
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw) { win[0][kw] = win[1][kw]; win[1][kw] = win[2][kw]; }

@@ -95,9 +95,21 @@ class Interp:
         pt, pl = op["pad_t"], op["pad_l"]
         pb = max(0, (Ho - 1) * s + 3 - pt - H)
         pr = max(0, (Wo - 1) * s + 3 - pl - W)
-        wsrc = op["w32"] if (not self.emu and op.get("w32") is not None) else op["w"]
-        w = torch.from_numpy(np.ascontiguousarray(wsrc)).view(3, 3, c).permute(2, 0, 1).unsqueeze(1).contiguous()
-        y = F.conv2d(F.pad(x, (pl, pr, pt, pb)), w, None, stride=s, groups=c)
+        xp = F.pad(x, (pl, pr, pt, pb))
+        if not self.emu:
+            wsrc = op["w32"] if op.get("w32") is not None else op["w"]
+            w = torch.from_numpy(np.ascontiguousarray(wsrc)).view(3, 3, c).permute(2, 0, 1).unsqueeze(1).contiguous()
+            y = F.conv2d(xp, w, None, stride=s, groups=c)
+        else:
+            # the device kernel accumulates the nine taps with packed half2 FMAs: fp16 accumulator, one rounding
+            # per tap, kh-major order.  x*w + acc is exact in float64, so one rounding to fp16 reproduces the FMA.
+            w = torch.from_numpy(np.ascontiguousarray(op["w"])).view(3, 3, c).double()
+            acc = torch.zeros(x.shape[0], c, Ho, Wo, dtype=torch.float64)
+            for kh in range(3):
+                for kw in range(3):
+                    tap = xp[:, :, kh:kh + (Ho - 1) * s + 1:s, kw:kw + (Wo - 1) * s + 1:s].double()
+                    acc = (acc + tap * w[kh, kw].view(1, -1, 1, 1)).to(torch.float16).double()
+            y = acc.float()
         self._store(op["y"], y.permute(0, 2, 3, 1))
 
     def _maxpool(self, op):
