@@ -13,7 +13,19 @@ namespace ccl {
 
 constexpr int TPB = 256;
 
-__device__ __forceinline__ int find_root(const int* __restrict__ L, int i) {
+// find with path halving: every visited node is re-pointed at its grandparent.  Labels only ever decrease towards
+// the root, so the racy plain stores are benign (any stored value is an ancestor).
+__device__ __forceinline__ int find_root(int* L, int i) {
+  int p = L[i];
+  while (p != i) {
+    const int g = L[p];
+    if (g != p) L[i] = g;
+    i = p;
+    p = g;
+  }
+  return i;
+}
+__device__ __forceinline__ int find_root_ro(const int* L, int i) {  // read-only walk
   int p = L[i];
   while (p != i) {
     i = p;
@@ -33,39 +45,78 @@ __device__ __forceinline__ void unite(int* L, int a, int b) {
   }
 }
 
-// L[p] = p where the predicate holds, else -1.  fg != 0: label the set pixels; fg == 0: label the zero pixels.
-static __global__ void __launch_bounds__(TPB) init_labels(const uint8_t* __restrict__ m, int* __restrict__ L, size_t n, int fg) {
-  for (size_t i = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * TPB)
-    L[i] = ((m[i] != 0) == (fg != 0)) ? static_cast<int>(i) : -1;
-}
-// 8-connectivity: neighbours already visited in raster order are W, NW, N, NE; N subsumes NW/NE/W (they are
-// 4-adjacent to it or joined through it by their own unions).
-static __global__ void __launch_bounds__(TPB) merge8(int* L, int H, int W) {
-  const size_t n = static_cast<size_t>(H) * W;
-  for (size_t i = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * TPB) {
-    if (L[i] < 0) continue;
-    const int x = static_cast<int>(i % W), y = static_cast<int>(i / W);
-    const int p = static_cast<int>(i);
-    if (y > 0 && L[i - W] >= 0) { unite(L, p, p - W); continue; }
-    if (x > 0 && L[i - 1] >= 0) unite(L, p, p - 1);
-    else if (y > 0 && x > 0 && L[i - W - 1] >= 0) unite(L, p, p - W - 1);
-    if (y > 0 && x + 1 < W && L[i - W + 1] >= 0) unite(L, p, p - W + 1);
+// Run-based labelling.  Pass 1: one warp per image row labels every pixel of the set with the index of the first
+// pixel of its horizontal run (ballot + carry, 32 pixels per step); unions then only happen where runs of
+// adjacent rows start to touch, O(#run adjacencies) instead of O(#pixels), and the flatten walks run starts only.
+// set = pixels with (m != 0) == (fg != 0).
+static __global__ void __launch_bounds__(TPB) init_runs(const uint8_t* __restrict__ m, int* __restrict__ L, int H, int W, int fg) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = TPB / 32;
+  for (int y = blockIdx.x * warps_per_block + (threadIdx.x >> 5); y < H; y += gridDim.x * warps_per_block) {
+    const size_t row = static_cast<size_t>(y) * W;
+    int carry = -1;  // run start (pixel index) of a run reaching the previous chunk's last pixel, else -1
+    for (int x0 = 0; x0 < W; x0 += 32) {
+      const int x = x0 + lane;
+      const bool in = x < W && ((m[row + x] != 0) == (fg != 0));
+      const unsigned mask = __ballot_sync(0xffffffffu, in);
+      int lab = -1;
+      if (in) {
+        const unsigned zeros_below = ~mask & ((1u << lane) - 1u);
+        if (zeros_below == 0) lab = carry >= 0 ? carry : static_cast<int>(row) + x0;
+        else lab = static_cast<int>(row) + x0 + (32 - __clz(zeros_below));
+      }
+      if (x < W) L[row + x] = lab;
+      carry = __shfl_sync(0xffffffffu, lab, 31);  // -1 if the chunk's last pixel is not in the set
+    }
   }
 }
-// 4-connectivity (background regions)
-static __global__ void __launch_bounds__(TPB) merge4(int* L, int H, int W) {
+// unions between runs of adjacent rows; CONN8: also diagonal contact
+template <bool CONN8>
+static __global__ void __launch_bounds__(TPB) merge_runs(int* L, int H, int W) {
   const size_t n = static_cast<size_t>(H) * W;
-  for (size_t i = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * TPB) {
-    if (L[i] < 0) continue;
-    const int x = static_cast<int>(i % W), y = static_cast<int>(i / W);
-    const int p = static_cast<int>(i);
-    if (y > 0 && L[i - W] >= 0) unite(L, p, p - W);
-    if (x > 0 && L[i - 1] >= 0) unite(L, p, p - 1);
+  for (size_t i = static_cast<size_t>(W) + blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * TPB) {
+    const int lp = L[i];
+    if (lp < 0) continue;
+    const int x = static_cast<int>(i % W);
+    const int up = L[i - W];
+    const int ul = x > 0 ? L[i - W - 1] : -1;
+    const bool start = x == 0 || L[i - 1] < 0;  // first pixel of its run (signs never change; L[i] itself may
+                                                 // already point at another run's start after a concurrent union)
+    if (up >= 0) {
+      if (start || ul < 0) unite(L, lp, up);  // where the lower run or the upper run begins inside the overlap
+    } else if (CONN8) {
+      if (ul >= 0 && start) unite(L, lp, ul);  // upper run ends diagonally before this run starts
+      if (x + 1 < W) {
+        const int ur = L[i - W + 1];
+        if (ur >= 0 && L[i + 1] < 0) unite(L, lp, ur);  // upper run starts diagonally after this run ends
+      }
+    }
   }
 }
-static __global__ void __launch_bounds__(TPB) flatten(int* L, size_t n) {
-  for (size_t i = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * TPB)
-    if (L[i] >= 0) L[i] = find_root(L, static_cast<int>(i));
+// Flatten in three passes.  (1) every run start walks to its root with path halving: racy, leaves a shallow but
+// not necessarily flat forest (a halving store may land after another thread's final store, so the result of
+// this pass is not used); (2) every run start takes its root by a read-only walk (all concurrent stores write
+// roots or leave ancestors, both valid for readers); (3) every other pixel takes its run start's root.
+static __global__ void __launch_bounds__(TPB) compress_runs(int* L, size_t n, int W) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * TPB) {
+    if (L[i] < 0) continue;
+    if ((i % W == 0) || L[i - 1] < 0) find_root(L, static_cast<int>(i));
+  }
+}
+static __global__ void __launch_bounds__(TPB) flatten_runs(int* L, size_t n, int W) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * TPB) {
+    if (L[i] < 0) continue;
+    if ((i % W == 0) || L[i - 1] < 0) L[i] = find_root_ro(L, static_cast<int>(i));
+  }
+}
+static __global__ void __launch_bounds__(TPB) flatten_pixels(int* L, size_t n, int W) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * TPB) {
+    const int l = L[i];
+    if (l < 0) continue;
+    const bool start = (i % W == 0) || L[i - 1] < 0;
+    if (!start) L[i] = L[l];  // l is this pixel's run start (a run start never has an in-set left neighbour)
+  }
 }
 
 // ---- hole filling: cv::fillPoly / drawContours(FILLED) of an external contour = the component plus every pixel

@@ -36,6 +36,8 @@ constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
 constexpr int OUT_CHUNK = 64;                             // channels per staging tile / TMA store
 constexpr int OUT_STAGE_BYTES = BLOCK_M * OUT_CHUNK * 2;  // 16 KB
 constexpr int MAX_TAPS = 18;
+// halo path: one (16+2) x (8+2) pixel halo box per 64-channel chunk feeds all nine taps of a 3x3 convolution
+constexpr int HALO_W = 10, HALO_H = 18, HALO_BYTES = HALO_W * HALO_H * 128, HALO_STAGE = 23 * 1024;
 constexpr int EPI_WARPS = 8;                 // two warps per TMEM lane quadrant, each takes half of a column chunk
 constexpr int THREADS = 64 + 32 * EPI_WARPS;
 
@@ -44,7 +46,9 @@ struct Params {
   int bw, bh, bn;
   int tiles_w, tiles_h, tiles_n, n_tiles, total_tiles;
   int block_n, kchunks, ntaps, stages, group, tmem_cols;  // group: k-blocks per shared-memory stage
-  int spec;  // 0 generic loops; 1 = 9 taps x 1 chunk, group 3; 2 = 9 taps x 2 chunks, group 2 (fully unrolled loops)
+  int spec;  // 0 generic loops; 1 = 9 taps x 1 chunk, group 3; 2 = 9 taps x 2 chunks, group 2 (fully unrolled loops);
+             // 3 = halo path: 3x3 stride 1, one halo box per chunk, weights resident in shared memory
+  int wres_bytes;  // bytes of resident weights (spec 3), 0 otherwise
   int tap_map[MAX_TAPS], tap_dy[MAX_TAPS], tap_dx[MAX_TAPS];
   float* y32;  // fp32 output path (Cout <= 16): direct stores
   int y_ctot, y_c0, y_H, y_W, out_scale, out_oy, out_ox;
@@ -177,6 +181,19 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
+// same layout, explicit stride between 8-row groups.  The swizzle is a function of the absolute shared-memory
+// address (measured: tools/micro/desc_shift.cu), so a descriptor may start at any 128-byte row of a TMA-written
+// tile and step between row groups by any multiple of 128 bytes -- which is what reading the nine shifted taps of
+// a 3x3 convolution out of one halo tile needs.
+__device__ __forceinline__ uint64_t make_sdesc_sbo(uint32_t saddr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
 // kind::f16 instruction descriptor: D=f32 (bit 4), A and B formats at [7,10) / [10,13) = 0 (fp16; 1 would be
 // bf16), both K-major, N>>3 at [17,23), M>>4 at [24,29)
 __device__ __forceinline__ uint32_t make_idesc(int n) {
@@ -208,13 +225,15 @@ __device__ __forceinline__ void ring_advance(Ring& r, const Params& p, uint32_t 
 }
 template <int NTAPS, int KCH, int G>
 __device__ __forceinline__ void produce_tile(const Maps& maps, const Params& p, Ring& r, uint32_t smem_base, uint32_t sub_bytes,
-                                             uint32_t full0, uint32_t empty0, int w0, int h0, int n0, int n_base) {
+                                             uint32_t full0, uint32_t empty0, int w0, int h0, int n0, int n_base, int& tr_i,
+                                             int tile) {
   static_assert((NTAPS * KCH) % G == 0, "group must divide the k-block count");
   const char* maps_a = reinterpret_cast<const char*>(&maps.a[0]);
 #pragma unroll
   for (int grp = 0; grp < NTAPS * KCH / G; ++grp) {
     mbar_wait(r.eb, r.ph ^ 1u);
     if (elect_one()) {
+      trace_ev(p, 0, tr_i, tile, grp);
       mbar_expect_tx(r.fb, sub_bytes * G);
 #pragma unroll
       for (int g = 0; g < G; ++g) {
@@ -231,13 +250,15 @@ __device__ __forceinline__ void produce_tile(const Maps& maps, const Params& p, 
 }
 template <int NTAPS, int KCH, int G>
 __device__ __forceinline__ void mma_tile(const Params& p, Ring& r, uint64_t desc0, uint32_t sub_bytes, uint32_t full0,
-                                         uint32_t empty0, uint32_t tacc, uint32_t idesc, uint32_t tfull_bar) {
+                                         uint32_t empty0, uint32_t tacc, uint32_t idesc, uint32_t tfull_bar, int& tr_i,
+                                         int tile) {
   const int last_c = p.Cin - (KCH - 1) * BLOCK_K;  // channels in the last chunk of a tap (runtime, 8..64)
 #pragma unroll
   for (int grp = 0; grp < NTAPS * KCH / G; ++grp) {
     mbar_wait(r.fb, r.ph);
     tc_fence_after();
     if (elect_one()) {
+      trace_ev(p, 1, tr_i, tile, grp);
       const uint64_t d = desc0 + (r.off >> 4);
 #pragma unroll
       for (int g = 0; g < G; ++g) {
@@ -274,14 +295,17 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t b_bytes = static_cast<uint32_t>(p.block_n) * 128u;
   const uint32_t sub_bytes = A_STAGE_BYTES + b_bytes;                       // one k-block: A box + W tile
-  const uint32_t stage_bytes = sub_bytes * static_cast<uint32_t>(p.group);  // a stage holds `group` k-blocks
-  const uint32_t out0 = smem_base + static_cast<uint32_t>(p.stages) * stage_bytes;  // 2 staging tiles
+  const uint32_t stage_bytes = p.spec == 3 ? static_cast<uint32_t>(HALO_STAGE)
+                                           : sub_bytes * static_cast<uint32_t>(p.group);  // a stage holds `group` k-blocks
+  const uint32_t wres0 = smem_base + static_cast<uint32_t>(p.stages) * stage_bytes;      // resident weights (spec 3)
+  const uint32_t out0 = wres0 + static_cast<uint32_t>(p.wres_bytes);                      // 2 staging tiles
   const uint32_t res0 = out0 + 2u * OUT_STAGE_BYTES;                                 // 2 residual tiles (if any)
   const uint32_t bar_base = res0 + (p.res ? 2u * OUT_STAGE_BYTES : 0u);              // 8-byte slots
   const uint32_t full0 = bar_base, empty0 = bar_base + 8u * p.stages;
   const uint32_t tfull0 = bar_base + 16u * p.stages, tempty0 = tfull0 + 16u;
   const uint32_t rbar0 = tempty0 + 16u;
-  const uint32_t holder = rbar0 + 16u;
+  const uint32_t wbar = rbar0 + 16u;
+  const uint32_t holder = wbar + 16u;
   volatile uint32_t* holder_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (holder - smem_base));
 
   if (threadIdx.x == 0) {
@@ -294,6 +318,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
       mbar_init(tempty0 + 8u * a, EPI_WARPS);  // one arrival per epilogue warp
       mbar_init(rbar0 + 8u * a, 1);
     }
+    mbar_init(wbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_async_smem();
   }
@@ -316,14 +341,34 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
     uint32_t s = 0, sub = 0, ph = 0, a_s = smem_base, fb = full0, eb = empty0;  // ring position, kept incrementally
     const char* maps_a = reinterpret_cast<const char*>(&maps.a[0]);
     Ring ring{0u, 0u, 0u, full0, empty0};
+    if (p.spec == 3 && elect_one()) {  // all weight tiles once: [tap][chunk] blocks of block_n x 128 B
+      mbar_expect_tx(wbar, static_cast<uint32_t>(p.wres_bytes));
+      uint32_t dst = wres0;
+      for (int tap = 0; tap < 9; ++tap)
+        for (int c = 0; c < p.Cin; c += BLOCK_K, dst += b_bytes) tma_load_3d(dst, &maps.b, wbar, c, 0, tap);
+    }
+    __syncwarp();
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       int nt = 0, mt = tile;
       if (p.n_tiles > 1) { nt = tile % p.n_tiles; mt = tile / p.n_tiles; }
       const int tw = mt % p.tiles_w, t2 = mt / p.tiles_w;
       const int th = t2 % p.tiles_h, tn = t2 / p.tiles_h;
       const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn, n_base = nt * p.block_n;
-      if (p.spec == 1) { produce_tile<9, 1, 3>(maps, p, ring, smem_base, sub_bytes, full0, empty0, w0, h0, n0, n_base); continue; }
-      if (p.spec == 2) { produce_tile<9, 2, 2>(maps, p, ring, smem_base, sub_bytes, full0, empty0, w0, h0, n0, n_base); continue; }
+      if (p.spec == 3) {  // one halo box per 64-channel chunk
+        for (int c = 0; c < p.Cin; c += BLOCK_K) {
+          mbar_wait(ring.eb, ring.ph ^ 1u);
+          if (elect_one()) {
+            trace_ev(p, 0, tr_i, tile, c);
+            mbar_expect_tx(ring.fb, HALO_BYTES);
+            tma_load_4d(smem_base + ring.off, &maps.a[0], ring.fb, c, w0 - 1, h0 - 1, n0);
+          }
+          __syncwarp();
+          ring_advance(ring, p, HALO_STAGE, full0, empty0);
+        }
+        continue;
+      }
+      if (p.spec == 1) { produce_tile<9, 1, 3>(maps, p, ring, smem_base, sub_bytes, full0, empty0, w0, h0, n0, n_base, tr_i, tile); continue; }
+      if (p.spec == 2) { produce_tile<9, 2, 2>(maps, p, ring, smem_base, sub_bytes, full0, empty0, w0, h0, n0, n_base, tr_i, tile); continue; }
       for (int tap = 0; tap < p.ntaps; ++tap) {
         const CUtensorMap* tm = reinterpret_cast<const CUtensorMap*>(maps_a + p.tap_map[tap] * sizeof(CUtensorMap));
         const int cx = w0 + p.tap_dx[tap], cy = h0 + p.tap_dy[tap];
@@ -357,8 +402,37 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
       mbar_wait(tempty0 + 8u * a, aph ^ 1u);  // epilogue has drained this accumulator stage
       tc_fence_after();
       const uint32_t tacc = tmem_base + a * static_cast<uint32_t>(p.block_n);
-      if (p.spec == 1) { mma_tile<9, 1, 3>(p, ring, desc0, sub_bytes, full0, empty0, tacc, idesc, tfull0 + 8u * a); continue; }
-      if (p.spec == 2) { mma_tile<9, 2, 2>(p, ring, desc0, sub_bytes, full0, empty0, tacc, idesc, tfull0 + 8u * a); continue; }
+      if (p.spec == 3) {
+        if (ti == 0) mbar_wait(wbar, 0);
+        const uint64_t wdesc0 = make_sdesc(wres0);
+        const uint32_t dkb = b_bytes >> 4;  // descriptor units per weight tile
+        uint32_t kc = 0;
+        for (int c = p.Cin; c > 0; c -= BLOCK_K, ++kc) {  // c = channels left
+          mbar_wait(ring.fb, ring.ph);
+          tc_fence_after();
+          if (elect_one()) {
+            trace_ev(p, 1, tr_i, tile, c);
+            const uint64_t hdesc = make_sdesc_sbo(smem_base + ring.off, HALO_W * 128);
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              // tap (kh, kw) reads the halo rows shifted by kh halo rows and kw pixels
+              const uint64_t adesc = hdesc + (((tap / 3) * HALO_W + tap % 3) * 128 >> 4);
+              const uint64_t bdesc = wdesc0 + (tap * static_cast<uint32_t>(p.kchunks) + kc) * dkb;
+              tc_mma_f16(tacc, adesc, bdesc, idesc, (tap > 0 || kc > 0) ? 1u : 0u);
+              if (c > 16) tc_mma_f16(tacc, adesc + 2u, bdesc + 2u, idesc, 1u);
+              if (c > 32) tc_mma_f16(tacc, adesc + 4u, bdesc + 4u, idesc, 1u);
+              if (c > 48) tc_mma_f16(tacc, adesc + 6u, bdesc + 6u, idesc, 1u);
+            }
+            tc_commit(ring.eb);
+            if (c <= BLOCK_K) tc_commit(tfull0 + 8u * a);
+          }
+          __syncwarp();
+          ring_advance(ring, p, HALO_STAGE, full0, empty0);
+        }
+        continue;
+      }
+      if (p.spec == 1) { mma_tile<9, 1, 3>(p, ring, desc0, sub_bytes, full0, empty0, tacc, idesc, tfull0 + 8u * a, tr_i, tile); continue; }
+      if (p.spec == 2) { mma_tile<9, 2, 2>(p, ring, desc0, sub_bytes, full0, empty0, tacc, idesc, tfull0 + 8u * a, tr_i, tile); continue; }
       uint32_t accum = 0;
       for (int tap = 0; tap < p.ntaps; ++tap) {
         for (int c = p.Cin; c > 0; c -= BLOCK_K) {  // c = channels left in this tap
@@ -453,23 +527,40 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
           const uint8_t* rsrow = gen_base + (res0 - smem_base) + (gc & 1u) * OUT_STAGE_BYTES + r * 128;
           uint8_t* srow = gen_base + (out0 - smem_base) + ob * OUT_STAGE_BYTES + r * 128;
           const int cc = c0 + 32 * half;  // this warp's 32 columns (block_n is a multiple of 16)
+          const bool last_chunk = c0 + OUT_CHUNK >= p.block_n;
           if (cc < p.block_n) {
             uint32_t acc[32];
-            if (cc + 32 <= p.block_n) tmem_ld32(trow + cc, acc);
+            const bool wide = cc + 32 <= p.block_n;
+            if (wide) tmem_ld32(trow + cc, acc);
             else tmem_ld16(trow + cc, acc);
+            // bias of this warp's columns: issued while the TMEM load is in flight
+            float bb[32];
+            const int ngrp = wide ? 4 : 2;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int ch = n_base + cc + 8 * g;
+              float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+              if (g < ngrp && ch < p.Cout) {
+                b0 = __ldg(reinterpret_cast<const float4*>(p.bias + ch));
+                b1 = __ldg(reinterpret_cast<const float4*>(p.bias + ch + 4));
+              }
+              bb[8 * g + 0] = b0.x; bb[8 * g + 1] = b0.y; bb[8 * g + 2] = b0.z; bb[8 * g + 3] = b0.w;
+              bb[8 * g + 4] = b1.x; bb[8 * g + 5] = b1.y; bb[8 * g + 6] = b1.z; bb[8 * g + 7] = b1.w;
+            }
             tmem_ld_wait();
-            const int ngrp = (cc + 32 <= p.block_n) ? 4 : 2;
+            if (last_chunk) {  // the accumulator now lives in registers: hand the TMEM stage back to the MMA warp
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(tempty0 + 8u * a);
+            }
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               if (g >= ngrp) break;
               const int ch = n_base + cc + 8 * g;
               float v[8];
               if (ch < p.Cout) {  // Cout is a multiple of 8 on this path
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + ch));
-                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + ch + 4));
-                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = apply_act(__uint_as_float(acc[8 * g + j]) + bb[j], p.act_pre);
+                for (int j = 0; j < 8; ++j) v[j] = apply_act(__uint_as_float(acc[8 * g + j]) + bb[8 * g + j], p.act_pre);
                 if (has_res) {  // same swizzled position in the residual tile as in the staging tile
                   float rf[8];
                   unpack8(*reinterpret_cast<const h16x8*>(rsrow + (((4 * half + g) ^ (r & 7)) * 16)), rf);
@@ -486,6 +577,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
               const int chunk = (4 * half + g) ^ (r & 7);
               *reinterpret_cast<h16x8*>(srow + chunk * 16) = pack8(v);
             }
+          } else if (last_chunk) {  // nothing to read in the last chunk (block_n % 64 <= 32): still release the stage
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty0 + 8u * a);
           }
           fence_async_smem();
           epi_bar_sync();
@@ -496,10 +591,11 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
         }
       }
       if (et == 0) trace_ev(p, 3, tr_j, tile, 0);
-      // accumulator stage drained: let the MMA warp reuse it
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty0 + 8u * a);
+      if (p.y32) {  // (the fp16 path released the accumulator stage right after its last TMEM load)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty0 + 8u * a);
+      }
     }
     if (et == 0) tma_store_wait_all();
   }
@@ -578,6 +674,9 @@ inline int prepare(Launch* L, const TView& x, const TView& y, const TView* res, 
   p.bw = std::min(16, floor_pow2(Wo));
   p.bh = std::min(BLOCK_M / p.bw, floor_pow2(Ho));
   p.bn = BLOCK_M / (p.bw * p.bh);
+  // halo path candidate: plain 3x3, stride 1, dilation 1 ('same' padding), map at least 8 x 16
+  bool halo = group_hint == 0 && ntaps == 9 && stride == 1 && out_scale == 1 && Wo >= 8 && Ho >= 16 && Wo == x.W && Ho == x.H;
+  for (int t = 0; t < ntaps && halo; ++t) halo = dy[t] == t / 3 - 1 && dx[t] == t % 3 - 1;
   p.tiles_w = cdiv(Wo, p.bw); p.tiles_h = cdiv(Ho, p.bh); p.tiles_n = cdiv(x.N, p.bn);
   const int cout16 = cdiv(Cout, 16) * 16;
   if (cout16 <= max_block_n) {
@@ -605,12 +704,24 @@ inline int prepare(Launch* L, const TView& x, const TView& y, const TView* res, 
     if (group_hint != 1 && num_kb % g == 0 && 2 * g * sub_bytes <= avail && p.block_n <= 128) { p.group = g; break; }
   if (group_hint > 1 && num_kb % group_hint == 0 && 2 * group_hint * sub_bytes <= avail) p.group = group_hint;
   p.spec = 0;
+  p.wres_bytes = 0;
+  const int wbytes = ntaps * p.kchunks * p.block_n * 128;
+  if (halo && p.n_tiles == 1 && wbytes + 2 * p.kchunks * HALO_STAGE <= avail && wbytes <= 112 * 1024) {
+    // halo path: weights resident, the ring holds one halo box per 64-channel chunk
+    p.spec = 3; p.group = 1; p.wres_bytes = wbytes;
+    p.bw = 8; p.bh = 16; p.bn = 1;
+    p.tiles_w = cdiv(Wo, p.bw); p.tiles_h = cdiv(Ho, p.bh); p.tiles_n = x.N;
+    p.stages = std::max(2, std::min(12, (avail - wbytes) / HALO_STAGE));
+    L->smem_bytes = p.stages * HALO_STAGE + wbytes + fixed;
+  } else
   if (group_hint == 0 && ntaps == 9 && p.kchunks == 1 && 2 * 3 * sub_bytes <= avail) { p.spec = 1; p.group = 3; }
   else if (group_hint == 0 && ntaps == 9 && p.kchunks == 2 && 2 * 2 * sub_bytes <= avail) { p.spec = 2; p.group = 2; }
-  const int stage_bytes = sub_bytes * p.group;
-  p.stages = std::max(2, std::min(12, avail / stage_bytes));
-  p.stages = std::min(p.stages, std::max(2, 2 * num_kb / p.group));
-  L->smem_bytes = p.stages * stage_bytes + fixed;
+  if (p.spec != 3) {
+    const int stage_bytes = sub_bytes * p.group;
+    p.stages = std::max(2, std::min(12, avail / stage_bytes));
+    p.stages = std::min(p.stages, std::max(2, 2 * num_kb / p.group));
+    L->smem_bytes = p.stages * stage_bytes + fixed;
+  }
   BD_CHECK(L->smem_bytes <= 227 * 1024, "umma conv smem budget exceeded");
 
   // parity views of the input for stride 2 (a single plain view for stride 1)
@@ -633,6 +744,7 @@ inline int prepare(Launch* L, const TView& x, const TView& y, const TView* res, 
                         static_cast<uint64_t>((x.H - py + stride - 1) / stride), static_cast<uint64_t>(x.N)};
     uint64_t strides[3] = {pitch * stride, pitch * x.W * stride, pitch * x.W * x.H};
     uint32_t box[4] = {BLOCK_K, static_cast<uint32_t>(p.bw), static_cast<uint32_t>(p.bh), static_cast<uint32_t>(p.bn)};
+    if (p.spec == 3) { box[1] = HALO_W; box[2] = HALO_H; box[3] = 1; }
     char* base = static_cast<char*>(x.base) + (static_cast<size_t>(py) * x.W + px) * pitch + static_cast<size_t>(x.c0) * 2;
     if (encode_h16(&L->maps.a[m], base, 4, dims, strides, box)) return 1;
     if (first < 0) first = m;

@@ -103,10 +103,12 @@ static inline int grid_for(size_t n, int sms) {
 int label8(bd_ctx* ctx, const uint8_t* m, int* L, int H, int W, cudaStream_t s) {
   const size_t n = static_cast<size_t>(H) * W;
   const int g = grid_for(n, ctx_sms(ctx));
-  ccl::init_labels<<<g, TPB, 0, s>>>(m, L, n, 1);
-  ccl::merge8<<<g, TPB, 0, s>>>(L, H, W);
-  ccl::flatten<<<g, TPB, 0, s>>>(L, n);
-  ctx_count(ctx, 3);
+  ccl::init_runs<<<grid_for(static_cast<size_t>(H) * 32, ctx_sms(ctx)), TPB, 0, s>>>(m, L, H, W, 1);
+  ccl::merge_runs<true><<<g, TPB, 0, s>>>(L, H, W);
+  ccl::compress_runs<<<g, TPB, 0, s>>>(L, n, W);
+  ccl::flatten_runs<<<g, TPB, 0, s>>>(L, n, W);
+  ccl::flatten_pixels<<<g, TPB, 0, s>>>(L, n, W);
+  ctx_count(ctx, 5);
   BD_CUDA(cudaGetLastError());
   return 0;
 }
@@ -115,12 +117,14 @@ int label8(bd_ctx* ctx, const uint8_t* m, int* L, int H, int W, cudaStream_t s) 
 int fill(bd_ctx* ctx, const uint8_t* m, int* Lbg, uint8_t* out, int H, int W, cudaStream_t s) {
   const size_t n = static_cast<size_t>(H) * W;
   const int g = grid_for(n, ctx_sms(ctx));
-  ccl::init_labels<<<g, TPB, 0, s>>>(m, Lbg, n, 0);
-  ccl::merge4<<<g, TPB, 0, s>>>(Lbg, H, W);
-  ccl::flatten<<<g, TPB, 0, s>>>(Lbg, n);
+  ccl::init_runs<<<grid_for(static_cast<size_t>(H) * 32, ctx_sms(ctx)), TPB, 0, s>>>(m, Lbg, H, W, 0);
+  ccl::merge_runs<false><<<g, TPB, 0, s>>>(Lbg, H, W);
+  ccl::compress_runs<<<g, TPB, 0, s>>>(Lbg, n, W);
+  ccl::flatten_runs<<<g, TPB, 0, s>>>(Lbg, n, W);
+  ccl::flatten_pixels<<<g, TPB, 0, s>>>(Lbg, n, W);
   ccl::mark_outside<<<grid_for(2 * (static_cast<size_t>(H) + W), ctx_sms(ctx)), TPB, 0, s>>>(Lbg, H, W);
   ccl::fill_holes<<<g, TPB, 0, s>>>(m, Lbg, out, n);
-  ctx_count(ctx, 5);
+  ctx_count(ctx, 7);
   BD_CUDA(cudaGetLastError());
   return 0;
 }
