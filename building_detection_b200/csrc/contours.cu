@@ -11,7 +11,9 @@
 #include "../../include/bd_b200.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -44,42 +46,60 @@ __constant__ int c_dx[8] = {1, 1, 0, -1, -1, -1, 0, 1};
 __constant__ int c_dy[8] = {0, -1, -1, -1, 0, 1, 1, 1};
 
 // Border following of one component (Suzuki-Abe outer border as implemented by cv::findContours): returns the
-// number of points; writes them when out != nullptr; accumulates the bounding box.
+// number of points; writes them when WRITE; accumulates the bounding box.  Every step loads the eight neighbours
+// of the current pixel with independent loads into a bit mask (bit d = neighbour in direction d is set) and finds
+// the next direction with a rotate + find-first-set, so a step costs one memory latency instead of up to seven.
+__device__ __forceinline__ unsigned neighbour_mask(const uint8_t* __restrict__ img, int H, int W, int x, int y) {
+  const bool l = x > 0, r = x + 1 < W, u = y > 0, d = y + 1 < H;
+  const uint8_t* c = img + static_cast<size_t>(y) * W + x;
+  // directions: 0 E, 1 NE, 2 N, 3 NW, 4 W, 5 SW, 6 S, 7 SE (image coordinates, y down)
+  const unsigned e = r ? c[1] : 0, ne = (r && u) ? c[1 - W] : 0, n = u ? c[-W] : 0, nw = (l && u) ? c[-1 - W] : 0;
+  const unsigned w = l ? c[-1] : 0, sw = (l && d) ? c[W - 1] : 0, s = d ? c[W] : 0, se = (r && d) ? c[W + 1] : 0;
+  return (e ? 1u : 0u) | (ne ? 2u : 0u) | (n ? 4u : 0u) | (nw ? 8u : 0u) | (w ? 16u : 0u) | (sw ? 32u : 0u) |
+         (s ? 64u : 0u) | (se ? 128u : 0u);
+}
 template <bool WRITE>
 __device__ int trace_one(const uint8_t* __restrict__ img, int H, int W, int root, int2* out, int* bb) {
-  auto at = [&](int x, int y) { return x >= 0 && x < W && y >= 0 && y < H && img[static_cast<size_t>(y) * W + x] != 0; };
   const int x0 = root % W, y0 = root / W;
   int minx = x0, maxx = x0, miny = y0, maxy = y0;
-  int s = 4, x1, y1;
-  bool found;
-  do {
-    s = (s - 1) & 7;
-    x1 = x0 + c_dx[s];
-    y1 = y0 + c_dy[s];
-    found = at(x1, y1);
-  } while (!found && s != 4);
+  // first neighbour clockwise from west (directions 3, 2, 1, 0, 7, 6, 5): the pixel the trace returns from
+  const unsigned m0 = neighbour_mask(img, H, W, x0, y0);
+  int s = -1;
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    const int d = (3 - k) & 7;
+    if (s < 0 && (m0 >> d) & 1u) s = d;
+  }
   int n = 0;
-  if (!found) {
+  if (s < 0) {
     if (WRITE) out[0] = make_int2(x0, y0);
     n = 1;
   } else {
+    const int x1 = x0 + c_dx[s], y1 = y0 + c_dy[s];
     int x3 = x0, y3 = y0;
+    unsigned m = m0;
     const long long limit = 8ll * H * W + 16;
     for (long long it = 0; it < limit; ++it) {
-      int x4, y4;
-      for (;;) {
-        ++s;
-        x4 = x3 + c_dx[s & 7];
-        y4 = y3 + c_dy[s & 7];
-        if (at(x4, y4)) break;
-      }
-      s &= 7;
+      // next set neighbour counter-clockwise starting after direction s
+      const unsigned rot = ((m >> ((s + 1) & 7)) | (m << (8 - ((s + 1) & 7)))) & 0xFFu;
+      s = (s + __ffs(rot)) & 7;  // rot != 0: the pixel we came from is set
+      const int x4 = x3 + c_dx[s], y4 = y3 + c_dy[s];
       if (WRITE) out[n] = make_int2(x3, y3);
       ++n;
       minx = min(minx, x3); maxx = max(maxx, x3); miny = min(miny, y3); maxy = max(maxy, y3);
       if (x4 == x0 && y4 == y0 && x3 == x1 && y3 == y1) break;
       x3 = x4; y3 = y4;
+      {  // long straight borders (a mask that fills the frame): pull the rows 12 steps ahead into L1 while we walk
+        const int px = x3 + 12 * c_dx[s], py = y3 + 12 * c_dy[s];
+        if (px >= 0 && px < W && py > 0 && py + 1 < H) {
+          const uint8_t* q = img + static_cast<size_t>(py) * W + px;
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(q));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(q - W));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(q + W));
+        }
+      }
       s = (s + 4) & 7;
+      m = neighbour_mask(img, H, W, x3, y3);
     }
   }
   if (!WRITE) { bb[0] = minx; bb[1] = miny; bb[2] = maxx + 1; bb[3] = maxy + 1; }  // x, y, x+w, y+h of cv::boundingRect
@@ -427,6 +447,17 @@ int bd_contours(bd_ctx* ctx, const uint8_t* mask_dev, int h, int w, bd_polys* ou
   const int gv = grid_for(static_cast<size_t>(h + 1) * (w + 1), ctx->num_sms);
   std::vector<void*> frees;
   struct Guard { std::vector<void*>& f; ~Guard() { for (void* p : f) cudaFree(p); } } guard{frees};
+  // BD_POST_TIMING=1: wall-clock of every phase (synchronises the stream; debugging aid)
+  const bool timing = getenv("BD_POST_TIMING") != nullptr;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto t_prev = now();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    cudaStreamSynchronize(s);
+    auto t = now();
+    fprintf(stderr, "[bd_contours] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t - t_prev).count());
+    t_prev = t;
+  };
 
   // edge_3.py:317-329: fill every external contour, erase polygon area <= 100 -> initial_img (ws->keep)
   if (post::fill(ctx, mask_dev, ws->Lh, ws->filled, h, w, s)) return 1;
@@ -447,11 +478,14 @@ int bd_contours(bd_ctx* ctx, const uint8_t* mask_dev, int h, int w, bd_polys* ou
   ccl::polygon_area2<<<gv, ccl::TPB, 0, s>>>(ws->Lv, h, w, ws->a2v);
   ctx->launches += 4;
   BD_CUDA(cudaGetLastError());
+  lap("fill/label/area/erode passes");
 
   HostSet ini, td, rl;
   if (trace_set(ctx, ws->keep, ws->L, ws->a2, 2 * 100, 0, h, w, s, &ini, frees)) return 1;
+  lap("trace initial contours");
   if (trace_set(ctx, er_h, ws->Lh, ws->a2h, 2 * 50, 1, h, w, s, &td, frees)) return 1;
   if (trace_set(ctx, er_v, ws->Lv, ws->a2v, 2 * 50, 1, h, w, s, &rl, frees)) return 1;
+  lap("trace eroded contours");
 
   // detction_overlap_building (:159-262): final list of (set, index); set < 0 marks None
   struct Ref { const HostSet* set; int idx; };
@@ -488,6 +522,7 @@ int bd_contours(bd_ctx* ctx, const uint8_t* mask_dev, int h, int w, bd_polys* ou
     }
   }
 
+  lap("match + list surgery");
   // :351-385 per contour
   std::vector<int> offsets{0};
   std::vector<float> xs, ys;
@@ -508,6 +543,7 @@ int bd_contours(bd_ctx* ctx, const uint8_t* mask_dev, int h, int w, bd_polys* ou
     kinds.push_back(kind == 1 ? 0 : 2);
     offsets.push_back(static_cast<int>(xs.size()));
   }
+  lap("simplify (host)");
   out->n_polys = static_cast<int>(kinds.size());
   out->n_points = static_cast<int>(xs.size());
   out->offsets = static_cast<int32_t*>(malloc(sizeof(int32_t) * offsets.size()));

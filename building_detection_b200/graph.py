@@ -148,6 +148,11 @@ class Net:
 
     # ------------------------------------------------------------------ buffers
     def buf(self, H, W, C, dtype="f16", kind="map"):
+        # fp16 maps wider than 64 channels get a pixel pitch that is a multiple of 64 channels (128 bytes), so that
+        # every 64-channel TMA row is one aligned 128-byte line (728 -> 768: the Xception middle flow); slices stay C
+        # wide, the padding channels are never written and stay zero.
+        if kind == "map" and dtype == "f16" and C > 64 and C % 64:
+            C = -(-C // 64) * 64
         b = Buf(len(self.plan.bufs), H, W, C, dtype, kind)
         self.plan.bufs.append(b)
         return b
@@ -205,6 +210,15 @@ class Net:
         """w_tco: (ntaps, Cout, Cin) fp32 (BN already folded)."""
         nt, cout, cin = w_tco.shape
         assert cin == x.C and len(taps) == nt
+        if macs_per_pixel is None:
+            macs_per_pixel = cout * cin * nt
+        if x.c0 == 0 and x.C > 64 and x.C % 64 and x.buf.C == -(-x.C // 64) * 64 and x.buf.dtype == "f16":
+            # read the whole padded buffer (its tail channels are zero) with zero weights for the tail: the weight
+            # rows become 128-byte aligned as well and every k-block is a full 64-channel chunk
+            wp = np.zeros((nt, cout, x.buf.C), np.float32)
+            wp[:, :, :cin] = w_tco
+            w_tco, cin = wp, x.buf.C
+            x = T(x.buf, 0, x.buf.C)
         assert out.C == cout and out.H == Ho * out_scale and out.W == Wo * out_scale, (name, out, Ho, Wo)
         if res is not None:
             assert res.C == cout and res.H == out.H and res.W == out.W and out_scale == 1
@@ -218,8 +232,9 @@ class Net:
             elif cout <= 16 and res is None and out_scale == 1:
                 path = "umma"  # fp32 logits / gate maps: one 16-column tile, direct stores
         # algorithmic work: true (unpadded) channel counts
-        self.plan.flops += 2 * self.plan.batch * Ho * Wo * (cout * cin * nt if macs_per_pixel is None else macs_per_pixel)
+        self.plan.flops += 2 * self.plan.batch * Ho * Wo * macs_per_pixel
         self._emit(op=OP_CONV, name=name, path=path, x=x.ref(), y=out.ref(),
+                   flops=2 * self.plan.batch * Ho * Wo * macs_per_pixel,  # algorithmic (unpadded channel counts)
                    res=None if res is None else res.ref(),
                    taps=[(int(dy), int(dx)) for dy, dx in taps], stride=stride, Ho=Ho, Wo=Wo,
                    act_pre=act_pre, act_post=act_post,

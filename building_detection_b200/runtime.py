@@ -271,6 +271,8 @@ class NativePlan:
             k, f = C.c_int(), C.c_double()
             check(lib().bd_plan_op_info(self.h, i, C.byref(k), C.byref(f)))
             kinds[i], flops[i] = k.value, f.value
+            if i < len(self.plan.ops) and "flops" in self.plan.ops[i]:
+                flops[i] = self.plan.ops[i]["flops"]  # algorithmic: the native count includes channel padding
         return ms, kinds, flops
 
     @property
