@@ -66,7 +66,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "500"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -230,12 +230,17 @@ def main():
             return r
         clock("forward_stitch_ms", lambda: job._forward(scene_dev))
         clock("gather_ms", job._gather)
-        if rank == 0 and not args.no_post:
-            from building_detection_b200 import edge_3, model_fuse
-            fused = clock("fuse_ms", lambda: model_fuse.fuse_device(job.masks))
-            res = clock("contours_ms", lambda: edge_3.contours_device(fused))
-            stages["polygons"] = len(res[0])
-            stages["fused_on_fraction"] = float((fused > 0).float().mean().item())
+        if not args.no_post:
+            if world == 1:
+                from building_detection_b200 import edge_3, model_fuse
+                fused = clock("fuse_ms", lambda: model_fuse.fuse_device(job.masks))
+                res = clock("contours_ms", lambda: edge_3.contours_device(fused))
+            else:  # per-model clean-ups on their owner ranks, vote + final clean-up + contours on rank 0
+                r = clock("post_ms", job._post)
+                fused, res = r if r is not None else (None, None)
+            if rank == 0:
+                stages["polygons"] = len(res[0])
+                stages["fused_on_fraction"] = float((fused > 0).float().mean().item())
 
     ntiles = len(origins)
     value = ntiles * args.steps / (ms / 1e3)

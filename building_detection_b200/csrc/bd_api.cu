@@ -139,6 +139,7 @@ void bd_destroy(bd_ctx* ctx) {
   if (ctx->d_ys) cudaFree(ctx->d_ys);
   if (ctx->d_xs) cudaFree(ctx->d_xs);
   ctx->post_ws.release();
+  ctx->pool.release();
   delete ctx;
 }
 

@@ -320,16 +320,15 @@ static int grid_for(size_t n, int sms) {
 
 // trace every component of `img` whose root passes the area threshold
 static int trace_set(bd_ctx* ctx, const uint8_t* img, const int* L, const long long* a2, long long thr2, int strict, int H,
-                     int W, cudaStream_t s, HostSet* out, std::vector<void*>& frees) {
+                     int W, cudaStream_t s, HostSet* out, int slot0) {
   const size_t n = static_cast<size_t>(H) * W;
+  post::DevPool& pool = ctx->pool;
   int* d_count = nullptr;
-  BD_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_count), sizeof(int)));
-  frees.push_back(d_count);
+  if (pool.get(slot0 + 0, sizeof(int), reinterpret_cast<void**>(&d_count))) return 1;
   BD_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int), s));
   int cap = static_cast<int>(std::min<size_t>(n, 1u << 22));
   int* d_list = nullptr;
-  BD_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_list), sizeof(int) * cap));
-  frees.push_back(d_list);
+  if (pool.get(slot0 + 1, sizeof(int) * cap, reinterpret_cast<void**>(&d_list))) return 1;
   collect_roots<<<grid_for(n, ctx->num_sms), TPB, 0, s>>>(L, a2, thr2, strict, n, d_list, d_count, cap);
   ctx->launches++;
   int cnt = 0;
@@ -345,10 +344,8 @@ static int trace_set(bd_ctx* ctx, const uint8_t* img, const int* L, const long l
   std::sort(roots.begin(), roots.end(), [](int a, int b) { return a > b; });  // findContours lists the last-found first
   BD_CUDA(cudaMemcpyAsync(d_list, roots.data(), sizeof(int) * cnt, cudaMemcpyHostToDevice, s));
   int *d_npts = nullptr, *d_bbox = nullptr;
-  BD_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_npts), sizeof(int) * cnt));
-  frees.push_back(d_npts);
-  BD_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_bbox), sizeof(int) * 4 * cnt));
-  frees.push_back(d_bbox);
+  if (pool.get(slot0 + 2, sizeof(int) * cnt, reinterpret_cast<void**>(&d_npts))) return 1;
+  if (pool.get(slot0 + 3, sizeof(int) * 4 * cnt, reinterpret_cast<void**>(&d_bbox))) return 1;
   trace_count<<<(cnt + 63) / 64, 64, 0, s>>>(img, H, W, d_list, cnt, d_npts, d_bbox);
   ctx->launches++;
   std::vector<int> npts(cnt);
@@ -359,10 +356,8 @@ static int trace_set(bd_ctx* ctx, const uint8_t* img, const int* L, const long l
   const long long total = out->off[cnt];
   long long* d_off = nullptr;
   int2* d_pts = nullptr;
-  BD_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_off), sizeof(long long) * (cnt + 1)));
-  frees.push_back(d_off);
-  BD_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_pts), sizeof(int2) * std::max<long long>(total, 1)));
-  frees.push_back(d_pts);
+  if (pool.get(slot0 + 4, sizeof(long long) * (cnt + 1), reinterpret_cast<void**>(&d_off))) return 1;
+  if (pool.get(slot0 + 5, sizeof(int2) * std::max<long long>(total, 1), reinterpret_cast<void**>(&d_pts))) return 1;
   BD_CUDA(cudaMemcpyAsync(d_off, out->off.data(), sizeof(long long) * (cnt + 1), cudaMemcpyHostToDevice, s));
   trace_write<<<(cnt + 63) / 64, 64, 0, s>>>(img, H, W, d_list, cnt, d_off, d_pts);
   ctx->launches++;
@@ -376,7 +371,7 @@ static int trace_set(bd_ctx* ctx, const uint8_t* img, const int* L, const long l
 // _match of the oracle (edge_3.py process_td / process_rl): lost = initial contours without counterpart,
 // fresh = eroded contours nobody claimed (ascending index)
 static int match_sets(bd_ctx* ctx, const HostSet& ini, const HostSet& ero, cudaStream_t s, std::vector<int>* lost,
-                      std::vector<int>* fresh, std::vector<void*>& frees) {
+                      std::vector<int>* fresh, int slot) {
   lost->clear();
   fresh->clear();
   if (ini.n == 0) {
@@ -388,8 +383,7 @@ static int match_sets(bd_ctx* ctx, const HostSet& ini, const HostSet& ero, cudaS
     return 2;
   }
   int* d_res = nullptr;
-  BD_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_res), sizeof(int) * ini.n));
-  frees.push_back(d_res);
+  if (ctx->pool.get(slot, sizeof(int) * ini.n, reinterpret_cast<void**>(&d_res))) return 1;
   match_boxes<<<(ini.n + TPB - 1) / TPB, TPB, 0, s>>>(ini.d_bbox, ini.n, ero.d_bbox, ero.n, d_res);
   ctx->launches++;
   std::vector<int> res(ini.n);
@@ -445,8 +439,6 @@ int bd_contours(bd_ctx* ctx, const uint8_t* mask_dev, int h, int w, bd_polys* ou
   const size_t n = static_cast<size_t>(h) * w;
   const int g = grid_for(n, ctx->num_sms);
   const int gv = grid_for(static_cast<size_t>(h + 1) * (w + 1), ctx->num_sms);
-  std::vector<void*> frees;
-  struct Guard { std::vector<void*>& f; ~Guard() { for (void* p : f) cudaFree(p); } } guard{frees};
   // BD_POST_TIMING=1: wall-clock of every phase (synchronises the stream; debugging aid)
   const bool timing = getenv("BD_POST_TIMING") != nullptr;
   auto now = [] { return std::chrono::steady_clock::now(); };
@@ -481,10 +473,10 @@ int bd_contours(bd_ctx* ctx, const uint8_t* mask_dev, int h, int w, bd_polys* ou
   lap("fill/label/area/erode passes");
 
   HostSet ini, td, rl;
-  if (trace_set(ctx, ws->keep, ws->L, ws->a2, 2 * 100, 0, h, w, s, &ini, frees)) return 1;
+  if (trace_set(ctx, ws->keep, ws->L, ws->a2, 2 * 100, 0, h, w, s, &ini, 0)) return 1;
   lap("trace initial contours");
-  if (trace_set(ctx, er_h, ws->Lh, ws->a2h, 2 * 50, 1, h, w, s, &td, frees)) return 1;
-  if (trace_set(ctx, er_v, ws->Lv, ws->a2v, 2 * 50, 1, h, w, s, &rl, frees)) return 1;
+  if (trace_set(ctx, er_h, ws->Lh, ws->a2h, 2 * 50, 1, h, w, s, &td, 8)) return 1;
+  if (trace_set(ctx, er_v, ws->Lv, ws->a2v, 2 * 50, 1, h, w, s, &rl, 16)) return 1;
   lap("trace eroded contours");
 
   // detction_overlap_building (:159-262): final list of (set, index); set < 0 marks None
@@ -494,8 +486,8 @@ int bd_contours(bd_ctx* ctx, const uint8_t* mask_dev, int h, int w, bd_polys* ou
   if (!(td.n == ini.n && rl.n == ini.n)) {
     std::vector<int> lost_td, new_td, lost_rl, new_rl;
     const bool do_td = td.n != ini.n, do_rl = rl.n != ini.n;
-    if (do_td) { int rc = match_sets(ctx, ini, td, s, &lost_td, &new_td, frees); if (rc) return rc; }
-    if (do_rl) { int rc = match_sets(ctx, ini, rl, s, &lost_rl, &new_rl, frees); if (rc) return rc; }
+    if (do_td) { int rc = match_sets(ctx, ini, td, s, &lost_td, &new_td, 24); if (rc) return rc; }
+    if (do_rl) { int rc = match_sets(ctx, ini, rl, s, &lost_rl, &new_rl, 25); if (rc) return rc; }
     for (int i : lost_td) finals[i].set = nullptr;
     for (int i : lost_rl) finals[i].set = nullptr;
     if (do_td && do_rl) {

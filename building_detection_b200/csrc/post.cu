@@ -182,7 +182,17 @@ int bd_fuse(bd_ctx* ctx, const uint8_t* masks5_dev, int h, int w, uint8_t* fused
   const size_t n = static_cast<size_t>(h) * w;
   for (int k = 0; k < 5; ++k)
     if (post::cleanup(ctx, masks5_dev + k * n, h, w, ws->cleaned + k * n, s)) return 1;
-  post::vote3of5<<<post::grid_for(n / 16 + 1, post::ctx_sms(ctx)), post::TPB, 0, s>>>(ws->cleaned, n, ws->voted);
+  return bd_fuse_cleaned(ctx, ws->cleaned, h, w, fused_dev, stream);
+}
+
+int bd_fuse_cleaned(bd_ctx* ctx, const uint8_t* cleaned5_dev, int h, int w, uint8_t* fused_dev, void* stream) {
+  BD_CHECK(ctx && cleaned5_dev && fused_dev && h >= 1 && w >= 1, "bad arguments");
+  BD_CHECK(static_cast<size_t>(h) * w < (1ull << 31), "scene too large for int32 pixel labels");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  post::Workspace* ws = nullptr;
+  if (post::workspace(ctx, h, w, &ws)) return 1;
+  const size_t n = static_cast<size_t>(h) * w;
+  post::vote3of5<<<post::grid_for(n / 16 + 1, post::ctx_sms(ctx)), post::TPB, 0, s>>>(cleaned5_dev, n, ws->voted);
   post::ctx_count(ctx, 1);
   BD_CUDA(cudaGetLastError());
   return post::cleanup(ctx, ws->voted, h, w, fused_dev, s);

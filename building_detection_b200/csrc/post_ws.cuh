@@ -23,6 +23,31 @@ struct Workspace {
 }  // namespace post
 }  // namespace bd
 
+namespace bd {
+namespace post {
+// grow-only device scratch slots for the contour stage (no cudaMalloc / cudaFree per call once warmed up)
+struct DevPool {
+  static constexpr int SLOTS = 32;
+  void* ptr[SLOTS] = {};
+  size_t cap[SLOTS] = {};
+  int get(int slot, size_t bytes, void** out) {
+    if (bytes > cap[slot]) {
+      if (ptr[slot]) cudaFree(ptr[slot]);
+      ptr[slot] = nullptr; cap[slot] = 0;
+      const size_t want = bytes + bytes / 4 + 256;
+      BD_CUDA(cudaMalloc(&ptr[slot], want));
+      cap[slot] = want;
+    }
+    *out = ptr[slot];
+    return 0;
+  }
+  void release() {
+    for (int i = 0; i < SLOTS; ++i) { if (ptr[i]) cudaFree(ptr[i]); ptr[i] = nullptr; cap[i] = 0; }
+  }
+};
+}  // namespace post
+}  // namespace bd
+
 struct bd_ctx {
   int device = 0;
   int num_sms = 148;
@@ -34,6 +59,7 @@ struct bd_ctx {
   int* d_xs = nullptr;
   int tile_cap = 0;
   bd::post::Workspace post_ws;
+  bd::post::DevPool pool;
   void* trace_buf = nullptr;  // BD_UMMA_TRACE debug buffer of the most recently built conv
 };
 

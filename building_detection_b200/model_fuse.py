@@ -29,6 +29,18 @@ def fuse_device(masks5):
     return out
 
 
+def fuse_cleaned_device(cleaned5):
+    """Vote >= 3 of five ALREADY cleaned masks, then the final clean-up (model_fuse.py:315-346): the second half of
+    bd_fuse, for the multi-GPU path where the five clean-ups ran on different ranks."""
+    t = _torch()
+    cleaned5 = cleaned5.contiguous()
+    _, h, w = cleaned5.shape
+    out = t.empty((h, w), dtype=t.uint8, device=cleaned5.device)
+    stream = t.cuda.current_stream(cleaned5.device).cuda_stream
+    R.check(R.lib().bd_fuse_cleaned(R.context(cleaned5.device.index), cleaned5.data_ptr(), h, w, out.data_ptr(), stream))
+    return out
+
+
 def cleanup_device(mask):
     """One clean-up pass (fill_and_delete + eroede_dilate_process + only_plt) of an (H,W) u8 cuda tensor."""
     t = _torch()

@@ -45,6 +45,55 @@ def gather_bands(masks, bands, rank, world, stage=None):
     return masks
 
 
+def model_owner(k, world):
+    """Rank that cleans model k's scene mask: the five per-model clean-ups of model_fuse.py:285-313 are independent,
+    so with several GPUs they run on different ranks."""
+    return k % world
+
+
+def exchange_by_model(masks, bands, rank, world):
+    """Every rank holds its band of all M model masks; afterwards the owner of model k holds the complete mask k
+    (band rows OR-ed in place into its own ``masks[k]``).  Plain send/recv, every rank walks k in the same order and
+    for a given k there is a single receiver, so there is no circular wait."""
+    if world == 1:
+        return masks
+    import torch
+    import torch.distributed as dist
+    for k in range(masks.shape[0]):
+        owner = model_owner(k, world)
+        if rank == owner:
+            for r in range(world):
+                r0, r1 = bands[r]
+                if r == rank or r1 <= r0:
+                    continue
+                buf = torch.empty_like(masks[k, r0:r1])
+                dist.recv(buf, src=r)
+                masks[k, r0:r1].bitwise_or_(buf)
+        else:
+            r0, r1 = bands[rank]
+            if r1 > r0:
+                dist.send(masks[k, r0:r1].contiguous(), dst=owner)
+    return masks
+
+
+def collect_cleaned(cleaned, n_models, rank, world, like):
+    """cleaned: {k: (H,W) u8 tensor} for the models this rank owns -> (M,H,W) on rank 0 (None elsewhere)."""
+    import torch
+    import torch.distributed as dist
+    if rank == 0:
+        out = torch.empty((n_models,) + tuple(like.shape[-2:]), dtype=torch.uint8, device=like.device)
+        for k in range(n_models):
+            owner = model_owner(k, world)
+            if owner == 0:
+                out[k].copy_(cleaned[k])
+            else:
+                dist.recv(out[k], src=owner)
+        return out
+    for k in sorted(cleaned):
+        dist.send(cleaned[k].contiguous(), dst=0)
+    return None
+
+
 class SceneJob:
     def __init__(self, runner, h, w, origins, rank=0, world=1, do_post=True):
         import torch
@@ -57,7 +106,7 @@ class SceneJob:
         self.bands = [band_of(S.shard_rows(self.all_origins, r, world), h) for r in range(world)]
         self.scene_dev = None
         self.stage = None
-        if world > 1 and rank == 0:
+        if world > 1 and rank == 0 and not do_post:
             rows = max(b[1] - b[0] for b in self.bands[1:])
             self.stage = torch.empty((len(runner.models), rows, w), dtype=torch.uint8, device=dev)
         self.h2d_bytes = 0
@@ -71,13 +120,26 @@ class SceneJob:
         self.runner.run(scene_dev, origins=self.origins, out=self.masks)
 
     def _gather(self):
-        gather_bands(self.masks, self.bands, self.rank, self.world, self.stage)
+        """N > 1 with post-processing: model k's complete mask goes to its owner rank (the five clean-ups run in
+        parallel on different GPUs); without post-processing all bands go to rank 0."""
+        if self.do_post:
+            exchange_by_model(self.masks, self.bands, self.rank, self.world)
+        else:
+            gather_bands(self.masks, self.bands, self.rank, self.world, self.stage)
 
     def _post(self):
-        if not self.do_post or self.rank != 0:
+        if not self.do_post:
             return None
         from . import edge_3, model_fuse
-        fused = model_fuse.fuse_device(self.masks)
+        if self.world == 1:
+            fused = model_fuse.fuse_device(self.masks)
+        else:
+            mine = {k: model_fuse.cleanup_device(self.masks[k]) for k in range(self.masks.shape[0])
+                    if model_owner(k, self.world) == self.rank}
+            cleaned = collect_cleaned(mine, self.masks.shape[0], self.rank, self.world, self.masks)
+            if self.rank != 0:
+                return None
+            fused = model_fuse.fuse_cleaned_device(cleaned)
         polys = edge_3.contours_device(fused)
         return fused, polys
 

@@ -142,6 +142,9 @@ int bd_stitch_or(bd_ctx* ctx, const uint8_t* tile_masks_dev, const int32_t* ys_h
  * Per mask: hole fill + drop polygon-area <= 1000, directional 1x21 / 21x1 erosion split with fragment
  * filter <= 500; vote >= 3 of 5; same clean-up again.  Synchronous. */
 int bd_fuse(bd_ctx* ctx, const uint8_t* masks5_dev, int h, int w, uint8_t* fused_dev, void* stream);
+/* second half of bd_fuse: vote >= 3 of five ALREADY cleaned masks, then the final clean-up (model_fuse.py:315-346);
+ * the multi-GPU path runs the five clean-ups on different ranks and finishes here */
+int bd_fuse_cleaned(bd_ctx* ctx, const uint8_t* cleaned5_dev, int h, int w, uint8_t* fused_dev, void* stream);
 /* the per-mask clean-up alone (fill_and_delete + eroede_dilate_process + only_plt, model_fuse.py:9-218) */
 int bd_mask_cleanup(bd_ctx* ctx, const uint8_t* mask_dev, int h, int w, uint8_t* out_dev, void* stream);
 
