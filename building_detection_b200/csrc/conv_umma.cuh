@@ -12,11 +12,14 @@
 //   warp 0 (one lane)  TMA producer: A box + W tile per k-block into a ring of shared-memory stages
 //   warp 1 (one lane)  MMA issuer: tcgen05.mma kind::f16 (fp16 x fp16 -> fp32) into one of TWO TMEM accumulator
 //                      stages; tcgen05.commit releases the smem stage / publishes the accumulator
-//   warps 2-9          epilogue (two warps per TMEM lane quadrant): tcgen05.ld the finished accumulator (warp w owns TMEM lanes 32*(w%4)..+31 =
-//                      tile rows), + bias (BatchNorm folded) / ReLU / residual / ReLU, pack to fp16 into a
-//                      swizzled staging tile and hand it to a TMA STORE (full-line writes, ragged tiles and the
-//                      destination channel slice clipped by the tensor map; the sub-pixel scatter of the
-//                      transposed convolutions is a strided output map).  fp32 outputs (2-channel logits,
+//   warps 2-9          epilogue, two warps per TMEM lane quadrant (warp w may read TMEM lanes 32*(w%4)..+31 = tile
+//                      rows).  The work units are (tile, 64-column chunk) pairs; the two warps of a quadrant take
+//                      alternate units and never synchronise with any other warp: tcgen05.ld its 32 rows x 64
+//                      columns, + bias (BatchNorm folded, staged in shared memory) / ReLU / residual / ReLU, pack to
+//                      fp16 into the warp's own swizzled 4 KB staging tile, one TMA STORE per unit (full-line
+//                      writes, ragged tiles and the destination channel slice clipped by the tensor map; the
+//                      sub-pixel scatter of the transposed convolutions is a strided output map).  Residual tiles
+//                      arrive by per-warp TMA loads issued one unit ahead.  fp32 outputs (2-channel logits,
 //                      1-channel gates) are stored directly.
 // so the epilogue of tile i overlaps the main loop of tile i+1.
 #pragma once
@@ -34,21 +37,32 @@ constexpr int BLOCK_K = 64;  // fp16 elements = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
 constexpr int OUT_CHUNK = 64;                             // channels per staging tile / TMA store
-constexpr int OUT_STAGE_BYTES = BLOCK_M * OUT_CHUNK * 2;  // 16 KB
+constexpr int EPI_TILE_BYTES = 32 * OUT_CHUNK * 2;        // 4 KB: one warp's 32 rows x 64 channels
 constexpr int MAX_TAPS = 18;
 // halo path: one (16+2) x (8+2) pixel halo box per 64-channel chunk feeds all nine taps of a 3x3 convolution
 constexpr int HALO_W = 10, HALO_H = 18, HALO_BYTES = HALO_W * HALO_H * 128, HALO_STAGE = 23 * 1024;
 constexpr int EPI_WARPS = 8;                 // two warps per TMEM lane quadrant, each takes half of a column chunk
 constexpr int THREADS = 64 + 32 * EPI_WARPS;
 
+// division by a launch constant: q = (umulhi(mul, n) + n) >> shr, exact for n < 2^31 (Granlund-Montgomery)
+struct FastDiv { uint32_t mul, shr; };
+inline FastDiv make_fastdiv(uint32_t d) {
+  uint32_t l = 0;
+  while ((1ull << l) < d) ++l;
+  return FastDiv{static_cast<uint32_t>(((1ull << 32) * ((1ull << l) - d)) / d + 1), l};
+}
+__device__ __forceinline__ uint32_t fd_div(uint32_t n, FastDiv f) { return (__umulhi(f.mul, n) + n) >> f.shr; }
+
 struct Params {
   int N, Ho, Wo, Cout, Cin;
+  FastDiv fd_nt, fd_tw, fd_th;  // dividers by n_tiles, tiles_w, tiles_h
   int bw, bh, bn;
   int tiles_w, tiles_h, tiles_n, n_tiles, total_tiles;
   int block_n, kchunks, ntaps, stages, group, tmem_cols;  // group: k-blocks per shared-memory stage
   int spec;  // 0 generic loops; 1 = 9 taps x 1 chunk, group 3; 2 = 9 taps x 2 chunks, group 2 (fully unrolled loops);
              // 3 = halo path: 3x3 stride 1, one halo box per chunk, weights resident in shared memory
   int wres_bytes;  // bytes of resident weights (spec 3), 0 otherwise
+  int bias_bytes;  // shared-memory bytes of the staged bias vector (all N tiles)
   int tap_map[MAX_TAPS], tap_dy[MAX_TAPS], tap_dx[MAX_TAPS];
   float* y32;  // fp32 output path (Cout <= 16): direct stores
   int y_ctot, y_c0, y_H, y_W, out_scale, out_oy, out_ox;
@@ -200,7 +214,12 @@ __device__ __forceinline__ uint32_t make_idesc(int n) {
   return (1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(BLOCK_M >> 4) << 24);
 }
 
-__device__ __forceinline__ float apply_act(float v, int act) { return act == 1 ? fmaxf(v, 0.0f) : v; }
+// two fp32 -> packed fp16x2 (lo = first argument), round to nearest, saturating at +-65504 (one F2FP instruction)
+__device__ __forceinline__ uint32_t pack2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
 
 // all tensor maps of one launch as a single kernel parameter: the producer selects the input parity view by
 // pointer arithmetic instead of a chain of selects
@@ -210,6 +229,18 @@ struct alignas(64) Maps {
   CUtensorMap y;
   CUtensorMap r;  // residual (same boxes as y), only valid when Params::res != nullptr
 };
+
+// tile index -> (N tile, column tile, row tile, image tile); the N tile runs fastest
+__device__ __forceinline__ void tile_coords(const Params& p, int tile, int& nt, int& tw, int& th, int& tn) {
+  const uint32_t t = static_cast<uint32_t>(tile);
+  const uint32_t mt = fd_div(t, p.fd_nt);
+  nt = static_cast<int>(t - mt * p.n_tiles);
+  const uint32_t t2 = fd_div(mt, p.fd_tw);
+  tw = static_cast<int>(mt - t2 * p.tiles_w);
+  const uint32_t t3 = fd_div(t2, p.fd_th);
+  th = static_cast<int>(t2 - t3 * p.tiles_h);
+  tn = static_cast<int>(t3);
+}
 
 // ------------------------------------------------------------------------------------------ unrolled loops
 // The small-channel 3x3 convolutions (Cin <= 128: most of res34 / scse / hrnet's time) have k-blocks whose MMAs take
@@ -298,13 +329,14 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
   const uint32_t stage_bytes = p.spec == 3 ? static_cast<uint32_t>(HALO_STAGE)
                                            : sub_bytes * static_cast<uint32_t>(p.group);  // a stage holds `group` k-blocks
   const uint32_t wres0 = smem_base + static_cast<uint32_t>(p.stages) * stage_bytes;      // resident weights (spec 3)
-  const uint32_t out0 = wres0 + static_cast<uint32_t>(p.wres_bytes);                      // 2 staging tiles
-  const uint32_t res0 = out0 + 2u * OUT_STAGE_BYTES;                                 // 2 residual tiles (if any)
-  const uint32_t bar_base = res0 + (p.res ? 2u * OUT_STAGE_BYTES : 0u);              // 8-byte slots
+  const uint32_t out0 = wres0 + static_cast<uint32_t>(p.wres_bytes);                      // 8 per-warp staging tiles
+  const uint32_t res0 = out0 + EPI_WARPS * EPI_TILE_BYTES;                           // 8 per-warp residual tiles (if any)
+  const uint32_t bias0 = res0 + (p.res ? EPI_WARPS * EPI_TILE_BYTES : 0u);           // bias of all N tiles, fp32
+  const uint32_t bar_base = bias0 + static_cast<uint32_t>(p.bias_bytes);             // 8-byte slots
   const uint32_t full0 = bar_base, empty0 = bar_base + 8u * p.stages;
   const uint32_t tfull0 = bar_base + 16u * p.stages, tempty0 = tfull0 + 16u;
-  const uint32_t rbar0 = tempty0 + 16u;
-  const uint32_t wbar = rbar0 + 16u;
+  const uint32_t rbar0 = tempty0 + 16u;  // one per epilogue warp
+  const uint32_t wbar = rbar0 + 8u * EPI_WARPS;
   const uint32_t holder = wbar + 16u;
   volatile uint32_t* holder_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (holder - smem_base));
 
@@ -316,8 +348,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull0 + 8u * a, 1);
       mbar_init(tempty0 + 8u * a, EPI_WARPS);  // one arrival per epilogue warp
-      mbar_init(rbar0 + 8u * a, 1);
     }
+    for (int w = 0; w < EPI_WARPS; ++w) mbar_init(rbar0 + 8u * w, 1);
     mbar_init(wbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_async_smem();
@@ -349,10 +381,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
     }
     __syncwarp();
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      int nt = 0, mt = tile;
-      if (p.n_tiles > 1) { nt = tile % p.n_tiles; mt = tile / p.n_tiles; }
-      const int tw = mt % p.tiles_w, t2 = mt / p.tiles_w;
-      const int th = t2 % p.tiles_h, tn = t2 / p.tiles_h;
+      int nt, tw, th, tn;
+      tile_coords(p, tile, nt, tw, th, tn);
       const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn, n_base = nt * p.block_n;
       if (p.spec == 3) {  // one halo box per 64-channel chunk
         for (int c = 0; c < p.Cin; c += BLOCK_K) {
@@ -425,6 +455,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
             }
             tc_commit(ring.eb);
             if (c <= BLOCK_K) tc_commit(tfull0 + 8u * a);
+            trace_ev(p, 1, tr_i, tile, -1);
           }
           __syncwarp();
           ring_advance(ring, p, HALO_STAGE, full0, empty0);
@@ -464,140 +495,149 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
       __syncwarp();
     }
   } else {
-    // ---------------- epilogue warps 2..9: warp w reads TMEM lane quadrant w % 4 (hardware rule); warps 2-5 take
-    // the first 32 columns of every 64-column chunk, warps 6-9 the second 32
-    const int q = warp & 3;             // TMEM lane quadrant this warp may access
-    const int half = (warp - 2) >> 2;   // 0 / 1: which 32 columns of a chunk
-    const int r = q * 32 + lane;        // tile row = TMEM lane
-    const int et = threadIdx.x - 64;    // 0 .. 32*EPI_WARPS-1
-    const int wl = r % p.bw, hl = (r / p.bw) % p.bh, nl = r / (p.bw * p.bh);
-    uint32_t ti = 0, ob = 0, gc = 0;  // gc: running chunk counter (residual buffer / barrier parity)
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
-      const uint32_t a = ti & 1u, aph = (ti >> 1) & 1u;
-      int nt = 0, mt = tile;
-      if (p.n_tiles > 1) { nt = tile % p.n_tiles; mt = tile / p.n_tiles; }
-      const int tw = mt % p.tiles_w, t2 = mt / p.tiles_w;
-      const int th = t2 % p.tiles_h, tn = t2 / p.tiles_h;
-      const int n_base = nt * p.block_n;
-      const int ow = tw * p.bw + wl, oh = th * p.bh + hl, on = tn * p.bn + nl;
-      const bool pix_ok = (ow < p.Wo) && (oh < p.Ho) && (on < p.N);
-      const size_t ypix = (static_cast<size_t>(on) * p.y_H + (oh * p.out_scale + p.out_oy)) * p.y_W +
-                          (ow * p.out_scale + p.out_ox);
-      const bool has_res = p.res != nullptr;
-      // residual tile of the first chunk: fetched by TMA while the main loop of this tile is still running
-      if (has_res && et == 0) {
-        mbar_expect_tx(rbar0 + 8u * (gc & 1u), OUT_STAGE_BYTES);
-        tma_load_4d(res0 + (gc & 1u) * OUT_STAGE_BYTES, &maps.r, rbar0 + 8u * (gc & 1u), n_base, tw * p.bw, th * p.bh,
-                    tn * p.bn);
+    // ---------------- epilogue warps 2..9: warp w reads TMEM lane quadrant w % 4 (hardware rule).  Units = (tile,
+    // 64-column chunk) in launch order; of the two warps of a quadrant, warp `half` takes the units of its parity.
+    const int q = warp & 3;            // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;  // 0 / 1: unit parity
+    const int ew = warp - 2;           // 0 .. EPI_WARPS-1
+    const int r = q * 32 + lane;       // tile row = TMEM lane
+    const int et = threadIdx.x - 64;   // 0 .. 32*EPI_WARPS-1
+    // the quadrant's 32 rows as a (bw x qbh x qbn) sub-box of the tile box, starting at row qh of image qn
+    const int hrows = 32 / p.bw, hq = q * hrows;
+    const int qh = hq % p.bh, qn = hq / p.bh;
+    const int wl = r % p.bw, hl = (r / p.bw) % p.bh, nl = r / (p.bw * p.bh);  // (fp32 path: per-row coordinates)
+    const uint32_t stg = out0 + static_cast<uint32_t>(ew) * EPI_TILE_BYTES;   // this warp's staging tile
+    const uint32_t rsb = res0 + static_cast<uint32_t>(ew) * EPI_TILE_BYTES;   // this warp's residual tile
+    uint8_t* srow = gen_base + (stg - smem_base) + lane * 128;
+    const uint8_t* rsrow = gen_base + (rsb - smem_base) + lane * 128;
+    const uint32_t rbar = rbar0 + 8u * static_cast<uint32_t>(ew);
+    const int swz = lane & 7;  // 128-byte swizzle: 16-byte chunk index XOR (row % 8)
+    const bool has_res = p.res != nullptr;
+    const int nch = (p.block_n + OUT_CHUNK - 1) / OUT_CHUNK;  // units per tile
+    const float lo_pre = p.act_pre == 1 ? 0.0f : -INFINITY, lo_post = p.act_post == 1 ? 0.0f : -INFINITY;
+    // bias of every N tile -> shared memory (broadcast reads in the unit loop instead of exposed global latency)
+    float* sbias = reinterpret_cast<float*>(gen_base + (bias0 - smem_base));
+    for (int i = et; i < p.n_tiles * p.block_n; i += 32 * EPI_WARPS) sbias[i] = i < p.Cout ? __ldg(p.bias + i) : 0.0f;
+    epi_bar_sync();
+    // residual tile of unit (tile, ci): 32 rows x 64 channels by TMA into this warp's buffer
+    auto issue_res = [&](int tile, int ci) {
+      int nt, tw, th, tn;
+      tile_coords(p, tile, nt, tw, th, tn);
+      if (lane == 0) {
+        mbar_expect_tx(rbar, EPI_TILE_BYTES);
+        tma_load_4d(rsb, &maps.r, rbar, nt * p.block_n + ci * OUT_CHUNK, tw * p.bw, th * p.bh + qh, tn * p.bn + qn);
       }
+    };
+    if (has_res) {  // first unit of this warp
+      int t0 = blockIdx.x, c = half;
+      while (c >= nch) { c -= nch; t0 += gridDim.x; }
+      if (t0 < p.total_tiles) issue_res(t0, c);
+    }
+    uint32_t ti = 0, u = 0, rcount = 0;  // tiles done, units before this tile, residual tiles consumed
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti, u += nch) {
+      const uint32_t a = ti & 1u, aph = (ti >> 1) & 1u;
+      int nt, tw, th, tn;
+      tile_coords(p, tile, nt, tw, th, tn);
+      const int n_base = nt * p.block_n;
+      const int first = ((u & 1u) == static_cast<uint32_t>(half)) ? 0 : 1;          // my first chunk of this tile
+      const int last = first < nch ? first + ((nch - 1 - first) & ~1) : -1;          // my last one (-1: none)
       mbar_wait(tfull0 + 8u * a, aph);
       tc_fence_after();
       if (et == 0) trace_ev(p, 2, tr_i, tile, 0);
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * static_cast<uint32_t>(p.block_n);
       if (p.y32) {
-        // fp32 output (logits / gate maps, Cout <= 16): one 16-column read, direct coalesced stores
-        if (half == 0) {
+        // fp32 output (logits / gate maps, Cout <= 16): one 16-column read, direct stores
+        if (last == 0) {
           uint32_t acc[16];
           tmem_ld16(trow, acc);
           tmem_ld_wait();
-          if (pix_ok) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty0 + 8u * a);
+          const int ow = tw * p.bw + wl, oh = th * p.bh + hl, on = tn * p.bn + nl;
+          if ((ow < p.Wo) && (oh < p.Ho) && (on < p.N)) {
+            const size_t ypix = (static_cast<size_t>(on) * p.y_H + (oh * p.out_scale + p.out_oy)) * p.y_W +
+                                (ow * p.out_scale + p.out_ox);
             float* yrow = p.y32 + ypix * p.y_ctot + p.y_c0;
 #pragma unroll
             for (int c = 0; c < 16; ++c)
-              if (c < p.Cout) {
-                const float v = apply_act(__uint_as_float(acc[c]) + __ldg(p.bias + c), p.act_pre);
-                yrow[c] = apply_act(v, p.act_post);
-              }
+              if (c < p.Cout) yrow[c] = fmaxf(fmaxf(__uint_as_float(acc[c]) + sbias[c], lo_pre), lo_post);
           }
+        } else {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty0 + 8u * a);
         }
-      } else {
-        for (int c0 = 0; c0 < p.block_n; c0 += OUT_CHUNK, ob ^= 1u, ++gc) {
-          // the TMA store that last read this staging tile must have finished reading it
-          if (et == 0) tma_store_wait_read<1>();
-          epi_bar_sync();
-          if (has_res) {
-            if (et == 0 && c0 + OUT_CHUNK < p.block_n) {  // prefetch the next chunk's residual tile
-              const uint32_t nb = (gc + 1u) & 1u;
-              mbar_expect_tx(rbar0 + 8u * nb, OUT_STAGE_BYTES);
-              tma_load_4d(res0 + nb * OUT_STAGE_BYTES, &maps.r, rbar0 + 8u * nb, n_base + c0 + OUT_CHUNK, tw * p.bw,
-                          th * p.bh, tn * p.bn);
-            }
-            mbar_wait(rbar0 + 8u * (gc & 1u), (gc >> 1) & 1u);
-          }
-          const uint8_t* rsrow = gen_base + (res0 - smem_base) + (gc & 1u) * OUT_STAGE_BYTES + r * 128;
-          uint8_t* srow = gen_base + (out0 - smem_base) + ob * OUT_STAGE_BYTES + r * 128;
-          const int cc = c0 + 32 * half;  // this warp's 32 columns (block_n is a multiple of 16)
-          const bool last_chunk = c0 + OUT_CHUNK >= p.block_n;
-          if (cc < p.block_n) {
-            uint32_t acc[32];
-            const bool wide = cc + 32 <= p.block_n;
-            if (wide) tmem_ld32(trow + cc, acc);
-            else tmem_ld16(trow + cc, acc);
-            // bias of this warp's columns: issued while the TMEM load is in flight
-            float bb[32];
-            const int ngrp = wide ? 4 : 2;
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int ch = n_base + cc + 8 * g;
-              float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
-              if (g < ngrp && ch < p.Cout) {
-                b0 = __ldg(reinterpret_cast<const float4*>(p.bias + ch));
-                b1 = __ldg(reinterpret_cast<const float4*>(p.bias + ch + 4));
-              }
-              bb[8 * g + 0] = b0.x; bb[8 * g + 1] = b0.y; bb[8 * g + 2] = b0.z; bb[8 * g + 3] = b0.w;
-              bb[8 * g + 4] = b1.x; bb[8 * g + 5] = b1.y; bb[8 * g + 6] = b1.z; bb[8 * g + 7] = b1.w;
-            }
-            tmem_ld_wait();
-            if (last_chunk) {  // the accumulator now lives in registers: hand the TMEM stage back to the MMA warp
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(tempty0 + 8u * a);
-            }
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              if (g >= ngrp) break;
-              const int ch = n_base + cc + 8 * g;
-              float v[8];
-              if (ch < p.Cout) {  // Cout is a multiple of 8 on this path
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = apply_act(__uint_as_float(acc[8 * g + j]) + bb[8 * g + j], p.act_pre);
-                if (has_res) {  // same swizzled position in the residual tile as in the staging tile
-                  float rf[8];
-                  unpack8(*reinterpret_cast<const h16x8*>(rsrow + (((4 * half + g) ^ (r & 7)) * 16)), rf);
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) v[j] += rf[j];
-                }
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], p.act_post);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = 0.0f;
-              }
-              // 128-byte-swizzled staging row: 16-byte chunk index XOR (row % 8)
-              const int chunk = (4 * half + g) ^ (r & 7);
-              *reinterpret_cast<h16x8*>(srow + chunk * 16) = pack8(v);
-            }
-          } else if (last_chunk) {  // nothing to read in the last chunk (block_n % 64 <= 32): still release the stage
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty0 + 8u * a);
-          }
-          fence_async_smem();
-          epi_bar_sync();
-          if (et == 0) {
-            tma_store_4d(&maps.y, out0 + ob * OUT_STAGE_BYTES, n_base + c0, tw * p.bw, th * p.bh, tn * p.bn);
-            tma_store_commit();
-          }
-        }
+        continue;
       }
-      if (et == 0) trace_ev(p, 3, tr_j, tile, 0);
-      if (p.y32) {  // (the fp16 path released the accumulator stage right after its last TMEM load)
+      if (last < 0) {  // no unit of this tile is mine: hand the accumulator stage back right away
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty0 + 8u * a);
       }
+      for (int ci = first; ci < nch; ci += 2) {
+        const int c0 = ci * OUT_CHUNK;
+        const int cw = min(OUT_CHUNK, p.block_n - c0);  // 16 / 32 / 48 / 64 columns
+        uint32_t acc[64];
+        tmem_ld16(trow + c0, acc);
+        if (cw > 16) tmem_ld16(trow + c0 + 16, acc + 16);
+        if (cw > 32) tmem_ld16(trow + c0 + 32, acc + 32);
+        if (cw > 48) tmem_ld16(trow + c0 + 48, acc + 48);
+        tmem_ld_wait();
+        if (et == 0) trace_ev(p, 3, tr_j, tile, 2);
+        if (ci == last) {  // the accumulator now lives in registers: hand the TMEM stage back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty0 + 8u * a);
+        }
+        if (has_res) mbar_wait(rbar, rcount & 1u);
+        if (lane == 0) tma_store_wait_read<0>();  // my previous TMA store has finished reading the staging tile
+        __syncwarp();
+        const float* bch = sbias + n_base + c0;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          if (8 * g < cw) {
+            const float4 b0 = *reinterpret_cast<const float4*>(bch + 8 * g);
+            const float4 b1 = *reinterpret_cast<const float4*>(bch + 8 * g + 4);
+            float v[8];
+            v[0] = __uint_as_float(acc[8 * g + 0]) + b0.x; v[1] = __uint_as_float(acc[8 * g + 1]) + b0.y;
+            v[2] = __uint_as_float(acc[8 * g + 2]) + b0.z; v[3] = __uint_as_float(acc[8 * g + 3]) + b0.w;
+            v[4] = __uint_as_float(acc[8 * g + 4]) + b1.x; v[5] = __uint_as_float(acc[8 * g + 5]) + b1.y;
+            v[6] = __uint_as_float(acc[8 * g + 6]) + b1.z; v[7] = __uint_as_float(acc[8 * g + 7]) + b1.w;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], lo_pre);
+            if (has_res) {  // same swizzled position in the residual tile as in the staging tile
+              float rf[8];
+              unpack8(*reinterpret_cast<const h16x8*>(rsrow + ((g ^ swz) * 16)), rf);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] += rf[j];
+            }
+            uint4 o;
+            o.x = pack2_sat(fmaxf(v[0], lo_post), fmaxf(v[1], lo_post));
+            o.y = pack2_sat(fmaxf(v[2], lo_post), fmaxf(v[3], lo_post));
+            o.z = pack2_sat(fmaxf(v[4], lo_post), fmaxf(v[5], lo_post));
+            o.w = pack2_sat(fmaxf(v[6], lo_post), fmaxf(v[7], lo_post));
+            *reinterpret_cast<uint4*>(srow + ((g ^ swz) * 16)) = o;
+          }
+        }
+        if (has_res) {  // every lane has read the residual tile: fetch the one of my next unit
+          __syncwarp();
+          ++rcount;
+          int t2 = tile, c2 = ci + 2;
+          while (c2 >= nch) { c2 -= nch; t2 += gridDim.x; }
+          if (t2 < p.total_tiles) issue_res(t2, c2);
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_4d(&maps.y, stg, n_base + c0, tw * p.bw, th * p.bh + qh, tn * p.bn + qn);
+          tma_store_commit();
+        }
+        if (et == 0) trace_ev(p, 3, tr_j, tile, 5);
+      }
+      if (et == 0) trace_ev(p, 3, tr_j, tile, 0);
     }
-    if (et == 0) tma_store_wait_all();
+    if (lane == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -693,7 +733,9 @@ inline int prepare(Launch* L, const TView& x, const TView& y, const TView* res, 
   p.tmem_cols = 32;
   while (p.tmem_cols < 2 * p.block_n) p.tmem_cols *= 2;
   const int sub_bytes = A_STAGE_BYTES + p.block_n * 128;
-  const int fixed = (res ? 4 : 2) * OUT_STAGE_BYTES + 1024 + 1024;  // staging (+ residual) tiles, alignment slack, barriers
+  p.bias_bytes = (p.n_tiles * p.block_n * 4 + 127) / 128 * 128;
+  // per-warp staging (+ residual) tiles, staged bias, alignment slack, barriers
+  const int fixed = (res ? 2 : 1) * EPI_WARPS * EPI_TILE_BYTES + p.bias_bytes + 1024 + 1024;
   const int avail = smem_budget_kb * 1024 - fixed;
   // Small-N layers are bound by the fixed cost of a barrier round in the single-thread producer / MMA loops, so
   // several k-blocks share one stage (one wait + one expect_tx + one commit per `group` k-blocks) whenever the
@@ -757,6 +799,10 @@ inline int prepare(Launch* L, const TView& x, const TView& y, const TView* res, 
     uint32_t box[3] = {BLOCK_K, static_cast<uint32_t>(p.block_n), 1};
     if (encode_h16(&L->maps.b, const_cast<h16*>(w_dev), 3, dims, strides, box)) return 1;
   }
+  // an epilogue warp stores (and fetches residuals for) its TMEM lane quadrant: 32 consecutive tile rows =
+  // a (bw x qbh x qbn) sub-box of the (bw x bh x bn) tile box
+  const int qbh = std::min(p.bh, 32 / p.bw), qbn = 32 / (p.bw * qbh);
+  p.fd_nt = make_fastdiv(p.n_tiles); p.fd_tw = make_fastdiv(p.tiles_w); p.fd_th = make_fastdiv(p.tiles_h);
   p.y_ctot = y.ctot; p.y_c0 = y.c0; p.y_H = y.H; p.y_W = y.W;
   p.out_scale = out_scale; p.out_oy = out_oy; p.out_ox = out_ox;
   if (y.f32) {
@@ -769,7 +815,7 @@ inline int prepare(Launch* L, const TView& x, const TView& y, const TView* res, 
     uint64_t dims[4] = {static_cast<uint64_t>(Cout), static_cast<uint64_t>(Wo), static_cast<uint64_t>(Ho),
                         static_cast<uint64_t>(x.N)};
     uint64_t strides[3] = {ypitch * out_scale, ypitch * y.W * out_scale, ypitch * y.W * y.H};
-    uint32_t box[4] = {OUT_CHUNK, static_cast<uint32_t>(p.bw), static_cast<uint32_t>(p.bh), static_cast<uint32_t>(p.bn)};
+    uint32_t box[4] = {OUT_CHUNK, static_cast<uint32_t>(p.bw), static_cast<uint32_t>(qbh), static_cast<uint32_t>(qbn)};
     char* base = static_cast<char*>(y.base) + (static_cast<size_t>(out_oy) * y.W + out_ox) * ypitch + static_cast<size_t>(y.c0) * 2;
     if (encode_h16(&L->maps.y, base, 4, dims, strides, box)) return 1;
   }
@@ -781,7 +827,7 @@ inline int prepare(Launch* L, const TView& x, const TView& y, const TView* res, 
     uint64_t dims[4] = {static_cast<uint64_t>(Cout), static_cast<uint64_t>(Wo), static_cast<uint64_t>(Ho),
                         static_cast<uint64_t>(x.N)};
     uint64_t strides[3] = {rpitch, rpitch * res->W, rpitch * res->W * res->H};
-    uint32_t box[4] = {OUT_CHUNK, static_cast<uint32_t>(p.bw), static_cast<uint32_t>(p.bh), static_cast<uint32_t>(p.bn)};
+    uint32_t box[4] = {OUT_CHUNK, static_cast<uint32_t>(p.bw), static_cast<uint32_t>(qbh), static_cast<uint32_t>(qbn)};
     char* base = static_cast<char*>(res->base) + static_cast<size_t>(res->c0) * 2;
     if (encode_h16(&L->maps.r, base, 4, dims, strides, box)) return 1;
   }

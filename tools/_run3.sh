@@ -1,0 +1,7 @@
+cd $GRAFT_REPO_ROOT
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15
+export TRACE_LINES=70 TRACE_SKIP=600
+python tools/umma_trace.py 512 64 64 3 > gpurun_out/t4_64_3x3.txt 2>&1
+python tools/umma_trace.py 256 64 256 1 > gpurun_out/t4_64_256_1x1.txt 2>&1
+python tools/op_table.py 16 12 > gpurun_out/op_table_r1j.txt 2>&1
+tail -12 gpurun_out/op_table_r1j.txt

@@ -37,9 +37,17 @@ evs.sort()
 t0 = evs[0][0]
 print(f"{len(evs)} events; conv {k}x{k} {Cin}->{Cout} @{H}")
 last = {}
-for c, role, a_, b_ in evs[:int(os.environ.get("TRACE_LINES", "120"))]:
+skip = int(os.environ.get("TRACE_SKIP", "0"))
+for c, role, a_, b_ in evs[skip:skip + int(os.environ.get("TRACE_LINES", "120"))]:
     d = c - last.get(role, c)
     last[role] = c
+    if role == 3 and b_:
+        nm = {1: "epi : staging free+bar", 2: "epi : tmem loaded", 3: "epi : packed+stored", 4: "epi : fence+bar", 5: "epi : tma store issued"}[b_]
+        print(f"{c - t0:9d} (+{d:6d})  {nm} tile {a_:6d}")
+        continue
+    if role == 1 and b_ == -1:
+        print(f"{c - t0:9d} (+{d:6d})  mma : issued+committed tile {a_:6d}")
+        continue
     print(f"{c - t0:9d} (+{d:6d})  {names[role]} tile {a_:6d} kb {b_}")
 for role in range(4):
     cs = np.array(sorted(c for c, r, _, _ in evs if r == role))
