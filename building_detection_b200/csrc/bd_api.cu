@@ -127,7 +127,7 @@ int bd_create(int device, bd_ctx** out) {
   bd_ctx* c = new bd_ctx();
   c->device = device;
   c->num_sms = prop.multiProcessorCount;
-  if (const char* s = getenv("BD_UMMA_SMEM_KB")) c->umma_smem_kb = std::max(48, std::min(224, atoi(s)));
+  if (const char* s = getenv("BD_UMMA_SMEM_KB")) c->umma_smem_kb = std::max(48, std::min(226, atoi(s)));
   if (const char* s = getenv("BD_UMMA_GROUP")) c->umma_group = std::max(0, std::min(9, atoi(s)));
   if (const char* s = getenv("BD_UMMA_MAX_N")) c->umma_max_block_n = std::max(16, std::min(256, atoi(s) / 16 * 16));
   *out = c;
@@ -270,16 +270,25 @@ int bd_plan_add_dwconv(bd_plan* p, bd_tref x, bd_tref y, int stride, int pad_t, 
     q.N = pl->batch; q.Ho = q.y.H; q.Wo = q.y.W; q.stride = stride; q.pad_t = pad_t; q.pad_l = pad_l; q.relu_in = relu_in;
     q.w = static_cast<const h16*>(wd);
     BD_CHECK(stride == 1 || stride == 2, "dwconv: stride must be 1 or 2");
-    const size_t total = static_cast<size_t>(pl->batch) * cdiv(q.Ho, k::DW_ROWS) * q.Wo * (x.c / 8);
+    // 4-channel vectors (half the registers, twice the resident warps) whenever the 8-channel version could not
+    // fill the machine with threads; both are exact and round identically
+    const size_t total8 = static_cast<size_t>(pl->batch) * cdiv(q.Ho, k::DW_ROWS) * q.Wo * (x.c / 8);
     bd_ctx* ctx = pl->ctx;
-    const int grid = grid_for(total, ctx->num_sms * 4);
+    const int vec = (x.c % 8 != 0 || total8 < static_cast<size_t>(ctx->num_sms) * 2048 * 2) ? 4 : 8;
+    BD_CHECK(q.x.c % vec == 0 && q.x.c0 % vec == 0 && q.x.ctot % vec == 0 && q.y.c0 % vec == 0 && q.y.ctot % vec == 0,
+             "dwconv: channel slices must be vector aligned");
+    const size_t total = total8 * (8 / vec);
+    BD_CHECK(total < (1ull << 31), "dwconv: too many work items");
+    const int grid = static_cast<int>(cdiv64(static_cast<int64_t>(total), k::TPB));
     Op op;
     op.kclass = 2; op.launches = 1;
     op.flops = 2.0 * pl->batch * q.Ho * q.Wo * static_cast<double>(x.c) * 9;
-    op.run = [q, grid, ctx, stride](cudaStream_t s) -> int {
+    op.run = [q, grid, ctx, stride, vec](cudaStream_t s) -> int {
       ctx->launches++;
-      if (stride == 1) k::dwconv3x3_kernel<1><<<grid, k::TPB, 0, s>>>(q);
-      else k::dwconv3x3_kernel<2><<<grid, k::TPB, 0, s>>>(q);
+      if (stride == 1 && vec == 8) k::dwconv3x3_kernel<1, 8><<<grid, k::TPB, 0, s>>>(q);
+      else if (stride == 1) k::dwconv3x3_kernel<1, 4><<<grid, k::TPB, 0, s>>>(q);
+      else if (vec == 8) k::dwconv3x3_kernel<2, 8><<<grid, k::TPB, 0, s>>>(q);
+      else k::dwconv3x3_kernel<2, 4><<<grid, k::TPB, 0, s>>>(q);
       BD_CUDA(cudaGetLastError());
       return 0;
     };

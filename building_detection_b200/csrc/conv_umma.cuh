@@ -114,6 +114,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
          parity);
   __trap();
 }
+// Non-blocking phase test.  A wait on an already completed mbarrier still costs a 200-300 cycle shared-memory round
+// trip in the single-threaded MMA loop; the halo path (one wait per 36 MMAs) tests the barriers it will need NEXT
+// while two thirds of the current chunk's MMAs are queued and only falls back to mbar_wait when the early test failed.
+__device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done;
+}
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2,
                                             int c3) {
   asm volatile(
@@ -254,6 +268,11 @@ __device__ __forceinline__ void ring_advance(Ring& r, const Params& p, uint32_t 
   if (++r.s == static_cast<uint32_t>(p.stages)) { r.s = 0; r.ph ^= 1u; r.off = 0; r.fb = full0; r.eb = empty0; }
   else { r.off += stage_bytes; r.fb += 8u; r.eb += 8u; }
 }
+// early test of the full barrier of the stage AFTER r
+__device__ __forceinline__ uint32_t ring_test_next_full(const Ring& r, const Params& p, uint32_t full0) {
+  const bool wrap = r.s + 1u == static_cast<uint32_t>(p.stages);
+  return mbar_test(wrap ? full0 : r.fb + 8u, wrap ? r.ph ^ 1u : r.ph);
+}
 template <int NTAPS, int KCH, int G>
 __device__ __forceinline__ void produce_tile(const Maps& maps, const Params& p, Ring& r, uint32_t smem_base, uint32_t sub_bytes,
                                              uint32_t full0, uint32_t empty0, int w0, int h0, int n0, int n_base, int& tr_i,
@@ -373,11 +392,11 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
     uint32_t s = 0, sub = 0, ph = 0, a_s = smem_base, fb = full0, eb = empty0;  // ring position, kept incrementally
     const char* maps_a = reinterpret_cast<const char*>(&maps.a[0]);
     Ring ring{0u, 0u, 0u, full0, empty0};
-    if (p.spec == 3 && elect_one()) {  // all weight tiles once: [tap][chunk] blocks of block_n x 128 B
+    if (p.spec == 3 && elect_one()) {  // all weight tiles once: [chunk][tap] blocks of block_n x 128 B
       mbar_expect_tx(wbar, static_cast<uint32_t>(p.wres_bytes));
       uint32_t dst = wres0;
-      for (int tap = 0; tap < 9; ++tap)
-        for (int c = 0; c < p.Cin; c += BLOCK_K, dst += b_bytes) tma_load_3d(dst, &maps.b, wbar, c, 0, tap);
+      for (int c = 0; c < p.Cin; c += BLOCK_K)
+        for (int tap = 0; tap < 9; ++tap, dst += b_bytes) tma_load_3d(dst, &maps.b, wbar, c, 0, tap);
     }
     __syncwarp();
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -427,43 +446,61 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
     const uint32_t dsub = sub_bytes >> 4;  // descriptor start-address field counts 16-byte units
     uint32_t s = 0, sub = 0, ph = 0, doff = 0, fb = full0, eb = empty0, ti = 0;
     Ring ring{0u, 0u, 0u, full0, empty0};
+    uint32_t f_ready = 0, te_ready = 0;  // early test results: next full barrier / this tile's accumulator stage
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
       const uint32_t a = ti & 1u, aph = (ti >> 1) & 1u;
-      mbar_wait(tempty0 + 8u * a, aph ^ 1u);  // epilogue has drained this accumulator stage
+      if (!te_ready) mbar_wait(tempty0 + 8u * a, aph ^ 1u);  // epilogue has drained this accumulator stage
       tc_fence_after();
       const uint32_t tacc = tmem_base + a * static_cast<uint32_t>(p.block_n);
+      // the NEXT tile's accumulator stage / phase, tested early during this tile's last k-block
+      const uint32_t te_bar = tempty0 + 8u * (a ^ 1u), te_par = (((ti + 1u) >> 1) & 1u) ^ 1u;
       if (p.spec == 3) {
         if (ti == 0) mbar_wait(wbar, 0);
-        const uint64_t wdesc0 = make_sdesc(wres0);
-        const uint32_t dkb = b_bytes >> 4;  // descriptor units per weight tile
-        uint32_t kc = 0;
-        for (int c = p.Cin; c > 0; c -= BLOCK_K, ++kc) {  // c = channels left
-          mbar_wait(ring.fb, ring.ph);
+        const uint32_t dkb = b_bytes >> 4;   // descriptor units per weight tile
+        uint64_t bdesc = make_sdesc(wres0);  // weights are laid out [chunk][tap]: a running descriptor
+        for (int c = p.Cin; c > 0; c -= BLOCK_K) {  // c = channels left
+          if (!f_ready) mbar_wait(ring.fb, ring.ph);
           tc_fence_after();
+          const uint64_t hdesc = make_sdesc_sbo(smem_base + ring.off, HALO_W * 128);
           if (elect_one()) {
             trace_ev(p, 1, tr_i, tile, c);
-            const uint64_t hdesc = make_sdesc_sbo(smem_base + ring.off, HALO_W * 128);
 #pragma unroll
-            for (int tap = 0; tap < 9; ++tap) {
+            for (int tap = 0; tap < 6; ++tap) {
               // tap (kh, kw) reads the halo rows shifted by kh halo rows and kw pixels
               const uint64_t adesc = hdesc + (((tap / 3) * HALO_W + tap % 3) * 128 >> 4);
-              const uint64_t bdesc = wdesc0 + (tap * static_cast<uint32_t>(p.kchunks) + kc) * dkb;
-              tc_mma_f16(tacc, adesc, bdesc, idesc, (tap > 0 || kc > 0) ? 1u : 0u);
-              if (c > 16) tc_mma_f16(tacc, adesc + 2u, bdesc + 2u, idesc, 1u);
-              if (c > 32) tc_mma_f16(tacc, adesc + 4u, bdesc + 4u, idesc, 1u);
-              if (c > 48) tc_mma_f16(tacc, adesc + 6u, bdesc + 6u, idesc, 1u);
+              const uint64_t bd = bdesc + static_cast<uint32_t>(tap) * dkb;
+              tc_mma_f16(tacc, adesc, bd, idesc, (tap > 0 || c < p.Cin) ? 1u : 0u);
+              if (c > 16) tc_mma_f16(tacc, adesc + 2u, bd + 2u, idesc, 1u);
+              if (c > 32) tc_mma_f16(tacc, adesc + 4u, bd + 4u, idesc, 1u);
+              if (c > 48) tc_mma_f16(tacc, adesc + 6u, bd + 6u, idesc, 1u);
+            }
+          }
+          __syncwarp();
+          // two thirds of this chunk's MMAs are queued: test what the next chunk / tile will wait for
+          f_ready = ring_test_next_full(ring, p, full0);
+          if (c <= BLOCK_K) te_ready = mbar_test(te_bar, te_par);
+          if (elect_one()) {
+#pragma unroll
+            for (int tap = 6; tap < 9; ++tap) {
+              const uint64_t adesc = hdesc + (((tap / 3) * HALO_W + tap % 3) * 128 >> 4);
+              const uint64_t bd = bdesc + static_cast<uint32_t>(tap) * dkb;
+              tc_mma_f16(tacc, adesc, bd, idesc, 1u);
+              if (c > 16) tc_mma_f16(tacc, adesc + 2u, bd + 2u, idesc, 1u);
+              if (c > 32) tc_mma_f16(tacc, adesc + 4u, bd + 4u, idesc, 1u);
+              if (c > 48) tc_mma_f16(tacc, adesc + 6u, bd + 6u, idesc, 1u);
             }
             tc_commit(ring.eb);
             if (c <= BLOCK_K) tc_commit(tfull0 + 8u * a);
             trace_ev(p, 1, tr_i, tile, -1);
           }
           __syncwarp();
+          bdesc += 9u * dkb;
           ring_advance(ring, p, HALO_STAGE, full0, empty0);
         }
         continue;
       }
-      if (p.spec == 1) { mma_tile<9, 1, 3>(p, ring, desc0, sub_bytes, full0, empty0, tacc, idesc, tfull0 + 8u * a, tr_i, tile); continue; }
-      if (p.spec == 2) { mma_tile<9, 2, 2>(p, ring, desc0, sub_bytes, full0, empty0, tacc, idesc, tfull0 + 8u * a, tr_i, tile); continue; }
+      if (p.spec == 1) { mma_tile<9, 1, 3>(p, ring, desc0, sub_bytes, full0, empty0, tacc, idesc, tfull0 + 8u * a, tr_i, tile); f_ready = te_ready = 0u; continue; }
+      if (p.spec == 2) { mma_tile<9, 2, 2>(p, ring, desc0, sub_bytes, full0, empty0, tacc, idesc, tfull0 + 8u * a, tr_i, tile); f_ready = te_ready = 0u; continue; }
       uint32_t accum = 0;
       for (int tap = 0; tap < p.ntaps; ++tap) {
         for (int c = p.Cin; c > 0; c -= BLOCK_K) {  // c = channels left in this tap
@@ -748,7 +785,7 @@ inline int prepare(Launch* L, const TView& x, const TView& y, const TView* res, 
   p.spec = 0;
   p.wres_bytes = 0;
   const int wbytes = ntaps * p.kchunks * p.block_n * 128;
-  if (halo && p.n_tiles == 1 && wbytes + 2 * p.kchunks * HALO_STAGE <= avail && wbytes <= 112 * 1024) {
+  if (halo && p.n_tiles == 1 && wbytes + 2 * HALO_STAGE <= avail && wbytes <= 148 * 1024) {
     // halo path: weights resident, the ring holds one halo box per 64-channel chunk
     p.spec = 3; p.group = 1; p.wres_bytes = wbytes;
     p.bw = 8; p.bh = 16; p.bn = 1;

@@ -93,74 +93,88 @@ struct DwParams {
   int N, Ho, Wo, stride, pad_t, pad_l, relu_in;
   const h16* w;  // [9][C] fp16
 };
-// thread = (8-channel group, output column, block of DW_ROWS output rows, image): the 9x8 fp16 weights stay packed
-// in registers and the 3-row input window slides down (3 new 16-byte loads per output at stride 1).  The 9-tap sum
-// runs on packed half2 FMAs (fp16 accumulate, one rounding per tap, tap order kh-major): 36 instructions per 8
-// output channels instead of ~290 with fp32 conversion; oracle/plan_interp.py mirrors this rounding sequence
-// exactly.  Consecutive threads are consecutive channel groups (coalesced 16-byte vectors).
-constexpr int DW_ROWS = 4;
-template <int STRIDE>
+// thread = (VEC-channel group, output column, band of DW_ROWS output rows, image).  The 9 x VEC fp16 weights stay
+// packed in registers; the input window is a ring of row slots (3 rows in use + the rows of the NEXT output row,
+// whose loads are issued one iteration ahead of their use), fully unrolled so the ring indices are compile-time
+// and the loads of row r+1 overlap the FMAs of row r.  The 9-tap sum runs on packed half2 FMAs (fp16 accumulate,
+// one rounding per tap, tap order kh-major); oracle/plan_interp.py mirrors this rounding sequence exactly.
+// Consecutive threads are consecutive channel groups (coalesced vectors).  VEC = 4 halves the registers per
+// thread (twice the resident warps) for the latency-bound small maps.
+constexpr int DW_ROWS = 8;
+template <int VEC> struct DwVec;
+template <> struct DwVec<8> { typedef uint4 T; };
+template <> struct DwVec<4> { typedef uint2 T; };
+template <int STRIDE, int VEC>
 __global__ void __launch_bounds__(TPB) dwconv3x3_kernel(const __grid_constant__ DwParams p) {
-  const int C = p.x.c, cg = C >> 3;
+  typedef typename DwVec<VEC>::T V;
+  constexpr int NH = VEC / 2;                       // half2 per vector
+  constexpr int SLOTS = STRIDE == 1 ? 4 : 5;        // input row r lives in slot r % SLOTS
+  union U { V v; __half2 h[NH]; };
+  const int C = p.x.c, cg = C / VEC;
   const int rb = (p.Ho + DW_ROWS - 1) / DW_ROWS;
-  const size_t total = static_cast<size_t>(p.N) * rb * p.Wo * cg;
+  const unsigned total = static_cast<unsigned>(p.N) * rb * p.Wo * cg;
   const __half2 zero2 = __float2half2_rn(0.0f);
-  for (size_t idx = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; idx < total;
-       idx += static_cast<size_t>(gridDim.x) * TPB) {
+  for (unsigned idx = blockIdx.x * TPB + threadIdx.x; idx < total; idx += gridDim.x * TPB) {
     const int g = static_cast<int>(idx % cg);
-    size_t t = idx / cg;
+    unsigned t = idx / cg;
     const int ow = static_cast<int>(t % p.Wo);
     t /= p.Wo;
     const int ob = static_cast<int>(t % rb), n = static_cast<int>(t / rb);
-    h16x8 wp[9];
+    U wp[9];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) wp[k] = *reinterpret_cast<const h16x8*>(p.w + k * C + g * 8);
+    for (int k = 0; k < 9; ++k) wp[k].v = *reinterpret_cast<const V*>(p.w + k * C + g * VEC);
     const int iw0 = ow * STRIDE - p.pad_l;
-    const h16* xb = static_cast<const h16*>(p.x.base) + p.x.c0 + g * 8;
-    const size_t img = static_cast<size_t>(n) * p.x.H;
-    auto load_row = [&](int ih, h16x8* row) {  // 3 taps of input row ih (zero outside the map), ReLU applied once
-      const bool rok = ih >= 0 && ih < p.x.H;
-#pragma unroll
-      for (int kw = 0; kw < 3; ++kw) {
-        const int iw = iw0 + kw;
-        h16x8 v{};
-        if (rok && iw >= 0 && iw < p.x.W) {
-          v = *reinterpret_cast<const h16x8*>(xb + ((img + ih) * p.x.W + iw) * p.x.ctot);
-          if (p.relu_in) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) v.v[j] = __hmax2(v.v[j], zero2);
-          }
-        }
-        row[kw] = v;
-      }
-    };
-    h16x8 win[3][3];  // input rows ih0 .. ih0+2 of the current output row
     const int oh0 = ob * DW_ROWS;
     const int ih0 = oh0 * STRIDE - p.pad_t;
-    load_row(ih0, win[0]);
-    load_row(ih0 + 1, win[1]);
+    const h16* xb = static_cast<const h16*>(p.x.base) + p.x.c0 + g * VEC +
+                    (static_cast<size_t>(n) * p.x.H * p.x.W) * p.x.ctot;
+    h16* yb = static_cast<h16*>(p.y.base) + p.y.c0 + g * VEC + (static_cast<size_t>(n) * p.Ho * p.Wo + ow) * p.y.ctot;
+    const bool cok0 = iw0 >= 0, cok1 = iw0 + 1 < p.x.W, cok2 = iw0 + 2 < p.x.W;  // iw0 + 1 >= 0 always
+    U win[SLOTS][3];
+    auto load_row = [&](int rel, U* row) {  // 3 taps of input row ih0 + rel (zero outside the map), ReLU applied once
+      const int ih = ih0 + rel;
+      const bool rok = ih >= 0 && ih < p.x.H;
+      const h16* xr = xb + (static_cast<size_t>(ih) * p.x.W + iw0) * p.x.ctot;
+      const V z = {};
+      row[0].v = (rok && cok0) ? *reinterpret_cast<const V*>(xr) : z;
+      row[1].v = (rok && cok1) ? *reinterpret_cast<const V*>(xr + p.x.ctot) : z;
+      row[2].v = (rok && cok2) ? *reinterpret_cast<const V*>(xr + 2 * p.x.ctot) : z;
+    };
+    auto relu_row = [&](U* row) {
+      if (p.relu_in) {
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+          for (int j = 0; j < NH; ++j) row[kw].h[j] = __hmax2(row[kw].h[j], zero2);
+      }
+    };
+    load_row(0, win[0]);
+    load_row(1, win[1]);
+    load_row(2, win[2]);
+    relu_row(win[0]); relu_row(win[1]); relu_row(win[2]);
 #pragma unroll
     for (int r = 0; r < DW_ROWS; ++r) {
       const int oh = oh0 + r;
       if (oh >= p.Ho) break;
-      const int ih = oh * STRIDE - p.pad_t;
-      if (STRIDE == 2 && r > 0) load_row(ih + 1, win[1]);
-      load_row(ih + 2, win[2]);
-      h16x8 acc{};
+      // rows of the next output row: STRIDE new ones, into the slots the current row no longer needs after this step
+      if (r + 1 < DW_ROWS) {
+#pragma unroll
+        for (int q = 0; q < STRIDE; ++q) load_row(STRIDE * r + 3 + q, win[(STRIDE * r + 3 + q) % SLOTS]);
+      }
+      U acc;
+#pragma unroll
+      for (int j = 0; j < NH; ++j) acc.h[j] = zero2;
 #pragma unroll
       for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc.v[j] = __hfma2(win[kh][kw].v[j], wp[kh * 3 + kw].v[j], acc.v[j]);
-      *reinterpret_cast<h16x8*>(static_cast<h16*>(p.y.base) +
-                                ((static_cast<size_t>(n) * p.Ho + oh) * p.Wo + ow) * p.y.ctot + p.y.c0 + g * 8) = acc;
-      if (STRIDE == 1) {
+          for (int j = 0; j < NH; ++j)
+            acc.h[j] = __hfma2(win[(STRIDE * r + kh) % SLOTS][kw].h[j], wp[kh * 3 + kw].h[j], acc.h[j]);
+      *reinterpret_cast<V*>(yb + static_cast<size_t>(oh) * p.Wo * p.y.ctot) = acc.v;
+      if (r + 1 < DW_ROWS) {
 #pragma unroll
-        for (int kw = 0; kw < 3; ++kw) { win[0][kw] = win[1][kw]; win[1][kw] = win[2][kw]; }
-      } else {
-#pragma unroll
-        for (int kw = 0; kw < 3; ++kw) win[0][kw] = win[2][kw];
+        for (int q = 0; q < STRIDE; ++q) relu_row(win[(STRIDE * r + 3 + q) % SLOTS]);
       }
     }
   }

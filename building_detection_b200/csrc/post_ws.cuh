@@ -52,7 +52,7 @@ struct bd_ctx {
   int device = 0;
   int num_sms = 148;
   int64_t launches = 0;
-  int umma_smem_kb = 222;   // per-CTA smem budget of the persistent tcgen05 conv (1 CTA / SM)
+  int umma_smem_kb = 226;   // per-CTA smem budget of the persistent tcgen05 conv (1 CTA / SM)
   int umma_max_block_n = 256;
   int umma_group = 0;       // k-blocks per smem stage: 0 = automatic, 1 = off (BD_UMMA_GROUP)
   int* d_ys = nullptr;      // tile origin scratch

@@ -45,8 +45,9 @@ for c, role, a_, b_ in evs[skip:skip + int(os.environ.get("TRACE_LINES", "120"))
         nm = {1: "epi : staging free+bar", 2: "epi : tmem loaded", 3: "epi : packed+stored", 4: "epi : fence+bar", 5: "epi : tma store issued"}[b_]
         print(f"{c - t0:9d} (+{d:6d})  {nm} tile {a_:6d}")
         continue
-    if role == 1 and b_ == -1:
-        print(f"{c - t0:9d} (+{d:6d})  mma : issued+committed tile {a_:6d}")
+    if role == 1 and b_ < 0:
+        nm = {-1: "committed", -2: "mmas issued", -10: "loop top", -11: "tempty ok", -12: "fence1", -13: "full ok", -14: "fence2"}[b_]
+        print(f"{c - t0:9d} (+{d:6d})  mma : {nm} tile {a_:6d}")
         continue
     print(f"{c - t0:9d} (+{d:6d})  {names[role]} tile {a_:6d} kb {b_}")
 for role in range(4):
