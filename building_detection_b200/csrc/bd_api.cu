@@ -364,20 +364,26 @@ int bd_plan_add_gap(bd_plan* p, bd_tref x, int y_vec) {
     k::GapParams q;
     q.x = pl->kview(x); q.N = pl->batch;
     const int HW = q.x.H * q.x.W;
-    q.splits = std::max(1, std::min(64, HW / 1024));
-    void* part = nullptr;
+    // enough blocks to fill the machine four times over, at least 32 pixels and (for the large maps) about 512
+    // pixels per block
+    bd_ctx* ctx = pl->ctx;
+    // (sized for batch 16, and NOT a function of the batch: a tile's result must not depend on its batch neighbours)
+    const int want = std::max(cdiv(HW, 512), cdiv(4 * 148, 16));
+    q.splits = std::max(1, std::min(std::min(want, 1024), std::max(1, HW / 32)));
+    void *part = nullptr, *tick = nullptr;
     if (pl->scratch(static_cast<size_t>(pl->batch) * q.splits * x.c * 4, &part)) return 1;
+    if (pl->scratch(static_cast<size_t>(pl->batch) * 4, &tick)) return 1;
+    BD_CUDA(cudaMemset(tick, 0, static_cast<size_t>(pl->batch) * 4));
     q.partial = static_cast<float*>(part);
+    q.tickets = static_cast<unsigned*>(tick);
     q.out = pl->vecptr(y_vec);
     const int rows = k::TPB / (x.c / 8);
     const size_t smem = static_cast<size_t>(rows) * x.c * 4;
-    bd_ctx* ctx = pl->ctx;
     Op op;
-    op.kclass = 2; op.launches = 2; op.flops = 0;
+    op.kclass = 2; op.launches = 1; op.flops = 0;
     op.run = [q, smem, ctx](cudaStream_t s) -> int {
-      ctx->launches += 2;
-      k::gap_partial_kernel<<<dim3(q.splits, q.N), k::TPB, smem, s>>>(q);
-      k::gap_final_kernel<<<cdiv(q.N * q.x.c, 256), 256, 0, s>>>(q);
+      ctx->launches += 1;
+      k::gap_kernel<<<dim3(q.splits, q.N), k::TPB, smem, s>>>(q);
       BD_CUDA(cudaGetLastError());
       return 0;
     };

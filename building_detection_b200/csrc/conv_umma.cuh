@@ -353,8 +353,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
   const uint32_t bias0 = res0 + (p.res ? EPI_WARPS * EPI_TILE_BYTES : 0u);           // bias of all N tiles, fp32
   const uint32_t bar_base = bias0 + static_cast<uint32_t>(p.bias_bytes);             // 8-byte slots
   const uint32_t full0 = bar_base, empty0 = bar_base + 8u * p.stages;
-  const uint32_t tfull0 = bar_base + 16u * p.stages, tempty0 = tfull0 + 16u;
-  const uint32_t rbar0 = tempty0 + 16u;  // one per epilogue warp
+  const uint32_t tfull0 = bar_base + 16u * p.stages, tempty0 = tfull0 + 16u;  // tempty: [stage][epilogue group]
+  const uint32_t rbar0 = tempty0 + 32u;  // one per epilogue warp
   const uint32_t wbar = rbar0 + 8u * EPI_WARPS;
   const uint32_t holder = wbar + 16u;
   volatile uint32_t* holder_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (holder - smem_base));
@@ -366,7 +366,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull0 + 8u * a, 1);
-      mbar_init(tempty0 + 8u * a, EPI_WARPS);  // one arrival per epilogue warp
+      mbar_init(tempty0 + 16u * a, EPI_WARPS / 2);       // one arrival per warp of epilogue group 0
+      mbar_init(tempty0 + 16u * a + 8u, EPI_WARPS / 2);  // ... of group 1
     }
     for (int w = 0; w < EPI_WARPS; ++w) mbar_init(rbar0 + 8u * w, 1);
     mbar_init(wbar, 1);
@@ -447,13 +448,20 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
     uint32_t s = 0, sub = 0, ph = 0, doff = 0, fb = full0, eb = empty0, ti = 0;
     Ring ring{0u, 0u, 0u, full0, empty0};
     uint32_t f_ready = 0, te_ready = 0;  // early test results: next full barrier / this tile's accumulator stage
+    const bool single_unit = p.block_n <= OUT_CHUNK;  // one epilogue unit per tile
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
       const uint32_t a = ti & 1u, aph = (ti >> 1) & 1u;
-      if (!te_ready) mbar_wait(tempty0 + 8u * a, aph ^ 1u);  // epilogue has drained this accumulator stage
+      // The epilogue groups that read accumulator stage a two tiles ago have drained it.  A tile of one 64-column
+      // chunk belongs to ONE group (group = tile parity = a), wider tiles to both; each (stage, group) barrier
+      // completes one phase per tile on that stage, so the parity is the same for all of them.
+      if (!te_ready) {
+        if (single_unit) mbar_wait(tempty0 + 16u * a + 8u * a, aph ^ 1u);
+        else { mbar_wait(tempty0 + 16u * a, aph ^ 1u); mbar_wait(tempty0 + 16u * a + 8u, aph ^ 1u); }
+      }
       tc_fence_after();
       const uint32_t tacc = tmem_base + a * static_cast<uint32_t>(p.block_n);
       // the NEXT tile's accumulator stage / phase, tested early during this tile's last k-block
-      const uint32_t te_bar = tempty0 + 8u * (a ^ 1u), te_par = (((ti + 1u) >> 1) & 1u) ^ 1u;
+      const uint32_t te_bar = tempty0 + 16u * (a ^ 1u), te_par = (((ti + 1u) >> 1) & 1u) ^ 1u;
       if (p.spec == 3) {
         if (ti == 0) mbar_wait(wbar, 0);
         const uint32_t dkb = b_bytes >> 4;   // descriptor units per weight tile
@@ -478,7 +486,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
           __syncwarp();
           // two thirds of this chunk's MMAs are queued: test what the next chunk / tile will wait for
           f_ready = ring_test_next_full(ring, p, full0);
-          if (c <= BLOCK_K) te_ready = mbar_test(te_bar, te_par);
+          if (c <= BLOCK_K)
+            te_ready = single_unit ? mbar_test(te_bar + 8u * (a ^ 1u), te_par)
+                                   : (mbar_test(te_bar, te_par) & mbar_test(te_bar + 8u, te_par));
           if (elect_one()) {
 #pragma unroll
             for (int tap = 6; tap < 9; ++tap) {
@@ -577,40 +587,31 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
       tile_coords(p, tile, nt, tw, th, tn);
       const int n_base = nt * p.block_n;
       const int first = ((u & 1u) == static_cast<uint32_t>(half)) ? 0 : 1;          // my first chunk of this tile
-      const int last = first < nch ? first + ((nch - 1 - first) & ~1) : -1;          // my last one (-1: none)
+      if (first >= nch) continue;  // no unit of this tile is mine (the MMA warp does not wait for my group then)
+      const int last = first + ((nch - 1 - first) & ~1);                             // my last one
+      const uint32_t tempty = tempty0 + 16u * a + 8u * static_cast<uint32_t>(half);
       mbar_wait(tfull0 + 8u * a, aph);
       tc_fence_after();
       if (et == 0) trace_ev(p, 2, tr_i, tile, 0);
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * static_cast<uint32_t>(p.block_n);
       if (p.y32) {
         // fp32 output (logits / gate maps, Cout <= 16): one 16-column read, direct stores
-        if (last == 0) {
-          uint32_t acc[16];
-          tmem_ld16(trow, acc);
-          tmem_ld_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tempty0 + 8u * a);
-          const int ow = tw * p.bw + wl, oh = th * p.bh + hl, on = tn * p.bn + nl;
-          if ((ow < p.Wo) && (oh < p.Ho) && (on < p.N)) {
-            const size_t ypix = (static_cast<size_t>(on) * p.y_H + (oh * p.out_scale + p.out_oy)) * p.y_W +
-                                (ow * p.out_scale + p.out_ox);
-            float* yrow = p.y32 + ypix * p.y_ctot + p.y_c0;
-#pragma unroll
-            for (int c = 0; c < 16; ++c)
-              if (c < p.Cout) yrow[c] = fmaxf(fmaxf(__uint_as_float(acc[c]) + sbias[c], lo_pre), lo_post);
-          }
-        } else {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tempty0 + 8u * a);
-        }
-        continue;
-      }
-      if (last < 0) {  // no unit of this tile is mine: hand the accumulator stage back right away
+        uint32_t acc[16];
+        tmem_ld16(trow, acc);
+        tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty0 + 8u * a);
+        if (lane == 0) mbar_arrive(tempty);
+        const int ow = tw * p.bw + wl, oh = th * p.bh + hl, on = tn * p.bn + nl;
+        if ((ow < p.Wo) && (oh < p.Ho) && (on < p.N)) {
+          const size_t ypix = (static_cast<size_t>(on) * p.y_H + (oh * p.out_scale + p.out_oy)) * p.y_W +
+                              (ow * p.out_scale + p.out_ox);
+          float* yrow = p.y32 + ypix * p.y_ctot + p.y_c0;
+#pragma unroll
+          for (int c = 0; c < 16; ++c)
+            if (c < p.Cout) yrow[c] = fmaxf(fmaxf(__uint_as_float(acc[c]) + sbias[c], lo_pre), lo_post);
+        }
+        continue;
       }
       for (int ci = first; ci < nch; ci += 2) {
         const int c0 = ci * OUT_CHUNK;
@@ -620,49 +621,64 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
         if (cw > 16) tmem_ld16(trow + c0 + 16, acc + 16);
         if (cw > 32) tmem_ld16(trow + c0 + 32, acc + 32);
         if (cw > 48) tmem_ld16(trow + c0 + 48, acc + 48);
+        // bias of the first 32 columns while the TMEM loads are in flight (broadcast reads)
+        const float4* bch = reinterpret_cast<const float4*>(sbias + n_base + c0);
+        float4 bb[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) bb[k] = bch[k];
         tmem_ld_wait();
         if (et == 0) trace_ev(p, 3, tr_j, tile, 2);
         if (ci == last) {  // the accumulator now lives in registers: hand the TMEM stage back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tempty0 + 8u * a);
+          if (lane == 0) mbar_arrive(tempty);
         }
-        if (has_res) mbar_wait(rbar, rcount & 1u);
-        if (lane == 0) tma_store_wait_read<0>();  // my previous TMA store has finished reading the staging tile
-        __syncwarp();
-        const float* bch = sbias + n_base + c0;
+        // bias + activation in place (columns beyond cw hold garbage that the output map clips)
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          if (8 * g < cw) {
-            const float4 b0 = *reinterpret_cast<const float4*>(bch + 8 * g);
-            const float4 b1 = *reinterpret_cast<const float4*>(bch + 8 * g + 4);
-            float v[8];
-            v[0] = __uint_as_float(acc[8 * g + 0]) + b0.x; v[1] = __uint_as_float(acc[8 * g + 1]) + b0.y;
-            v[2] = __uint_as_float(acc[8 * g + 2]) + b0.z; v[3] = __uint_as_float(acc[8 * g + 3]) + b0.w;
-            v[4] = __uint_as_float(acc[8 * g + 4]) + b1.x; v[5] = __uint_as_float(acc[8 * g + 5]) + b1.y;
-            v[6] = __uint_as_float(acc[8 * g + 6]) + b1.z; v[7] = __uint_as_float(acc[8 * g + 7]) + b1.w;
+        for (int hlf = 0; hlf < 2; ++hlf) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], lo_pre);
-            if (has_res) {  // same swizzled position in the residual tile as in the staging tile
-              float rf[8];
-              unpack8(*reinterpret_cast<const h16x8*>(rsrow + ((g ^ swz) * 16)), rf);
+          for (int k = 0; k < 8; ++k) {
+            const int c = 32 * hlf + 4 * k;
+            acc[c + 0] = __float_as_uint(fmaxf(__uint_as_float(acc[c + 0]) + bb[k].x, lo_pre));
+            acc[c + 1] = __float_as_uint(fmaxf(__uint_as_float(acc[c + 1]) + bb[k].y, lo_pre));
+            acc[c + 2] = __float_as_uint(fmaxf(__uint_as_float(acc[c + 2]) + bb[k].z, lo_pre));
+            acc[c + 3] = __float_as_uint(fmaxf(__uint_as_float(acc[c + 3]) + bb[k].w, lo_pre));
+          }
+          if (hlf == 0) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] += rf[j];
-            }
-            uint4 o;
-            o.x = pack2_sat(fmaxf(v[0], lo_post), fmaxf(v[1], lo_post));
-            o.y = pack2_sat(fmaxf(v[2], lo_post), fmaxf(v[3], lo_post));
-            o.z = pack2_sat(fmaxf(v[4], lo_post), fmaxf(v[5], lo_post));
-            o.w = pack2_sat(fmaxf(v[6], lo_post), fmaxf(v[7], lo_post));
-            *reinterpret_cast<uint4*>(srow + ((g ^ swz) * 16)) = o;
+            for (int k = 0; k < 8; ++k) bb[k] = bch[8 + k];
           }
         }
-        if (has_res) {  // every lane has read the residual tile: fetch the one of my next unit
+        if (has_res) {  // same swizzled position in the residual tile as in the staging tile
+          mbar_wait(rbar, rcount & 1u);
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const uint4 rv = *reinterpret_cast<const uint4*>(rsrow + ((g ^ swz) * 16));
+            const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 rf = __half22float2(*reinterpret_cast<const __half2*>(&rw[j]));
+              acc[8 * g + 2 * j] = __float_as_uint(__uint_as_float(acc[8 * g + 2 * j]) + rf.x);
+              acc[8 * g + 2 * j + 1] = __float_as_uint(__uint_as_float(acc[8 * g + 2 * j + 1]) + rf.y);
+            }
+          }
+          // every lane has read the residual tile: fetch the one of my next unit
           __syncwarp();
           ++rcount;
           int t2 = tile, c2 = ci + 2;
           while (c2 >= nch) { c2 -= nch; t2 += gridDim.x; }
           if (t2 < p.total_tiles) issue_res(t2, c2);
+        }
+        if (lane == 0) tma_store_wait_read<0>();  // my previous TMA store has finished reading the staging tile
+        __syncwarp();
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          uint4 o;
+          o.x = pack2_sat(fmaxf(__uint_as_float(acc[8 * g + 0]), lo_post), fmaxf(__uint_as_float(acc[8 * g + 1]), lo_post));
+          o.y = pack2_sat(fmaxf(__uint_as_float(acc[8 * g + 2]), lo_post), fmaxf(__uint_as_float(acc[8 * g + 3]), lo_post));
+          o.z = pack2_sat(fmaxf(__uint_as_float(acc[8 * g + 4]), lo_post), fmaxf(__uint_as_float(acc[8 * g + 5]), lo_post));
+          o.w = pack2_sat(fmaxf(__uint_as_float(acc[8 * g + 6]), lo_post), fmaxf(__uint_as_float(acc[8 * g + 7]), lo_post));
+          *reinterpret_cast<uint4*>(srow + ((g ^ swz) * 16)) = o;
         }
         fence_async_smem();
         __syncwarp();

@@ -242,16 +242,19 @@ __global__ void __launch_bounds__(TPB) addn_kernel(const __grid_constant__ AddnP
 }
 
 // ---------------------------------------------------------------------------------- global average pool
-// pass 1: partial[n][split][c] = sum over the split's pixels; pass 2: out[n][c] = sum(partials)/(H*W).
-// Deterministic (no atomics).
+// One kernel: block (split, n) sums its pixel range into partial[n][split][c]; the LAST block of image n to finish
+// (ticket counter) adds the partials in split order and writes out[n][c] = sum / (H*W).  Deterministic: the
+// summation order is fixed by the grid, not by arrival order.
 struct GapParams {
   View x;
   int N, splits;
-  float* partial;  // [N][splits][C]
-  float* out;      // [N][C]
+  float* partial;      // [N][splits][C]
+  float* out;          // [N][C]
+  unsigned* tickets;   // [N], zero between launches (the last block resets its counter)
 };
-__global__ void __launch_bounds__(TPB) gap_partial_kernel(const __grid_constant__ GapParams p) {
+__global__ void __launch_bounds__(TPB) gap_kernel(const __grid_constant__ GapParams p) {
   extern __shared__ float sh[];  // [TPB/cg rows][C]
+  __shared__ unsigned s_last;
   const int C = p.x.c, cg = C >> 3;
   const int n = blockIdx.y, split = blockIdx.x;
   const int rows = TPB / cg;  // pixel lanes per block (host guarantees cg <= TPB)
@@ -261,9 +264,23 @@ __global__ void __launch_bounds__(TPB) gap_partial_kernel(const __grid_constant_
   const int beg = split * per, end = min(HW, beg + per);
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (row < rows) {
-    for (int i = beg + row; i < end; i += rows) {
+    const h16* xb = static_cast<const h16*>(p.x.base) + p.x.c0 + g * 8 + static_cast<size_t>(n) * HW * p.x.ctot;
+    int i = beg + row;
+    for (; i + 3 * rows < end; i += 4 * rows) {  // four independent 16-byte loads in flight
+      h16x8 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const h16x8*>(xb + static_cast<size_t>(i + u * rows) * p.x.ctot);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float xv[8];
+        unpack8(v[u], xv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += xv[j];
+      }
+    }
+    for (; i < end; i += rows) {
       float xv[8];
-      ld8(p.x, static_cast<size_t>(n) * HW + i, g * 8, xv);
+      unpack8(*reinterpret_cast<const h16x8*>(xb + static_cast<size_t>(i) * p.x.ctot), xv);
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] += xv[j];
     }
@@ -276,15 +293,18 @@ __global__ void __launch_bounds__(TPB) gap_partial_kernel(const __grid_constant_
     for (int r2 = 0; r2 < rows; ++r2) s += sh[r2 * C + c];
     p.partial[(static_cast<size_t>(n) * p.splits + split) * C + c] = s;
   }
-}
-__global__ void gap_final_kernel(const __grid_constant__ GapParams p) {
-  const int C = p.x.c;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= p.N * C) return;
-  const int n = i / C, c = i % C;
-  float s = 0.0f;
-  for (int k2 = 0; k2 < p.splits; ++k2) s += p.partial[(static_cast<size_t>(n) * p.splits + k2) * C + c];
-  p.out[i] = s / static_cast<float>(p.x.H * p.x.W);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(p.tickets + n, 1u) == static_cast<unsigned>(p.splits - 1) ? 1u : 0u;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int c = threadIdx.x; c < C; c += TPB) {
+    float s = 0.0f;
+    for (int k2 = 0; k2 < p.splits; ++k2) s += __ldcg(p.partial + (static_cast<size_t>(n) * p.splits + k2) * C + c);
+    p.out[static_cast<size_t>(n) * C + c] = s / static_cast<float>(HW);
+  }
+  if (threadIdx.x == 0) p.tickets[n] = 0u;
 }
 
 // ---------------------------------------------------------------------------------- dense on pooled vectors

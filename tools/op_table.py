@@ -24,6 +24,20 @@ for name in MODEL_NAMES:
         best = ms if best is None else np.minimum(best, ms)
     ms = best
     assert len(ms) == len(plan.ops), (len(ms), len(plan.ops))
+    # the whole plan back to back without per-op events (what the scene loop sees)
+    import torch
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    st = torch.cuda.current_stream().cuda_stream
+    for _ in range(2):
+        nat.run_device(0, 0, 0, st)
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(5):
+        nat.run_device(0, 0, 0, st)
+    ev1.record()
+    torch.cuda.synchronize()
+    whole = ev0.elapsed_time(ev1) / 5
+    whole_all = whole_all + whole if "whole_all" in dir() else whole
     rows = []
     for i, op in enumerate(plan.ops):
         k = KIND[op["op"]]
@@ -38,7 +52,8 @@ for name in MODEL_NAMES:
         rows.append((ms[i], k, op.get("name", ""), desc, flops[i]))
         grand.setdefault(k, [0.0, 0.0]); grand[k][0] += ms[i]; grand[k][1] += flops[i]
     tot = ms.sum()
-    print(f"==== {name}: {tot:.2f} ms / batch {batch}  ({m.flops_per_tile * batch / tot / 1e9:.0f} TFLOP/s algorithmic), {len(ms)} ops")
+    print(f"==== {name}: {tot:.2f} ms / batch {batch}  ({m.flops_per_tile * batch / tot / 1e9:.0f} TFLOP/s algorithmic), {len(ms)} ops; "
+          f"whole plan back to back {whole:.2f} ms")
     agg = {}
     for r in rows:
         key = (r[1], r[3])
@@ -46,6 +61,7 @@ for name in MODEL_NAMES:
     for (k, desc), (t, n, fl) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
         print(f"   {t:8.3f} ms {100 * t / tot:5.1f}%  x{n:<3d} {k:12s} {desc:40s} {fl / max(t, 1e-9) / 1e9:8.1f} TFLOP/s")
 tot = sum(v[0] for v in grand.values())
-print(f"==== all five: {tot:.2f} ms / batch {batch} -> {batch / tot * 1e3:.1f} tiles/s")
+print(f"==== all five: {tot:.2f} ms / batch {batch} -> {batch / tot * 1e3:.1f} tiles/s; whole plans back to back {whole_all:.2f} ms "
+      f"-> {batch / whole_all * 1e3:.1f} tiles/s")
 for k, (t, fl) in sorted(grand.items(), key=lambda kv: -kv[1][0]):
     print(f"   {k:12s} {t:8.2f} ms {100 * t / tot:5.1f}%  {fl / max(t, 1e-9) / 1e9:8.1f} TFLOP/s")

@@ -42,7 +42,7 @@ for c, role, a_, b_ in evs[skip:skip + int(os.environ.get("TRACE_LINES", "120"))
     d = c - last.get(role, c)
     last[role] = c
     if role == 3 and b_:
-        nm = {1: "epi : staging free+bar", 2: "epi : tmem loaded", 3: "epi : packed+stored", 4: "epi : fence+bar", 5: "epi : tma store issued"}[b_]
+        nm = {1: "epi : before wait_read", 2: "epi : tmem loaded", 3: "epi : staging free", 4: "epi : fence+bar", 5: "epi : tma store issued"}[b_]
         print(f"{c - t0:9d} (+{d:6d})  {nm} tile {a_:6d}")
         continue
     if role == 1 and b_ < 0:
