@@ -40,6 +40,13 @@ struct Op {
   std::function<int(cudaStream_t)> run;
 };
 
+// programmatic dependent launch of every plan kernel (BD_PDL=0 turns it off for A/B measurements)
+inline bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("BD_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
+#define BD_LAUNCH(...) BD_CUDA(::bd::launch_k(pdl_enabled(), __VA_ARGS__))
+
 inline int grid_for(size_t total, int num_sms) {
   size_t b = (total + k::TPB - 1) / k::TPB;
   size_t cap = static_cast<size_t>(num_sms) * 8;
@@ -225,7 +232,7 @@ int bd_plan_add_conv(bd_plan* p, const bd_conv_desc* dptr) {
         (void)tr;
       }
       op.kclass = 0;
-      op.run = [L, ctx](cudaStream_t s) -> int { ctx->launches++; return umma::launch(*L, s); };
+      op.run = [L, ctx](cudaStream_t s) -> int { ctx->launches++; return umma::launch(*L, s, pdl_enabled()); };
     } else {
       k::DirectParams q;
       memset(&q, 0, sizeof(q));
@@ -240,7 +247,7 @@ int bd_plan_add_conv(bd_plan* p, const bd_conv_desc* dptr) {
       op.kclass = 1;
       op.run = [q, grid, ctx](cudaStream_t s) -> int {
         ctx->launches++;
-        k::conv_direct_kernel<<<grid, k::TPB, 0, s>>>(q);
+        BD_LAUNCH(k::conv_direct_kernel, dim3(grid), dim3(k::TPB), 0, s, q);
         BD_CUDA(cudaGetLastError());
         return 0;
       };
@@ -285,10 +292,10 @@ int bd_plan_add_dwconv(bd_plan* p, bd_tref x, bd_tref y, int stride, int pad_t, 
     op.flops = 2.0 * pl->batch * q.Ho * q.Wo * static_cast<double>(x.c) * 9;
     op.run = [q, grid, ctx, stride, vec](cudaStream_t s) -> int {
       ctx->launches++;
-      if (stride == 1 && vec == 8) k::dwconv3x3_kernel<1, 8><<<grid, k::TPB, 0, s>>>(q);
-      else if (stride == 1) k::dwconv3x3_kernel<1, 4><<<grid, k::TPB, 0, s>>>(q);
-      else if (vec == 8) k::dwconv3x3_kernel<2, 8><<<grid, k::TPB, 0, s>>>(q);
-      else k::dwconv3x3_kernel<2, 4><<<grid, k::TPB, 0, s>>>(q);
+      if (stride == 1 && vec == 8) BD_LAUNCH(k::dwconv3x3_kernel<1, 8>, dim3(grid), dim3(k::TPB), 0, s, q);
+      else if (stride == 1) BD_LAUNCH(k::dwconv3x3_kernel<1, 4>, dim3(grid), dim3(k::TPB), 0, s, q);
+      else if (vec == 8) BD_LAUNCH(k::dwconv3x3_kernel<2, 8>, dim3(grid), dim3(k::TPB), 0, s, q);
+      else BD_LAUNCH(k::dwconv3x3_kernel<2, 4>, dim3(grid), dim3(k::TPB), 0, s, q);
       BD_CUDA(cudaGetLastError());
       return 0;
     };
@@ -313,7 +320,7 @@ int bd_plan_add_maxpool(bd_plan* p, bd_tref x, bd_tref y, int kk, int stride, in
     op.kclass = 2; op.launches = 1; op.flops = 0;
     op.run = [q, grid, ctx](cudaStream_t s) -> int {
       ctx->launches++;
-      k::maxpool_kernel<<<grid, k::TPB, 0, s>>>(q);
+      BD_LAUNCH(k::maxpool_kernel, dim3(grid), dim3(k::TPB), 0, s, q);
       BD_CUDA(cudaGetLastError());
       return 0;
     };
@@ -346,7 +353,7 @@ int bd_plan_add_addn(bd_plan* p, int n, const bd_tref* xs, const int32_t* fs, bd
     op.kclass = 2; op.launches = 1; op.flops = 0;
     op.run = [q, grid, ctx](cudaStream_t s) -> int {
       ctx->launches++;
-      k::addn_kernel<<<grid, k::TPB, 0, s>>>(q);
+      BD_LAUNCH(k::addn_kernel, dim3(grid), dim3(k::TPB), 0, s, q);
       BD_CUDA(cudaGetLastError());
       return 0;
     };
@@ -383,7 +390,7 @@ int bd_plan_add_gap(bd_plan* p, bd_tref x, int y_vec) {
     op.kclass = 2; op.launches = 1; op.flops = 0;
     op.run = [q, smem, ctx](cudaStream_t s) -> int {
       ctx->launches += 1;
-      k::gap_kernel<<<dim3(q.splits, q.N), k::TPB, smem, s>>>(q);
+      BD_LAUNCH(k::gap_kernel, dim3(dim3(q.splits, q.N)), dim3(k::TPB), smem, s, q);
       BD_CUDA(cudaGetLastError());
       return 0;
     };
@@ -416,7 +423,7 @@ int bd_plan_add_dense(bd_plan* p, int n_in, const int32_t* x_vecs, int y_vec, in
     op.kclass = 2; op.launches = 1; op.flops = 2.0 * pl->batch * cin * static_cast<double>(cout);
     op.run = [q, grid, ctx](cudaStream_t s) -> int {
       ctx->launches++;
-      k::dense_kernel<<<grid, k::TPB, 0, s>>>(q);
+      BD_LAUNCH(k::dense_kernel, dim3(grid), dim3(k::TPB), 0, s, q);
       BD_CUDA(cudaGetLastError());
       return 0;
     };
@@ -462,7 +469,7 @@ int bd_plan_add_gate(bd_plan* p, int mode, bd_tref x, bd_tref y, int v_vec, bd_t
       const int grid = grid_for(warps * 32, ctx->num_sms * 4);
       op.run = [q, grid, lanes, ctx](cudaStream_t s) -> int {
         ctx->launches++;
-        k::gate_scse_kernel<<<grid, k::TPB, 0, s>>>(q, lanes);
+        BD_LAUNCH(k::gate_scse_kernel, dim3(grid), dim3(k::TPB), 0, s, q, lanes);
         BD_CUDA(cudaGetLastError());
         return 0;
       };
@@ -470,7 +477,7 @@ int bd_plan_add_gate(bd_plan* p, int mode, bd_tref x, bd_tref y, int v_vec, bd_t
       const int grid = grid_for(npix * (x.c / 8), ctx->num_sms * 4);
       op.run = [q, grid, ctx](cudaStream_t s) -> int {
         ctx->launches++;
-        k::gate_kernel<<<grid, k::TPB, 0, s>>>(q);
+        BD_LAUNCH(k::gate_kernel, dim3(grid), dim3(k::TPB), 0, s, q);
         BD_CUDA(cudaGetLastError());
         return 0;
       };
@@ -511,7 +518,7 @@ int bd_plan_add_skfuse(bd_plan* p, const bd_tref* xs4, int g_vec, const int32_t*
     op.kclass = 2; op.launches = 1; op.flops = 0;
     op.run = [q, grid, ctx](cudaStream_t s) -> int {
       ctx->launches++;
-      k::skfuse_kernel<<<grid, k::TPB, 0, s>>>(q);
+      BD_LAUNCH(k::skfuse_kernel, dim3(grid), dim3(k::TPB), 0, s, q);
       BD_CUDA(cudaGetLastError());
       return 0;
     };
@@ -534,7 +541,7 @@ int bd_plan_add_bcast(bd_plan* p, int v_vec, bd_tref y) {
     op.kclass = 2; op.launches = 1; op.flops = 0;
     op.run = [q, grid, ctx](cudaStream_t s) -> int {
       ctx->launches++;
-      k::bcast_kernel<<<grid, k::TPB, 0, s>>>(q);
+      BD_LAUNCH(k::bcast_kernel, dim3(grid), dim3(k::TPB), 0, s, q);
       BD_CUDA(cudaGetLastError());
       return 0;
     };
@@ -581,7 +588,7 @@ int bd_plan_finalize(bd_plan* p, int input_buf, int logits_buf, int logits_up) {
     op.run = [p, lg, N, H, W, up, grid, ctx](cudaStream_t s) -> int {
       if (!p->cur_probs && !p->cur_mask) return 0;
       ctx->launches++;
-      k::softmax2_kernel<<<grid, k::TPB, 0, s>>>(lg, N, H, W, up, p->cur_probs, p->cur_mask);
+      BD_LAUNCH(k::softmax2_kernel, dim3(grid), dim3(k::TPB), 0, s, lg, N, H, W, up, p->cur_probs, p->cur_mask);
       BD_CUDA(cudaGetLastError());
       return 0;
     };
@@ -601,8 +608,8 @@ int bd_plan_run(bd_plan* p, const float* x_dev, float* probs_dev, uint8_t* mask_
     const size_t work = static_cast<size_t>(p->batch) * ib.H * ib.W * 4;
     p->ctx->launches++;
     h16* dst = reinterpret_cast<h16*>(p->arena + ib.offset);
-    if (ib.H == 512) k::input_convert_kernel<1><<<grid_for(work, p->ctx->num_sms * 4), k::TPB, 0, s>>>(x_dev, p->batch, dst);
-    else k::input_convert_kernel<2><<<grid_for(work, p->ctx->num_sms * 4), k::TPB, 0, s>>>(x_dev, p->batch, dst);
+    if (ib.H == 512) BD_LAUNCH(k::input_convert_kernel<1>, dim3(grid_for(work, p->ctx->num_sms * 4)), dim3(k::TPB), 0, s, x_dev, p->batch, dst);
+    else BD_LAUNCH(k::input_convert_kernel<2>, dim3(grid_for(work, p->ctx->num_sms * 4)), dim3(k::TPB), 0, s, x_dev, p->batch, dst);
     BD_CUDA(cudaGetLastError());
   }
   p->cur_probs = probs_dev;
@@ -726,10 +733,10 @@ int bd_tiles_gather(bd_ctx* ctx, const uint8_t* scene_bgr_dev, int h, int w, con
   ctx->launches++;
   const size_t work = static_cast<size_t>(n) * (512 / stem_stride) * (512 / stem_stride) * 4;
   if (stem_stride == 1)
-    k::tiles_gather_kernel<1><<<grid_for(work, ctx->num_sms * 4), k::TPB, 0, s>>>(scene_bgr_dev, h, w, ctx->d_ys, ctx->d_xs, n,
+    BD_LAUNCH(k::tiles_gather_kernel<1>, dim3(grid_for(work, ctx->num_sms * 4)), dim3(k::TPB), 0, s, scene_bgr_dev, h, w, ctx->d_ys, ctx->d_xs, n,
                                                                                 static_cast<h16*>(x_dev));
   else
-    k::tiles_gather_kernel<2><<<grid_for(work, ctx->num_sms * 4), k::TPB, 0, s>>>(scene_bgr_dev, h, w, ctx->d_ys, ctx->d_xs, n,
+    BD_LAUNCH(k::tiles_gather_kernel<2>, dim3(grid_for(work, ctx->num_sms * 4)), dim3(k::TPB), 0, s, scene_bgr_dev, h, w, ctx->d_ys, ctx->d_xs, n,
                                                                                 static_cast<h16*>(x_dev));
   BD_CUDA(cudaGetLastError());
   return 0;
@@ -743,7 +750,7 @@ int bd_stitch_or(bd_ctx* ctx, const uint8_t* tile_masks_dev, const int32_t* ys_h
   BD_CUDA(cudaMemcpyAsync(ctx->d_ys, ys_host, sizeof(int) * n, cudaMemcpyHostToDevice, s));
   BD_CUDA(cudaMemcpyAsync(ctx->d_xs, xs_host, sizeof(int) * n, cudaMemcpyHostToDevice, s));
   ctx->launches++;
-  k::stitch_or_kernel<<<grid_for(static_cast<size_t>(n) * 512 * 512, ctx->num_sms * 4), k::TPB, 0, s>>>(
+  BD_LAUNCH(k::stitch_or_kernel, dim3(grid_for(static_cast<size_t>(n) * 512 * 512, ctx->num_sms * 4)), dim3(k::TPB), 0, s, 
       tile_masks_dev, ctx->d_ys, ctx->d_xs, n, scene_mask_dev, h, w);
   BD_CUDA(cudaGetLastError());
   return 0;

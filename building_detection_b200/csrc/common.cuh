@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <utility>
 
 namespace bd {
 
@@ -33,6 +34,27 @@ int fail(const std::string& msg);
     if (!(cond)) return ::bd::fail(std::string(msg) + " (" #cond ") @" + __FILE__ + ":" +         \
                                    std::to_string(__LINE__));                                     \
   } while (0)
+
+// Programmatic dependent launch: every kernel of a plan starts with pdl_prologue() -- it lets the NEXT kernel of the
+// stream begin launching (its CTAs run their own prologue as SM resources free up) and then waits until the
+// PREVIOUS kernel has completed and its writes are visible.  Launched through launch_k() with pdl = true this hides
+// the drain + launch latency between the ~700 dependent kernels of a batch; without the attribute both
+// instructions are no-ops.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() { pdl_trigger(); pdl_wait(); }
+
+template <typename... Params, typename... Args>
+inline cudaError_t launch_k(bool pdl, void (*kern)(Params...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                            Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }

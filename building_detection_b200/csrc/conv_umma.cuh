@@ -340,6 +340,7 @@ __device__ __forceinline__ void mma_tile(const Params& p, Ring& r, uint64_t desc
 __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_constant__ Maps maps,
                                                                const __grid_constant__ Params p) {
   extern __shared__ uint8_t smem_raw[];
+  pdl_trigger();  // the next kernel may begin launching; it waits for THIS grid's completion in its own pdl_wait()
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -383,6 +384,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *holder_ptr;
+  // barrier set-up and TMEM allocation above overlap the previous kernel's tail; nothing below may touch global
+  // memory before that kernel has completed
+  pdl_wait();
 
   int tr_i = 0, tr_j = 0;  // debug trace cursors
 
@@ -890,14 +894,13 @@ inline int prepare(Launch* L, const TView& x, const TView& y, const TView* res, 
   return 0;
 }
 
-inline int launch(const Launch& L, cudaStream_t stream) {
+inline int launch(const Launch& L, cudaStream_t stream, bool pdl = false) {
   static bool attr_set = false;
   if (!attr_set) {
     BD_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  conv_umma_kernel<<<L.grid, THREADS, L.smem_bytes, stream>>>(L.maps, L.p);
-  BD_CUDA(cudaGetLastError());
+  BD_CUDA(launch_k(pdl, conv_umma_kernel, L.grid, dim3(THREADS), static_cast<size_t>(L.smem_bytes), stream, L.maps, L.p));
   return 0;
 }
 

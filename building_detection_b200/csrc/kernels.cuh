@@ -49,6 +49,7 @@ constexpr int DC_CO = 4;  // output channels per thread
 
 // thread = (output pixel, group of DC_CO output channels); weights are warp-uniform broadcasts.
 __global__ void __launch_bounds__(TPB) conv_direct_kernel(const __grid_constant__ DirectParams p) {
+  pdl_prologue();
   const int cog = (p.y.c + DC_CO - 1) / DC_CO;
   const size_t total = static_cast<size_t>(p.N) * p.Ho * p.Wo * cog;
   for (size_t idx = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; idx < total;
@@ -106,6 +107,7 @@ template <> struct DwVec<8> { typedef uint4 T; };
 template <> struct DwVec<4> { typedef uint2 T; };
 template <int STRIDE, int VEC>
 __global__ void __launch_bounds__(TPB) dwconv3x3_kernel(const __grid_constant__ DwParams p) {
+  pdl_prologue();
   typedef typename DwVec<VEC>::T V;
   constexpr int NH = VEC / 2;                       // half2 per vector
   constexpr int SLOTS = STRIDE == 1 ? 4 : 5;        // input row r lives in slot r % SLOTS
@@ -186,6 +188,7 @@ struct PoolParams {
   int N, Ho, Wo, k, stride, pad_t, pad_l;
 };
 __global__ void __launch_bounds__(TPB) maxpool_kernel(const __grid_constant__ PoolParams p) {
+  pdl_prologue();
   const int cg = p.x.c >> 3;
   const size_t total = static_cast<size_t>(p.N) * p.Ho * p.Wo * cg;
   for (size_t idx = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; idx < total;
@@ -220,6 +223,7 @@ struct AddnParams {
   int n_in, N, act;
 };
 __global__ void __launch_bounds__(TPB) addn_kernel(const __grid_constant__ AddnParams p) {
+  pdl_prologue();
   const int cg = p.y.c >> 3;
   const size_t total = static_cast<size_t>(p.N) * p.y.H * p.y.W * cg;
   for (size_t idx = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; idx < total;
@@ -253,6 +257,7 @@ struct GapParams {
   unsigned* tickets;   // [N], zero between launches (the last block resets its counter)
 };
 __global__ void __launch_bounds__(TPB) gap_kernel(const __grid_constant__ GapParams p) {
+  pdl_prologue();
   extern __shared__ float sh[];  // [TPB/cg rows][C]
   __shared__ unsigned s_last;
   const int C = p.x.c, cg = C >> 3;
@@ -317,6 +322,7 @@ struct DenseParams {
 };
 // one warp per (n, output channel)
 __global__ void __launch_bounds__(TPB) dense_kernel(const __grid_constant__ DenseParams p) {
+  pdl_prologue();
   const int wid = (blockIdx.x * TPB + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (wid >= p.N * p.cout) return;
   const int n = wid / p.cout, co = wid % p.cout;
@@ -341,6 +347,7 @@ struct GateParams {
 };
 // SE: y = x*v ; BAM: y = x*(1+sigmoid(v+s))
 __global__ void __launch_bounds__(TPB) gate_kernel(const __grid_constant__ GateParams p) {
+  pdl_prologue();
   const int C = p.x.c, cg = C >> 3;
   const size_t HW = static_cast<size_t>(p.x.H) * p.x.W;
   const size_t total = static_cast<size_t>(p.N) * HW * cg;
@@ -366,6 +373,7 @@ __global__ void __launch_bounds__(TPB) gate_kernel(const __grid_constant__ GateP
 // scSE: y = x*(sigmoid(w.x + b) + v): a group of min(32, C/8) lanes owns one pixel; the per-pixel dot
 // product over channels is a shuffle reduction inside the group.
 __global__ void __launch_bounds__(TPB) gate_scse_kernel(const __grid_constant__ GateParams p, int lanes_per_pix) {
+  pdl_prologue();
   const int C = p.x.c, cg = C >> 3;
   const size_t HW = static_cast<size_t>(p.x.H) * p.x.W;
   const size_t npix = static_cast<size_t>(p.N) * HW;
@@ -412,6 +420,7 @@ struct SkParams {
   int N;
 };
 __global__ void __launch_bounds__(TPB) skfuse_kernel(const __grid_constant__ SkParams p) {
+  pdl_prologue();
   const int C = p.y.c, cg = C >> 3;
   const size_t HW = static_cast<size_t>(p.y.H) * p.y.W;
   const size_t total = static_cast<size_t>(p.N) * HW * cg;
@@ -450,6 +459,7 @@ struct BcastParams {
   int N;
 };
 __global__ void __launch_bounds__(TPB) bcast_kernel(const __grid_constant__ BcastParams p) {
+  pdl_prologue();
   const int C = p.y.c, cg = C >> 3;
   const size_t HW = static_cast<size_t>(p.y.H) * p.y.W;
   const size_t total = static_cast<size_t>(p.N) * HW * cg;
@@ -469,6 +479,7 @@ __global__ void __launch_bounds__(TPB) bcast_kernel(const __grid_constant__ Bcas
 // logits fp32 (N, 512/up, 512/up, 2) -> probs fp32 (N,512,512,2) and/or mask u8 (argmax, ties -> class 0)
 __global__ void __launch_bounds__(TPB) softmax2_kernel(const float* __restrict__ logits, int N, int H, int W, int up,
                                                        float* __restrict__ probs, uint8_t* __restrict__ mask) {
+  pdl_prologue();
   const size_t total = static_cast<size_t>(N) * H * W;
   const int h2 = H / up, w2 = W / up;
   for (size_t idx = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; idx < total;
@@ -496,6 +507,7 @@ template <int S>
 __global__ void __launch_bounds__(TPB) tiles_gather_kernel(const uint8_t* __restrict__ scene, int H, int W,
                                                            const int* __restrict__ ys, const int* __restrict__ xs,
                                                            int n, h16* __restrict__ out) {
+  pdl_prologue();
   constexpr int O = 512 / S, PAD = S == 1 ? 1 : 0;
   const size_t total = static_cast<size_t>(n) * O * O * 4;
   for (size_t idx = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; idx < total;
@@ -524,6 +536,7 @@ __global__ void __launch_bounds__(TPB) tiles_gather_kernel(const uint8_t* __rest
 // model.predict(x) path: fp32 (N,512,512,3) in [-1,1] -> the same layout (255*x rounded to fp16)
 template <int S>
 __global__ void __launch_bounds__(TPB) input_convert_kernel(const float* __restrict__ x, int n, h16* __restrict__ out) {
+  pdl_prologue();
   constexpr int O = 512 / S, PAD = S == 1 ? 1 : 0;
   const size_t total = static_cast<size_t>(n) * O * O * 4;
   for (size_t idx = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; idx < total;
@@ -550,6 +563,7 @@ __global__ void __launch_bounds__(TPB) input_convert_kernel(const float* __restr
 __global__ void __launch_bounds__(TPB) stitch_or_kernel(const uint8_t* __restrict__ tiles, const int* __restrict__ ys,
                                                         const int* __restrict__ xs, int n, uint8_t* __restrict__ scene,
                                                         int H, int W) {
+  pdl_prologue();
   const size_t total = static_cast<size_t>(n) * 512 * 512;
   for (size_t idx = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; idx < total;
        idx += static_cast<size_t>(gridDim.x) * TPB) {

@@ -285,6 +285,42 @@ class Net:
             out = T(out.buf, out.c0, out.C, ctrue=cout_true)
         return out
 
+    def conv_up2(self, x, name, cout, bn=False, act=None, out=None):
+        """Conv2D(3x3, 'same')(UpSampling2D(2, nearest)(x)) [+BN] [+ReLU] without materialising the up-sampled map:
+        every output pixel of sub-pixel phase (py, px) sees only a 2x2 neighbourhood of x, so the 3x3 kernel collapses
+        into four 2x2 kernels of summed taps (source row of up-sampled row 2i+py+kh-1 is i + floor((py+kh-1)/2):
+        py=0 -> {i-1: W0, i: W1+W2}, py=1 -> {i: W0+W1, i+1: W2}; same for columns).  The zero padding of the
+        up-sampled map coincides with the zero padding of x.  4/9 of the multiply-adds, and neither the write nor
+        the nine-fold re-read of the 4x larger map (hrnet.py:198-199, v3plus.py:341-342)."""
+        kern = self._get(name + "/k", (3, 3, x.cin, cout), "glorot_uniform")
+        bias = self._get(name + "/b", (cout,), "zeros")
+        w = kern.reshape(9, x.cin, cout).transpose(0, 2, 1).copy()  # (taps, Cout, Cin)
+        if bn:
+            sc, sh = self._bn(bn if isinstance(bn, str) else name + "_bn", cout)
+            w = w * sc[None, :, None]
+            bias = bias * sc + sh
+        w = w * np.float32(x.wscale)
+        if x.cin != x.C:
+            wp = np.zeros((9, cout, x.C), np.float32)
+            wp[:, :, :x.cin] = w
+            w = wp
+        w = w.reshape(3, 3, cout, x.C)
+        if out is None:
+            out = self.new(2 * x.H, 2 * x.W, cout)
+        a = ACT_RELU if act == "relu" else ACT_NONE
+        groups = {0: [(-1, (0,)), (0, (1, 2))], 1: [(0, (0, 1)), (1, (2,))]}  # phase -> [(source offset, summed taps)]
+        for py in (0, 1):
+            for px in (0, 1):
+                taps, ws = [], []
+                for dy, khs in groups[py]:
+                    for dx, kws in groups[px]:
+                        taps.append((dy, dx))
+                        ws.append(sum(w[kh, kw] for kh in khs for kw in kws))
+                self._conv_op(x, np.stack(ws), bias, taps, 1, x.H, x.W, a, None, ACT_NONE, out,
+                              out_scale=2, out_oy=py, out_ox=px, name=f"{name}[{py}{px}]",
+                              macs_per_pixel=cout * x.cin * 9)
+        return out
+
     def conv_transpose(self, x, name, cout, k, act=None, out=None):
         """Conv2DTranspose(k in {2,3}, strides=2, padding='same') as 4 sub-pixel convs:
         y[2m+a] = sum over kh with kh = a (mod 2) of x[m - (kh-a)/2] W[kh]."""

@@ -60,8 +60,8 @@ def build(g: Net):
     g.upsample(cb(b32, "f3_2", 32, k=1, act=None), 4, out=T(cat, 64, 32))
     g.upsample(cb(b33, "f3_3", 32, k=1, act=None), 8, out=T(cat, 96, 32))
 
-    o = g.upsample(T(cat, 0, 128), 2)  # hrnet.py:198
-    o = cb(o, "head_conv", 64)
+    # UpSampling2D(2) + conv3x3 + BN + ReLU (hrnet.py:198-199) as four sub-pixel 2x2 convolutions of the 256^2 map
+    o = g.conv_up2(T(cat, 0, 128), "head_conv", 64, bn=True, act="relu")
     logits = g.conv(o, "head_out", 2, k=1, f32_out=True)  # hrnet.py:200
     g.softmax_head(logits)
 

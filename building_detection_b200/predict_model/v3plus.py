@@ -25,8 +25,8 @@ def build(g: Net):
     t = stage(cat2, "dec2", 128)
     g.conv_transpose(t, "dec3_up", 64, 3, out=T(cat3, 64, 64))  # v3plus.py:335
     t = stage(cat3, "dec3", 64)
-    o = g.upsample(t, 2)  # v3plus.py:341
-    o = g.conv(o, "head_a", 32, k=3, bn=True, act="relu")
+    # UpSampling2D(2) + conv3x3 + BN + ReLU (v3plus.py:341-342) as four sub-pixel 2x2 convolutions of the 256^2 map
+    o = g.conv_up2(t, "head_a", 32, bn=True, act="relu")
     o = g.conv(o, "head_b", 32, k=3, bn=True, act="relu")
     logits = g.conv(o, "head_out", 2, k=1, f32_out=True)  # v3plus.py:345
     g.softmax_head(logits)
