@@ -145,6 +145,8 @@ void bd_destroy(bd_ctx* ctx) {
   if (!ctx) return;
   if (ctx->d_ys) cudaFree(ctx->d_ys);
   if (ctx->d_xs) cudaFree(ctx->d_xs);
+  if (ctx->d_all_ys) cudaFree(ctx->d_all_ys);
+  if (ctx->d_all_xs) cudaFree(ctx->d_all_xs);
   ctx->post_ws.release();
   ctx->pool.release();
   delete ctx;
@@ -207,12 +209,25 @@ int bd_plan_add_conv(bd_plan* p, const bd_conv_desc* dptr) {
                         "conv: residual geometry mismatch");
   std::shared_ptr<std::vector<uint16_t>> w(new std::vector<uint16_t>(d.w_host, d.w_host + static_cast<size_t>(d.ntaps) * cout * cin));
   std::shared_ptr<std::vector<float>> b(new std::vector<float>(d.bias_host, d.bias_host + cout));
-  d.w_host = nullptr; d.bias_host = nullptr;
-  p->builders.push_back([d, w, b, has_res, cin, cout](bd_plan* pl) -> int {
-    void *wd = nullptr, *bdv = nullptr;
+  // fused SeparableConv2D: depthwise weights [9][cin] -> fp16 (the values are fp16-representable, graph.py)
+  std::shared_ptr<std::vector<uint16_t>> dww;
+  if (d.dw_w_host) {
+    BD_CHECK(d.path == BD_CONV_UMMA && d.ntaps == 1 && d.stride == 1 && d.out_scale == 1,
+             "fused separable conv: the pointwise stage must be a stride-1 1x1 UMMA convolution");
+    dww.reset(new std::vector<uint16_t>(static_cast<size_t>(9) * cin));
+    for (size_t i = 0; i < dww->size(); ++i) {
+      const __half h = __float2half_rn(d.dw_w_host[i]);
+      memcpy(&(*dww)[i], &h, 2);
+    }
+  }
+  const int dw_relu = d.dw_relu_in;
+  d.w_host = nullptr; d.bias_host = nullptr; d.dw_w_host = nullptr;
+  p->builders.push_back([d, w, b, dww, dw_relu, has_res, cin, cout](bd_plan* pl) -> int {
+    void *wd = nullptr, *bdv = nullptr, *dwd = nullptr;
     if (pl->upload(w->data(), w->size() * 2, &wd) || pl->upload(b->data(), b->size() * 4, &bdv)) return 1;
+    if (dww && pl->upload(dww->data(), dww->size() * 2, &dwd)) return 1;
     Op op;
-    op.flops = 2.0 * pl->batch * d.ho * d.wo * static_cast<double>(cout) * cin * d.ntaps;
+    op.flops = 2.0 * pl->batch * d.ho * d.wo * (static_cast<double>(cout) * cin * d.ntaps + (dww ? 9.0 * cin : 0.0));
     op.launches = 1;
     bd_ctx* ctx = pl->ctx;
     if (d.path == BD_CONV_UMMA) {
@@ -221,7 +236,8 @@ int bd_plan_add_conv(bd_plan* p, const bd_conv_desc* dptr) {
       if (has_res) r = pl->tview(d.res);
       if (umma::prepare(L.get(), x, y, has_res ? &r : nullptr, d.ntaps, d.dy, d.dx, d.stride, d.ho, d.wo, d.act_pre,
                         d.act_post, d.out_scale, d.out_oy, d.out_ox, static_cast<const h16*>(wd),
-                        static_cast<const float*>(bdv), ctx->umma_smem_kb, ctx->umma_max_block_n, ctx->num_sms, ctx->umma_group))
+                        static_cast<const float*>(bdv), ctx->umma_smem_kb, ctx->umma_max_block_n, ctx->num_sms, ctx->umma_group,
+                        static_cast<const h16*>(dwd), dw_relu))
         return 1;
       if (const char* tr = getenv("BD_UMMA_TRACE")) {  // debug: event trace of CTA 0 (tools/umma_trace.py)
         void* tbuf = nullptr;
@@ -753,6 +769,56 @@ int bd_stitch_or(bd_ctx* ctx, const uint8_t* tile_masks_dev, const int32_t* ys_h
   BD_LAUNCH(k::stitch_or_kernel, dim3(grid_for(static_cast<size_t>(n) * 512 * 512, ctx->num_sms * 4)), dim3(k::TPB), 0, s, 
       tile_masks_dev, ctx->d_ys, ctx->d_xs, n, scene_mask_dev, h, w);
   BD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// The origins of ALL tiles of a scene, uploaded once: the per-batch calls below index into them, so the scene loop
+// issues no host->device copies between the kernels of consecutive batches.
+int bd_tiles_set_origins(bd_ctx* ctx, const int32_t* ys_host, const int32_t* xs_host, int n, void* stream) {
+  BD_CHECK(ctx && ys_host && xs_host && n >= 1, "bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (n > ctx->origin_cap) {
+    if (ctx->d_all_ys) cudaFree(ctx->d_all_ys);
+    if (ctx->d_all_xs) cudaFree(ctx->d_all_xs);
+    ctx->d_all_ys = ctx->d_all_xs = nullptr;
+    ctx->origin_cap = 0;
+    BD_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->d_all_ys), sizeof(int) * n));
+    BD_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->d_all_xs), sizeof(int) * n));
+    ctx->origin_cap = n;
+  }
+  BD_CUDA(cudaMemcpyAsync(ctx->d_all_ys, ys_host, sizeof(int) * n, cudaMemcpyHostToDevice, s));
+  BD_CUDA(cudaMemcpyAsync(ctx->d_all_xs, xs_host, sizeof(int) * n, cudaMemcpyHostToDevice, s));
+  BD_CUDA(cudaStreamSynchronize(s));  // the host arrays may be temporaries
+  ctx->n_origins = n;
+  return 0;
+}
+
+int bd_tiles_gather_at(bd_ctx* ctx, const uint8_t* scene_bgr_dev, int h, int w, int first, int n, void* x_dev,
+                       int stem_stride, void* stream) {
+  BD_CHECK(ctx && scene_bgr_dev && x_dev && n >= 1 && h >= 1 && w >= 1, "bad arguments");
+  BD_CHECK(first >= 0 && first + n <= ctx->n_origins, "tile range outside the origins set by bd_tiles_set_origins");
+  BD_CHECK(stem_stride == 1 || stem_stride == 2, "stem stride must be 1 or 2");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  ctx->launches++;
+  const size_t work = static_cast<size_t>(n) * (512 / stem_stride) * (512 / stem_stride) * 4;
+  if (stem_stride == 1)
+    BD_LAUNCH(k::tiles_gather_kernel<1>, dim3(grid_for(work, ctx->num_sms * 4)), dim3(k::TPB), 0, s, scene_bgr_dev, h, w,
+              static_cast<const int*>(ctx->d_all_ys + first), static_cast<const int*>(ctx->d_all_xs + first), n, static_cast<h16*>(x_dev));
+  else
+    BD_LAUNCH(k::tiles_gather_kernel<2>, dim3(grid_for(work, ctx->num_sms * 4)), dim3(k::TPB), 0, s, scene_bgr_dev, h, w,
+              static_cast<const int*>(ctx->d_all_ys + first), static_cast<const int*>(ctx->d_all_xs + first), n, static_cast<h16*>(x_dev));
+  return 0;
+}
+
+int bd_stitch_or_at(bd_ctx* ctx, const uint8_t* tile_masks_dev, int first, int n, uint8_t* scene_mask_dev, int h, int w,
+                    void* stream) {
+  BD_CHECK(ctx && tile_masks_dev && scene_mask_dev && n >= 1, "bad arguments");
+  BD_CHECK(first >= 0 && first + n <= ctx->n_origins, "tile range outside the origins set by bd_tiles_set_origins");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  ctx->launches++;
+  BD_LAUNCH(k::stitch_or_kernel, dim3(grid_for(static_cast<size_t>(n) * 512 * 512, ctx->num_sms * 4)), dim3(k::TPB), 0, s,
+            tile_masks_dev, static_cast<const int*>(ctx->d_all_ys + first), static_cast<const int*>(ctx->d_all_xs + first), n,
+            scene_mask_dev, h, w);
   return 0;
 }
 

@@ -60,9 +60,14 @@ struct Params {
   int tiles_w, tiles_h, tiles_n, n_tiles, total_tiles;
   int block_n, kchunks, ntaps, stages, group, tmem_cols;  // group: k-blocks per shared-memory stage
   int spec;  // 0 generic loops; 1 = 9 taps x 1 chunk, group 3; 2 = 9 taps x 2 chunks, group 2 (fully unrolled loops);
-             // 3 = halo path: 3x3 stride 1, one halo box per chunk, weights resident in shared memory
+             // 3 = halo path: 3x3 stride 1, one halo box per chunk, weights resident in shared memory;
+             // 4 = fused separable convolution: warps 2-5 compute the depthwise 3x3 of a halo box into the A tile of
+             //     the pointwise 1x1 GEMM, warps 6-9 are the epilogue
   int wres_bytes;  // bytes of resident weights (spec 3), 0 otherwise
   int bias_bytes;  // shared-memory bytes of the staged bias vector (all N tiles)
+  int aux_bytes;   // spec 4: shared-memory bytes of the staged depthwise weights [9][Cin]
+  const h16* dw_w; // spec 4: depthwise 3x3 weights [9][Cin] fp16 (nullptr otherwise)
+  int dw_relu;     // spec 4: ReLU on the depthwise input
   int tap_map[MAX_TAPS], tap_dy[MAX_TAPS], tap_dx[MAX_TAPS];
   float* y32;  // fp32 output path (Cout <= 16): direct stores
   int y_ctot, y_c0, y_H, y_W, out_scale, out_oy, out_ox;
@@ -347,23 +352,31 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
   const uint32_t b_bytes = static_cast<uint32_t>(p.block_n) * 128u;
   const uint32_t sub_bytes = A_STAGE_BYTES + b_bytes;                       // one k-block: A box + W tile
   const uint32_t stage_bytes = p.spec == 3 ? static_cast<uint32_t>(HALO_STAGE)
-                                           : sub_bytes * static_cast<uint32_t>(p.group);  // a stage holds `group` k-blocks
+                               : p.spec == 4 ? static_cast<uint32_t>(HALO_STAGE) + b_bytes  // halo box + pointwise W tile
+                                             : sub_bytes * static_cast<uint32_t>(p.group);  // a stage holds `group` k-blocks
   const uint32_t wres0 = smem_base + static_cast<uint32_t>(p.stages) * stage_bytes;      // resident weights (spec 3)
   const uint32_t out0 = wres0 + static_cast<uint32_t>(p.wres_bytes);                      // 8 per-warp staging tiles
-  const uint32_t res0 = out0 + EPI_WARPS * EPI_TILE_BYTES;                           // 8 per-warp residual tiles (if any)
-  const uint32_t bias0 = res0 + (p.res ? EPI_WARPS * EPI_TILE_BYTES : 0u);           // bias of all N tiles, fp32
-  const uint32_t bar_base = bias0 + static_cast<uint32_t>(p.bias_bytes);             // 8-byte slots
+  const uint32_t n_epi_warps = p.spec == 4 ? EPI_WARPS / 2 : EPI_WARPS;              // spec 4: warps 2-5 are depthwise warps
+  const uint32_t res0 = out0 + n_epi_warps * EPI_TILE_BYTES;                         // per-warp residual tiles (if any)
+  const uint32_t bias0 = res0 + (p.res ? n_epi_warps * EPI_TILE_BYTES : 0u);         // bias of all N tiles, fp32
+  const uint32_t aux0 = bias0 + static_cast<uint32_t>(p.bias_bytes);                 // depthwise weights (spec 4)
+  const uint32_t bar_base = aux0 + static_cast<uint32_t>(p.aux_bytes);               // 8-byte slots
   const uint32_t full0 = bar_base, empty0 = bar_base + 8u * p.stages;
   const uint32_t tfull0 = bar_base + 16u * p.stages, tempty0 = tfull0 + 16u;  // tempty: [stage][epilogue group]
   const uint32_t rbar0 = tempty0 + 32u;  // one per epilogue warp
   const uint32_t wbar = rbar0 + 8u * EPI_WARPS;
-  const uint32_t holder = wbar + 16u;
+  const uint32_t afull0 = wbar + 16u, aempty0 = afull0 + 16u;  // spec 4: two depthwise-output (A tile) slots
+  const uint32_t holder = aempty0 + 16u;
   volatile uint32_t* holder_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (holder - smem_base));
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(full0 + 8u * s, 1);
-      mbar_init(empty0 + 8u * s, 1);
+      mbar_init(empty0 + 8u * s, p.spec == 4 ? 5 : 1);  // spec 4: four depthwise warps + the MMA commit free a stage
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(afull0 + 8u * a, 4);   // one arrival per depthwise warp
+      mbar_init(aempty0 + 8u * a, 1);  // MMA commit
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull0 + 8u * a, 1);
@@ -421,6 +434,20 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
         }
         continue;
       }
+      if (p.spec == 4) {  // per 64-channel chunk: the halo box of the depthwise input + the pointwise weight tile
+        for (int c = 0; c < p.Cin; c += BLOCK_K) {
+          mbar_wait(ring.eb, ring.ph ^ 1u);
+          if (elect_one()) {
+            trace_ev(p, 0, tr_i, tile, c);
+            mbar_expect_tx(ring.fb, HALO_BYTES + b_bytes);
+            tma_load_4d(smem_base + ring.off, &maps.a[0], ring.fb, c, w0 - 1, h0 - 1, n0);
+            tma_load_3d(smem_base + ring.off + HALO_STAGE, &maps.b, ring.fb, c, n_base, 0);
+          }
+          __syncwarp();
+          ring_advance(ring, p, stage_bytes, full0, empty0);
+        }
+        continue;
+      }
       if (p.spec == 1) { produce_tile<9, 1, 3>(maps, p, ring, smem_base, sub_bytes, full0, empty0, w0, h0, n0, n_base, tr_i, tile); continue; }
       if (p.spec == 2) { produce_tile<9, 2, 2>(maps, p, ring, smem_base, sub_bytes, full0, empty0, w0, h0, n0, n_base, tr_i, tile); continue; }
       for (int tap = 0; tap < p.ntaps; ++tap) {
@@ -452,9 +479,36 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
     uint32_t s = 0, sub = 0, ph = 0, doff = 0, fb = full0, eb = empty0, ti = 0;
     Ring ring{0u, 0u, 0u, full0, empty0};
     uint32_t f_ready = 0, te_ready = 0;  // early test results: next full barrier / this tile's accumulator stage
+    uint32_t it4 = 0;                    // spec 4: running k-block counter (A slot / parity)
     const bool single_unit = p.block_n <= OUT_CHUNK;  // one epilogue unit per tile
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
       const uint32_t a = ti & 1u, aph = (ti >> 1) & 1u;
+      if (p.spec == 4) {
+        mbar_wait(tempty0 + 16u * a + 8u, aph ^ 1u);  // the single epilogue group (warps 6-9) is group 1
+        tc_fence_after();
+        const uint32_t tacc4 = tmem_base + a * static_cast<uint32_t>(p.block_n);
+        for (int c = 0; c < p.Cin; c += BLOCK_K, ++it4) {
+          const uint32_t slot = it4 & 1u;
+          mbar_wait(ring.fb, ring.ph);                            // pointwise weight tile has landed
+          mbar_wait(afull0 + 8u * slot, (it4 >> 1) & 1u);         // depthwise warps have written the A tile
+          tc_fence_after();
+          if (elect_one()) {
+            trace_ev(p, 1, tr_i, tile, c);
+            const uint64_t adesc = make_sdesc(wres0 + slot * A_STAGE_BYTES);
+            const uint64_t bdesc = make_sdesc(smem_base + ring.off + HALO_STAGE);
+            tc_mma_f16(tacc4, adesc, bdesc, idesc, c > 0 ? 1u : 0u);
+            tc_mma_f16(tacc4, adesc + 2u, bdesc + 2u, idesc, 1u);
+            tc_mma_f16(tacc4, adesc + 4u, bdesc + 4u, idesc, 1u);
+            tc_mma_f16(tacc4, adesc + 6u, bdesc + 6u, idesc, 1u);
+            tc_commit(aempty0 + 8u * slot);
+            tc_commit(ring.eb);
+            if (c + BLOCK_K >= p.Cin) tc_commit(tfull0 + 8u * a);
+          }
+          __syncwarp();
+          ring_advance(ring, p, stage_bytes, full0, empty0);
+        }
+        continue;
+      }
       // The epilogue groups that read accumulator stage a two tiles ago have drained it.  A tile of one 64-column
       // chunk belongs to ONE group (group = tile parity = a), wider tiles to both; each (stage, group) barrier
       // completes one phase per tile on that stage, so the parity is the same for all of them.
@@ -545,14 +599,96 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
       if (elect_one()) tc_commit(tfull0 + 8u * a);  // accumulator complete
       __syncwarp();
     }
+  } else if (p.spec == 4 && warp < 6) {
+    // ---------------- depthwise warps 2..5 (spec 4): A tile of the pointwise GEMM = depthwise 3x3 of the halo box.
+    // thread = (4-channel group g4 of the 64-channel chunk, 4x4 output patch of the 8 x 16 tile): a 6x6 window of
+    // 8-byte vectors in registers serves 16 outputs (2.25 shared-memory loads per output instead of 9 -- the
+    // shared-memory pipe is shared with the TMA writes and the tensor core's operand reads and is what bounds this
+    // kernel).  The nine taps run on packed half2 FMAs in exactly the order and rounding of k::dwconv3x3_kernel
+    // (fp16 accumulate, kh-major), so the fused result is bit-identical to the two-kernel sequence.  The 16 threads
+    // of a half-warp phase read / write the 16 x 8 bytes of ONE 128-byte pixel row: conflict-free.
+    const int dt = threadIdx.x - 64;  // 0..127
+    const int g4 = dt & 15, patch = dt >> 4, px0 = (patch & 1) * 4, py0 = (patch >> 1) * 4;
+    {  // stage the depthwise weights [9][Cin] (constant data: no dependence on the previous kernel's output)
+      const uint4* src = reinterpret_cast<const uint4*>(p.dw_w);
+      uint4* dst = reinterpret_cast<uint4*>(gen_base + (aux0 - smem_base));
+      for (int i = dt; i < 9 * p.Cin / 8; i += 128) dst[i] = __ldg(src + i);
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+    }
+    const __half2 zero2 = __float2half2_rn(0.0f);
+    union U { uint2 v; __half2 h[2]; };
+    Ring ring{0u, 0u, 0u, full0, empty0};
+    uint32_t it = 0;
+    const uint32_t sub8 = (g4 & 1) * 8;  // byte offset of my 4 channels inside their 16-byte chunk
+    const int gc = g4 >> 1;              // 16-byte chunk of my channels
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int c = 0; c < p.Cin; c += BLOCK_K, ++it) {
+        const uint32_t slot = it & 1u;
+        U wp[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k)
+          wp[k].v = *reinterpret_cast<const uint2*>(gen_base + (aux0 - smem_base) + (static_cast<size_t>(k) * p.Cin + c + g4 * 4) * 2);
+        if (dt == 0) trace_ev(p, 3, tr_j, tile, 1);
+        mbar_wait(ring.fb, ring.ph);                                // halo box has landed
+        mbar_wait(aempty0 + 8u * slot, ((it >> 1) & 1u) ^ 1u);      // the MMAs that read this A slot are done
+        if (dt == 0) trace_ev(p, 3, tr_j, tile, 3);
+        const uint8_t* halo = gen_base + ring.off;
+        uint8_t* atile = gen_base + (wres0 - smem_base) + slot * A_STAGE_BYTES;
+        U win[6][6];  // halo rows py0 .. py0+5, columns px0 .. px0+5
+#pragma unroll
+        for (int hy = 0; hy < 6; ++hy)
+#pragma unroll
+          for (int hx = 0; hx < 6; ++hx) {
+            const int P = (py0 + hy) * HALO_W + px0 + hx;  // halo pixel; its 16-byte chunks are XOR-swizzled by P % 8
+            win[hy][hx].v = *reinterpret_cast<const uint2*>(halo + P * 128 + ((gc ^ (P & 7)) << 4) + sub8);
+          }
+        if (p.dw_relu) {
+#pragma unroll
+          for (int hy = 0; hy < 6; ++hy)
+#pragma unroll
+            for (int hx = 0; hx < 6; ++hx) {
+              win[hy][hx].h[0] = __hmax2(win[hy][hx].h[0], zero2);
+              win[hy][hx].h[1] = __hmax2(win[hy][hx].h[1], zero2);
+            }
+        }
+#pragma unroll
+        for (int oy = 0; oy < 4; ++oy)
+#pragma unroll
+          for (int ox = 0; ox < 4; ++ox) {
+            U acc;
+            acc.h[0] = zero2; acc.h[1] = zero2;
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+              for (int kw = 0; kw < 3; ++kw) {
+                acc.h[0] = __hfma2(win[oy + kh][ox + kw].h[0], wp[kh * 3 + kw].h[0], acc.h[0]);
+                acc.h[1] = __hfma2(win[oy + kh][ox + kw].h[1], wp[kh * 3 + kw].h[1], acc.h[1]);
+              }
+            const int m = (py0 + oy) * 8 + px0 + ox;  // tile row (w fastest)
+            *reinterpret_cast<uint2*>(atile + m * 128 + ((gc ^ (m & 7)) << 4) + sub8) = acc.v;
+          }
+        if (dt == 0) trace_ev(p, 3, tr_j, tile, 5);
+        fence_async_smem();  // generic-proxy writes of the A tile -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(afull0 + 8u * slot);
+          mbar_arrive(ring.eb);  // this warp is done with the halo box
+        }
+        if (dt == 0) trace_ev(p, 3, tr_j, tile, 0);
+        ring_advance(ring, p, stage_bytes, full0, empty0);
+      }
+    }
   } else {
-    // ---------------- epilogue warps 2..9: warp w reads TMEM lane quadrant w % 4 (hardware rule).  Units = (tile,
-    // 64-column chunk) in launch order; of the two warps of a quadrant, warp `half` takes the units of its parity.
+    // ---------------- epilogue warps (2..9; 6..9 in spec 4): warp w reads TMEM lane quadrant w % 4 (hardware rule).
+    // Units = (tile, 64-column chunk) in launch order; with two groups the two warps of a quadrant take alternate
+    // units (group = unit parity), with one group (spec 4) warps 6..9 take them all.
     const int q = warp & 3;            // TMEM lane quadrant this warp may access
-    const int half = (warp - 2) >> 2;  // 0 / 1: unit parity
-    const int ew = warp - 2;           // 0 .. EPI_WARPS-1
+    const int half = (warp - 2) >> 2;  // epilogue group of this warp: 0 / 1
+    const int ew = warp - (p.spec == 4 ? 6 : 2);  // 0 .. (epilogue warps)-1: staging / residual tile, residual barrier
     const int r = q * 32 + lane;       // tile row = TMEM lane
-    const int et = threadIdx.x - 64;   // 0 .. 32*EPI_WARPS-1
+    const int ustep = p.spec == 4 ? 1 : 2;                       // number of epilogue groups = unit stride
+    const int et = threadIdx.x - (p.spec == 4 ? 192 : 64);       // 0 .. 32 * (epilogue warps) - 1
+    const int n_epi = p.spec == 4 ? 128 : 32 * EPI_WARPS;        // epilogue threads
     // the quadrant's 32 rows as a (bw x qbh x qbn) sub-box of the tile box, starting at row qh of image qn
     const int hrows = 32 / p.bw, hq = q * hrows;
     const int qh = hq % p.bh, qn = hq / p.bh;
@@ -568,8 +704,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
     const float lo_pre = p.act_pre == 1 ? 0.0f : -INFINITY, lo_post = p.act_post == 1 ? 0.0f : -INFINITY;
     // bias of every N tile -> shared memory (broadcast reads in the unit loop instead of exposed global latency)
     float* sbias = reinterpret_cast<float*>(gen_base + (bias0 - smem_base));
-    for (int i = et; i < p.n_tiles * p.block_n; i += 32 * EPI_WARPS) sbias[i] = i < p.Cout ? __ldg(p.bias + i) : 0.0f;
-    epi_bar_sync();
+    for (int i = et; i < p.n_tiles * p.block_n; i += n_epi) sbias[i] = i < p.Cout ? __ldg(p.bias + i) : 0.0f;
+    asm volatile("bar.sync 1, %0;" ::"r"(n_epi) : "memory");
     // residual tile of unit (tile, ci): 32 rows x 64 channels by TMA into this warp's buffer
     auto issue_res = [&](int tile, int ci) {
       int nt, tw, th, tn;
@@ -580,7 +716,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
       }
     };
     if (has_res) {  // first unit of this warp
-      int t0 = blockIdx.x, c = half;
+      int t0 = blockIdx.x, c = ustep == 1 ? 0 : half;
       while (c >= nch) { c -= nch; t0 += gridDim.x; }
       if (t0 < p.total_tiles) issue_res(t0, c);
     }
@@ -590,9 +726,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
       int nt, tw, th, tn;
       tile_coords(p, tile, nt, tw, th, tn);
       const int n_base = nt * p.block_n;
-      const int first = ((u & 1u) == static_cast<uint32_t>(half)) ? 0 : 1;          // my first chunk of this tile
+      const int first = (ustep == 1 || (u & 1u) == static_cast<uint32_t>(half)) ? 0 : 1;  // my first chunk of this tile
       if (first >= nch) continue;  // no unit of this tile is mine (the MMA warp does not wait for my group then)
-      const int last = first + ((nch - 1 - first) & ~1);                             // my last one
+      const int last = first + (nch - 1 - first) / ustep * ustep;                          // my last one
       const uint32_t tempty = tempty0 + 16u * a + 8u * static_cast<uint32_t>(half);
       mbar_wait(tfull0 + 8u * a, aph);
       tc_fence_after();
@@ -617,7 +753,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
         }
         continue;
       }
-      for (int ci = first; ci < nch; ci += 2) {
+      for (int ci = first; ci < nch; ci += ustep) {
         const int c0 = ci * OUT_CHUNK;
         const int cw = min(OUT_CHUNK, p.block_n - c0);  // 16 / 32 / 48 / 64 columns
         uint32_t acc[64];
@@ -631,7 +767,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
 #pragma unroll
         for (int k = 0; k < 8; ++k) bb[k] = bch[k];
         tmem_ld_wait();
-        if (et == 0) trace_ev(p, 3, tr_j, tile, 2);
+        if (et == 0 && p.spec != 4) trace_ev(p, 3, tr_j, tile, 2);
         if (ci == last) {  // the accumulator now lives in registers: hand the TMEM stage back to the MMA warp
           tc_fence_before();
           __syncwarp();
@@ -669,7 +805,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
           // every lane has read the residual tile: fetch the one of my next unit
           __syncwarp();
           ++rcount;
-          int t2 = tile, c2 = ci + 2;
+          int t2 = tile, c2 = ci + ustep;
           while (c2 >= nch) { c2 -= nch; t2 += gridDim.x; }
           if (t2 < p.total_tiles) issue_res(t2, c2);
         }
@@ -690,9 +826,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
           tma_store_4d(&maps.y, stg, n_base + c0, tw * p.bw, th * p.bh + qh, tn * p.bn + qn);
           tma_store_commit();
         }
-        if (et == 0) trace_ev(p, 3, tr_j, tile, 5);
+        if (et == 0 && p.spec != 4) trace_ev(p, 3, tr_j, tile, 5);
       }
-      if (et == 0) trace_ev(p, 3, tr_j, tile, 0);
+      if (et == 0 && p.spec != 4) trace_ev(p, 3, tr_j, tile, 0);
     }
     if (lane == 0) tma_store_wait_all();
   }
@@ -757,7 +893,7 @@ inline int floor_pow2(int v) {
 inline int prepare(Launch* L, const TView& x, const TView& y, const TView* res, int ntaps, const int* dy,
                    const int* dx, int stride, int Ho, int Wo, int act_pre, int act_post, int out_scale, int out_oy,
                    int out_ox, const h16* w_dev, const float* bias_dev, int smem_budget_kb, int max_block_n,
-                   int num_sms, int group_hint = 0) {
+                   int num_sms, int group_hint = 0, const h16* dw_w_dev = nullptr, int dw_relu = 0) {
   const int Cin = x.c, Cout = y.c;
   BD_CHECK(!x.f32, "umma conv needs an fp16 input map");
   BD_CHECK(Cin % 8 == 0 && x.c0 % 8 == 0 && x.ctot % 8 == 0, "umma conv needs 16-byte aligned input channel slices");
@@ -804,7 +940,26 @@ inline int prepare(Launch* L, const TView& x, const TView& y, const TView* res, 
   if (group_hint > 1 && num_kb % group_hint == 0 && 2 * group_hint * sub_bytes <= avail) p.group = group_hint;
   p.spec = 0;
   p.wres_bytes = 0;
+  p.aux_bytes = 0;
+  p.dw_w = dw_w_dev; p.dw_relu = dw_relu;
   const int wbytes = ntaps * p.kchunks * p.block_n * 128;
+  if (dw_w_dev) {
+    // fused separable convolution: x is the DEPTHWISE input; per k-block a halo box + the pointwise weight tile
+    BD_CHECK(ntaps == 1 && stride == 1 && out_scale == 1 && !y.f32 && Cin % BLOCK_K == 0 && Wo >= 8 && Ho >= 16 &&
+                 Wo == x.W && Ho == x.H && dy[0] == 0 && dx[0] == 0,
+             "fused separable conv: needs a stride-1 1x1 pointwise stage, Cin % 64 == 0 and a map of at least 8 x 16");
+    p.spec = 4; p.group = 1;
+    const int fixed4 = fixed - (res ? 2 : 1) * (EPI_WARPS / 2) * EPI_TILE_BYTES;  // four epilogue warps only
+    const int avail4 = smem_budget_kb * 1024 - fixed4;
+    p.wres_bytes = 2 * A_STAGE_BYTES;                       // two A-tile slots
+    p.aux_bytes = (9 * Cin * 2 + 127) / 128 * 128;          // staged depthwise weights
+    p.bw = 8; p.bh = 16; p.bn = 1;
+    p.tiles_w = cdiv(Wo, p.bw); p.tiles_h = cdiv(Ho, p.bh); p.tiles_n = x.N;
+    const int stage4 = HALO_STAGE + p.block_n * 128;
+    p.stages = std::min(6, (avail4 - p.wres_bytes - p.aux_bytes) / stage4);
+    BD_CHECK(p.stages >= 2, "fused separable conv: shared memory budget too small");
+    L->smem_bytes = p.stages * stage4 + p.wres_bytes + p.aux_bytes + fixed4;
+  } else
   if (halo && p.n_tiles == 1 && wbytes + 2 * HALO_STAGE <= avail && wbytes <= 148 * 1024) {
     // halo path: weights resident, the ring holds one halo box per 64-channel chunk
     p.spec = 3; p.group = 1; p.wres_bytes = wbytes;
@@ -815,7 +970,7 @@ inline int prepare(Launch* L, const TView& x, const TView& y, const TView* res, 
   } else
   if (group_hint == 0 && ntaps == 9 && p.kchunks == 1 && 2 * 3 * sub_bytes <= avail) { p.spec = 1; p.group = 3; }
   else if (group_hint == 0 && ntaps == 9 && p.kchunks == 2 && 2 * 2 * sub_bytes <= avail) { p.spec = 2; p.group = 2; }
-  if (p.spec != 3) {
+  if (p.spec != 3 && p.spec != 4) {
     const int stage_bytes = sub_bytes * p.group;
     p.stages = std::max(2, std::min(12, avail / stage_bytes));
     p.stages = std::min(p.stages, std::max(2, 2 * num_kb / p.group));
@@ -843,7 +998,7 @@ inline int prepare(Launch* L, const TView& x, const TView& y, const TView* res, 
                         static_cast<uint64_t>((x.H - py + stride - 1) / stride), static_cast<uint64_t>(x.N)};
     uint64_t strides[3] = {pitch * stride, pitch * x.W * stride, pitch * x.W * x.H};
     uint32_t box[4] = {BLOCK_K, static_cast<uint32_t>(p.bw), static_cast<uint32_t>(p.bh), static_cast<uint32_t>(p.bn)};
-    if (p.spec == 3) { box[1] = HALO_W; box[2] = HALO_H; box[3] = 1; }
+    if (p.spec == 3 || p.spec == 4) { box[1] = HALO_W; box[2] = HALO_H; box[3] = 1; }
     char* base = static_cast<char*>(x.base) + (static_cast<size_t>(py) * x.W + px) * pitch + static_cast<size_t>(x.c0) * 2;
     if (encode_h16(&L->maps.a[m], base, 4, dims, strides, box)) return 1;
     if (first < 0) first = m;

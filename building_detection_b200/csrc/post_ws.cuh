@@ -58,6 +58,9 @@ struct bd_ctx {
   int* d_ys = nullptr;      // tile origin scratch
   int* d_xs = nullptr;
   int tile_cap = 0;
+  int* d_all_ys = nullptr;  // origins of all tiles of the current scene (bd_tiles_set_origins)
+  int* d_all_xs = nullptr;
+  int origin_cap = 0, n_origins = 0;
   bd::post::Workspace post_ws;
   bd::post::DevPool pool;
   void* trace_buf = nullptr;  // BD_UMMA_TRACE debug buffer of the most recently built conv

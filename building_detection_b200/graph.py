@@ -361,8 +361,23 @@ class Net:
         if out is None:
             out = self.new(Ho, Wo, cout)
         a = ACT_RELU if act == "relu" else ACT_NONE
+        i_dw = len(self.plan.ops) - 1
         self._conv_op(mid, w, bias, [(0, 0)], 1, Ho, Wo, ACT_NONE if res is not None else a, res,
                       a if res is not None else ACT_NONE, out, name=name + "/pw")
+        pw_op = self.plan.ops[-1]
+        # One kernel for both stages (runtime.NativePlan, bd_conv_desc::dw_w_host) when the pointwise stage runs on
+        # the tensor cores with full 64-channel k-blocks: stride 1, map at least 8 x 16, and the depthwise input
+        # readable at the width the pointwise stage reads the intermediate (padded buffers have zero tails).
+        cin_k = pw_op["x"][2]
+        # Only with a single N tile (Cout <= 256): every N tile of a pixel tile would recompute the depthwise stage,
+        # and the shared-memory pipe (TMA writes + tensor-core operand reads + depthwise window reads) is what bounds
+        # the fused kernel -- measured on B200: 728->728 @32^2 55 us fused vs 22 + 29 us as two kernels, but
+        # 128->128 @256^2 156 vs 280 us, 256->256 @128^2 84 vs 150 us.
+        if (s == 1 and cout <= 256 and pw_op["path"] == "umma" and cin_k % 64 == 0 and x.W >= 8 and x.H >= 16
+                and out.buf.dtype == "f16" and x.buf.dtype == "f16"
+                and (cin_k == x.C or (x.c0 == 0 and x.buf.C == cin_k))):
+            self.plan.ops[i_dw]["fuse"] = True
+            pw_op["fused_dw"] = i_dw
         return out
 
     # ------------------------------------------------------------------ memory-bound ops

@@ -26,7 +26,8 @@ class ConvDesc(C.Structure):
                 ("stride", C.c_int32), ("ho", C.c_int32), ("wo", C.c_int32),
                 ("act_pre", C.c_int32), ("act_post", C.c_int32),
                 ("out_scale", C.c_int32), ("out_oy", C.c_int32), ("out_ox", C.c_int32),
-                ("path", C.c_int32), ("w_host", C.c_void_p), ("bias_host", C.c_void_p)]
+                ("path", C.c_int32), ("w_host", C.c_void_p), ("bias_host", C.c_void_p),
+                ("dw_w_host", C.c_void_p), ("dw_relu_in", C.c_int32)]
 
 
 class Polys(C.Structure):
@@ -73,6 +74,10 @@ _SIGS = {
                                   C.c_void_p, C.c_int, C.c_void_p]),
     "bd_stitch_or": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                C.c_void_p]),
+    "bd_tiles_set_origins": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "bd_tiles_gather_at": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                     C.c_void_p]),
+    "bd_stitch_or_at": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "bd_fuse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "bd_fuse_cleaned": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "bd_mask_cleanup": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
@@ -155,8 +160,12 @@ class NativePlan:
             bid = L.bd_plan_add_buffer(self.h, b.H, b.W, b.C, 1 if b.dtype == "f32" else 0, 1 if b.kind == "vec" else 0)
             if bid != b.id:
                 raise NativeError("buffer id mismatch: " + L.bd_last_error().decode())
-        for op in plan.ops:
+        fuse_sep = os.environ.get("BD_FUSE_SEPCONV", "1") != "0"
+        self.native_to_plan = []  # native op index -> plan op index (fused depthwise stages have no native op)
+        for i_op, op in enumerate(plan.ops):
             kind = op["op"]
+            if not (kind == G.OP_DWCONV and op.get("fuse") and fuse_sep):
+                self.native_to_plan.append(i_op)
             if kind == G.OP_CONV:
                 d = ConvDesc()
                 d.x, d.y, d.res = _tref(op["x"]), _tref(op["y"]), _tref(op["res"])
@@ -171,7 +180,20 @@ class NativePlan:
                 b = np.ascontiguousarray(op["b"], np.float32)
                 keep += [w, b]
                 d.w_host, d.bias_host = w.ctypes.data, b.ctypes.data
+                d.dw_w_host, d.dw_relu_in = None, 0
+                if op.get("fused_dw") is not None and fuse_sep:
+                    # SeparableConv2D in one kernel: x becomes the depthwise input (whole padded buffer when the
+                    # pointwise stage reads the padded intermediate), depthwise weights padded to the same width
+                    dwop = plan.ops[op["fused_dw"]]
+                    cin_k = op["x"][2]
+                    dww = np.zeros((9, cin_k), np.float32)
+                    dww[:, :dwop["x"][2]] = dwop["w"]
+                    keep.append(dww)
+                    d.x = _tref((dwop["x"][0], dwop["x"][1], cin_k))
+                    d.dw_w_host, d.dw_relu_in = dww.ctypes.data, int(dwop["relu_in"])
                 check(L.bd_plan_add_conv(self.h, C.byref(d)))
+            elif kind == G.OP_DWCONV and op.get("fuse") and fuse_sep:
+                pass  # runs inside the pointwise convolution that follows
             elif kind == G.OP_DWCONV:
                 w = np.ascontiguousarray(op["w"], np.float32)
                 keep.append(w)
@@ -263,17 +285,28 @@ class NativePlan:
         check(lib().bd_plan_write_buffer(self.h, buf, _ptr(a), a.nbytes))
 
     def time_ops(self, stream=0):
+        """Per plan op: device ms (CUDA events around every native op), kernel class, algorithmic FLOPs.  A depthwise
+        stage fused into its pointwise convolution reports 0 ms; its FLOPs are counted on the fused op."""
         n = lib().bd_plan_num_ops(self.h)
-        ms = np.zeros(n, np.float32)
-        check(lib().bd_plan_time_ops(self.h, _ptr(ms), stream or None))
-        kinds = np.zeros(n, np.int32)
-        flops = np.zeros(n, np.float64)
+        assert n == len(self.native_to_plan), (n, len(self.native_to_plan))
+        ms_n = np.zeros(n, np.float32)
+        check(lib().bd_plan_time_ops(self.h, _ptr(ms_n), stream or None))
+        nplan = len(self.plan.ops)
+        ms = np.zeros(nplan, np.float32)
+        kinds = np.full(nplan, 2, np.int32)
+        flops = np.zeros(nplan, np.float64)
+        native_set = set(self.native_to_plan)
         for i in range(n):
             k, f = C.c_int(), C.c_double()
             check(lib().bd_plan_op_info(self.h, i, C.byref(k), C.byref(f)))
-            kinds[i], flops[i] = k.value, f.value
-            if i < len(self.plan.ops) and "flops" in self.plan.ops[i]:
-                flops[i] = self.plan.ops[i]["flops"]  # algorithmic: the native count includes channel padding
+            j = self.native_to_plan[i]
+            ms[j], kinds[j], flops[j] = ms_n[i], k.value, f.value
+            op = self.plan.ops[j]
+            if "flops" in op:
+                flops[j] = op["flops"]  # algorithmic: the native count includes channel padding
+            if op.get("fused_dw") is not None and op["fused_dw"] not in native_set:
+                dw = self.plan.ops[op["fused_dw"]]
+                flops[j] += 2.0 * self.plan.batch * op["Ho"] * op["Wo"] * dw["x"][2] * 9
         return ms, kinds, flops
 
     @property

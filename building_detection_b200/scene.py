@@ -82,17 +82,19 @@ class SceneRunner:
             out = t.zeros((len(self.models), h, w), dtype=t.uint8, device=self.device)
         stream = t.cuda.current_stream(self.device).cuda_stream
         L, C = self.lib, R.C
+        if not len(origins):
+            return out
+        # all tile origins go to the device once; the batches below are pure kernel launches
+        ys = np.ascontiguousarray([o[0] for o in origins], np.int32)
+        xs = np.ascontiguousarray([o[1] for o in origins], np.int32)
+        R.check(L.bd_tiles_set_origins(self.ctx, R._ptr(ys), R._ptr(xs), len(origins), stream))
         for b0 in range(0, len(origins), self.batch):
-            chunk = origins[b0:b0 + self.batch]
-            n = len(chunk)
-            ys = np.asarray([o[0] for o in chunk], np.int32)
-            xs = np.asarray([o[1] for o in chunk], np.int32)
+            n = min(self.batch, len(origins) - b0)
             for mi, m in enumerate(self.models):
                 plan = m.native_plan(n)
                 x_ptr = plan.buffer_ptr(plan.plan.input)
-                R.check(L.bd_tiles_gather(self.ctx, scene_dev.data_ptr(), h, w, R._ptr(ys), R._ptr(xs), n, x_ptr,
-                                          plan.plan.input_stride, stream))
+                R.check(L.bd_tiles_gather_at(self.ctx, scene_dev.data_ptr(), h, w, b0, n, x_ptr,
+                                             plan.plan.input_stride, stream))
                 plan.run_device(0, 0, self.tile_masks.data_ptr(), stream)
-                R.check(L.bd_stitch_or(self.ctx, self.tile_masks.data_ptr(), R._ptr(ys), R._ptr(xs), n,
-                                       out[mi].data_ptr(), h, w, stream))
+                R.check(L.bd_stitch_or_at(self.ctx, self.tile_masks.data_ptr(), b0, n, out[mi].data_ptr(), h, w, stream))
         return out

@@ -54,6 +54,12 @@ typedef struct bd_conv_desc {
   int32_t path;                 /* bd_conv_path */
   const uint16_t* w_host;
   const float* bias_host;
+  /* Fused SeparableConv2D (v3plus.py / bam.py Xception blocks): when dw_w_host != NULL this 1x1 stride-1 UMMA
+   * convolution is the pointwise stage and x is the input of the DEPTHWISE 3x3 ('same', stride 1) stage, whose
+   * weights are dw_w_host [9][x.c] fp32 (fp16-representable) and whose input optionally passes a ReLU.  The
+   * depthwise result never goes to HBM; it is bit-identical to bd_plan_add_dwconv + bd_plan_add_conv. */
+  const float* dw_w_host;
+  int32_t dw_relu_in;
 } bd_conv_desc;
 
 /* ---- context ---------------------------------------------------------------------------- */
@@ -136,6 +142,13 @@ int bd_tiles_gather(bd_ctx* ctx, const uint8_t* scene_bgr_dev, int h, int w, con
  * (predict.py:113-114: int8 accumulate then >=1 -> 255). */
 int bd_stitch_or(bd_ctx* ctx, const uint8_t* tile_masks_dev, const int32_t* ys_host, const int32_t* xs_host,
                  int n, uint8_t* scene_mask_dev, int h, int w, void* stream);
+/* The same two steps for a whole scene without per-batch host->device copies: upload the origins of ALL tiles
+ * once (predict.py:105-107 enumerates them), then address batches by their first tile. */
+int bd_tiles_set_origins(bd_ctx* ctx, const int32_t* ys_host, const int32_t* xs_host, int n, void* stream);
+int bd_tiles_gather_at(bd_ctx* ctx, const uint8_t* scene_bgr_dev, int h, int w, int first, int n, void* x_dev,
+                       int stem_stride, void* stream);
+int bd_stitch_or_at(bd_ctx* ctx, const uint8_t* tile_masks_dev, int first, int n, uint8_t* scene_mask_dev, int h, int w,
+                    void* stream);
 
 /* ---- fusion: replaces model_fuse.py:model_confuse (271-350) --------------------------------- */
 /* masks5_dev: 5 u8 masks (5,h,w) with values {0,255}; fused_dev: u8 (h,w) {0,255}.

@@ -178,6 +178,33 @@ def test_separable_conv(gpu, C, H, s, relu_in):
     run_case(b, ulps=4.0, rel_rms=1e-3)
 
 
+@pytest.mark.parametrize("C,Cout,H,N,relu_in,res", [(728, 256, 32, 2, True, True), (64, 128, 64, 1, False, False),
+                                                     (128, 128, 32, 3, True, False), (1024, 192, 16, 1, True, False),
+                                                     (256, 256, 40, 1, False, False)])
+def test_fused_separable_conv_equals_two_kernels(gpu, monkeypatch, C, Cout, H, N, relu_in, res):
+    """The one-kernel SeparableConv2D (depthwise warps feed the A tile of the pointwise tcgen05 GEMM,
+    bd_conv_desc::dw_w_host) against the two-kernel sequence: same fp16 rounding points, so bit-identical."""
+    def b(g):
+        x = g.new(H, H, C)
+        r = g.new(H, H, Cout) if res else None
+        return x, r, g.sepconv(x, "s", Cout, relu_in=relu_in, act="relu", res=r)
+    plan, (x, r, y), _ = build_two_pass(b, N)
+    assert plan.ops[0].get("fuse") and plan.ops[1].get("fused_dw") == 0
+    rng = np.random.default_rng(3)
+    inputs = {x.buf.id: rand_map(rng, plan, x.buf.id)}
+    if r is not None:
+        inputs[r.buf.id] = rand_map(rng, plan, r.buf.id)
+    outs = []
+    for fuse in ("1", "0"):
+        monkeypatch.setenv("BD_FUSE_SEPCONV", fuse)
+        nat = run_native(plan, inputs)
+        assert (len(nat.native_to_plan) == 1) == (fuse == "1")
+        outs.append(nat.read_buffer(y.buf.id))
+        nat.close()
+    np.testing.assert_array_equal(outs[0], outs[1])
+    assert_close(outs[0], run_interp(plan, inputs).get(y.buf.id), ulps=4.0, rel_rms=1e-3)
+
+
 def test_maxpools(gpu):
     """MaxPool 2x2/s2 (scse.py:54), 2x2/s4 valid (res34.py:153), 3x3/s2 same (v3plus.py:192): exact."""
     def b(g):

@@ -16,6 +16,8 @@ H, Cin, Cout, k = (int(a) for a in sys.argv[1:5]) if len(sys.argv) >= 5 else (51
 
 def builder(g):
     x = g.new(H, H, Cin)
+    if k == 0:  # fused separable convolution
+        return x, g.sepconv(x, "s", Cout, relu_in=True, act="relu")
     return x, g.conv(x, "c", Cout, k=k, bn=True, act="relu")
 
 
@@ -42,7 +44,7 @@ for c, role, a_, b_ in evs[skip:skip + int(os.environ.get("TRACE_LINES", "120"))
     d = c - last.get(role, c)
     last[role] = c
     if role == 3 and b_:
-        nm = {1: "epi : before wait_read", 2: "epi : tmem loaded", 3: "epi : staging free", 4: "epi : fence+bar", 5: "epi : tma store issued"}[b_]
+        nm = {1: "epi/dw: wait", 2: "epi : tmem loaded", 3: "epi/dw: go", 4: "epi : fence+bar", 5: "epi/dw: stored"}[b_]
         print(f"{c - t0:9d} (+{d:6d})  {nm} tile {a_:6d}")
         continue
     if role == 1 and b_ < 0:
