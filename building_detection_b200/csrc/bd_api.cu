@@ -9,6 +9,7 @@
 
 #include "common.cuh"
 #include "conv_umma.cuh"
+#include "dw_tma.cuh"
 #include "kernels.cuh"
 #include "post_ws.cuh"
 
@@ -293,6 +294,23 @@ int bd_plan_add_dwconv(bd_plan* p, bd_tref x, bd_tref y, int stride, int pad_t, 
     q.N = pl->batch; q.Ho = q.y.H; q.Wo = q.y.W; q.stride = stride; q.pad_t = pad_t; q.pad_l = pad_l; q.relu_in = relu_in;
     q.w = static_cast<const h16*>(wd);
     BD_CHECK(stride == 1 || stride == 2, "dwconv: stride must be 1 or 2");
+    {
+      // shared-memory tiles moved by TMA (dw_tma.cuh) for the stride-1 'same' case on maps small enough that the
+      // register-window kernel is latency bound (BD_DW_TMA=0 turns it off)
+      TView xv = pl->tview(x), yv = pl->tview(y);
+      static const bool dw_tma_on = [] { const char* e = getenv("BD_DW_TMA"); return !(e && e[0] == '0'); }();
+      if (dw_tma_on && dwt::eligible(xv, yv, stride, pad_t, pad_l)) {
+        std::shared_ptr<dwt::Launch> L(new dwt::Launch());
+        if (dwt::prepare(L.get(), xv, yv, static_cast<const h16*>(wd), relu_in, pl->ctx->num_sms)) return 1;
+        bd_ctx* ctx = pl->ctx;
+        Op op;
+        op.kclass = 2; op.launches = 1;
+        op.flops = 2.0 * pl->batch * q.Ho * q.Wo * static_cast<double>(x.c) * 9;
+        op.run = [L, ctx](cudaStream_t s) -> int { ctx->launches++; return dwt::launch(*L, s, pdl_enabled()); };
+        pl->ops.push_back(op);
+        return 0;
+      }
+    }
     // 4-channel vectors (half the registers, twice the resident warps) whenever the 8-channel version could not
     // fill the machine with threads; both are exact and round identically
     const size_t total8 = static_cast<size_t>(pl->batch) * cdiv(q.Ho, k::DW_ROWS) * q.Wo * (x.c / 8);
