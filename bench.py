@@ -55,6 +55,17 @@ def peaks():
     return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm": 6650.0, "source": "fallback"}
 
 
+def conv_traffic():
+    """DRAM bytes (read + write) per conv_umma launch, averaged over the launches of one batch-16 pass of the five
+    plans, from the committed ncu capture (tools/traffic_batch.py); None when no capture is committed."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_conv_umma_traffic.json")))
+    if not files:
+        return None, None
+    d = json.load(open(files[-1]))
+    return d["dram_bytes_per_launch"], f"{os.path.relpath(files[-1], ROOT)} ({d['launches']} launches)"
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -119,6 +130,7 @@ def run_reference(args):
     import torch
     from building_detection_b200 import graph as G
     from building_detection_b200.predict_model import CTORS, MODEL_NAMES
+    from building_detection_b200 import scene as S
     from oracle import nets
     rng = np.random.default_rng(0)
     x = (rng.integers(0, 256, (1, 512, 512, 3), dtype=np.uint8) / 127.5 - 1).astype(np.float32)
@@ -141,7 +153,12 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"5-model ensemble forward, 512x512 tiles (sample of the {args.scene}^2 scene job)"},
+        "config": {"workload": f"5-model ensemble (res34,hrnet,v3plus,scse,bam) + OR-stitch + 3-of-5 fuse + contours on a "
+                               f"{args.scene}x{args.scene} px scene",
+                   "tiles": len(S.tile_origins(args.scene, args.scene)), "tile": 512, "stride": 360, "batch": 1,
+                   "parallelism": "host threads", "weights": "seeded Keras-default random init",
+                   "sample": "one 512x512 tile of that scene through the five networks per step (the forwards are "
+                             "> 99 % of the reference's time per tile; its fuse is O(#objects x H x W), see DESIGN.md)"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -265,7 +282,9 @@ def main():
             n_umma += int((kinds == 0).sum())
         ach = tot_fl[0] / (tot_ms[0] * 1e-3) / 1e12
         roof = {"kernel": "conv_umma_kernel", "bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"],
-                "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"], "traffic": None,
+                "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"], "traffic": conv_traffic()[0],
+                "traffic_unit": "DRAM bytes per launch (read + write, ncu)", "traffic_source": conv_traffic()[1],
+                "algorithmic_flop_per_launch": tot_fl[0] / max(n_umma, 1),
                 "peak_source": pk["source"] + " cuBLAS 16-bit sustained (kernel timed inside a long step); burst "
                                f"{pk['bf16_burst']}",
                 "launches_per_batch": n_umma, "avg_launch_ms": tot_ms[0] / max(n_umma, 1),

@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
       mbar_expect_tx(wbar, static_cast<uint32_t>(p.wres_bytes));
       uint32_t dst = wres0;
       for (int c = 0; c < p.Cin; c += BLOCK_K)
-        for (int tap = 0; tap < 9; ++tap, dst += b_bytes) tma_load_3d(dst, &maps.b, wbar, c, 0, tap);
+        for (int tap = 0; tap < p.ntaps; ++tap, dst += b_bytes) tma_load_3d(dst, &maps.b, wbar, c, 0, tap);
     }
     __syncwarp();
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -528,41 +528,49 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
           if (!f_ready) mbar_wait(ring.fb, ring.ph);
           tc_fence_after();
           const uint64_t hdesc = make_sdesc_sbo(smem_base + ring.off, HALO_W * 128);
-          if (elect_one()) {
-            trace_ev(p, 1, tr_i, tile, c);
+          const int reps = p.ntaps / 9;  // 1, or 2 with hi/lo-split weights (the nine offsets twice)
+          for (int rep = 0; rep < reps; ++rep) {
+            const bool last_rep = rep + 1 == reps;
+            if (elect_one()) {
+              if (rep == 0) trace_ev(p, 1, tr_i, tile, c);
 #pragma unroll
-            for (int tap = 0; tap < 6; ++tap) {
-              // tap (kh, kw) reads the halo rows shifted by kh halo rows and kw pixels
-              const uint64_t adesc = hdesc + (((tap / 3) * HALO_W + tap % 3) * 128 >> 4);
-              const uint64_t bd = bdesc + static_cast<uint32_t>(tap) * dkb;
-              tc_mma_f16(tacc, adesc, bd, idesc, (tap > 0 || c < p.Cin) ? 1u : 0u);
-              if (c > 16) tc_mma_f16(tacc, adesc + 2u, bd + 2u, idesc, 1u);
-              if (c > 32) tc_mma_f16(tacc, adesc + 4u, bd + 4u, idesc, 1u);
-              if (c > 48) tc_mma_f16(tacc, adesc + 6u, bd + 6u, idesc, 1u);
+              for (int tap = 0; tap < 6; ++tap) {
+                // tap (kh, kw) reads the halo rows shifted by kh halo rows and kw pixels
+                const uint64_t adesc = hdesc + (((tap / 3) * HALO_W + tap % 3) * 128 >> 4);
+                const uint64_t bd = bdesc + static_cast<uint32_t>(tap) * dkb;
+                tc_mma_f16(tacc, adesc, bd, idesc, (tap > 0 || rep > 0 || c < p.Cin) ? 1u : 0u);
+                if (c > 16) tc_mma_f16(tacc, adesc + 2u, bd + 2u, idesc, 1u);
+                if (c > 32) tc_mma_f16(tacc, adesc + 4u, bd + 4u, idesc, 1u);
+                if (c > 48) tc_mma_f16(tacc, adesc + 6u, bd + 6u, idesc, 1u);
+              }
             }
-          }
-          __syncwarp();
-          // two thirds of this chunk's MMAs are queued: test what the next chunk / tile will wait for
-          f_ready = ring_test_next_full(ring, p, full0);
-          if (c <= BLOCK_K)
-            te_ready = single_unit ? mbar_test(te_bar + 8u * (a ^ 1u), te_par)
-                                   : (mbar_test(te_bar, te_par) & mbar_test(te_bar + 8u, te_par));
-          if (elect_one()) {
+            __syncwarp();
+            if (last_rep) {
+              // most of this chunk's MMAs are queued: test what the next chunk / tile will wait for
+              f_ready = ring_test_next_full(ring, p, full0);
+              if (c <= BLOCK_K)
+                te_ready = single_unit ? mbar_test(te_bar + 8u * (a ^ 1u), te_par)
+                                       : (mbar_test(te_bar, te_par) & mbar_test(te_bar + 8u, te_par));
+            }
+            if (elect_one()) {
 #pragma unroll
-            for (int tap = 6; tap < 9; ++tap) {
-              const uint64_t adesc = hdesc + (((tap / 3) * HALO_W + tap % 3) * 128 >> 4);
-              const uint64_t bd = bdesc + static_cast<uint32_t>(tap) * dkb;
-              tc_mma_f16(tacc, adesc, bd, idesc, 1u);
-              if (c > 16) tc_mma_f16(tacc, adesc + 2u, bd + 2u, idesc, 1u);
-              if (c > 32) tc_mma_f16(tacc, adesc + 4u, bd + 4u, idesc, 1u);
-              if (c > 48) tc_mma_f16(tacc, adesc + 6u, bd + 6u, idesc, 1u);
+              for (int tap = 6; tap < 9; ++tap) {
+                const uint64_t adesc = hdesc + (((tap / 3) * HALO_W + tap % 3) * 128 >> 4);
+                const uint64_t bd = bdesc + static_cast<uint32_t>(tap) * dkb;
+                tc_mma_f16(tacc, adesc, bd, idesc, 1u);
+                if (c > 16) tc_mma_f16(tacc, adesc + 2u, bd + 2u, idesc, 1u);
+                if (c > 32) tc_mma_f16(tacc, adesc + 4u, bd + 4u, idesc, 1u);
+                if (c > 48) tc_mma_f16(tacc, adesc + 6u, bd + 6u, idesc, 1u);
+              }
+              if (last_rep) {
+                tc_commit(ring.eb);
+                if (c <= BLOCK_K) tc_commit(tfull0 + 8u * a);
+                trace_ev(p, 1, tr_i, tile, -1);
+              }
             }
-            tc_commit(ring.eb);
-            if (c <= BLOCK_K) tc_commit(tfull0 + 8u * a);
-            trace_ev(p, 1, tr_i, tile, -1);
+            __syncwarp();
+            bdesc += 9u * dkb;
           }
-          __syncwarp();
-          bdesc += 9u * dkb;
           ring_advance(ring, p, HALO_STAGE, full0, empty0);
         }
         continue;
@@ -908,8 +916,10 @@ inline int prepare(Launch* L, const TView& x, const TView& y, const TView* res, 
   p.bh = std::min(BLOCK_M / p.bw, floor_pow2(Ho));
   p.bn = BLOCK_M / (p.bw * p.bh);
   // halo path candidate: plain 3x3, stride 1, dilation 1 ('same' padding), map at least 8 x 16
-  bool halo = group_hint == 0 && ntaps == 9 && stride == 1 && out_scale == 1 && Wo >= 8 && Ho >= 16 && Wo == x.W && Ho == x.H;
-  for (int t = 0; t < ntaps && halo; ++t) halo = dy[t] == t / 3 - 1 && dx[t] == t % 3 - 1;
+  // (18 taps: a hi/lo weight split, the 3x3 offsets twice)
+  bool halo = group_hint == 0 && (ntaps == 9 || ntaps == 18) && stride == 1 && out_scale == 1 && Wo >= 8 && Ho >= 16 &&
+              Wo == x.W && Ho == x.H;
+  for (int t = 0; t < ntaps && halo; ++t) halo = dy[t] == (t % 9) / 3 - 1 && dx[t] == (t % 9) % 3 - 1;
   p.tiles_w = cdiv(Wo, p.bw); p.tiles_h = cdiv(Ho, p.bh); p.tiles_n = cdiv(x.N, p.bn);
   const int cout16 = cdiv(Cout, 16) * 16;
   if (cout16 <= max_block_n) {

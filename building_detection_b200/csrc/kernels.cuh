@@ -40,7 +40,7 @@ __device__ __forceinline__ float actf(float v, int act) {
 struct DirectParams {
   View x, y, res;  // res.base == nullptr: none
   int N, Ho, Wo, stride, ntaps;
-  int dy[9], dx[9];
+  int dy[18], dx[18];
   int act_pre, act_post, out_scale, out_oy, out_ox;
   const h16* w;  // [ntaps][Cout][Cin]
   const float* bias;

@@ -29,6 +29,7 @@ INPUT_C = 32         # the network input is stored im2col'ed for its 3x3 stem co
 INPUT_SCALE = 255.0  # ... holding 255 * x (exact integers for 8-bit imagery)
 
 # op codes shared with csrc/bd_api.cu (enum bd_op_kind in include/bd_b200.h)
+MAX_TAPS = 18  # bd_b200.h BD_MAX_TAPS
 OP_CONV, OP_DWCONV, OP_MAXPOOL, OP_ADDN, OP_GAP, OP_DENSE, OP_GATE, OP_SKFUSE, OP_BCAST, OP_SOFTMAX2 = range(10)
 GATE_SE, GATE_SCSE, GATE_BAM = range(3)
 ACT_NONE, ACT_RELU, ACT_SIGMOID = range(3)
@@ -121,6 +122,7 @@ class Net:
 
     def __init__(self, model, batch, weights=None, umma=True, keep_f32=False):
         self.plan = Plan(model, batch)
+        self.split_weights = False  # see _conv_op
         self.w = weights
         self.spec = {}  # name -> (shape, init)
         self.umma = umma
@@ -212,6 +214,13 @@ class Net:
         assert cin == x.C and len(taps) == nt
         if macs_per_pixel is None:
             macs_per_pixel = cout * cin * nt
+        if self.split_weights and 2 * nt <= MAX_TAPS:
+            # hi/lo split: W = fp16(W) + fp16(W - fp16(W)) as a second set of taps at the same offsets -- the weights
+            # reach the tensor core to ~2^-22 instead of 2^-11 (HRNet's stem and layer1, DESIGN.md "Numerics")
+            hi = h16_to_f32(to_h16(w_tco))
+            w_tco = np.concatenate([hi, (w_tco - hi).astype(np.float32)], axis=0)
+            taps = list(taps) + list(taps)
+            nt *= 2
         if x.c0 == 0 and x.C > 64 and x.C % 64 and x.buf.C == -(-x.C // 64) * 64 and x.buf.dtype == "f16":
             # read the whole padded buffer (its tail channels are zero) with zero weights for the tail: the weight
             # rows become 128-byte aligned as well and every k-block is a full 64-channel chunk

@@ -21,6 +21,10 @@ def build(g: Net):
             t = cb(c, f"{name}_{i}_2", t.C, act="relu", res=t, out=out if i == 3 else None)
         return t
 
+    # (graph.Net.split_weights -- hi/lo fp16 weight taps -- was tried on the stem + layer1: the fp32-weight study
+    # predicted 2.20e-2 -> 1.80e-2 max|dp|, the real split gave 2.09e-2: at this depth the maximum over 10^6
+    # probabilities of a random-init network is dominated by chaotic amplification of ANY rounding change, so the
+    # split is left off; tools/hrnet_split_study.py, DESIGN.md "Numerics")
     t = cb(x, "stem", 64, s=2)  # hrnet.py:168
     t = bottleneck(t, "l1_0", True)  # layer1, hrnet.py:62-67
     for i in range(1, 4):

@@ -13,7 +13,7 @@ from . import graph as G
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbd_b200.so")
-MAX_TAPS = 9
+MAX_TAPS = 18
 
 
 class TRef(C.Structure):

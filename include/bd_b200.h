@@ -37,7 +37,7 @@ enum bd_conv_path { BD_CONV_DIRECT = 0 /* CUDA cores */, BD_CONV_UMMA = 1 /* tcg
 
 typedef struct bd_tref { int32_t buf, c0, c; } bd_tref;
 
-#define BD_MAX_TAPS 9
+#define BD_MAX_TAPS 18
 
 /* Fused convolution: y = act_post( act_pre( sum_t W[t] . x[h*stride+dy[t], w*stride+dx[t]] + bias ) + res )
  * written to y[(h*out_scale+out_oy), (w*out_scale+out_ox)].  Out-of-range taps read zero ('same'

@@ -55,8 +55,8 @@ class Interp:
     def _conv(self, op):
         x = self._load(op["x"]).permute(0, 3, 1, 2)  # NCHW
         n, cin, H, W = x.shape
-        if not self.emu and op.get("w32") is not None:
-            w = torch.from_numpy(op["w32"])
+        if (not self.emu or op.get("w_exact")) and op.get("w32") is not None:
+            w = torch.from_numpy(op["w32"])  # (study switch w_exact: fp32 weights with fp16 activations)
         else:
             w = torch.from_numpy(G.h16_to_f32(op["w"]).copy())  # (taps, Cout, Cin)
         s, Ho, Wo = op["stride"], op["Ho"], op["Wo"]

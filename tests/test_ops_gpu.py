@@ -19,8 +19,9 @@ def assert_close(got, ref, ulps=2.0, rel_rms=2e-4):
 
 
 def conv_case(N, H, W, Cin, Cout, k=3, s=1, d=1, res=False, res_after_act=False, act="relu", umma=True, bn=True,
-              in_slice=None, out_slice=None, seed=0, expect=None):
+              in_slice=None, out_slice=None, seed=0, expect=None, split=False):
     def builder(g):
+        g.split_weights = split  # hi/lo fp16 weight taps (18-tap halo path / 2-tap 1x1)
         x = G.T(g.buf(H, W, in_slice[1]), in_slice[0], Cin) if in_slice else g.new(H, W, Cin)
         Ho, Wo = -(-H // s), -(-W // s)
         r = g.new(Ho, Wo, Cout) if res else None
@@ -69,6 +70,9 @@ UMMA_CASES = {
     "3x3_640_640": dict(N=1, H=64, W=64, Cin=640, Cout=640),
     "3x3_64_64_256x256": dict(N=1, H=256, W=256, Cin=64, Cout=64),
     "3x3_1024_1024": dict(N=1, H=32, W=32, Cin=1024, Cout=1024),
+    "3x3_64_64_split_weights_halo18": dict(N=2, H=32, W=32, Cin=64, Cout=64, split=True),
+    "3x3_256_256_split_weights": dict(N=1, H=32, W=32, Cin=256, Cout=256, split=True),
+    "1x1_64_256_split_weights": dict(N=1, H=32, W=32, Cin=64, Cout=256, k=1, split=True),
 }
 
 
