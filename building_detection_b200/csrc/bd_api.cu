@@ -733,9 +733,14 @@ int bd_plan_time_ops(bd_plan* p, float* ms_out, void* stream) {
   std::vector<cudaEvent_t> ev(n + 1);
   for (auto& e : ev) BD_CUDA(cudaEventCreate(&e));
   BD_CUDA(cudaEventRecord(ev[0], s));
+  const bool sync_each = getenv("BD_SYNC_EACH_OP") != nullptr;  // debugging aid: name the op that faults
   for (size_t i = 0; i < n; ++i) {
     if (p->ops[i].run(s)) return 1;
     BD_CUDA(cudaEventRecord(ev[i + 1], s));
+    if (sync_each) {
+      const cudaError_t e = cudaStreamSynchronize(s);
+      if (e != cudaSuccess) return fail("native op " + std::to_string(i) + " failed: " + cudaGetErrorString(e));
+    }
   }
   BD_CUDA(cudaStreamSynchronize(s));
   for (size_t i = 0; i < n; ++i) BD_CUDA(cudaEventElapsedTime(&ms_out[i], ev[i], ev[i + 1]));

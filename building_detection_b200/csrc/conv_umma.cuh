@@ -42,7 +42,8 @@ constexpr int MAX_TAPS = 18;
 // halo path: one (16+2) x (8+2) pixel halo box per 64-channel chunk feeds all nine taps of a 3x3 convolution
 constexpr int HALO_W = 10, HALO_H = 18, HALO_BYTES = HALO_W * HALO_H * 128, HALO_STAGE = 23 * 1024;
 constexpr int EPI_WARPS = 8;                 // two warps per TMEM lane quadrant, each takes half of a column chunk
-constexpr int THREADS = 64 + 32 * EPI_WARPS;
+constexpr int MMA2_WARP = 2 + EPI_WARPS;       // second MMA issuer (tiles of odd index), see the kernel
+constexpr int THREADS = 64 + 32 * EPI_WARPS + 32;
 
 // division by a launch constant: q = (umulhi(mul, n) + n) >> shr, exact for n < 2^31 (Granlund-Montgomery)
 struct FastDiv { uint32_t mul, shr; };
@@ -59,6 +60,8 @@ struct Params {
   int bw, bh, bn;
   int tiles_w, tiles_h, tiles_n, n_tiles, total_tiles;
   int block_n, kchunks, ntaps, stages, group, tmem_cols;  // group: k-blocks per shared-memory stage
+  int dbg;      // debug switches (BD_UMMA_DBG): 1 = every thread waits for the previous grid before the role split, 2 = no early launch_dependents
+  int issuers;  // MMA-issuing warps: 2 = warp 1 takes the even tiles of a CTA, warp MMA2_WARP the odd ones
   int spec;  // 0 generic loops; 1 = 9 taps x 1 chunk, group 3; 2 = 9 taps x 2 chunks, group 2 (fully unrolled loops);
              // 3 = halo path: 3x3 stride 1, one halo box per chunk, weights resident in shared memory;
              // 4 = fused separable convolution: warps 2-5 compute the depthwise 3x3 of a halo box into the A tile of
@@ -105,7 +108,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
-  for (uint32_t it = 0; it < (1u << 26); ++it) {
+  for (uint32_t it = 0; it < (1u << 25); ++it) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -342,21 +345,26 @@ __device__ __forceinline__ void mma_tile(const Params& p, Ring& r, uint64_t desc
 // The producer and the MMA issuer are single threads executing dependent scalar code: every instruction in
 // their per-k-block loops costs several cycles of latency (a k-block's four N=64 MMAs take only 128 cycles), so
 // those loops keep their ring position incrementally and contain no integer division.
+// KSPEC: 0 = generic / unrolled ring paths (Params::spec 0-2), 3 = halo path, 4 = fused separable convolution; REPS:
+// halo path only, 2 = hi/lo-split weights (the nine offsets twice).  Separate instantiations, so that the register
+// allocation and scheduling of one path's hot loops do not depend on the code of the others (adding the spec-4 role to
+// a single kernel cost the halo path 9 %).
+template <int KSPEC, int REPS>
 __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_constant__ Maps maps,
                                                                const __grid_constant__ Params p) {
   extern __shared__ uint8_t smem_raw[];
-  pdl_trigger();  // the next kernel may begin launching; it waits for THIS grid's completion in its own pdl_wait()
+  if (!(p.dbg & 2)) pdl_trigger();  // the next kernel may begin launching; it waits for THIS grid's completion in its own pdl_wait()
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t b_bytes = static_cast<uint32_t>(p.block_n) * 128u;
   const uint32_t sub_bytes = A_STAGE_BYTES + b_bytes;                       // one k-block: A box + W tile
-  const uint32_t stage_bytes = p.spec == 3 ? static_cast<uint32_t>(HALO_STAGE)
-                               : p.spec == 4 ? static_cast<uint32_t>(HALO_STAGE) + b_bytes  // halo box + pointwise W tile
+  const uint32_t stage_bytes = (KSPEC == 3) ? static_cast<uint32_t>(HALO_STAGE)
+                               : (KSPEC == 4) ? static_cast<uint32_t>(HALO_STAGE) + b_bytes  // halo box + pointwise W tile
                                              : sub_bytes * static_cast<uint32_t>(p.group);  // a stage holds `group` k-blocks
   const uint32_t wres0 = smem_base + static_cast<uint32_t>(p.stages) * stage_bytes;      // resident weights (spec 3)
   const uint32_t out0 = wres0 + static_cast<uint32_t>(p.wres_bytes);                      // 8 per-warp staging tiles
-  const uint32_t n_epi_warps = p.spec == 4 ? EPI_WARPS / 2 : EPI_WARPS;              // spec 4: warps 2-5 are depthwise warps
+  const uint32_t n_epi_warps = (KSPEC == 4) ? EPI_WARPS / 2 : EPI_WARPS;              // spec 4: warps 2-5 are depthwise warps
   const uint32_t res0 = out0 + n_epi_warps * EPI_TILE_BYTES;                         // per-warp residual tiles (if any)
   const uint32_t bias0 = res0 + (p.res ? n_epi_warps * EPI_TILE_BYTES : 0u);         // bias of all N tiles, fp32
   const uint32_t aux0 = bias0 + static_cast<uint32_t>(p.bias_bytes);                 // depthwise weights (spec 4)
@@ -372,7 +380,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(full0 + 8u * s, 1);
-      mbar_init(empty0 + 8u * s, p.spec == 4 ? 5 : 1);  // spec 4: four depthwise warps + the MMA commit free a stage
+      mbar_init(empty0 + 8u * s, (KSPEC == 4) ? 5 : 1);  // spec 4: four depthwise warps + the MMA commit free a stage
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(afull0 + 8u * a, 4);   // one arrival per depthwise warp
@@ -397,10 +405,11 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *holder_ptr;
-  // barrier set-up and TMEM allocation above overlap the previous kernel's tail; nothing below may touch global
-  // memory before that kernel has completed
-  pdl_wait();
+  // Barrier set-up and TMEM allocation above overlap the previous kernel's tail.  Each role calls pdl_wait() itself,
+  // after whatever it can do on CONSTANT data (resident weights, bias, depthwise weights are never written by a
+  // kernel) and before its first access to activations; the MMA warp touches only shared memory and TMEM.
 
+  if (p.dbg & 1) pdl_wait();
   int tr_i = 0, tr_j = 0;  // debug trace cursors
 
   // Warps 0 and 1 run their loops with all 32 lanes (every value is warp-uniform, so the compiler keeps the ring
@@ -410,18 +419,19 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
     uint32_t s = 0, sub = 0, ph = 0, a_s = smem_base, fb = full0, eb = empty0;  // ring position, kept incrementally
     const char* maps_a = reinterpret_cast<const char*>(&maps.a[0]);
     Ring ring{0u, 0u, 0u, full0, empty0};
-    if (p.spec == 3 && elect_one()) {  // all weight tiles once: [chunk][tap] blocks of block_n x 128 B
+    if ((KSPEC == 3) && elect_one()) {  // all weight tiles once: [chunk][tap] blocks of block_n x 128 B
       mbar_expect_tx(wbar, static_cast<uint32_t>(p.wres_bytes));
       uint32_t dst = wres0;
       for (int c = 0; c < p.Cin; c += BLOCK_K)
         for (int tap = 0; tap < p.ntaps; ++tap, dst += b_bytes) tma_load_3d(dst, &maps.b, wbar, c, 0, tap);
     }
     __syncwarp();
+    pdl_wait();  // activations of the previous kernel from here on
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       int nt, tw, th, tn;
       tile_coords(p, tile, nt, tw, th, tn);
       const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn, n_base = nt * p.block_n;
-      if (p.spec == 3) {  // one halo box per 64-channel chunk
+      if ((KSPEC == 3)) {  // one halo box per 64-channel chunk
         for (int c = 0; c < p.Cin; c += BLOCK_K) {
           mbar_wait(ring.eb, ring.ph ^ 1u);
           if (elect_one()) {
@@ -434,7 +444,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
         }
         continue;
       }
-      if (p.spec == 4) {  // per 64-channel chunk: the halo box of the depthwise input + the pointwise weight tile
+      if ((KSPEC == 4)) {  // per 64-channel chunk: the halo box of the depthwise input + the pointwise weight tile
         for (int c = 0; c < p.Cin; c += BLOCK_K) {
           mbar_wait(ring.eb, ring.ph ^ 1u);
           if (elect_one()) {
@@ -448,8 +458,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
         }
         continue;
       }
-      if (p.spec == 1) { produce_tile<9, 1, 3>(maps, p, ring, smem_base, sub_bytes, full0, empty0, w0, h0, n0, n_base, tr_i, tile); continue; }
-      if (p.spec == 2) { produce_tile<9, 2, 2>(maps, p, ring, smem_base, sub_bytes, full0, empty0, w0, h0, n0, n_base, tr_i, tile); continue; }
+      if (KSPEC == 0 && p.spec == 1) { produce_tile<9, 1, 3>(maps, p, ring, smem_base, sub_bytes, full0, empty0, w0, h0, n0, n_base, tr_i, tile); continue; }
+      if (KSPEC == 0 && p.spec == 2) { produce_tile<9, 2, 2>(maps, p, ring, smem_base, sub_bytes, full0, empty0, w0, h0, n0, n_base, tr_i, tile); continue; }
       for (int tap = 0; tap < p.ntaps; ++tap) {
         const CUtensorMap* tm = reinterpret_cast<const CUtensorMap*>(maps_a + p.tap_map[tap] * sizeof(CUtensorMap));
         const int cx = w0 + p.tap_dx[tap], cy = h0 + p.tap_dy[tap];
@@ -471,8 +481,15 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
         }
       }
     }
-  } else if (warp == 1) {
-    // ---------------- MMA issuer
+  } else if (warp == 1 || warp == MMA2_WARP) {
+    // ---------------- MMA issuers.  A single thread issues a tcgen05.mma every ~50 clk but spends 450-700 clk per
+    // tile on barrier round trips and bookkeeping, during which the tensor pipe drains (a 3x3 64->64 tile is only
+    // 36 MMAs).  With two issuers, warp 1 takes the even tiles of this CTA (TMEM stage 0) and warp MMA2_WARP the odd
+    // ones (stage 1): while one sits between two tiles the other keeps the pipe fed.  Both walk the shared-memory
+    // ring in tile order and skip the stages of the other's tiles; each commits the stages it consumed.
+    const uint32_t issuer = warp == 1 ? 0u : 1u;
+    const bool dual = p.issuers == 2;
+    if (issuer == 1) tr_i = 1 << 20;  // (debug trace: issuer 0 only)
     const uint32_t idesc = make_idesc(p.block_n);
     const uint64_t desc0 = make_sdesc(smem_base);
     const uint32_t dsub = sub_bytes >> 4;  // descriptor start-address field counts 16-byte units
@@ -481,9 +498,29 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
     uint32_t f_ready = 0, te_ready = 0;  // early test results: next full barrier / this tile's accumulator stage
     uint32_t it4 = 0;                    // spec 4: running k-block counter (A slot / parity)
     const bool single_unit = p.block_n <= OUT_CHUNK;  // one epilogue unit per tile
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
+    const int num_kb_all = p.ntaps * p.kchunks;
+    for (int tile = blockIdx.x; tile < p.total_tiles && (dual || issuer == 0); tile += gridDim.x, ++ti) {
       const uint32_t a = ti & 1u, aph = (ti >> 1) & 1u;
-      if (p.spec == 4) {
+      if (dual && a != issuer) {  // the other issuer's tile: step over its ring stages
+        if ((KSPEC == 3)) {
+          for (int c = 0; c < p.kchunks; ++c) ring_advance(ring, p, HALO_STAGE, full0, empty0);
+        } else if (KSPEC == 0 && p.spec == 1) {
+          for (int g2 = 0; g2 < 3; ++g2) ring_advance(ring, p, sub_bytes * 3, full0, empty0);
+        } else if (KSPEC == 0 && p.spec == 2) {
+          for (int g2 = 0; g2 < 9; ++g2) ring_advance(ring, p, sub_bytes * 2, full0, empty0);
+        } else {
+          for (int kb = 0; kb < num_kb_all; ++kb) {
+            doff += dsub;
+            if (++sub == static_cast<uint32_t>(p.group)) {
+              sub = 0;
+              if (++s == static_cast<uint32_t>(p.stages)) { s = 0; ph ^= 1u; doff = 0; fb = full0; eb = empty0; }
+              else { fb += 8u; eb += 8u; }
+            }
+          }
+        }
+        continue;
+      }
+      if ((KSPEC == 4)) {
         mbar_wait(tempty0 + 16u * a + 8u, aph ^ 1u);  // the single epilogue group (warps 6-9) is group 1
         tc_fence_after();
         const uint32_t tacc4 = tmem_base + a * static_cast<uint32_t>(p.block_n);
@@ -520,15 +557,16 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
       const uint32_t tacc = tmem_base + a * static_cast<uint32_t>(p.block_n);
       // the NEXT tile's accumulator stage / phase, tested early during this tile's last k-block
       const uint32_t te_bar = tempty0 + 16u * (a ^ 1u), te_par = (((ti + 1u) >> 1) & 1u) ^ 1u;
-      if (p.spec == 3) {
-        if (ti == 0) mbar_wait(wbar, 0);
+      if ((KSPEC == 3)) {
+        if (ti < 2) mbar_wait(wbar, 0);  // (each issuer before its first tile; completes once, parity 0)
         const uint32_t dkb = b_bytes >> 4;   // descriptor units per weight tile
         uint64_t bdesc = make_sdesc(wres0);  // weights are laid out [chunk][tap]: a running descriptor
         for (int c = p.Cin; c > 0; c -= BLOCK_K) {  // c = channels left
           if (!f_ready) mbar_wait(ring.fb, ring.ph);
           tc_fence_after();
           const uint64_t hdesc = make_sdesc_sbo(smem_base + ring.off, HALO_W * 128);
-          const int reps = p.ntaps / 9;  // 1, or 2 with hi/lo-split weights (the nine offsets twice)
+          constexpr int reps = REPS;  // 1, or 2 with hi/lo-split weights (the nine offsets twice)
+#pragma unroll
           for (int rep = 0; rep < reps; ++rep) {
             const bool last_rep = rep + 1 == reps;
             if (elect_one()) {
@@ -545,7 +583,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
               }
             }
             __syncwarp();
-            if (last_rep) {
+            if (last_rep && !dual) {
               // most of this chunk's MMAs are queued: test what the next chunk / tile will wait for
               f_ready = ring_test_next_full(ring, p, full0);
               if (c <= BLOCK_K)
@@ -575,8 +613,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
         }
         continue;
       }
-      if (p.spec == 1) { mma_tile<9, 1, 3>(p, ring, desc0, sub_bytes, full0, empty0, tacc, idesc, tfull0 + 8u * a, tr_i, tile); f_ready = te_ready = 0u; continue; }
-      if (p.spec == 2) { mma_tile<9, 2, 2>(p, ring, desc0, sub_bytes, full0, empty0, tacc, idesc, tfull0 + 8u * a, tr_i, tile); f_ready = te_ready = 0u; continue; }
+      if (KSPEC == 0 && p.spec == 1) { mma_tile<9, 1, 3>(p, ring, desc0, sub_bytes, full0, empty0, tacc, idesc, tfull0 + 8u * a, tr_i, tile); f_ready = te_ready = 0u; continue; }
+      if (KSPEC == 0 && p.spec == 2) { mma_tile<9, 2, 2>(p, ring, desc0, sub_bytes, full0, empty0, tacc, idesc, tfull0 + 8u * a, tr_i, tile); f_ready = te_ready = 0u; continue; }
       uint32_t accum = 0;
       for (int tap = 0; tap < p.ntaps; ++tap) {
         for (int c = p.Cin; c > 0; c -= BLOCK_K) {  // c = channels left in this tap
@@ -607,7 +645,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
       if (elect_one()) tc_commit(tfull0 + 8u * a);  // accumulator complete
       __syncwarp();
     }
-  } else if (p.spec == 4 && warp < 6) {
+  } else if ((KSPEC == 4) && warp < 6) {
     // ---------------- depthwise warps 2..5 (spec 4): A tile of the pointwise GEMM = depthwise 3x3 of the halo box.
     // thread = (4-channel group g4 of the 64-channel chunk, 4x4 output patch of the 8 x 16 tile): a 6x6 window of
     // 8-byte vectors in registers serves 16 outputs (2.25 shared-memory loads per output instead of 9 -- the
@@ -692,11 +730,11 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
     // units (group = unit parity), with one group (spec 4) warps 6..9 take them all.
     const int q = warp & 3;            // TMEM lane quadrant this warp may access
     const int half = (warp - 2) >> 2;  // epilogue group of this warp: 0 / 1
-    const int ew = warp - (p.spec == 4 ? 6 : 2);  // 0 .. (epilogue warps)-1: staging / residual tile, residual barrier
+    const int ew = warp - ((KSPEC == 4) ? 6 : 2);  // 0 .. (epilogue warps)-1: staging / residual tile, residual barrier
     const int r = q * 32 + lane;       // tile row = TMEM lane
-    const int ustep = p.spec == 4 ? 1 : 2;                       // number of epilogue groups = unit stride
-    const int et = threadIdx.x - (p.spec == 4 ? 192 : 64);       // 0 .. 32 * (epilogue warps) - 1
-    const int n_epi = p.spec == 4 ? 128 : 32 * EPI_WARPS;        // epilogue threads
+    const int ustep = (KSPEC == 4) ? 1 : 2;                       // number of epilogue groups = unit stride
+    const int et = threadIdx.x - ((KSPEC == 4) ? 192 : 64);       // 0 .. 32 * (epilogue warps) - 1
+    const int n_epi = (KSPEC == 4) ? 128 : 32 * EPI_WARPS;        // epilogue threads
     // the quadrant's 32 rows as a (bw x qbh x qbn) sub-box of the tile box, starting at row qh of image qn
     const int hrows = 32 / p.bw, hq = q * hrows;
     const int qh = hq % p.bh, qn = hq / p.bh;
@@ -714,6 +752,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
     float* sbias = reinterpret_cast<float*>(gen_base + (bias0 - smem_base));
     for (int i = et; i < p.n_tiles * p.block_n; i += n_epi) sbias[i] = i < p.Cout ? __ldg(p.bias + i) : 0.0f;
     asm volatile("bar.sync 1, %0;" ::"r"(n_epi) : "memory");
+    pdl_wait();  // residual loads and output stores touch activations
     // residual tile of unit (tile, ci): 32 rows x 64 channels by TMA into this warp's buffer
     auto issue_res = [&](int tile, int ci) {
       int nt, tw, th, tn;
@@ -775,7 +814,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
 #pragma unroll
         for (int k = 0; k < 8; ++k) bb[k] = bch[k];
         tmem_ld_wait();
-        if (et == 0 && p.spec != 4) trace_ev(p, 3, tr_j, tile, 2);
+        if (et == 0 && (KSPEC != 4)) trace_ev(p, 3, tr_j, tile, 2);
         if (ci == last) {  // the accumulator now lives in registers: hand the TMEM stage back to the MMA warp
           tc_fence_before();
           __syncwarp();
@@ -834,12 +873,13 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
           tma_store_4d(&maps.y, stg, n_base + c0, tw * p.bw, th * p.bh + qh, tn * p.bn + qn);
           tma_store_commit();
         }
-        if (et == 0 && p.spec != 4) trace_ev(p, 3, tr_j, tile, 5);
+        if (et == 0 && (KSPEC != 4)) trace_ev(p, 3, tr_j, tile, 5);
       }
-      if (et == 0 && p.spec != 4) trace_ev(p, 3, tr_j, tile, 0);
+      if (et == 0 && (KSPEC != 4)) trace_ev(p, 3, tr_j, tile, 0);
     }
     if (lane == 0) tma_store_wait_all();
   }
+  if (p.dbg & 4) __nanosleep(5000);
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -987,6 +1027,22 @@ inline int prepare(Launch* L, const TView& x, const TView& y, const TView* res, 
     L->smem_bytes = p.stages * stage_bytes + fixed;
   }
   BD_CHECK(L->smem_bytes <= 227 * 1024, "umma conv smem budget exceeded");
+  {
+    // Two MMA issuers when a whole tile fits into the shared-memory ring (BD_UMMA_ISSUERS=1 turns it off for A/B
+    // measurements; the fused separable path has one).  An issuer that has finished its tile steps over the other
+    // issuer's ring stages and waits on a full barrier that far ahead; mbarrier parity waits are only sound at most
+    // one phase ahead of the barrier: the stage `stages` before the awaited one must already have landed, which is
+    // guaranteed (it belongs to the tile this issuer has just consumed) iff a tile spans fewer than `stages` stages.
+    // These are exactly the short-K tiles that lose the most to per-tile bookkeeping.
+    static const int env_dbg = [] { const char* e = getenv("BD_UMMA_DBG"); return e ? atoi(e) : 0; }();
+    p.dbg = env_dbg;
+    static const int env_issuers = [] { const char* e = getenv("BD_UMMA_ISSUERS"); return e ? atoi(e) : 2; }();
+    const int stages_per_tile = p.spec == 3 ? p.kchunks : num_kb / p.group;
+    // Only on the halo path: there one elected lane issues a whole tile (36 MMAs + both commits) in one go.  On the
+    // grouped generic ring (several elect blocks per stage) two issuers showed an intermittent hang on B200 that
+    // is not understood yet, so those layers keep the single issuer.
+    p.issuers = (p.spec != 3 || env_issuers != 2 || stages_per_tile >= p.stages) ? 1 : 2;
+  }
 
   // parity views of the input for stride 2 (a single plain view for stride 1)
   bool used[4] = {false, false, false, false};
@@ -1062,10 +1118,16 @@ inline int prepare(Launch* L, const TView& x, const TView& y, const TView* res, 
 inline int launch(const Launch& L, cudaStream_t stream, bool pdl = false) {
   static bool attr_set = false;
   if (!attr_set) {
-    BD_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    BD_CUDA(cudaFuncSetAttribute(conv_umma_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    BD_CUDA(cudaFuncSetAttribute(conv_umma_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    BD_CUDA(cudaFuncSetAttribute(conv_umma_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    BD_CUDA(cudaFuncSetAttribute(conv_umma_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  BD_CUDA(launch_k(pdl, conv_umma_kernel, L.grid, dim3(THREADS), static_cast<size_t>(L.smem_bytes), stream, L.maps, L.p));
+  void (*kern)(Maps, Params) = conv_umma_kernel<0, 1>;
+  if (L.p.spec == 3) kern = L.p.ntaps == 18 ? conv_umma_kernel<3, 2> : conv_umma_kernel<3, 1>;
+  else if (L.p.spec == 4) kern = conv_umma_kernel<4, 1>;
+  BD_CUDA(launch_k(pdl, kern, L.grid, dim3(THREADS), static_cast<size_t>(L.smem_bytes), stream, L.maps, L.p));
   return 0;
 }
 
