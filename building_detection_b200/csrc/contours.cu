@@ -16,6 +16,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "ccl.cuh"
@@ -320,7 +322,7 @@ static int grid_for(size_t n, int sms) {
 
 // trace every component of `img` whose root passes the area threshold
 static int trace_set(bd_ctx* ctx, const uint8_t* img, const int* L, const long long* a2, long long thr2, int strict, int H,
-                     int W, cudaStream_t s, HostSet* out, int slot0) {
+                     int W, cudaStream_t s, HostSet* out, int slot0, int* n_launch) {
   const size_t n = static_cast<size_t>(H) * W;
   post::DevPool& pool = ctx->pool;
   int* d_count = nullptr;
@@ -330,7 +332,7 @@ static int trace_set(bd_ctx* ctx, const uint8_t* img, const int* L, const long l
   int* d_list = nullptr;
   if (pool.get(slot0 + 1, sizeof(int) * cap, reinterpret_cast<void**>(&d_list))) return 1;
   collect_roots<<<grid_for(n, ctx->num_sms), TPB, 0, s>>>(L, a2, thr2, strict, n, d_list, d_count, cap);
-  ctx->launches++;
+  ++*n_launch;
   int cnt = 0;
   BD_CUDA(cudaMemcpyAsync(&cnt, d_count, sizeof(int), cudaMemcpyDeviceToHost, s));
   BD_CUDA(cudaStreamSynchronize(s));
@@ -347,7 +349,7 @@ static int trace_set(bd_ctx* ctx, const uint8_t* img, const int* L, const long l
   if (pool.get(slot0 + 2, sizeof(int) * cnt, reinterpret_cast<void**>(&d_npts))) return 1;
   if (pool.get(slot0 + 3, sizeof(int) * 4 * cnt, reinterpret_cast<void**>(&d_bbox))) return 1;
   trace_count<<<(cnt + 63) / 64, 64, 0, s>>>(img, H, W, d_list, cnt, d_npts, d_bbox);
-  ctx->launches++;
+  ++*n_launch;
   std::vector<int> npts(cnt);
   BD_CUDA(cudaMemcpyAsync(npts.data(), d_npts, sizeof(int) * cnt, cudaMemcpyDeviceToHost, s));
   BD_CUDA(cudaMemcpyAsync(out->bbox.data(), d_bbox, sizeof(int) * 4 * cnt, cudaMemcpyDeviceToHost, s));
@@ -360,7 +362,7 @@ static int trace_set(bd_ctx* ctx, const uint8_t* img, const int* L, const long l
   if (pool.get(slot0 + 5, sizeof(int2) * std::max<long long>(total, 1), reinterpret_cast<void**>(&d_pts))) return 1;
   BD_CUDA(cudaMemcpyAsync(d_off, out->off.data(), sizeof(long long) * (cnt + 1), cudaMemcpyHostToDevice, s));
   trace_write<<<(cnt + 63) / 64, 64, 0, s>>>(img, H, W, d_list, cnt, d_off, d_pts);
-  ctx->launches++;
+  ++*n_launch;
   out->pts.resize(total);
   BD_CUDA(cudaMemcpyAsync(out->pts.data(), d_pts, sizeof(int2) * total, cudaMemcpyDeviceToHost, s));
   BD_CUDA(cudaStreamSynchronize(s));
@@ -472,12 +474,40 @@ int bd_contours(bd_ctx* ctx, const uint8_t* mask_dev, int h, int w, bd_polys* ou
   BD_CUDA(cudaGetLastError());
   lap("fill/label/area/erode passes");
 
+  // The three contour sets are traced concurrently, each on its own stream from its own host thread: border
+  // following is one thread per component, so a scene-sized component (random-init masks fuse into one) leaves
+  // the GPU empty while it is walked -- three walks at once cost the time of the longest.
   HostSet ini, td, rl;
-  if (trace_set(ctx, ws->keep, ws->L, ws->a2, 2 * 100, 0, h, w, s, &ini, 0)) return 1;
-  lap("trace initial contours");
-  if (trace_set(ctx, er_h, ws->Lh, ws->a2h, 2 * 50, 1, h, w, s, &td, 8)) return 1;
-  if (trace_set(ctx, er_v, ws->Lv, ws->a2v, 2 * 50, 1, h, w, s, &rl, 16)) return 1;
-  lap("trace eroded contours");
+  {
+    static thread_local cudaStream_t aux[2] = {nullptr, nullptr};
+    static thread_local cudaEvent_t ready = nullptr;
+    if (!aux[0]) {
+      BD_CUDA(cudaStreamCreateWithFlags(&aux[0], cudaStreamNonBlocking));
+      BD_CUDA(cudaStreamCreateWithFlags(&aux[1], cudaStreamNonBlocking));
+      BD_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    }
+    BD_CUDA(cudaEventRecord(ready, s));
+    BD_CUDA(cudaStreamWaitEvent(aux[0], ready, 0));
+    BD_CUDA(cudaStreamWaitEvent(aux[1], ready, 0));
+    int rc[3] = {0, 0, 0}, nl[3] = {0, 0, 0};
+    std::string err[3];
+    const int device = ctx->device;
+    auto job = [&](int k, const uint8_t* img, const int* L, const long long* a2, long long thr2, int strict,
+                   cudaStream_t st, HostSet* out_set, int slot0) {
+      if (cudaSetDevice(device) != cudaSuccess) { rc[k] = 1; err[k] = "cudaSetDevice failed in a contour worker"; return; }
+      rc[k] = trace_set(ctx, img, L, a2, thr2, strict, h, w, st, out_set, slot0, &nl[k]);
+      if (rc[k]) err[k] = bd::last_error();  // thread-local message of the worker
+    };
+    std::thread t1(job, 1, er_h, ws->Lh, ws->a2h, 2LL * 50, 1, aux[0], &td, 8);
+    std::thread t2(job, 2, er_v, ws->Lv, ws->a2v, 2LL * 50, 1, aux[1], &rl, 16);
+    job(0, ws->keep, ws->L, ws->a2, 2LL * 100, 0, s, &ini, 0);
+    t1.join();
+    t2.join();
+    ctx->launches += nl[0] + nl[1] + nl[2];
+    for (int k = 0; k < 3; ++k)
+      if (rc[k]) return bd::fail(err[k]);
+  }
+  lap("trace initial + eroded contours (three streams)");
 
   // detction_overlap_building (:159-262): final list of (set, index); set < 0 marks None
   struct Ref { const HostSet* set; int idx; };
