@@ -61,6 +61,7 @@ struct Params {
   int tiles_w, tiles_h, tiles_n, n_tiles, total_tiles;
   int block_n, kchunks, ntaps, stages, group, tmem_cols;  // group: k-blocks per shared-memory stage
   int dbg;      // debug switches (BD_UMMA_DBG): 1 = every thread waits for the previous grid before the role split, 2 = no early launch_dependents
+  int halo_subset;  // spec 3 with a runtime tap list (kernel instance <3, 0>)
   int issuers;  // MMA-issuing warps: 2 = warp 1 takes the even tiles of a CTA, warp MMA2_WARP the odd ones
   int spec;  // 0 generic loops; 1 = 9 taps x 1 chunk, group 3; 2 = 9 taps x 2 chunks, group 2 (fully unrolled loops);
              // 3 = halo path: 3x3 stride 1, one halo box per chunk, weights resident in shared memory;
@@ -565,7 +566,27 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
           if (!f_ready) mbar_wait(ring.fb, ring.ph);
           tc_fence_after();
           const uint64_t hdesc = make_sdesc_sbo(smem_base + ring.off, HALO_W * 128);
-          constexpr int reps = REPS;  // 1, or 2 with hi/lo-split weights (the nine offsets twice)
+          if (REPS == 0) {
+            // tap subset (sub-pixel phases of up-sample+conv / transposed convolutions: 2 or 4 taps of the 3x3
+            // window, any order): runtime tap list, halo offset of tap t from its (dy, dx)
+            if (elect_one()) {
+              trace_ev(p, 1, tr_i, tile, c);
+              for (int t = 0; t < p.ntaps; ++t) {
+                const uint64_t adesc = hdesc + static_cast<uint32_t>(((p.tap_dy[t] + 1) * HALO_W + p.tap_dx[t] + 1) * 8);
+                const uint64_t bd = bdesc + static_cast<uint32_t>(t) * dkb;
+                tc_mma_f16(tacc, adesc, bd, idesc, (t > 0 || c < p.Cin) ? 1u : 0u);
+                if (c > 16) tc_mma_f16(tacc, adesc + 2u, bd + 2u, idesc, 1u);
+                if (c > 32) tc_mma_f16(tacc, adesc + 4u, bd + 4u, idesc, 1u);
+                if (c > 48) tc_mma_f16(tacc, adesc + 6u, bd + 6u, idesc, 1u);
+              }
+              tc_commit(ring.eb);
+              if (c <= BLOCK_K) tc_commit(tfull0 + 8u * a);
+              trace_ev(p, 1, tr_i, tile, -1);
+            }
+            __syncwarp();
+            bdesc += static_cast<uint32_t>(p.ntaps) * dkb;
+          }
+          constexpr int reps = REPS;  // 1, or 2 with hi/lo-split weights (the nine offsets twice); 0: tap subset above
 #pragma unroll
           for (int rep = 0; rep < reps; ++rep) {
             const bool last_rep = rep + 1 == reps;
@@ -956,10 +977,16 @@ inline int prepare(Launch* L, const TView& x, const TView& y, const TView* res, 
   p.bh = std::min(BLOCK_M / p.bw, floor_pow2(Ho));
   p.bn = BLOCK_M / (p.bw * p.bh);
   // halo path candidate: plain 3x3, stride 1, dilation 1 ('same' padding), map at least 8 x 16
-  // (18 taps: a hi/lo weight split, the 3x3 offsets twice)
-  bool halo = group_hint == 0 && (ntaps == 9 || ntaps == 18) && stride == 1 && out_scale == 1 && Wo >= 8 && Ho >= 16 &&
-              Wo == x.W && Ho == x.H;
-  for (int t = 0; t < ntaps && halo; ++t) halo = dy[t] == (t % 9) / 3 - 1 && dx[t] == (t % 9) % 3 - 1;
+  // (18 taps: a hi/lo weight split, the 3x3 offsets twice; 2..8 taps: any subset of the 3x3 window, e.g. the
+  // sub-pixel phases of up-sample+conv heads and 3x3 transposed convolutions)
+  bool full3x3 = (ntaps == 9 || ntaps == 18);
+  for (int t = 0; t < ntaps && full3x3; ++t) full3x3 = dy[t] == (t % 9) / 3 - 1 && dx[t] == (t % 9) % 3 - 1;
+  static const bool subset_on = [] { const char* e = getenv("BD_HALO_SUBSET"); return !(e && e[0] == '0'); }();
+  bool subset = subset_on && !full3x3 && ntaps >= 2 && ntaps <= 9;
+  for (int t = 0; t < ntaps && subset; ++t) subset = dy[t] >= -1 && dy[t] <= 1 && dx[t] >= -1 && dx[t] <= 1;
+  const bool halo = group_hint == 0 && (full3x3 || subset) && stride == 1 && (out_scale == 1 || subset) && Wo >= 8 &&
+                    Ho >= 16 && Wo == x.W && Ho == x.H;
+  p.halo_subset = subset ? 1 : 0;
   p.tiles_w = cdiv(Wo, p.bw); p.tiles_h = cdiv(Ho, p.bh); p.tiles_n = cdiv(x.N, p.bn);
   const int cout16 = cdiv(Cout, 16) * 16;
   if (cout16 <= max_block_n) {
@@ -1041,7 +1068,11 @@ inline int prepare(Launch* L, const TView& x, const TView& y, const TView* res, 
     // Only on the halo path: there one elected lane issues a whole tile (36 MMAs + both commits) in one go.  On the
     // grouped generic ring (several elect blocks per stage) two issuers showed an intermittent hang on B200 that
     // is not understood yet, so those layers keep the single issuer.
-    p.issuers = (p.spec != 3 || env_issuers != 2 || stages_per_tile >= p.stages) ? 1 : 2;
+    // ... and there only for the configuration that has been stress-tested: the full 3x3 with one 64-channel chunk
+    // per tile (the 64->64 and 32->32 layers, which are the ones that gain).  With the tap-subset variant (two
+    // chunks per tile) the two-issuer scheme faulted under tools/stress.py; single-issuer it is clean.
+    p.issuers = (p.spec != 3 || p.halo_subset || p.kchunks != 1 || ntaps != 9 || env_issuers != 2 ||
+                 stages_per_tile >= p.stages) ? 1 : 2;
   }
 
   // parity views of the input for stride 2 (a single plain view for stride 1)
@@ -1121,11 +1152,12 @@ inline int launch(const Launch& L, cudaStream_t stream, bool pdl = false) {
     BD_CUDA(cudaFuncSetAttribute(conv_umma_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     BD_CUDA(cudaFuncSetAttribute(conv_umma_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     BD_CUDA(cudaFuncSetAttribute(conv_umma_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    BD_CUDA(cudaFuncSetAttribute(conv_umma_kernel<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     BD_CUDA(cudaFuncSetAttribute(conv_umma_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   void (*kern)(Maps, Params) = conv_umma_kernel<0, 1>;
-  if (L.p.spec == 3) kern = L.p.ntaps == 18 ? conv_umma_kernel<3, 2> : conv_umma_kernel<3, 1>;
+  if (L.p.spec == 3) kern = L.p.halo_subset ? conv_umma_kernel<3, 0> : L.p.ntaps == 18 ? conv_umma_kernel<3, 2> : conv_umma_kernel<3, 1>;
   else if (L.p.spec == 4) kern = conv_umma_kernel<4, 1>;
   BD_CUDA(launch_k(pdl, kern, L.grid, dim3(THREADS), static_cast<size_t>(L.smem_bytes), stream, L.maps, L.p));
   return 0;
