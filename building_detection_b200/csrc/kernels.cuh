@@ -386,12 +386,17 @@ __global__ void __launch_bounds__(TPB) gate_scse_kernel(const __grid_constant__ 
     const size_t pix = base + lane / lanes_per_pix;
     const bool ok = pix < npix;
     float dot = 0.0f;
+    float x0[8];  // the lane's first vector stays in registers (the only one for C <= 256)
     if (ok) {
       for (int g = sub; g < cg; g += lanes_per_pix) {
         float xv[8];
         ld8(p.x, pix, g * 8, xv);
 #pragma unroll
         for (int j = 0; j < 8; ++j) dot = fmaf(xv[j], p.w[g * 8 + j], dot);
+        if (g == sub) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) x0[j] = xv[j];
+        }
       }
     }
     for (int o = lanes_per_pix >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
@@ -400,7 +405,12 @@ __global__ void __launch_bounds__(TPB) gate_scse_kernel(const __grid_constant__ 
       const int n = static_cast<int>(pix / HW);
       for (int g = sub; g < cg; g += lanes_per_pix) {
         float xv[8];
-        ld8(p.x, pix, g * 8, xv);
+        if (g == sub) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) xv[j] = x0[j];
+        } else {
+          ld8(p.x, pix, g * 8, xv);
+        }
         const float* vv = p.v + static_cast<size_t>(n) * C + g * 8;
 #pragma unroll
         for (int j = 0; j < 8; ++j) xv[j] = xv[j] * sp + xv[j] * vv[j];
