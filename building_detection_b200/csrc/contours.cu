@@ -60,8 +60,11 @@ __device__ __forceinline__ unsigned neighbour_mask(const uint8_t* __restrict__ i
   return (e ? 1u : 0u) | (ne ? 2u : 0u) | (n ? 4u : 0u) | (nw ? 8u : 0u) | (w ? 16u : 0u) | (sw ? 32u : 0u) |
          (s ? 64u : 0u) | (se ? 128u : 0u);
 }
+// cap: points that may be written (WRITE only); a longer contour keeps counting without writing (the caller
+// detects n > cap and falls back to the two-pass scheme)
 template <bool WRITE>
-__device__ int trace_one(const uint8_t* __restrict__ img, int H, int W, int root, int2* out, int* bb) {
+__device__ int trace_one(const uint8_t* __restrict__ img, int H, int W, int root, int2* out, int* bb,
+                         long long cap = (1ll << 62)) {
   const int x0 = root % W, y0 = root / W;
   int minx = x0, maxx = x0, miny = y0, maxy = y0;
   // first neighbour clockwise from west (directions 3, 2, 1, 0, 7, 6, 5): the pixel the trace returns from
@@ -74,7 +77,7 @@ __device__ int trace_one(const uint8_t* __restrict__ img, int H, int W, int root
   }
   int n = 0;
   if (s < 0) {
-    if (WRITE) out[0] = make_int2(x0, y0);
+    if (WRITE && cap > 0) out[0] = make_int2(x0, y0);
     n = 1;
   } else {
     const int x1 = x0 + c_dx[s], y1 = y0 + c_dy[s];
@@ -86,7 +89,7 @@ __device__ int trace_one(const uint8_t* __restrict__ img, int H, int W, int root
       const unsigned rot = ((m >> ((s + 1) & 7)) | (m << (8 - ((s + 1) & 7)))) & 0xFFu;
       s = (s + __ffs(rot)) & 7;  // rot != 0: the pixel we came from is set
       const int x4 = x3 + c_dx[s], y4 = y3 + c_dy[s];
-      if (WRITE) out[n] = make_int2(x3, y3);
+      if (WRITE && n < cap) out[n] = make_int2(x3, y3);
       ++n;
       minx = min(minx, x3); maxx = max(maxx, x3); miny = min(miny, y3); maxy = max(maxy, y3);
       if (x4 == x0 && y4 == y0 && x3 == x1 && y3 == y1) break;
@@ -104,7 +107,7 @@ __device__ int trace_one(const uint8_t* __restrict__ img, int H, int W, int root
       m = neighbour_mask(img, H, W, x3, y3);
     }
   }
-  if (!WRITE) { bb[0] = minx; bb[1] = miny; bb[2] = maxx + 1; bb[3] = maxy + 1; }  // x, y, x+w, y+h of cv::boundingRect
+  if (bb) { bb[0] = minx; bb[1] = miny; bb[2] = maxx + 1; bb[3] = maxy + 1; }  // x, y, x+w, y+h of cv::boundingRect
   return n;
 }
 static __global__ void trace_count(const uint8_t* __restrict__ img, int H, int W, const int* __restrict__ roots, int n,
@@ -116,6 +119,53 @@ static __global__ void trace_write(const uint8_t* __restrict__ img, int H, int W
                             const long long* __restrict__ off, int2* __restrict__ pts) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) trace_one<true>(img, H, W, roots[i], pts + off[i], nullptr);
+}
+
+// ---- one-walk tracing.  The number of contour points of a component is bounded by its number of boundary cracks
+// (pixel edges between the component and background or the frame: every move of the border follower passes at
+// least one of them), and the cracks can be counted in parallel.  With bound-sized slots a single walk writes the
+// points and counts them; a parallel copy then packs the contours.  Halves the serial walk of a scene-sized
+// component, which is what bounds the contour stage.
+static __global__ void __launch_bounds__(TPB) crack_count(const uint8_t* __restrict__ img, const int* __restrict__ L, int H,
+                                                   int W, int* __restrict__ cracks /* per root pixel, zeroed */) {
+  const size_t n = static_cast<size_t>(H) * W;
+  const size_t step = static_cast<size_t>(gridDim.x) * TPB;
+  for (size_t base = blockIdx.x * static_cast<size_t>(TPB); base < n; base += step) {  // whole warps stay converged
+    const size_t i = base + threadIdx.x;
+    int root = -1, c = 0;
+    if (i < n && img[i]) {
+      const int x = static_cast<int>(i % W), y = static_cast<int>(i / W);
+      c = (x == 0 || !img[i - 1]) + (x + 1 == W || !img[i + 1]) + (y == 0 || !img[i - W]) + (y + 1 == H || !img[i + W]);
+      if (c) root = L[i];
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, root);
+    const int sum = __reduce_add_sync(peers, c);
+    if (root >= 0 && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(cracks + root, sum);
+  }
+}
+static __global__ void gather_bounds(const int* __restrict__ cracks, const int* __restrict__ roots, int n,
+                                     int* __restrict__ bound) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) bound[i] = max(cracks[roots[i]], 1);
+}
+static __global__ void trace_both(const uint8_t* __restrict__ img, int H, int W, const int* __restrict__ roots, int n,
+                                  const long long* __restrict__ off_bound, int2* __restrict__ tmp, int* __restrict__ npts,
+                                  int* __restrict__ bbox, int* __restrict__ overflow) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long cap = off_bound[i + 1] - off_bound[i];
+  const int m = trace_one<true>(img, H, W, roots[i], tmp + off_bound[i], bbox + 4 * i, cap);
+  npts[i] = m;
+  if (m > cap) atomicExch(overflow, 1);
+}
+// pack: contour i occupies tmp[off_bound[i] ...) and goes to pts[off[i] ...); one block per contour
+static __global__ void __launch_bounds__(TPB) pack_points(const int2* __restrict__ tmp, const long long* __restrict__ off_bound,
+                                                   const long long* __restrict__ off, int2* __restrict__ pts) {
+  const int i = blockIdx.x;
+  const long long m = off[i + 1] - off[i];
+  const int2* src = tmp + off_bound[i];
+  int2* dst = pts + off[i];
+  for (long long k = threadIdx.x; k < m; k += TPB) dst[k] = src[k];
 }
 
 // edge_3.py:26-47 for every initial box against all eroded boxes: index of the first maximum IoU if any IoU
@@ -348,6 +398,53 @@ static int trace_set(bd_ctx* ctx, const uint8_t* img, const int* L, const long l
   int *d_npts = nullptr, *d_bbox = nullptr;
   if (pool.get(slot0 + 2, sizeof(int) * cnt, reinterpret_cast<void**>(&d_npts))) return 1;
   if (pool.get(slot0 + 3, sizeof(int) * 4 * cnt, reinterpret_cast<void**>(&d_bbox))) return 1;
+  static const bool one_walk = [] { const char* e = getenv("BD_CONTOUR_ONE_WALK"); return e && e[0] == '1'; }();  // off until validated on the GPU
+  if (one_walk) {
+    // crack bound per component -> slots -> a single walk that writes and counts -> parallel pack
+    int *d_cracks = nullptr, *d_bound = nullptr, *d_ovf = nullptr;
+    if (pool.get(slot0 + 6, sizeof(int) * n, reinterpret_cast<void**>(&d_cracks))) return 1;
+    if (pool.get(slot0 + 7, sizeof(int) * (cnt + 1), reinterpret_cast<void**>(&d_bound))) return 1;
+    d_ovf = d_bound + cnt;
+    BD_CUDA(cudaMemsetAsync(d_cracks, 0, sizeof(int) * n, s));
+    BD_CUDA(cudaMemsetAsync(d_ovf, 0, sizeof(int), s));
+    crack_count<<<grid_for(n, ctx->num_sms), TPB, 0, s>>>(img, L, H, W, d_cracks);
+    gather_bounds<<<(cnt + 255) / 256, 256, 0, s>>>(d_cracks, d_list, cnt, d_bound);
+    *n_launch += 2;
+    std::vector<int> bound(cnt + 1);
+    BD_CUDA(cudaMemcpyAsync(bound.data(), d_bound, sizeof(int) * cnt, cudaMemcpyDeviceToHost, s));
+    BD_CUDA(cudaStreamSynchronize(s));
+    std::vector<long long> off_bound(cnt + 1, 0);
+    for (int i = 0; i < cnt; ++i) off_bound[i + 1] = off_bound[i] + bound[i];
+    long long *d_offb = nullptr, *d_off = nullptr;
+    int2 *d_tmp = nullptr, *d_pts = nullptr;
+    // slot0+4 holds both offset arrays, slot0+5 the slots followed by the packed points
+    if (pool.get(slot0 + 4, sizeof(long long) * 2 * (cnt + 1), reinterpret_cast<void**>(&d_offb))) return 1;
+    d_off = d_offb + (cnt + 1);
+    if (pool.get(slot0 + 5, sizeof(int2) * 2 * std::max<long long>(off_bound[cnt], 1), reinterpret_cast<void**>(&d_tmp))) return 1;
+    d_pts = d_tmp + off_bound[cnt];
+    BD_CUDA(cudaMemcpyAsync(d_offb, off_bound.data(), sizeof(long long) * (cnt + 1), cudaMemcpyHostToDevice, s));
+    trace_both<<<(cnt + 63) / 64, 64, 0, s>>>(img, H, W, d_list, cnt, d_offb, d_tmp, d_npts, d_bbox, d_ovf);
+    ++*n_launch;
+    std::vector<int> npts1(cnt);
+    int ovf = 0;
+    BD_CUDA(cudaMemcpyAsync(npts1.data(), d_npts, sizeof(int) * cnt, cudaMemcpyDeviceToHost, s));
+    BD_CUDA(cudaMemcpyAsync(out->bbox.data(), d_bbox, sizeof(int) * 4 * cnt, cudaMemcpyDeviceToHost, s));
+    BD_CUDA(cudaMemcpyAsync(&ovf, d_ovf, sizeof(int), cudaMemcpyDeviceToHost, s));
+    BD_CUDA(cudaStreamSynchronize(s));
+    if (!ovf) {
+      for (int i = 0; i < cnt; ++i) out->off[i + 1] = out->off[i] + npts1[i];
+      const long long total1 = out->off[cnt];
+      BD_CUDA(cudaMemcpyAsync(d_off, out->off.data(), sizeof(long long) * (cnt + 1), cudaMemcpyHostToDevice, s));
+      pack_points<<<cnt, TPB, 0, s>>>(d_tmp, d_offb, d_off, d_pts);
+      ++*n_launch;
+      out->pts.resize(total1);
+      BD_CUDA(cudaMemcpyAsync(out->pts.data(), d_pts, sizeof(int2) * total1, cudaMemcpyDeviceToHost, s));
+      BD_CUDA(cudaStreamSynchronize(s));
+      out->d_bbox = d_bbox;
+      return 0;
+    }
+    // a contour longer than its crack bound (not expected): the two-pass scheme below is always right
+  }
   trace_count<<<(cnt + 63) / 64, 64, 0, s>>>(img, H, W, d_list, cnt, d_npts, d_bbox);
   ++*n_launch;
   std::vector<int> npts(cnt);

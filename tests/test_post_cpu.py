@@ -177,3 +177,28 @@ def test_device_algorithm_twins_match_cv2():
             assert np.array_equal(np.array(trace_twin(filled, x0, y0)).reshape(-1, 1, 2), c)
             n += 1
     assert n > 500
+
+
+def test_contour_length_is_bounded_by_boundary_cracks():
+    """The one-walk tracer of csrc/contours.cu sizes every contour's slot by the component's number of boundary
+    cracks (pixel edges towards background or the frame); cv2's CHAIN_APPROX_NONE external contour must never be
+    longer than that (holes only add cracks)."""
+    import cv2
+    rng = np.random.default_rng(0)
+    worst = 0.0
+    for trial in range(120):
+        H, W = rng.integers(8, 64, 2)
+        m = (rng.random((H, W)) < rng.choice([0.3, 0.5, 0.6, 0.7, 0.9])).astype(np.uint8)
+        if trial % 3 == 0:
+            m = cv2.dilate(m, np.ones((3, 3), np.uint8))
+        n, lab = cv2.connectedComponents(m, connectivity=8)
+        for k in range(1, n):
+            comp = (lab == k).astype(np.uint8)
+            cs, _ = cv2.findContours(comp, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_NONE)
+            pad = np.pad(comp, 1)
+            c = pad[1:-1, 1:-1] == 1
+            cracks = int((c & (pad[1:-1, :-2] == 0)).sum() + (c & (pad[1:-1, 2:] == 0)).sum()
+                         + (c & (pad[:-2, 1:-1] == 0)).sum() + (c & (pad[2:, 1:-1] == 0)).sum())
+            assert len(cs) == 1 and len(cs[0]) <= cracks
+            worst = max(worst, len(cs[0]) / cracks)
+    assert worst > 0.9  # the bound is tight enough to be worth using

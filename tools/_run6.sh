@@ -1,3 +1,5 @@
 cd $GRAFT_REPO_ROOT
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --scene 5912 --steps 2 --warmup 2 > gpurun_out/bench_2gpu_r1d.json 2> gpurun_out/bench_2gpu_r1d.err
-tail -c 1200 gpurun_out/bench_2gpu_r1d.json; tail -3 gpurun_out/bench_2gpu_r1d.err
+timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29544 bench.py --gpus 4 --steps 2 --warmup 2 > gpurun_out/bench_4gpu_20k_r1e.json 2> gpurun_out/bench_4gpu_20k_r1e.err
+python -c "
+import json; d=json.loads(open('gpurun_out/bench_4gpu_20k_r1e.json').read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['stages'])"
+tail -2 gpurun_out/bench_4gpu_20k_r1e.err | cut -c1-300
