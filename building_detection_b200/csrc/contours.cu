@@ -398,7 +398,7 @@ static int trace_set(bd_ctx* ctx, const uint8_t* img, const int* L, const long l
   int *d_npts = nullptr, *d_bbox = nullptr;
   if (pool.get(slot0 + 2, sizeof(int) * cnt, reinterpret_cast<void**>(&d_npts))) return 1;
   if (pool.get(slot0 + 3, sizeof(int) * 4 * cnt, reinterpret_cast<void**>(&d_bbox))) return 1;
-  static const bool one_walk = [] { const char* e = getenv("BD_CONTOUR_ONE_WALK"); return e && e[0] == '1'; }();  // off until validated on the GPU
+  static const bool one_walk = [] { const char* e = getenv("BD_CONTOUR_ONE_WALK"); return !(e && e[0] == '0'); }();
   if (one_walk) {
     // crack bound per component -> slots -> a single walk that writes and counts -> parallel pack
     int *d_cracks = nullptr, *d_bound = nullptr, *d_ovf = nullptr;
