@@ -121,6 +121,9 @@ static __global__ void trace_write(const uint8_t* __restrict__ img, int H, int W
   if (i < n) trace_one<true>(img, H, W, roots[i], pts + off[i], nullptr);
 }
 
+constexpr int BIG_T = 128;     // trace_big: window edge (pixels); the walker stays in [1, BIG_T - 2]
+constexpr int BIG_MIN = 4096;  // crack bound from which a contour is walked by trace_big instead of trace_both
+
 // ---- one-walk tracing.  The number of contour points of a component is bounded by its number of boundary cracks
 // (pixel edges between the component and background or the frame: every move of the border follower passes at
 // least one of them), and the cracks can be counted in parallel.  With bound-sized slots a single walk writes the
@@ -154,10 +157,101 @@ static __global__ void trace_both(const uint8_t* __restrict__ img, int H, int W,
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const long long cap = off_bound[i + 1] - off_bound[i];
+  if (cap >= BIG_MIN) return;  // long contours: trace_big
   const int m = trace_one<true>(img, H, W, roots[i], tmp + off_bound[i], bbox + 4 * i, cap);
   npts[i] = m;
   if (m > cap) atomicExch(overflow, 1);
 }
+// Long contours: one block per contour.  A single walking thread pays a full memory latency per step (~425 ns
+// measured: 51 ms for 120 000 points), so the block keeps a BIG_T x BIG_T window of the image around the walker in
+// shared memory (all threads load it, thread 0 walks inside it at shared-memory latency and re-centres the window
+// when it reaches its rim).  Same stepping rule as trace_one, point for point.
+static __global__ void __launch_bounds__(128) trace_big(const uint8_t* __restrict__ img, int H, int W,
+                                                        const int* __restrict__ roots, const int* __restrict__ big, int nbig,
+                                                        const long long* __restrict__ off_bound, int2* __restrict__ tmp,
+                                                        int* __restrict__ npts, int* __restrict__ bbox, int* __restrict__ overflow) {
+  __shared__ uint8_t tile[BIG_T][BIG_T];
+  __shared__ int sh_cx, sh_cy, sh_done;
+  const int i = big[blockIdx.x];
+  const int root = roots[i];
+  const int x0 = root % W, y0 = root / W;
+  const long long cap = off_bound[i + 1] - off_bound[i];
+  int2* out = tmp + off_bound[i];
+  // walker state (thread 0)
+  int x1 = 0, y1 = 0, x3 = x0, y3 = y0, s = -1, n = 0, phase = 0;
+  int minx = x0, maxx = x0, miny = y0, maxy = y0;
+  long long steps = 0;
+  const long long limit = 8ll * H * W + 16;
+  if (threadIdx.x == 0) { sh_cx = x0; sh_cy = y0; sh_done = 0; }
+  __syncthreads();
+  while (true) {
+    const int ox = sh_cx - BIG_T / 2, oy = sh_cy - BIG_T / 2;  // window origin (may lie outside the image: zeros)
+    {  // 32 independent loads in flight per thread (a load -> store loop would pay one memory latency per row)
+      const int xx = ox + static_cast<int>(threadIdx.x);
+      const bool xok = xx >= 0 && xx < W;
+#pragma unroll 1
+      for (int r0 = 0; r0 < BIG_T; r0 += 32) {
+        uint8_t v[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          const int yy = oy + r0 + k;
+          v[k] = (xok && yy >= 0 && yy < H) ? __ldg(img + static_cast<size_t>(yy) * W + xx) : 0;
+        }
+#pragma unroll
+        for (int k = 0; k < 32; ++k) tile[r0 + k][threadIdx.x] = v[k];
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      auto tmask = [&](int x, int y) -> unsigned {
+        const int lx = x - ox, ly = y - oy;  // 1 .. BIG_T-2
+        return (tile[ly][lx + 1] ? 1u : 0u) | (tile[ly - 1][lx + 1] ? 2u : 0u) | (tile[ly - 1][lx] ? 4u : 0u) |
+               (tile[ly - 1][lx - 1] ? 8u : 0u) | (tile[ly][lx - 1] ? 16u : 0u) | (tile[ly + 1][lx - 1] ? 32u : 0u) |
+               (tile[ly + 1][lx] ? 64u : 0u) | (tile[ly + 1][lx + 1] ? 128u : 0u);
+      };
+      unsigned m = tmask(x3, y3);  // the window is centred on (x3, y3)
+      if (phase == 0) {
+        // first neighbour clockwise from west (directions 3, 2, 1, 0, 7, 6, 5): the pixel the trace returns from
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+          const int d = (3 - k) & 7;
+          if (s < 0 && (m >> d) & 1u) s = d;
+        }
+        if (s < 0) {
+          if (cap > 0) out[0] = make_int2(x0, y0);
+          n = 1;
+          phase = 2;
+        } else {
+          x1 = x0 + c_dx[s]; y1 = y0 + c_dy[s];
+          phase = 1;
+        }
+      }
+      while (phase == 1) {
+        const unsigned rot = ((m >> ((s + 1) & 7)) | (m << (8 - ((s + 1) & 7)))) & 0xFFu;
+        s = (s + __ffs(rot)) & 7;
+        const int x4 = x3 + c_dx[s], y4 = y3 + c_dy[s];
+        if (n < cap) out[n] = make_int2(x3, y3);
+        ++n;
+        minx = min(minx, x3); maxx = max(maxx, x3); miny = min(miny, y3); maxy = max(maxy, y3);
+        if ((x4 == x0 && y4 == y0 && x3 == x1 && y3 == y1) || ++steps >= limit) { phase = 2; break; }
+        x3 = x4; y3 = y4;
+        s = (s + 4) & 7;
+        const int lx = x3 - ox, ly = y3 - oy;
+        if (lx < 1 || lx > BIG_T - 2 || ly < 1 || ly > BIG_T - 2) break;  // re-centre the window
+        m = tmask(x3, y3);
+      }
+      sh_cx = x3; sh_cy = y3; sh_done = phase == 2;
+    }
+    __syncthreads();
+    if (sh_done) break;
+  }
+  if (threadIdx.x == 0) {
+    npts[i] = n;
+    bbox[4 * i] = minx; bbox[4 * i + 1] = miny; bbox[4 * i + 2] = maxx + 1; bbox[4 * i + 3] = maxy + 1;
+    if (n > cap) atomicExch(overflow, 1);
+  }
+}
+
 // pack: contour i occupies tmp[off_bound[i] ...) and goes to pts[off[i] ...); one block per contour
 static __global__ void __launch_bounds__(TPB) pack_points(const int2* __restrict__ tmp, const long long* __restrict__ off_bound,
                                                    const long long* __restrict__ off, int2* __restrict__ pts) {
@@ -375,6 +469,15 @@ static int trace_set(bd_ctx* ctx, const uint8_t* img, const int* L, const long l
                      int W, cudaStream_t s, HostSet* out, int slot0, int* n_launch) {
   const size_t n = static_cast<size_t>(H) * W;
   post::DevPool& pool = ctx->pool;
+  const bool timing = getenv("BD_POST_TIMING") != nullptr;  // per-step wall clock of this set (synchronises)
+  auto t_last = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    cudaStreamSynchronize(s);
+    const auto t = std::chrono::steady_clock::now();
+    fprintf(stderr, "[trace_set %2d] %-28s %8.2f ms\n", slot0, what, std::chrono::duration<double, std::milli>(t - t_last).count());
+    t_last = t;
+  };
   int* d_count = nullptr;
   if (pool.get(slot0 + 0, sizeof(int), reinterpret_cast<void**>(&d_count))) return 1;
   BD_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int), s));
@@ -392,7 +495,10 @@ static int trace_set(bd_ctx* ctx, const uint8_t* img, const int* L, const long l
   out->bbox.assign(static_cast<size_t>(cnt) * 4, 0);
   if (cnt == 0) return 0;
   std::vector<int> roots(cnt);
-  BD_CUDA(cudaMemcpy(roots.data(), d_list, sizeof(int) * cnt, cudaMemcpyDeviceToHost));
+  BD_CUDA(cudaMemcpyAsync(roots.data(), d_list, sizeof(int) * cnt, cudaMemcpyDeviceToHost, s));
+  BD_CUDA(cudaStreamSynchronize(s));  // (a synchronous cudaMemcpy would queue on the legacy default stream behind
+                                      // the other sets' single-thread walk kernels)
+  lap("collect roots");
   std::sort(roots.begin(), roots.end(), [](int a, int b) { return a > b; });  // findContours lists the last-found first
   BD_CUDA(cudaMemcpyAsync(d_list, roots.data(), sizeof(int) * cnt, cudaMemcpyHostToDevice, s));
   int *d_npts = nullptr, *d_bbox = nullptr;
@@ -413,6 +519,7 @@ static int trace_set(bd_ctx* ctx, const uint8_t* img, const int* L, const long l
     std::vector<int> bound(cnt + 1);
     BD_CUDA(cudaMemcpyAsync(bound.data(), d_bound, sizeof(int) * cnt, cudaMemcpyDeviceToHost, s));
     BD_CUDA(cudaStreamSynchronize(s));
+    lap("crack bounds");
     std::vector<long long> off_bound(cnt + 1, 0);
     for (int i = 0; i < cnt; ++i) off_bound[i + 1] = off_bound[i] + bound[i];
     long long *d_offb = nullptr, *d_off = nullptr;
@@ -425,12 +532,26 @@ static int trace_set(bd_ctx* ctx, const uint8_t* img, const int* L, const long l
     BD_CUDA(cudaMemcpyAsync(d_offb, off_bound.data(), sizeof(long long) * (cnt + 1), cudaMemcpyHostToDevice, s));
     trace_both<<<(cnt + 63) / 64, 64, 0, s>>>(img, H, W, d_list, cnt, d_offb, d_tmp, d_npts, d_bbox, d_ovf);
     ++*n_launch;
+    std::vector<int> big;
+    for (int i = 0; i < cnt; ++i)
+      if (bound[i] >= BIG_MIN) big.push_back(i);
+    if (!big.empty()) {
+      int* d_big = nullptr;
+      if (pool.get(slot0 + 0, sizeof(int) * (1 + big.size()), reinterpret_cast<void**>(&d_big))) return 1;
+      d_big += 1;  // (slot0+0 also holds the root counter, consumed above)
+      BD_CUDA(cudaMemcpyAsync(d_big, big.data(), sizeof(int) * big.size(), cudaMemcpyHostToDevice, s));
+      trace_big<<<static_cast<int>(big.size()), 128, 0, s>>>(img, H, W, d_list, d_big, static_cast<int>(big.size()), d_offb,
+                                                             d_tmp, d_npts, d_bbox, d_ovf);
+      ++*n_launch;
+    }
     std::vector<int> npts1(cnt);
     int ovf = 0;
     BD_CUDA(cudaMemcpyAsync(npts1.data(), d_npts, sizeof(int) * cnt, cudaMemcpyDeviceToHost, s));
     BD_CUDA(cudaMemcpyAsync(out->bbox.data(), d_bbox, sizeof(int) * 4 * cnt, cudaMemcpyDeviceToHost, s));
     BD_CUDA(cudaMemcpyAsync(&ovf, d_ovf, sizeof(int), cudaMemcpyDeviceToHost, s));
     BD_CUDA(cudaStreamSynchronize(s));
+    lap("walk");
+    if (timing) fprintf(stderr, "[trace_set %2d] %d contours, %lld crack slots\n", slot0, cnt, off_bound[cnt]);
     if (!ovf) {
       for (int i = 0; i < cnt; ++i) out->off[i + 1] = out->off[i] + npts1[i];
       const long long total1 = out->off[cnt];
@@ -440,6 +561,8 @@ static int trace_set(bd_ctx* ctx, const uint8_t* img, const int* L, const long l
       out->pts.resize(total1);
       BD_CUDA(cudaMemcpyAsync(out->pts.data(), d_pts, sizeof(int2) * total1, cudaMemcpyDeviceToHost, s));
       BD_CUDA(cudaStreamSynchronize(s));
+      lap("pack + copy out");
+      if (timing) fprintf(stderr, "[trace_set %2d] %lld points\n", slot0, total1);
       out->d_bbox = d_bbox;
       return 0;
     }
