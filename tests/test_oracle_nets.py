@@ -59,3 +59,73 @@ def test_keras_surface():
         m.load_weights("/nonexistent/hrnet.h5")
     with pytest.raises(ValueError):
         m.predict(np.zeros((1, 256, 256, 3), np.float32))
+
+
+def _tiny(builder, batch=1, seed=0):
+    n0 = G.Net("case", batch, None)
+    builder(n0)
+    w = G.init_weights(n0.spec, seed=seed, randomize_bn=True)
+    n1 = G.Net("case", batch, w, keep_f32=True)
+    out = builder(n1)
+    return n1.plan, out
+
+
+def test_conv_up2_is_conv_of_the_upsampled_map():
+    """graph.conv_up2 (four sub-pixel 2x2 convolutions, hrnet.py:198-199 / v3plus.py:341-342) against the literal
+    lowering: nearest up-sampling followed by the 3x3 convolution with the same weights, in fp32."""
+    def fused(g):
+        x = g.new(16, 16, 24)
+        return x, g.conv_up2(x, "c", 8, bn=True, act="relu")
+
+    def literal(g):
+        x = g.new(16, 16, 24)
+        return x, g.conv(g.upsample(x, 2), "c", 8, k=3, bn=True, act="relu")
+
+    rng = np.random.default_rng(1)
+    xin = rng.standard_normal((1, 16, 16, 24)).astype(np.float32)
+    outs = []
+    for b in (fused, literal):
+        plan, (x, y) = _tiny(b)
+        it = plan_interp.Interp(plan, emulate_h16=False)
+        it.set(x.buf.id, xin)
+        with torch.no_grad():
+            it.run(None)
+        outs.append(it.get(y.buf.id))
+    assert outs[0].shape == outs[1].shape == (1, 32, 32, 8)
+    np.testing.assert_allclose(outs[0], outs[1], atol=2e-5, rtol=1e-5)
+    # 4 taps per phase instead of 9, algorithmic FLOPs of the reference layer
+    plan, _ = _tiny(fused)
+    assert [len(op["taps"]) for op in plan.ops] == [4, 4, 4, 4]
+    assert sum(op["flops"] for op in plan.ops) == 2 * 32 * 32 * 8 * 24 * 9
+
+
+def test_split_weights_reproduce_fp32_weights():
+    """graph.Net.split_weights: every weight as two fp16 taps at the same offset whose sum is the fp32 weight to
+    ~2^-22 relative; in fp32 the lowering is unchanged."""
+    def b(split):
+        def f(g):
+            g.split_weights = split
+            x = g.new(16, 16, 32)
+            return x, g.conv(x, "c", 16, k=3, bn=True, act="relu")
+        return f
+    plan_s, _ = _tiny(b(True))
+    plan_n, _ = _tiny(b(False))
+    ops, opn = plan_s.ops[0], plan_n.ops[0]
+    assert len(ops["taps"]) == 18 and ops["taps"][:9] == ops["taps"][9:] == opn["taps"]
+    w16 = G.h16_to_f32(ops["w"])
+    rec = w16[:9] + w16[9:]
+    ref = opn["w32"]
+    assert np.abs(rec - ref).max() <= 2.0 ** -21 * np.abs(ref).max()
+    assert ops["flops"] == opn["flops"]
+
+
+def test_separable_convs_are_marked_for_fusion_only_with_one_n_tile():
+    def b(cout):
+        def f(g):
+            x = g.new(32, 32, 128)
+            return x, g.sepconv(x, "s", cout, act="relu")
+        return f
+    small, _ = _tiny(b(256))
+    big, _ = _tiny(b(728))
+    assert small.ops[0].get("fuse") and small.ops[1].get("fused_dw") == 0
+    assert not big.ops[0].get("fuse") and big.ops[1].get("fused_dw") is None
