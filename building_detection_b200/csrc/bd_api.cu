@@ -128,7 +128,7 @@ int bd_create(int device, bd_ctx** out) {
   if (e != cudaSuccess || count == 0)
     return fail(std::string("no CUDA device available (this library has no CPU path): ") + cudaGetErrorString(e));
   BD_CHECK(device >= 0 && device < count, "device index out of range");
-  BD_CUDA(cudaSetDevice(device));
+  DeviceGuard guard(device);  // the caller's current device is restored on return
   cudaDeviceProp prop;
   BD_CUDA(cudaGetDeviceProperties(&prop, device));
   BD_CHECK(prop.major == 10, "this library is built for sm_100a (Blackwell B200) only");
@@ -143,6 +143,7 @@ int bd_create(int device, bd_ctx** out) {
 }
 
 void bd_destroy(bd_ctx* ctx) {
+  BD_ON_CTX(ctx);
   if (!ctx) return;
   if (ctx->d_ys) cudaFree(ctx->d_ys);
   if (ctx->d_xs) cudaFree(ctx->d_xs);
@@ -156,6 +157,7 @@ void bd_destroy(bd_ctx* ctx) {
 int64_t bd_launch_count(bd_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int bd_debug_read_trace(bd_ctx* ctx, long long* host_dst, int max_events) {
+  BD_ON_CTX(ctx);
   BD_CHECK(ctx && ctx->trace_buf && host_dst, "no trace buffer (set BD_UMMA_TRACE=1 before building the plan)");
   BD_CUDA(cudaDeviceSynchronize());
   (void)max_events;
@@ -176,6 +178,7 @@ int bd_plan_create(bd_ctx* ctx, int batch, bd_plan** out) {
 }
 
 void bd_plan_destroy(bd_plan* p) {
+  BD_ON_PLAN(p);
   if (!p) return;
   for (void* d : p->dev_allocs) cudaFree(d);
   if (p->arena) cudaFree(p->arena);
@@ -586,8 +589,8 @@ int bd_plan_add_bcast(bd_plan* p, int v_vec, bd_tref y) {
 }
 
 int bd_plan_finalize(bd_plan* p, int input_buf, int logits_buf, int logits_up) {
+  BD_ON_PLAN(p);
   BD_CHECK(p && !p->finalized, "bad arguments");
-  BD_CUDA(cudaSetDevice(p->ctx->device));
   const int nb = static_cast<int>(p->bufs.size());
   if (input_buf >= 0) {
     const BufInfo& ib = p->bufs[input_buf];
@@ -634,6 +637,7 @@ int bd_plan_finalize(bd_plan* p, int input_buf, int logits_buf, int logits_up) {
 }
 
 int bd_plan_run(bd_plan* p, const float* x_dev, float* probs_dev, uint8_t* mask_dev, void* stream) {
+  BD_ON_PLAN(p);
   BD_CHECK(p && p->finalized, "plan not finalized");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (x_dev) {
@@ -654,6 +658,7 @@ int bd_plan_run(bd_plan* p, const float* x_dev, float* probs_dev, uint8_t* mask_
 }
 
 int bd_plan_run_head(bd_plan* p, float* probs_dev, uint8_t* mask_dev, void* stream) {
+  BD_ON_PLAN(p);
   BD_CHECK(p && p->finalized && p->logits_buf >= 0, "plan has no softmax head");
   p->cur_probs = probs_dev;
   p->cur_mask = mask_dev;
@@ -661,6 +666,7 @@ int bd_plan_run_head(bd_plan* p, float* probs_dev, uint8_t* mask_dev, void* stre
 }
 
 int bd_plan_run_host(bd_plan* p, const float* x_host, float* probs_host, uint8_t* mask_host) {
+  BD_ON_PLAN(p);
   BD_CHECK(p && p->finalized && p->input_buf >= 0 && p->logits_buf >= 0, "plan not runnable from host buffers");
   const BufInfo& ib = p->bufs[p->input_buf];
   const BufInfo& lb = p->bufs[p->logits_buf];
@@ -699,6 +705,7 @@ size_t bd_plan_buffer_bytes(bd_plan* p, int buf) {
   return p->bufs[buf].bytes;
 }
 int bd_plan_read_buffer(bd_plan* p, int buf, void* host_dst, size_t bytes) {
+  BD_ON_PLAN(p);
   BD_CHECK(p && p->finalized && buf >= 0 && buf < static_cast<int>(p->bufs.size()) && bytes <= p->bufs[buf].bytes,
            "bad arguments");
   BD_CUDA(cudaDeviceSynchronize());
@@ -706,6 +713,7 @@ int bd_plan_read_buffer(bd_plan* p, int buf, void* host_dst, size_t bytes) {
   return 0;
 }
 int bd_plan_write_buffer(bd_plan* p, int buf, const void* host_src, size_t bytes) {
+  BD_ON_PLAN(p);
   BD_CHECK(p && p->finalized && buf >= 0 && buf < static_cast<int>(p->bufs.size()) && bytes <= p->bufs[buf].bytes,
            "bad arguments");
   BD_CUDA(cudaMemcpy(p->arena + p->bufs[buf].offset, host_src, bytes, cudaMemcpyHostToDevice));
@@ -725,6 +733,7 @@ int bd_plan_op_info(bd_plan* p, int i, int* kind, double* flops) {
   return 0;
 }
 int bd_plan_time_ops(bd_plan* p, float* ms_out, void* stream) {
+  BD_ON_PLAN(p);
   BD_CHECK(p && p->finalized && ms_out, "bad arguments");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const size_t n = p->ops.size();
@@ -763,6 +772,7 @@ static int ensure_tile_scratch(bd_ctx* ctx, int n) {
 
 int bd_tiles_gather(bd_ctx* ctx, const uint8_t* scene_bgr_dev, int h, int w, const int32_t* ys_host,
                     const int32_t* xs_host, int n, void* x_dev, int stem_stride, void* stream) {
+  BD_ON_CTX(ctx);
   BD_CHECK(ctx && scene_bgr_dev && ys_host && xs_host && x_dev && n >= 1 && h >= 1 && w >= 1, "bad arguments");
   BD_CHECK(stem_stride == 1 || stem_stride == 2, "stem stride must be 1 or 2");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -783,6 +793,7 @@ int bd_tiles_gather(bd_ctx* ctx, const uint8_t* scene_bgr_dev, int h, int w, con
 
 int bd_stitch_or(bd_ctx* ctx, const uint8_t* tile_masks_dev, const int32_t* ys_host, const int32_t* xs_host, int n,
                  uint8_t* scene_mask_dev, int h, int w, void* stream) {
+  BD_ON_CTX(ctx);
   BD_CHECK(ctx && tile_masks_dev && ys_host && xs_host && scene_mask_dev && n >= 1, "bad arguments");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (ensure_tile_scratch(ctx, std::max(n, 64))) return 1;
@@ -798,6 +809,7 @@ int bd_stitch_or(bd_ctx* ctx, const uint8_t* tile_masks_dev, const int32_t* ys_h
 // The origins of ALL tiles of a scene, uploaded once: the per-batch calls below index into them, so the scene loop
 // issues no host->device copies between the kernels of consecutive batches.
 int bd_tiles_set_origins(bd_ctx* ctx, const int32_t* ys_host, const int32_t* xs_host, int n, void* stream) {
+  BD_ON_CTX(ctx);
   BD_CHECK(ctx && ys_host && xs_host && n >= 1, "bad arguments");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (n > ctx->origin_cap) {
@@ -818,6 +830,7 @@ int bd_tiles_set_origins(bd_ctx* ctx, const int32_t* ys_host, const int32_t* xs_
 
 int bd_tiles_gather_at(bd_ctx* ctx, const uint8_t* scene_bgr_dev, int h, int w, int first, int n, void* x_dev,
                        int stem_stride, void* stream) {
+  BD_ON_CTX(ctx);
   BD_CHECK(ctx && scene_bgr_dev && x_dev && n >= 1 && h >= 1 && w >= 1, "bad arguments");
   BD_CHECK(first >= 0 && first + n <= ctx->n_origins, "tile range outside the origins set by bd_tiles_set_origins");
   BD_CHECK(stem_stride == 1 || stem_stride == 2, "stem stride must be 1 or 2");
@@ -835,6 +848,7 @@ int bd_tiles_gather_at(bd_ctx* ctx, const uint8_t* scene_bgr_dev, int h, int w, 
 
 int bd_stitch_or_at(bd_ctx* ctx, const uint8_t* tile_masks_dev, int first, int n, uint8_t* scene_mask_dev, int h, int w,
                     void* stream) {
+  BD_ON_CTX(ctx);
   BD_CHECK(ctx && tile_masks_dev && scene_mask_dev && n >= 1, "bad arguments");
   BD_CHECK(first >= 0 && first + n <= ctx->n_origins, "tile range outside the origins set by bd_tiles_set_origins");
   cudaStream_t s = static_cast<cudaStream_t>(stream);

@@ -56,6 +56,24 @@ inline cudaError_t launch_k(bool pdl, void (*kern)(Params...), dim3 grid, dim3 b
   return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 
+// Every C-ABI entry point runs on its context's device and leaves the caller's current device as it found it.
+struct DeviceGuard {
+  int prev = -1, dev;
+  explicit DeviceGuard(int d) : dev(d) {  // d < 0: no-op (null context; the entry point rejects it itself)
+    if (dev < 0) return;
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    if (dev >= 0 && prev >= 0 && prev != dev) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
+#define BD_ON_CTX(ctx_) ::bd::DeviceGuard bd_dev_guard_((ctx_) ? (ctx_)->device : -1)
+#define BD_ON_PLAN(p_) ::bd::DeviceGuard bd_dev_guard_(((p_) && (p_)->ctx) ? (p_)->ctx->device : -1)
+
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

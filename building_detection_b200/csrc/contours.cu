@@ -651,6 +651,7 @@ void bd_polys_free(bd_polys* p) {
 }
 
 int bd_contours(bd_ctx* ctx, const uint8_t* mask_dev, int h, int w, bd_polys* out, void* stream) {
+  BD_ON_CTX(ctx);
   BD_CHECK(ctx && mask_dev && out && h >= 1 && w >= 1, "bad arguments");
   BD_CHECK(static_cast<size_t>(h) * w < (1ull << 31), "scene too large for int32 pixel labels");
   using namespace bd::cont;

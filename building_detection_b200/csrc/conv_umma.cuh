@@ -1153,7 +1153,11 @@ inline int prepare(Launch* L, const TView& x, const TView& y, const TView* res, 
 }
 
 inline int launch(const Launch& L, cudaStream_t stream, bool pdl = false) {
-  static bool attr_set = false;
+  // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: set it once per device of this process
+  static bool attr_set_dev[64] = {};
+  int dev_ = 0;
+  BD_CUDA(cudaGetDevice(&dev_));
+  bool& attr_set = attr_set_dev[dev_ & 63];
   if (!attr_set) {
     BD_CUDA(cudaFuncSetAttribute(conv_umma_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     BD_CUDA(cudaFuncSetAttribute(conv_umma_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

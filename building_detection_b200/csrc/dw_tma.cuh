@@ -208,7 +208,10 @@ inline int prepare(Launch* L, const TView& x, const TView& y, const h16* w_dev, 
 }
 
 inline int launch(const Launch& L, cudaStream_t stream, bool pdl) {
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {};  // per-device attribute
+  int dev_ = 0;
+  BD_CUDA(cudaGetDevice(&dev_));
+  bool& attr_set = attr_set_dev[dev_ & 63];
   if (!attr_set) {
     BD_CUDA(cudaFuncSetAttribute(dwconv_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;

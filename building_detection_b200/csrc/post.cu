@@ -168,12 +168,14 @@ int cleanup(bd_ctx* ctx, const uint8_t* mask, int H, int W, uint8_t* out, cudaSt
 extern "C" {
 
 int bd_mask_cleanup(bd_ctx* ctx, const uint8_t* mask_dev, int h, int w, uint8_t* out_dev, void* stream) {
+  BD_ON_CTX(ctx);
   BD_CHECK(ctx && mask_dev && out_dev && h >= 1 && w >= 1, "bad arguments");
   BD_CHECK(static_cast<size_t>(h) * w < (1ull << 31), "scene too large for int32 pixel labels");
   return post::cleanup(ctx, mask_dev, h, w, out_dev, static_cast<cudaStream_t>(stream));
 }
 
 int bd_fuse(bd_ctx* ctx, const uint8_t* masks5_dev, int h, int w, uint8_t* fused_dev, void* stream) {
+  BD_ON_CTX(ctx);
   BD_CHECK(ctx && masks5_dev && fused_dev && h >= 1 && w >= 1, "bad arguments");
   BD_CHECK(static_cast<size_t>(h) * w < (1ull << 31), "scene too large for int32 pixel labels");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -186,6 +188,7 @@ int bd_fuse(bd_ctx* ctx, const uint8_t* masks5_dev, int h, int w, uint8_t* fused
 }
 
 int bd_fuse_cleaned(bd_ctx* ctx, const uint8_t* cleaned5_dev, int h, int w, uint8_t* fused_dev, void* stream) {
+  BD_ON_CTX(ctx);
   BD_CHECK(ctx && cleaned5_dev && fused_dev && h >= 1 && w >= 1, "bad arguments");
   BD_CHECK(static_cast<size_t>(h) * w < (1ull << 31), "scene too large for int32 pixel labels");
   cudaStream_t s = static_cast<cudaStream_t>(stream);

@@ -69,12 +69,25 @@ class Model:
             p.close()
         self._native = {}
 
-    def native_plan(self, batch, umma=True):
-        from .runtime import NativePlan
-        key = (batch, umma)
+    def native_plan(self, batch, umma=True, device=None):
+        """The native plan of this model for ``batch`` tiles on ``device`` (None: the device the C ABI context
+        resolves from LOCAL_RANK / BD_DEVICE).  One arena per (batch, device): callers that see ragged batch
+        sizes go through ``plan_batch_for`` so that the cache stays bounded."""
+        from .runtime import NativePlan, resolve_device
+        device = resolve_device(device)
+        key = (batch, umma, device)
         if key not in self._native:
-            self._native[key] = NativePlan(self.build_plan(batch, umma=umma))
+            self._native[key] = NativePlan(self.build_plan(batch, umma=umma), device)
         return self._native[key]
+
+    @staticmethod
+    def plan_batch_for(n):
+        """Plan batch that serves ``n`` tiles: the next power of two up to MAX_PLAN_BATCH, so that at most
+        five plans per model and device ever exist (a tile's result does not depend on its batch neighbours)."""
+        b = 1
+        while b < n and b < MAX_PLAN_BATCH:
+            b *= 2
+        return b
 
     # ------------------------------------------------------------------ inference
     def predict(self, x, batch_size=None, verbose=0):
@@ -88,7 +101,11 @@ class Model:
         i = 0
         while i < x.shape[0]:
             n = min(MAX_PLAN_BATCH, x.shape[0] - i)
-            out[i:i + n] = self.native_plan(n).run_host(x[i:i + n])
+            b = self.plan_batch_for(n)
+            xb = x[i:i + n]
+            if b != n:  # ragged tail: pad with zero tiles, drop their outputs
+                xb = np.concatenate([xb, np.zeros((b - n,) + x.shape[1:], np.float32)], axis=0)
+            out[i:i + n] = self.native_plan(b).run_host(xb)[:n]
             i += n
         return out
 

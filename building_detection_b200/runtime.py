@@ -120,10 +120,16 @@ def check(rc):
 _ctx = {}
 
 
-def context(device=None):
-    """One bd_ctx per GPU (per process)."""
+def resolve_device(device=None):
+    """None -> BD_DEVICE, else LOCAL_RANK (torchrun: one process per GPU), else 0."""
     if device is None:
         device = int(os.environ.get("LOCAL_RANK", "0")) if "BD_DEVICE" not in os.environ else int(os.environ["BD_DEVICE"])
+    return int(device)
+
+
+def context(device=None):
+    """One bd_ctx per GPU (per process)."""
+    device = resolve_device(device)
     if device not in _ctx:
         h = C.c_void_p()
         check(lib().bd_create(device, C.byref(h)))

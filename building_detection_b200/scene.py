@@ -88,10 +88,14 @@ class SceneRunner:
         ys = np.ascontiguousarray([o[0] for o in origins], np.int32)
         xs = np.ascontiguousarray([o[1] for o in origins], np.int32)
         R.check(L.bd_tiles_set_origins(self.ctx, R._ptr(ys), R._ptr(xs), len(origins), stream))
-        for b0 in range(0, len(origins), self.batch):
-            n = min(self.batch, len(origins) - b0)
+        # A ragged last batch runs through the SAME batch-sized plan: only n tiles are gathered and stitched, the
+        # remaining slots of the input buffer keep stale tiles whose outputs are ignored (no per-n plan arenas).
+        # Scenes with fewer tiles than the batch use the next power of two (engine.Model.plan_batch_for).
+        pb = self.batch if len(origins) >= self.batch else min(self.batch, self.models[0].plan_batch_for(len(origins)))
+        for b0 in range(0, len(origins), pb):
+            n = min(pb, len(origins) - b0)
             for mi, m in enumerate(self.models):
-                plan = m.native_plan(n)
+                plan = m.native_plan(pb, device=self.device.index)
                 x_ptr = plan.buffer_ptr(plan.plan.input)
                 R.check(L.bd_tiles_gather_at(self.ctx, scene_dev.data_ptr(), h, w, b0, n, x_ptr,
                                              plan.plan.input_stride, stream))

@@ -27,3 +27,20 @@ def gpu():
     if not have_gpu():
         pytest.skip("no CUDA device")
     return True
+
+
+@pytest.fixture(scope="session")
+def parity_models():
+    """name -> engine.Model carrying the parity-test weights (oracle.nets.parity_weights), built once per session:
+    the calibration pass is a CPU forward of the oracle."""
+    from building_detection_b200.predict_model import CTORS
+    from oracle import nets
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            m = CTORS[name]()
+            m.set_weights(nets.parity_weights(name, m.spec))
+            cache[name] = m
+        return cache[name]
+    return get

@@ -6,10 +6,12 @@
  (b) oracle/plan_interp.py -- the fp16-faithful interpreter of the same plan -- which isolates kernel
      bugs from fp16 rounding.
 
-Weights: seeded Keras-default initialisers with randomised BN gamma/beta and BN moving variance
-calibrated to each layer's input (nets.calibrated_weights), the same dict on both sides.  Uncalibrated
-random-init networks are numerically chaotic (DESIGN.md "Numerics") and cannot meet any tolerance in
-reduced precision; the reference ships no trained checkpoints.
+Weights (oracle.nets.parity_weights, the same dict on both sides): seeded Keras-default initialisers with
+randomised BN gamma/beta and BN moving variance calibrated to each layer's input for the four networks that
+have BatchNormalization; He-scaled kernels for the SCSE U-Net, which has none (with glorot_uniform its output
+collapses to p1 in [0.42, 0.51] and a parity test says nothing).  Uncalibrated random-init networks are
+numerically chaotic (DESIGN.md "Numerics") and cannot meet any tolerance in reduced precision; the reference
+ships no trained checkpoints.
 Inputs: SURVEY.md section 8d -- rng.integers(0,256) RGB tiles, x/127.5-1.
 """
 import numpy as np
@@ -31,18 +33,19 @@ def tiles(seed, n):
     return (rng.integers(0, 256, (n, 512, 512, 3), dtype=np.uint8) / 127.5 - 1).astype(np.float32)
 
 
+MAX_EXCLUDED = 0.12  # pixels within 2e-2 of the decision boundary that the mask comparison may skip
+
+
 @pytest.fixture(scope="module")
-def prepared():
+def prepared(parity_models):
     cache = {}
 
     def get(name):
         if name not in cache:
-            m = CTORS[name]()
+            m = parity_models(name)
             x = tiles(SEEDS[name], 2)
-            w = nets.calibrated_weights(name, m.spec, 1, tiles(99, 1))
-            m.set_weights(w)
             with torch.no_grad():
-                ref = nets.FORWARD[name](w, x)
+                ref = nets.FORWARD[name](m.get_weights(), x)
             cache[name] = (m, x, ref)
         return cache[name]
     return get
@@ -59,12 +62,9 @@ def test_forward_matches_fp32_oracle(gpu, prepared, name):
     print(f"{name}: max|dp|={err:.3e} mean|dp|={np.abs(got - ref).mean():.3e} mask agree all={agree.mean():.5f} "
           f"sure={agree[sure].mean():.5f} (excluded {1 - sure.mean():.4f})")
     assert agree[sure].mean() >= MASK_AGREE
-    if name == "hrnet" and PROB_TOL < err < 2 * PROB_TOL:
-        # Known gap, stated in DESIGN.md "Numerics": the 43-conv-deep critical path of a *random-init* HRNet
-        # amplifies the 2^-11 rounding of 16-bit tensor-core operands (weights and activations contribute
-        # 1.6e-2 each) to ~2.5e-2 max-abs on the probabilities; masks still agree on 100 % of the pixels that
-        # are not within 2e-2 of the decision boundary.
-        pytest.xfail(f"hrnet max|dp|={err:.3e} exceeds the 2e-2 bar (fp16 operand rounding, see DESIGN.md)")
+    assert 1 - sure.mean() <= MAX_EXCLUDED, f"{1 - sure.mean():.3f} of the pixels sit within 2e-2 of the boundary"
+    # the comparison must bite: both classes present and the probabilities spread out
+    assert ref[..., 1].std() >= 0.1 and 0.02 < (ref[..., 1] > 0.5).mean() < 0.98, (ref[..., 1].std(), (ref[..., 1] > 0.5).mean())
     assert err <= PROB_TOL, err
 
 
@@ -74,15 +74,40 @@ def test_forward_matches_fp16_interpreter(gpu, prepared, name):
     plan = m.build_plan(1)
     want = plan_interp.run_plan(plan, x[:1], emulate_h16=True)
     got, mask = m.native_plan(1).run_host(x[:1], want_probs=True, want_mask=True)
-    # summation order is the only difference; HRNet's chaotic random-init dynamics amplify it (DESIGN.md "Numerics")
-    assert np.abs(got - want).max() < (3e-2 if name == "hrnet" else 5e-3), np.abs(got - want).max()
+    # summation order is the only difference
+    assert np.abs(got - want).max() < 5e-3, np.abs(got - want).max()
     np.testing.assert_array_equal(mask, (got[..., 1] > got[..., 0]).astype(np.uint8))
 
 
-def test_batch16_equals_batch1(gpu, prepared):
-    """BASELINE configs 2-4 run batch 16; a tile's result must not depend on its batch neighbours."""
-    m, x, _ = prepared("v3plus")
+@pytest.mark.parametrize("name", MODEL_NAMES)
+def test_batch16_equals_batch1(gpu, prepared, name):
+    """BASELINE configs 2-4 and the scene loop run batch 16; a tile's result must not depend on its batch
+    neighbours, nor on the slot it occupies (the ragged last batch of a scene leaves stale tiles in the others)."""
+    m, x, _ = prepared(name)
     xb = np.concatenate([x, tiles(7, 14)], axis=0)
     full = m.predict(xb)
-    one = m.predict(xb[5:6])
-    np.testing.assert_array_equal(full[5:6], one)
+    np.testing.assert_array_equal(full[5:6], m.predict(xb[5:6]))
+    np.testing.assert_array_equal(full[15:16], m.predict(xb[15:16]))
+    three = m.predict(xb[13:16])  # 3 tiles -> batch-4 plan, zero-padded
+    np.testing.assert_array_equal(full[13:16], three)
+
+
+def test_hrnet_undamped_recipe_stays_within_its_conditioning(gpu):
+    """HRNet with gamma ~ U(0.5,1.5) on every BatchNormalization (the recipe round 1 tested, 2.6e-2): the map is
+    ill conditioned -- tests/test_oracle_nets.py shows on the CPU that one-ulp flips of 1e-4 of the stored
+    activations move the probabilities by > 1e-2 -- so the kernels are held to the spread the interpreter itself
+    shows under such flips (hard limit 4e-2) and to full mask agreement on the sure pixels; the 2e-2 bar is
+    asserted on the well-conditioned parity recipe above."""
+    m = CTORS["hrnet"]()
+    w = nets.parity_weights("hrnet", m.spec, hrnet_damped=False)
+    m.set_weights(w)
+    x = tiles(SEEDS["hrnet"], 1)
+    with torch.no_grad():
+        ref = nets.FORWARD["hrnet"](w, x)
+    got = m.predict(x)
+    err = np.abs(got - ref).max()
+    sure = np.abs(ref[..., 1] - 0.5) > PROB_TOL
+    agree = got.argmax(-1) == ref.argmax(-1)
+    print(f"hrnet undamped: max|dp|={err:.3e} p99.99={np.quantile(np.abs(got - ref), 0.9999):.3e} sure-agree={agree[sure].mean():.5f}")
+    assert err < 4e-2 and agree[sure].mean() >= MASK_AGREE
+    m._drop_native()

@@ -1,0 +1,99 @@
+"""Why a random-init HRNet cannot be held to max|dp| <= 2e-2 with 16-bit operands, and what the parity recipe does
+about it.  CPU only (fp32 oracle + fp16-faithful plan interpreter); output committed as profiles/r2_hrnet_chaos.txt.
+
+ 1. precision policies (undamped recipe): fp16 storage everywhere / fp32 carry on the residual streams / every
+    buffer fp32 with fp16 tensor-core operands -- the error does not move, so it is not the carry precision;
+ 2. amplification (undamped recipe): flip a fraction f of the stored fp16 activations by ONE ulp in every layer and
+    compare with the unperturbed interpreter -- the output moves by ~1.5e-2 already at f = 1e-4 and saturates: any
+    rounding difference (summation order on the GPU included) is amplified to the size of the whole fp16-fp32 gap;
+ 3. the damped recipe (gamma of the BN closing each residual block x 0.5 / x 0.25): the same graph becomes well
+    conditioned and the fp16 error drops below the bar with margin.
+usage: python tools/hrnet_chaos_study.py"""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+from building_detection_b200 import graph as G  # noqa: E402
+from building_detection_b200.predict_model import CTORS  # noqa: E402
+from oracle import nets, plan_interp  # noqa: E402
+from oracle.plan_interp import _q  # noqa: E402
+
+rng = np.random.default_rng(3)
+x = (rng.integers(0, 256, (2, 512, 512, 3), dtype=np.uint8) / 127.5 - 1).astype(np.float32)[:1]
+m = CTORS["hrnet"]()
+
+
+class InterpPolicy(plan_interp.Interp):
+    """f32_bufs: buffers that keep fp32 values (a carry); a convolution reading one still sees fp16 operands."""
+
+    def __init__(self, plan, f32_bufs):
+        super().__init__(plan, True)
+        self.f32_bufs = f32_bufs
+
+    def _store(self, ref, val):
+        bid, c0, c = ref
+        if self.p.bufs[bid].dtype == "f16" and bid not in self.f32_bufs:
+            val = _q(val)
+        self.b[bid][..., c0:c0 + c] = val
+
+    def _conv(self, op):
+        bid = op["x"][0]
+        if bid in self.f32_bufs:
+            save = self.b[bid]
+            self.b[bid] = _q(save)
+            super()._conv(op)
+            self.b[bid] = save
+        else:
+            super()._conv(op)
+
+
+class InterpPerturb(plan_interp.Interp):
+    def __init__(self, plan, frac, seed=0):
+        super().__init__(plan, True)
+        self.frac, self.rng = frac, np.random.default_rng(seed)
+
+    def _store(self, ref, val):
+        bid, c0, c = ref
+        if self.p.bufs[bid].dtype == "f16":
+            h = _q(val).to(torch.float16).contiguous().numpy().view(np.int16).copy()
+            h[self.rng.random(h.shape) < self.frac] += 1  # next representable magnitude
+            val = torch.from_numpy(h.view(np.float16).astype(np.float32))
+        self.b[bid][..., c0:c0 + c] = val
+
+
+def stats(a, b):
+    d = np.abs(a - b)
+    return f"max {d.max():.3e}  p99.99 {np.quantile(d, 0.9999):.3e}  mean {d.mean():.3e}"
+
+
+w = nets.parity_weights("hrnet", m.spec, hrnet_damped=False)
+m.set_weights(w)
+with torch.no_grad():
+    ref = nets.FORWARD["hrnet"](w, x)
+plan = m.build_plan(1, keep_f32=True)
+res_out = {op["y"][0] for op in plan.ops if (op["op"] == G.OP_CONV and op["res"] is not None) or op["op"] == G.OP_ADDN}
+allb = {b.id for b in plan.bufs if b.kind == "map" and b.dtype == "f16" and b.id != plan.input}
+print("== undamped recipe (gamma ~ U(0.5,1.5) on every BN), |prob - fp32 oracle|, 1 tile, seed 3")
+with torch.no_grad():
+    base = InterpPolicy(plan, set()).run(x)
+    print(f"fp16 storage everywhere                    : {stats(base, ref)}")
+    print(f"fp32 carry on {len(res_out)} residual-stream buffers   : {stats(InterpPolicy(plan, res_out).run(x), ref)}")
+    print(f"all {len(allb)} buffers fp32, fp16 operands        : {stats(InterpPolicy(plan, allb).run(x), ref)}")
+    print("== amplification: one-ulp flips of a fraction f of the stored activations, vs the unperturbed interpreter")
+    for f in (1e-4, 1e-3, 1e-2):
+        print(f"f = {f:7.0e}                                : {stats(InterpPerturb(plan, f).run(x), base)}")
+print("== damped recipe: gamma of the BN closing each residual block scaled")
+for damp in (1.0, 0.5, 0.25):
+    nets.HRNET_RESIDUAL_GAMMA = damp
+    w = nets.parity_weights("hrnet", m.spec, hrnet_damped=True)
+    m.set_weights(w)
+    with torch.no_grad():
+        ref = nets.FORWARD["hrnet"](w, x)
+        got = plan_interp.run_plan(m.build_plan(1), x, emulate_h16=True)
+        pert = InterpPerturb(m.build_plan(1), 1e-4).run(x)
+    print(f"x{damp:4.2f}: oracle p1 std {ref[..., 1].std():.3f}, class-1 {float((ref[..., 1] > 0.5).mean()):.3f} | fp16 vs fp32: "
+          f"{stats(got, ref)} | one-ulp flips f=1e-4: {stats(pert, got)}")
