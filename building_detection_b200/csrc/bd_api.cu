@@ -135,6 +135,7 @@ int bd_create(int device, bd_ctx** out) {
   bd_ctx* c = new bd_ctx();
   c->device = device;
   c->num_sms = prop.multiProcessorCount;
+  BD_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->h_scalar), 64));
   if (const char* s = getenv("BD_UMMA_SMEM_KB")) c->umma_smem_kb = std::max(48, std::min(226, atoi(s)));
   if (const char* s = getenv("BD_UMMA_GROUP")) c->umma_group = std::max(0, std::min(9, atoi(s)));
   if (const char* s = getenv("BD_UMMA_MAX_N")) c->umma_max_block_n = std::max(16, std::min(256, atoi(s) / 16 * 16));
@@ -149,8 +150,9 @@ void bd_destroy(bd_ctx* ctx) {
   if (ctx->d_xs) cudaFree(ctx->d_xs);
   if (ctx->d_all_ys) cudaFree(ctx->d_all_ys);
   if (ctx->d_all_xs) cudaFree(ctx->d_all_xs);
-  ctx->post_ws.release();
+  ctx->arena.release();
   ctx->pool.release();
+  if (ctx->h_scalar) cudaFreeHost(ctx->h_scalar);
   delete ctx;
 }
 

@@ -486,7 +486,7 @@ __global__ void __launch_bounds__(TPB) bcast_kernel(const __grid_constant__ Bcas
 }
 
 // ---------------------------------------------------------------------------------- softmax head
-// logits fp32 (N, 512/up, 512/up, 2) -> probs fp32 (N,512,512,2) and/or mask u8 (argmax, ties -> class 0)
+// logits fp32 (N, 512/up, 512/up, 2) -> probs fp32 (N,512,512,2) and/or mask u8 (argmax of the probabilities, ties -> class 0)
 __global__ void __launch_bounds__(TPB) softmax2_kernel(const float* __restrict__ logits, int N, int H, int W, int up,
                                                        float* __restrict__ probs, uint8_t* __restrict__ mask) {
   pdl_prologue();
@@ -497,13 +497,14 @@ __global__ void __launch_bounds__(TPB) softmax2_kernel(const float* __restrict__
     const int ow = static_cast<int>(idx % W), oh = static_cast<int>((idx / W) % H);
     const int n = static_cast<int>(idx / (static_cast<size_t>(W) * H));
     const float2 l = *reinterpret_cast<const float2*>(logits + ((static_cast<size_t>(n) * h2 + oh / up) * w2 + ow / up) * 2);
-    if (probs) {
-      const float m = fmaxf(l.x, l.y);
-      const float e0 = expf(l.x - m), e1 = expf(l.y - m);
-      const float inv = 1.0f / (e0 + e1);
-      *reinterpret_cast<float2*>(probs + idx * 2) = make_float2(e0 * inv, e1 * inv);
-    }
-    if (mask) mask[idx] = l.y > l.x ? 1 : 0;
+    // The mask is the argmax of the float32 PROBABILITIES (predict.py:109-110: tf.argmax of the softmax output, first
+    // maximum on ties), not of the logits: logits closer than one float32 ulp of 0.5 tie after the softmax.
+    const float m = fmaxf(l.x, l.y);
+    const float e0 = expf(l.x - m), e1 = expf(l.y - m);
+    const float inv = 1.0f / (e0 + e1);
+    const float p0 = e0 * inv, p1 = e1 * inv;
+    if (probs) *reinterpret_cast<float2*>(probs + idx * 2) = make_float2(p0, p1);
+    if (mask) mask[idx] = p1 > p0 ? 1 : 0;
   }
 }
 

@@ -1,5 +1,6 @@
-// post_ws.cuh -- bd_ctx (shared by bd_api.cu / post.cu / contours.cu) and the scene-sized workspace of the
-// fusion and contour stages.  The workspace grows on demand and is reused across calls.
+// post_ws.cuh -- bd_ctx (shared by bd_api.cu / post.cu / contours.cu), the constants of the fusion and contour stages,
+// and their device scratch: a bump arena for the scene-sized planes and grow-only slots for the arrays whose size
+// depends on the number of runs / contours.  Nothing is allocated per call once warmed up.
 #pragma once
 #include <algorithm>
 
@@ -7,27 +8,59 @@
 
 namespace bd {
 namespace post {
-struct Workspace {
-  size_t cap = 0;            // pixels
-  int *L = nullptr, *Lh = nullptr, *Lv = nullptr;              // parent / fragment labels
-  long long *a2 = nullptr, *a2h = nullptr, *a2v = nullptr;    // 2 x signed polygon area, indexed by root pixel
-  int *cntH = nullptr, *survH = nullptr, *cntV = nullptr, *survV = nullptr;
-  uint8_t *filled = nullptr, *keep = nullptr, *er = nullptr, *voted = nullptr, *cleaned = nullptr;  // cleaned: 5 masks
+
+// The literals of model_fuse.py and edge_3.py in one place, with the reference line each one
+// comes from.  bd_post_constants() exposes them; building_detection_b200/constants.py mirrors them on the host.
+struct PostConstants {
+  // model_fuse.py
+  int fuse_min_area = 1000;      // fill_and_delete: polygons of area <= 1000 are erased            (:22)
+  int fuse_min_fragment = 500;   // fill_small_target: fragments of area <= 500 are erased          (:57)
+  int fuse_split_half = 10;      // 1x5 / 5x1 kernel, 5 iterations == one 1x21 / 21x1 erosion       (:180-181, :67)
+  int fuse_votes = 3;            // sum of five masks >= 3                                            (:323)
+  // edge_3.py
+  int edge_min_area = 100;       // _detection: polygons of area <= 100 are erased                   (:326)
+  int edge_min_fragment = 50;    // erode_images_process: fragments of area < 50 are erased          (:131)
+  int edge_split_half = 3;       // 1x7 / 7x1 erosion, one iteration                                  (:128)
+  double edge_iou = 0.5;         // process_td / process_rl: boxes match above IoU 0.5               (:42)
+  double edge_min_moment = 10;   // contours with m00 <= 10 are skipped                              (:331)
+  // area tiers of the polygon simplification (:351-378): epsilon = factor x perimeter
+  double tier_small = 150, tier_mid = 300, tier_big0 = 3000, tier_big1 = 8000, tier_big2 = 15000;
+  double eps_default = 0.01, eps_mid_mult = 5, eps_big0 = 0.005, eps_big1 = 0.004, eps_big2 = 0.002;
+  double small_rate0 = 0.002, small_rate_step = 0.002;  // small_target retries (:265-286)
+  int small_max_tries = 10;
+};
+
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0, off = 0;
+  // make room for `bytes` and start carving from the beginning
+  int reserve(size_t bytes) {
+    if (bytes > cap) {
+      if (base) cudaFree(base);
+      base = nullptr; cap = 0;
+      const size_t want = bytes + bytes / 8 + (1 << 20);
+      BD_CUDA(cudaMalloc(reinterpret_cast<void**>(&base), want));
+      cap = want;
+    }
+    off = 0;
+    return 0;
+  }
+  template <class T>
+  T* take(size_t n) {
+    off = (off + 255) & ~static_cast<size_t>(255);
+    T* p = reinterpret_cast<T*>(base + off);
+    off += n * sizeof(T);
+    return p;  // (reserve() was sized for the whole call; overflow is checked by the callers' byte budgets)
+  }
   void release() {
-    void* ptrs[] = {L, Lh, Lv, a2, a2h, a2v, cntH, survH, cntV, survV, filled, keep, er, voted, cleaned};
-    for (void* p : ptrs)
-      if (p) cudaFree(p);
-    *this = Workspace();
+    if (base) cudaFree(base);
+    base = nullptr; cap = off = 0;
   }
 };
-}  // namespace post
-}  // namespace bd
 
-namespace bd {
-namespace post {
-// grow-only device scratch slots for the contour stage (no cudaMalloc / cudaFree per call once warmed up)
+// grow-only device scratch slots (no cudaMalloc / cudaFree per call once warmed up)
 struct DevPool {
-  static constexpr int SLOTS = 32;
+  static constexpr int SLOTS = 64;
   void* ptr[SLOTS] = {};
   size_t cap[SLOTS] = {};
   int get(int slot, size_t bytes, void** out) {
@@ -45,6 +78,18 @@ struct DevPool {
     for (int i = 0; i < SLOTS; ++i) { if (ptr[i]) cudaFree(ptr[i]); ptr[i] = nullptr; cap[i] = 0; }
   }
 };
+
+// slot map: 0..31 contour tracing (three sets x 8, two for the box matching), 32.. fusion / labelling
+enum {
+  SLOT_IN5 = 32,  // five packed input planes of bd_fuse
+  SLOT_BG = 33,   // +1: background parents, outside flags
+  SLOT_F = 35,    // +1: object parents, areas
+  SLOT_EH = 37,   // +1
+  SLOT_EV = 39,   // +1
+  SLOT_CNT = 41,  // fragment counters
+  SLOT_IMG = 42,  // +2: u8 images of the three traced planes
+};
+
 }  // namespace post
 }  // namespace bd
 
@@ -61,36 +106,9 @@ struct bd_ctx {
   int* d_all_ys = nullptr;  // origins of all tiles of the current scene (bd_tiles_set_origins)
   int* d_all_xs = nullptr;
   int origin_cap = 0, n_origins = 0;
-  bd::post::Workspace post_ws;
+  bd::post::PostConstants consts;
+  bd::post::Arena arena;
   bd::post::DevPool pool;
+  int* h_scalar = nullptr;    // pinned host word for device -> host counters
   void* trace_buf = nullptr;  // BD_UMMA_TRACE debug buffer of the most recently built conv
 };
-
-namespace bd {
-namespace post {
-// defined in post.cu
-int label8(bd_ctx* ctx, const uint8_t* m, int* L, int H, int W, cudaStream_t s);                 // 8-connected labels of m
-int fill(bd_ctx* ctx, const uint8_t* m, int* Lbg, uint8_t* out, int H, int W, cudaStream_t s);  // hole fill
-inline int ctx_sms(bd_ctx* c) { return c->num_sms; }
-inline void ctx_count(bd_ctx* c, int n) { c->launches += n; }
-
-inline int workspace(bd_ctx* ctx, int H, int W, Workspace** out) {
-  Workspace& w = ctx->post_ws;
-  const size_t n = static_cast<size_t>(H) * W;
-  if (n > w.cap) {
-    w.release();
-    const size_t cap = n + 64;
-#define BD_WS_ALLOC(field, type, count) BD_CUDA(cudaMalloc(reinterpret_cast<void**>(&w.field), sizeof(type) * (count)))
-    BD_WS_ALLOC(L, int, cap); BD_WS_ALLOC(Lh, int, cap); BD_WS_ALLOC(Lv, int, cap);
-    BD_WS_ALLOC(a2, long long, cap); BD_WS_ALLOC(a2h, long long, cap); BD_WS_ALLOC(a2v, long long, cap);
-    BD_WS_ALLOC(cntH, int, cap); BD_WS_ALLOC(survH, int, cap); BD_WS_ALLOC(cntV, int, cap); BD_WS_ALLOC(survV, int, cap);
-    BD_WS_ALLOC(filled, uint8_t, cap); BD_WS_ALLOC(keep, uint8_t, cap); BD_WS_ALLOC(er, uint8_t, cap);
-    BD_WS_ALLOC(voted, uint8_t, cap); BD_WS_ALLOC(cleaned, uint8_t, 5 * cap);
-#undef BD_WS_ALLOC
-    w.cap = n;
-  }
-  *out = &w;
-  return 0;
-}
-}  // namespace post
-}  // namespace bd

@@ -52,6 +52,66 @@ def cleanup_device(mask):
     return out
 
 
+def plane_words(w):
+    """words per row of a bit-packed mask plane (csrc/rle.cuh)"""
+    return int(R.lib().bd_plane_words_per_row(int(w)))
+
+
+def pack_device(mask):
+    """(H,W) u8 cuda tensor -> (H, plane_words(W)) int32 cuda tensor, 1 bit per pixel (nonzero = set).  Rows are
+    independent, so a band of rows can be packed, shipped and OR-ed on its own (multi-GPU gather)."""
+    t = _torch()
+    mask = mask.contiguous()
+    h, w = mask.shape
+    out = t.empty((h, plane_words(w)), dtype=t.int32, device=mask.device)
+    stream = t.cuda.current_stream(mask.device).cuda_stream
+    R.check(R.lib().bd_mask_pack(R.context(mask.device.index), mask.data_ptr(), h, w, out.data_ptr(), stream))
+    return out
+
+
+def unpack_device(plane, w):
+    t = _torch()
+    plane = plane.contiguous()
+    h = plane.shape[0]
+    out = t.empty((h, w), dtype=t.uint8, device=plane.device)
+    stream = t.cuda.current_stream(plane.device).cuda_stream
+    R.check(R.lib().bd_mask_unpack(R.context(plane.device.index), plane.data_ptr(), h, w, out.data_ptr(), stream))
+    return out
+
+
+def fuse_planes_device(planes5, w, cleaned=False):
+    """planes5: (5, H, plane_words(W)) int32 cuda tensor of packed masks -> fused (H,W) u8 cuda tensor."""
+    t = _torch()
+    planes5 = planes5.contiguous()
+    assert planes5.dim() == 3 and planes5.shape[0] == 5 and planes5.shape[2] == plane_words(w)
+    h = planes5.shape[1]
+    out = t.empty((h, w), dtype=t.uint8, device=planes5.device)
+    stream = t.cuda.current_stream(planes5.device).cuda_stream
+    R.check(R.lib().bd_fuse_planes(R.context(planes5.device.index), planes5.data_ptr(), 1 if cleaned else 0, h, w,
+                                   out.data_ptr(), None, stream))
+    return out
+
+
+def debug_stage(mask, stage):
+    """test hook: an intermediate plane of one clean-up pass (bd_debug_cleanup_stage) of a host (H,W) u8 mask"""
+    t = _torch()
+    m = t.from_numpy(np.ascontiguousarray(mask, np.uint8)).cuda()
+    out = t.empty_like(m)
+    R.check(R.lib().bd_debug_cleanup_stage(R.context(m.device.index), m.data_ptr(), m.shape[0], m.shape[1], stage,
+                                           out.data_ptr(), t.cuda.current_stream().cuda_stream))
+    return out.cpu().numpy()
+
+
+def debug_labels(mask, fg=1, conn8=1):
+    """test hook: run-based component labels as per-pixel labels (bd_debug_labels)"""
+    t = _torch()
+    m = t.from_numpy(np.ascontiguousarray(mask, np.uint8)).cuda()
+    out = t.empty(m.shape, dtype=t.int32, device=m.device)
+    R.check(R.lib().bd_debug_labels(R.context(m.device.index), m.data_ptr(), m.shape[0], m.shape[1], fg, conn8,
+                                    out.data_ptr(), t.cuda.current_stream().cuda_stream))
+    return out.cpu().numpy()
+
+
 def fuse(masks5):
     """Host arrays in, host array out: five (H,W) u8 masks -> fused (H,W) u8."""
     t = _torch()

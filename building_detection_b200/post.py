@@ -3,9 +3,11 @@
 device-resident pipeline; bench.py and predict.predict() drive it.
 
 Multi-GPU (SURVEY section 8e): every rank owns a contiguous band of tile rows and all five models' weights;
-no collective per tile.  Band masks (5 x rows x W u8) are sent to rank 0 over NCCL and OR-ed into its scene
-masks (adjacent bands overlap by 152 rows; OR is idempotent), then fusion and contour extraction -- which
-need whole connected components -- run on rank 0.
+no collective per tile.  Every rank packs its band of the five masks to 1 bit per pixel (bd_mask_pack: rows are
+independent) and sends it to rank 0 in ONE message (grouped NCCL send/recv, 1/8 of the u8 bytes); rank 0 ORs the
+bands into five scene planes (adjacent bands overlap by 152 rows; OR is idempotent) and runs fusion and contour
+extraction -- which need whole connected components -- on them (bd_fuse_planes, bd_contours: ~20 ms at 20 000^2,
+so sharding them further would cost more in exchange than it saves).
 """
 from __future__ import annotations
 
@@ -45,53 +47,34 @@ def gather_bands(masks, bands, rank, world, stage=None):
     return masks
 
 
-def model_owner(k, world):
-    """Rank that cleans model k's scene mask: the five per-model clean-ups of model_fuse.py:285-313 are independent,
-    so with several GPUs they run on different ranks."""
-    return k % world
-
-
-def exchange_by_model(masks, bands, rank, world):
-    """Every rank holds its band of all M model masks; afterwards the owner of model k holds the complete mask k
-    (band rows OR-ed in place into its own ``masks[k]``).  Plain send/recv, every rank walks k in the same order and
-    for a given k there is a single receiver, so there is no circular wait."""
+def gather_packed(band_planes, bands, rank, world, h):
+    """band_planes: (M, rows, wp) int32 -- this rank's band of the M masks, bit-packed -> (M, h, wp) planes of the
+    whole scene on rank 0 (None elsewhere).  One message per rank, posted as one group."""
+    import torch
+    import torch.distributed as dist
     if world == 1:
-        return masks
-    import torch
-    import torch.distributed as dist
-    for k in range(masks.shape[0]):
-        owner = model_owner(k, world)
-        if rank == owner:
-            for r in range(world):
-                r0, r1 = bands[r]
-                if r == rank or r1 <= r0:
-                    continue
-                buf = torch.empty_like(masks[k, r0:r1])
-                dist.recv(buf, src=r)
-                masks[k, r0:r1].bitwise_or_(buf)
-        else:
-            r0, r1 = bands[rank]
-            if r1 > r0:
-                dist.send(masks[k, r0:r1].contiguous(), dst=owner)
-    return masks
-
-
-def collect_cleaned(cleaned, n_models, rank, world, like):
-    """cleaned: {k: (H,W) u8 tensor} for the models this rank owns -> (M,H,W) on rank 0 (None elsewhere)."""
-    import torch
-    import torch.distributed as dist
-    if rank == 0:
-        out = torch.empty((n_models,) + tuple(like.shape[-2:]), dtype=torch.uint8, device=like.device)
-        for k in range(n_models):
-            owner = model_owner(k, world)
-            if owner == 0:
-                out[k].copy_(cleaned[k])
-            else:
-                dist.recv(out[k], src=owner)
-        return out
-    for k in sorted(cleaned):
-        dist.send(cleaned[k].contiguous(), dst=0)
-    return None
+        return band_planes
+    m, _, wp = band_planes.shape
+    if rank != 0:
+        if band_planes.shape[1]:
+            dist.send(band_planes.contiguous(), dst=0)
+        return None
+    planes = torch.zeros((m, h, wp), dtype=band_planes.dtype, device=band_planes.device)
+    r0, r1 = bands[0]
+    planes[:, r0:r1] = band_planes
+    stage, ops = {}, []
+    for r in range(1, world):
+        r0, r1 = bands[r]
+        if r1 > r0:
+            stage[r] = torch.empty((m, r1 - r0, wp), dtype=band_planes.dtype, device=band_planes.device)
+            ops.append(dist.P2POp(dist.irecv, stage[r], r))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    for r, buf in stage.items():
+        r0, r1 = bands[r]
+        planes[:, r0:r1].bitwise_or_(buf)
+    return planes
 
 
 class SceneJob:
@@ -106,6 +89,7 @@ class SceneJob:
         self.bands = [band_of(S.shard_rows(self.all_origins, r, world), h) for r in range(world)]
         self.scene_dev = None
         self.stage = None
+        self.planes = None
         if world > 1 and rank == 0 and not do_post:
             rows = max(b[1] - b[0] for b in self.bands[1:])
             self.stage = torch.empty((len(runner.models), rows, w), dtype=torch.uint8, device=dev)
@@ -120,10 +104,18 @@ class SceneJob:
         self.runner.run(scene_dev, origins=self.origins, out=self.masks)
 
     def _gather(self):
-        """N > 1 with post-processing: model k's complete mask goes to its owner rank (the five clean-ups run in
-        parallel on different GPUs); without post-processing all bands go to rank 0."""
+        """N > 1 with post-processing: every rank's bit-packed band goes to rank 0 in one message; without
+        post-processing the u8 bands go to rank 0."""
+        self.planes = None
+        if self.world == 1:
+            return
         if self.do_post:
-            exchange_by_model(self.masks, self.bands, self.rank, self.world)
+            from . import model_fuse
+            r0, r1 = self.bands[self.rank]
+            band = self.t.stack([model_fuse.pack_device(self.masks[k, r0:r1]) for k in range(self.masks.shape[0])]) \
+                if r1 > r0 else self.t.empty((self.masks.shape[0], 0, model_fuse.plane_words(self.w)), dtype=self.t.int32,
+                                             device=self.masks.device)
+            self.planes = gather_packed(band, self.bands, self.rank, self.world, self.h)
         else:
             gather_bands(self.masks, self.bands, self.rank, self.world, self.stage)
 
@@ -134,12 +126,9 @@ class SceneJob:
         if self.world == 1:
             fused = model_fuse.fuse_device(self.masks)
         else:
-            mine = {k: model_fuse.cleanup_device(self.masks[k]) for k in range(self.masks.shape[0])
-                    if model_owner(k, self.world) == self.rank}
-            cleaned = collect_cleaned(mine, self.masks.shape[0], self.rank, self.world, self.masks)
             if self.rank != 0:
                 return None
-            fused = model_fuse.fuse_cleaned_device(cleaned)
+            fused = model_fuse.fuse_planes_device(self.planes, self.w)
         polys = edge_3.contours_device(fused)
         return fused, polys
 

@@ -30,6 +30,13 @@ class ConvDesc(C.Structure):
                 ("dw_w_host", C.c_void_p), ("dw_relu_in", C.c_int32)]
 
 
+class PostConstants(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("fuse_min_area", "fuse_min_fragment", "fuse_split_width", "fuse_votes",
+                                         "edge_min_area", "edge_min_fragment", "edge_split_width")] + \
+               [(n, C.c_double) for n in ("edge_iou", "edge_min_moment", "tier_small", "tier_mid", "tier_big0", "tier_big1",
+                                          "tier_big2", "eps_default", "eps_mid_mult", "eps_big0", "eps_big1", "eps_big2")]
+
+
 class Polys(C.Structure):
     _fields_ = [("n_polys", C.c_int32), ("n_points", C.c_int32), ("offsets", C.POINTER(C.c_int32)),
                 ("xs", C.POINTER(C.c_float)), ("ys", C.POINTER(C.c_float)), ("is_float", C.POINTER(C.c_uint8))]
@@ -81,6 +88,13 @@ _SIGS = {
     "bd_fuse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "bd_fuse_cleaned": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "bd_mask_cleanup": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "bd_post_constants": (C.c_int, [C.c_void_p, C.POINTER(PostConstants)]),
+    "bd_plane_words_per_row": (C.c_size_t, [C.c_int]),
+    "bd_mask_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "bd_mask_unpack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "bd_fuse_planes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bd_debug_cleanup_stage": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "bd_debug_labels": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "bd_contours": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(Polys), C.c_void_p]),
     "bd_polys_free": (None, [C.POINTER(Polys)]),
     "bd_host_contour_area": (C.c_double, [C.c_void_p, C.c_int]),

@@ -151,15 +151,47 @@ int bd_stitch_or_at(bd_ctx* ctx, const uint8_t* tile_masks_dev, int first, int n
                     void* stream);
 
 /* ---- fusion: replaces model_fuse.py:model_confuse (271-350) --------------------------------- */
-/* masks5_dev: 5 u8 masks (5,h,w) with values {0,255}; fused_dev: u8 (h,w) {0,255}.
+/* The literals of model_fuse.py / edge_3.py the library was built with (reference line in the comment). */
+typedef struct bd_post_constants_t {
+  int32_t fuse_min_area;      /* model_fuse.py:22   polygons of area <= 1000 are erased */
+  int32_t fuse_min_fragment;  /* model_fuse.py:57   fragments of area <= 500 are erased */
+  int32_t fuse_split_width;   /* model_fuse.py:180-181,67   1x5 kernel x 5 iterations = 21 */
+  int32_t fuse_votes;         /* model_fuse.py:323  >= 3 of 5 */
+  int32_t edge_min_area;      /* edge_3.py:326      <= 100 erased */
+  int32_t edge_min_fragment;  /* edge_3.py:131      < 50 erased */
+  int32_t edge_split_width;   /* edge_3.py:128      7 */
+  double edge_iou;            /* edge_3.py:42       0.5 */
+  double edge_min_moment;     /* edge_3.py:331      m00 <= 10 skipped */
+  double tier_small, tier_mid, tier_big0, tier_big1, tier_big2;          /* edge_3.py:360-375: 150, 300, 3000, 8000, 15000 */
+  double eps_default, eps_mid_mult, eps_big0, eps_big1, eps_big2;        /* 0.01, x5, 0.005, 0.004, 0.002 (x perimeter) */
+} bd_post_constants_t;
+int bd_post_constants(bd_ctx* ctx, bd_post_constants_t* out);
+
+/* masks5_dev: 5 u8 masks (5,h,w), nonzero = building; fused_dev: u8 (h,w) {0,255}.
  * Per mask: hole fill + drop polygon-area <= 1000, directional 1x21 / 21x1 erosion split with fragment
- * filter <= 500; vote >= 3 of 5; same clean-up again.  Synchronous. */
+ * filter <= 500; vote >= 3 of 5; same clean-up again.  Internally the masks are packed to 1 bit per pixel and
+ * labelled by horizontal runs (csrc/rle.cuh).  Synchronises the stream (run counts size the scratch). */
 int bd_fuse(bd_ctx* ctx, const uint8_t* masks5_dev, int h, int w, uint8_t* fused_dev, void* stream);
-/* second half of bd_fuse: vote >= 3 of five ALREADY cleaned masks, then the final clean-up (model_fuse.py:315-346);
- * the multi-GPU path runs the five clean-ups on different ranks and finishes here */
+/* second half of bd_fuse: vote >= 3 of five ALREADY cleaned masks, then the final clean-up (model_fuse.py:315-346) */
 int bd_fuse_cleaned(bd_ctx* ctx, const uint8_t* cleaned5_dev, int h, int w, uint8_t* fused_dev, void* stream);
 /* the per-mask clean-up alone (fill_and_delete + eroede_dilate_process + only_plt, model_fuse.py:9-218) */
 int bd_mask_cleanup(bd_ctx* ctx, const uint8_t* mask_dev, int h, int w, uint8_t* out_dev, void* stream);
+/* Bit-packed masks ("planes": bit j of word wd of row y = pixel (32 wd + j, y), bd_plane_words_per_row(w) words per
+ * row, bits beyond w zero) -- what the multi-GPU path ships between ranks (1/8 of the u8 bytes) and what bd_fuse works
+ * on.  Rows are independent: a band of rows packs to the same words as the corresponding rows of the whole mask. */
+size_t bd_plane_words_per_row(int w);
+int bd_mask_pack(bd_ctx* ctx, const uint8_t* mask_dev, int h, int w, uint32_t* plane_dev, void* stream);
+int bd_mask_unpack(bd_ctx* ctx, const uint32_t* plane_dev, int h, int w, uint8_t* mask_dev, void* stream);
+/* bd_fuse on five planes stored back to back (cleaned != 0: they are already cleaned, like bd_fuse_cleaned); writes
+ * the fused mask as u8 (fused_dev, may be NULL) and / or as a plane (fused_plane_dev, may be NULL) */
+int bd_fuse_planes(bd_ctx* ctx, const uint32_t* planes5_dev, int cleaned, int h, int w, uint8_t* fused_dev,
+                   uint32_t* fused_plane_dev, void* stream);
+/* test hooks: an intermediate plane of one clean-up pass as a u8 mask (stage 0 holes filled, 1 area filter, 2 / 3
+ * horizontal / vertical erosion, 4 objects kept whole, 5 / 6 surviving fragments of the two splits, 7 result), and the
+ * run-based labelling as per-pixel labels (raster index of the component's first pixel, -1 outside the set; fg: label
+ * the set or the clear pixels; conn8: 8- or 4-connected) */
+int bd_debug_cleanup_stage(bd_ctx* ctx, const uint8_t* mask_dev, int h, int w, int stage, uint8_t* out_dev, void* stream);
+int bd_debug_labels(bd_ctx* ctx, const uint8_t* mask_dev, int h, int w, int fg, int conn8, int32_t* labels_dev, void* stream);
 
 /* ---- contours: replaces edge_3.py:_detection (310-387) -------------------------------------- */
 typedef struct bd_polys {

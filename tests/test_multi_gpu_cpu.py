@@ -27,25 +27,30 @@ def stitched(origins, img):
     return out
 
 
-def fake_cleanup(mask):
-    """stand-in for bd_mask_cleanup in the CPU test: any deterministic whole-mask transform (3x3 dilation)"""
-    import cv2 as cv
-    return torch.from_numpy(cv.dilate(mask.numpy(), np.ones((3, 3), np.uint8)))
+def pack_rows(mask):
+    """numpy twin of bd_mask_pack: bit j of word wd = pixel 32 wd + j, rows padded to a multiple of 4 words"""
+    h, w = mask.shape
+    wp = ((w + 31) // 32 + 3) & ~3
+    bits = np.zeros((h, wp * 32), np.uint8)
+    bits[:, :w] = mask > 0
+    return np.packbits(bits, axis=1, bitorder="little").view(np.int32).reshape(h, wp)
 
 
-def worker_by_model(rank, world, port, q):
+def worker_packed(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     img = scene_image(H, W)
     origins = S.tile_origins(H, W)
     bands = [post.band_of(S.shard_rows(origins, r, world), H) for r in range(world)]
     two = stitched(S.shard_rows(origins, rank, world), img)
-    masks = torch.from_numpy(np.concatenate([two, two[:1] // 255 * 255, two[1:], two[:1]], axis=0))  # 5 "models"
-    post.exchange_by_model(masks, bands, rank, world)
-    mine = {k: fake_cleanup(masks[k]) for k in range(5) if post.model_owner(k, world) == rank}
-    out = post.collect_cleaned(mine, 5, rank, world, masks)
+    masks = np.concatenate([two, two[:1], two[1:], two[:1]], axis=0)  # 5 "models"
+    r0, r1 = bands[rank]
+    band = torch.from_numpy(np.stack([pack_rows(m[r0:r1]) for m in masks]))
+    planes = post.gather_packed(band, bands, rank, world, H)
     if rank == 0:
-        q.put(out.numpy())
+        q.put(planes.numpy())
+    else:
+        assert planes is None
     dist.barrier()
     dist.destroy_process_group()
 
@@ -84,15 +89,15 @@ def test_band_shard_gather_equals_single_process():
     assert bands[0][1] - bands[1][0] == 152  # the overlap the OR has to absorb
 
 
-def test_per_model_cleanup_exchange_equals_single_process():
-    """multi-GPU post-processing: model k's complete mask is assembled on rank k % world, cleaned there, and the
-    cleaned masks are collected on rank 0 -- must equal cleaning the single-process masks."""
+def test_packed_band_gather_equals_single_process():
+    """multi-GPU post-processing: every rank ships its bit-packed band of the five masks to rank 0 in one message;
+    the OR of the bands (they overlap by 152 rows) must equal the packed single-process masks."""
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=worker_by_model, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=worker_packed, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
     got = q.get(timeout=180)
@@ -100,6 +105,9 @@ def test_per_model_cleanup_exchange_equals_single_process():
         p.join(timeout=60)
         assert p.exitcode == 0
     two = stitched(S.tile_origins(H, W), scene_image(H, W))
-    full = np.concatenate([two, two[:1] // 255 * 255, two[1:], two[:1]], axis=0)
-    want = np.stack([fake_cleanup(torch.from_numpy(m)).numpy() for m in full])
+    full = np.concatenate([two, two[:1], two[1:], two[:1]], axis=0)
+    want = np.stack([pack_rows(m) for m in full])
     np.testing.assert_array_equal(got, want)
+    # and the packing is what the u8 masks say
+    bits = np.unpackbits(got[0].view(np.uint8), axis=1, bitorder="little")[:, :W]
+    np.testing.assert_array_equal(bits * 255, full[0])

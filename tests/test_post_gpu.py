@@ -47,6 +47,66 @@ def test_cleanup_matches_oracle_noise(gpu, size, seed, p, blur):
     assert (got != want).sum() == 0, f"{(got != want).sum()} of {want.size} px differ"
 
 
+def _canon(lab):
+    flat = lab.ravel()
+    first = np.full(lab.max() + 1, -1, np.int64)
+    order = np.argsort(flat, kind="stable")
+    vals, start = np.unique(flat[order], return_index=True)
+    first[vals] = np.arange(flat.size)[order][start]
+    out = first[flat].reshape(lab.shape)
+    out[lab == 0] = -1
+    return out.astype(np.int32)
+
+
+@pytest.mark.parametrize("size,seed,kind", [(333, 1, "base"), (700, 3, "base"), (1024, 4, "noise"), (257, 5, "noise1"),
+                                            (2048, 6, "base"), (31, 8, "noise"), (1, 9, "one")])
+def test_run_labels_and_stages_match_opencv(gpu, size, seed, kind):
+    """the run-based labelling (4- and 8-connected, set and clear pixels) against cv2.connectedComponents, and the
+    intermediate planes of a clean-up pass against the OpenCV steps of model_fuse.py -- on the GPU, where the unions
+    race (the same checks run on the host-compiled kernels in tests/test_rle_emul.py)"""
+    import cv2 as cv
+    from building_detection_b200 import model_fuse
+    if kind == "base":
+        m = PS.base_mask(size, seed, n_objects=max(3, size * size // 9000))
+    elif kind == "one":
+        m = np.full((1, 1), 255, np.uint8)
+    else:
+        m = PS.noise_mask(size, seed, 0.5, 1 if kind == "noise1" else 5)
+    if seed % 2:
+        m = np.ascontiguousarray(m[:, :max(1, size - 5)])
+    for fg, conn8 in ((1, 1), (0, 0), (1, 0), (0, 1)):
+        _, want = cv.connectedComponents(m if fg else 255 - m, connectivity=8 if conn8 else 4)
+        np.testing.assert_array_equal(model_fuse.debug_labels(m, fg, conn8), _canon(want))
+    filled, _ = post_ref.fill_and_delete(m, min_area=-1)
+    np.testing.assert_array_equal(model_fuse.debug_stage(m, 0), filled)
+    keep, _ = post_ref.fill_and_delete(m)
+    np.testing.assert_array_equal(model_fuse.debug_stage(m, 1), keep)
+    np.testing.assert_array_equal(model_fuse.debug_stage(m, 2), cv.erode(keep, np.ones((1, 21), np.uint8)))
+    np.testing.assert_array_equal(model_fuse.debug_stage(m, 3), cv.erode(keep, np.ones((21, 1), np.uint8)))
+    if size <= 1024:
+        np.testing.assert_array_equal(model_fuse.debug_stage(m, 7), post_ref.clean_mask(m))
+
+
+def test_packed_planes_round_trip_and_fuse(gpu):
+    """bd_mask_pack / bd_mask_unpack / bd_fuse_planes: what the multi-GPU gather ships; bands pack like the whole"""
+    import torch
+    from building_detection_b200 import model_fuse
+    for size, cut in ((640, 0), (333, 4)):  # 16-byte aligned rows (vector path) and ragged ones
+        masks = np.stack(PS.five_masks(size, 12))[:, :, :size - cut]
+        w = masks.shape[2]
+        d = torch.from_numpy(np.ascontiguousarray(masks)).cuda()
+        planes = torch.stack([model_fuse.pack_device(d[k]) for k in range(5)])
+        assert planes.shape == (5, size, model_fuse.plane_words(w))
+        for k in range(5):
+            assert torch.equal(model_fuse.unpack_device(planes[k], w), d[k])
+        band = model_fuse.pack_device(d[2, 100:300])
+        assert torch.equal(band, planes[2, 100:300])
+        bits = np.unpackbits(planes[0].cpu().numpy().view(np.uint8), axis=1, bitorder="little")[:, :w]
+        np.testing.assert_array_equal(bits * 255, masks[0])
+        assert torch.equal(model_fuse.fuse_planes_device(planes, w), model_fuse.fuse_device(d))
+        np.testing.assert_array_equal(model_fuse.fuse_device(d).cpu().numpy(), post_ref.model_confuse(list(masks)))
+
+
 def test_fuse_edge_cases(gpu):
     from building_detection_b200 import model_fuse
     z = np.zeros((64, 80), np.uint8)
