@@ -69,6 +69,10 @@ struct bd_plan {
   int input_buf = -1, logits_buf = -1, logits_up = 1;
   float* cur_probs = nullptr;
   uint8_t* cur_mask = nullptr;
+  // CUDA graph of one forward writing the argmax masks to graph_mask (bd_scene_run): captured on first use
+  cudaGraphExec_t graph_exec = nullptr;
+  uint8_t* graph_mask = nullptr;
+  bool graph_failed = false;
 
   int upload(const void* host, size_t bytes, void** out) {
     void* d = nullptr;
@@ -153,6 +157,8 @@ void bd_destroy(bd_ctx* ctx) {
   ctx->arena.release();
   ctx->pool.release();
   if (ctx->h_scalar) cudaFreeHost(ctx->h_scalar);
+  for (void* hp : ctx->h_pts)
+    if (hp) cudaFreeHost(hp);
   delete ctx;
 }
 
@@ -182,6 +188,7 @@ int bd_plan_create(bd_ctx* ctx, int batch, bd_plan** out) {
 void bd_plan_destroy(bd_plan* p) {
   BD_ON_PLAN(p);
   if (!p) return;
+  if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
   for (void* d : p->dev_allocs) cudaFree(d);
   if (p->arena) cudaFree(p->arena);
   delete p;
@@ -859,6 +866,87 @@ int bd_stitch_or_at(bd_ctx* ctx, const uint8_t* tile_masks_dev, int first, int n
             tile_masks_dev, static_cast<const int*>(ctx->d_all_ys + first), static_cast<const int*>(ctx->d_all_xs + first), n,
             scene_mask_dev, h, w);
   return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------ whole-scene entry
+// One forward of `p` writing the argmax masks to mask_dev, replayed from a CUDA graph when it can be captured (the
+// ~140 kernels of a plan become one launch; BD_GRAPHS=0 turns it off).  Falls back to direct launches.
+static int plan_run_masks(bd_plan* p, uint8_t* mask_dev, cudaStream_t s) {
+  static const bool graphs_on = [] { const char* e = getenv("BD_GRAPHS"); return !(e && e[0] == '0'); }();
+  if (graphs_on && !p->graph_failed && (!p->graph_exec || p->graph_mask != mask_dev)) {
+    if (p->graph_exec) { cudaGraphExecDestroy(p->graph_exec); p->graph_exec = nullptr; }
+    cudaGraph_t g = nullptr;
+    bool ok = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if (ok) {
+      p->cur_probs = nullptr;
+      p->cur_mask = mask_dev;
+      const int64_t launches0 = p->ctx->launches;
+      int rc = 0;
+      for (Op& op : p->ops)
+        if ((rc = op.run(s))) break;
+      p->ctx->launches = launches0;  // capturing is not launching
+      ok = cudaStreamEndCapture(s, &g) == cudaSuccess && rc == 0 && g != nullptr;
+    }
+    if (ok) ok = cudaGraphInstantiate(&p->graph_exec, g, 0) == cudaSuccess;
+    if (g) cudaGraphDestroy(g);
+    if (!ok) {
+      cudaGetLastError();  // clear the sticky-free error of a refused capture
+      p->graph_exec = nullptr;
+      p->graph_failed = true;
+    } else {
+      p->graph_mask = mask_dev;
+    }
+  }
+  if (p->graph_exec) {
+    BD_CUDA(cudaGraphLaunch(p->graph_exec, s));
+    p->ctx->launches += bd_plan_num_launches(p);
+    return 0;
+  }
+  return bd_plan_run(p, nullptr, nullptr, mask_dev, s);
+}
+
+// The tiled forward of a scene, predict.py:98-114 for every model: the batch loop lives here, so a scene is ONE call
+// from the host language (196 batches x 5 models x {gather, forward, stitch} at 20 000^2).
+int bd_scene_run(bd_ctx* ctx, bd_plan* const* plans, int n_plans, const uint8_t* scene_bgr_dev, int h, int w,
+                 const int32_t* ys_host, const int32_t* xs_host, int n_tiles, uint8_t* masks_dev, void* stream) {
+  BD_ON_CTX(ctx);
+  BD_CHECK(ctx && plans && n_plans >= 1 && scene_bgr_dev && masks_dev && h >= 1 && w >= 1 && n_tiles >= 0, "bad arguments");
+  if (n_tiles == 0) return 0;
+  BD_CHECK(ys_host && xs_host, "bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int B = plans[0]->batch;
+  for (int k = 0; k < n_plans; ++k) {
+    BD_CHECK(plans[k] && plans[k]->finalized && plans[k]->ctx == ctx && plans[k]->batch == B && plans[k]->input_buf >= 0 &&
+                 plans[k]->logits_buf >= 0,
+             "bd_scene_run: plans must be finalized on this context with one common batch size");
+  }
+  const size_t tm_bytes = static_cast<size_t>(B) * 512 * 512;
+  void* tm = nullptr;
+  if (ctx->pool.get(bd::post::SLOT_TILEMASK, tm_bytes, &tm)) return 1;
+  if (bd_tiles_set_origins(ctx, ys_host, xs_host, n_tiles, stream)) return 1;
+  const size_t plane = static_cast<size_t>(h) * w;
+  for (int b0 = 0; b0 < n_tiles; b0 += B) {
+    const int n = std::min(B, n_tiles - b0);  // a ragged last batch leaves stale tiles in the other slots: ignored
+    for (int k = 0; k < n_plans; ++k) {
+      bd_plan* p = plans[k];
+      const BufInfo& ib = p->bufs[p->input_buf];
+      if (bd_tiles_gather_at(ctx, scene_bgr_dev, h, w, b0, n, p->arena + ib.offset, ib.H == 512 ? 1 : 2, stream)) return 1;
+      if (plan_run_masks(p, static_cast<uint8_t*>(tm), s)) return 1;
+      if (bd_stitch_or_at(ctx, static_cast<const uint8_t*>(tm), b0, n, masks_dev + k * plane, h, w, stream)) return 1;
+    }
+  }
+  BD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// device bytes a context holds for the scene-level stages at (h, w): fusion / contour arena + pools (weights and
+// activation arenas belong to the plans: bd_plan_arena_bytes)
+size_t bd_workspace_bytes(bd_ctx* ctx) {
+  if (!ctx) return 0;
+  size_t b = ctx->arena.cap;
+  for (int i = 0; i < bd::post::DevPool::SLOTS; ++i) b += ctx->pool.cap[i];
+  return b;
 }
 
 }  // extern "C"

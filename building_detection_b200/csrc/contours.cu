@@ -43,207 +43,6 @@ namespace cont {
 
 constexpr int TPB = 256;
 
-__constant__ int c_dx[8] = {1, 1, 0, -1, -1, -1, 0, 1};
-__constant__ int c_dy[8] = {0, -1, -1, -1, 0, 1, 1, 1};
-
-// Border following of one component (Suzuki-Abe outer border as implemented by cv::findContours): returns the
-// number of points; writes them when WRITE; accumulates the bounding box.  Every step loads the eight neighbours
-// of the current pixel with independent loads into a bit mask (bit d = neighbour in direction d is set) and finds
-// the next direction with a rotate + find-first-set, so a step costs one memory latency instead of up to seven.
-__device__ __forceinline__ unsigned neighbour_mask(const uint8_t* __restrict__ img, int H, int W, int x, int y) {
-  const bool l = x > 0, r = x + 1 < W, u = y > 0, d = y + 1 < H;
-  const uint8_t* c = img + static_cast<size_t>(y) * W + x;
-  // directions: 0 E, 1 NE, 2 N, 3 NW, 4 W, 5 SW, 6 S, 7 SE (image coordinates, y down)
-  const unsigned e = r ? c[1] : 0, ne = (r && u) ? c[1 - W] : 0, n = u ? c[-W] : 0, nw = (l && u) ? c[-1 - W] : 0;
-  const unsigned w = l ? c[-1] : 0, sw = (l && d) ? c[W - 1] : 0, s = d ? c[W] : 0, se = (r && d) ? c[W + 1] : 0;
-  return (e ? 1u : 0u) | (ne ? 2u : 0u) | (n ? 4u : 0u) | (nw ? 8u : 0u) | (w ? 16u : 0u) | (sw ? 32u : 0u) |
-         (s ? 64u : 0u) | (se ? 128u : 0u);
-}
-// cap: points that may be written (WRITE only); a longer contour keeps counting without writing (the caller
-// detects n > cap and falls back to the two-pass scheme)
-template <bool WRITE>
-__device__ int trace_one(const uint8_t* __restrict__ img, int H, int W, int root, int2* out, int* bb,
-                         long long cap = (1ll << 62)) {
-  const int x0 = root % W, y0 = root / W;
-  int minx = x0, maxx = x0, miny = y0, maxy = y0;
-  // first neighbour clockwise from west (directions 3, 2, 1, 0, 7, 6, 5): the pixel the trace returns from
-  const unsigned m0 = neighbour_mask(img, H, W, x0, y0);
-  int s = -1;
-#pragma unroll
-  for (int k = 0; k < 7; ++k) {
-    const int d = (3 - k) & 7;
-    if (s < 0 && (m0 >> d) & 1u) s = d;
-  }
-  int n = 0;
-  if (s < 0) {
-    if (WRITE && cap > 0) out[0] = make_int2(x0, y0);
-    n = 1;
-  } else {
-    const int x1 = x0 + c_dx[s], y1 = y0 + c_dy[s];
-    int x3 = x0, y3 = y0;
-    unsigned m = m0;
-    const long long limit = 8ll * H * W + 16;
-    for (long long it = 0; it < limit; ++it) {
-      // next set neighbour counter-clockwise starting after direction s
-      const unsigned rot = ((m >> ((s + 1) & 7)) | (m << (8 - ((s + 1) & 7)))) & 0xFFu;
-      s = (s + __ffs(rot)) & 7;  // rot != 0: the pixel we came from is set
-      const int x4 = x3 + c_dx[s], y4 = y3 + c_dy[s];
-      if (WRITE && n < cap) out[n] = make_int2(x3, y3);
-      ++n;
-      minx = min(minx, x3); maxx = max(maxx, x3); miny = min(miny, y3); maxy = max(maxy, y3);
-      if (x4 == x0 && y4 == y0 && x3 == x1 && y3 == y1) break;
-      x3 = x4; y3 = y4;
-      {  // long straight borders (a mask that fills the frame): pull the rows 12 steps ahead into L1 while we walk
-        const int px = x3 + 12 * c_dx[s], py = y3 + 12 * c_dy[s];
-        if (px >= 0 && px < W && py > 0 && py + 1 < H) {
-          const uint8_t* q = img + static_cast<size_t>(py) * W + px;
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(q));
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(q - W));
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(q + W));
-        }
-      }
-      s = (s + 4) & 7;
-      m = neighbour_mask(img, H, W, x3, y3);
-    }
-  }
-  if (bb) { bb[0] = minx; bb[1] = miny; bb[2] = maxx + 1; bb[3] = maxy + 1; }  // x, y, x+w, y+h of cv::boundingRect
-  return n;
-}
-static __global__ void trace_count(const uint8_t* __restrict__ img, int H, int W, const int* __restrict__ roots, int n,
-                            int* __restrict__ npts, int* __restrict__ bbox) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) npts[i] = trace_one<false>(img, H, W, roots[i], nullptr, bbox + 4 * i);
-}
-static __global__ void trace_write(const uint8_t* __restrict__ img, int H, int W, const int* __restrict__ roots, int n,
-                            const long long* __restrict__ off, int2* __restrict__ pts) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) trace_one<true>(img, H, W, roots[i], pts + off[i], nullptr);
-}
-
-constexpr int BIG_T = 128;     // trace_big: window edge (pixels); the walker stays in [1, BIG_T - 2]
-constexpr int BIG_MIN = 4096;  // crack bound from which a contour is walked by trace_big instead of trace_both
-
-// ---- one-walk tracing.  The number of contour points of a component is bounded by its number of boundary cracks
-// (pixel edges between the component and background or the frame: every move of the border follower passes at
-// least one of them), and the cracks can be counted in parallel.  With bound-sized slots a single walk writes the
-// points and counts them; a parallel copy then packs the contours.  Halves the serial walk of a scene-sized
-// component, which is what bounds the contour stage.
-static __global__ void gather_bounds(const int* __restrict__ cracks, const int* __restrict__ root_runs, int n,
-                                     int* __restrict__ bound) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) bound[i] = max(cracks[root_runs[i]], 1);
-}
-static __global__ void trace_both(const uint8_t* __restrict__ img, int H, int W, const int* __restrict__ roots, int n,
-                                  const long long* __restrict__ off_bound, int2* __restrict__ tmp, int* __restrict__ npts,
-                                  int* __restrict__ bbox, int* __restrict__ overflow) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const long long cap = off_bound[i + 1] - off_bound[i];
-  if (cap >= BIG_MIN) return;  // long contours: trace_big
-  const int m = trace_one<true>(img, H, W, roots[i], tmp + off_bound[i], bbox + 4 * i, cap);
-  npts[i] = m;
-  if (m > cap) atomicExch(overflow, 1);
-}
-// Long contours: one block per contour.  A single walking thread pays a full memory latency per step (~425 ns
-// measured: 51 ms for 120 000 points), so the block keeps a BIG_T x BIG_T window of the image around the walker in
-// shared memory (all threads load it, thread 0 walks inside it at shared-memory latency and re-centres the window
-// when it reaches its rim).  Same stepping rule as trace_one, point for point.
-static __global__ void __launch_bounds__(128) trace_big(const uint8_t* __restrict__ img, int H, int W,
-                                                        const int* __restrict__ roots, const int* __restrict__ big, int nbig,
-                                                        const long long* __restrict__ off_bound, int2* __restrict__ tmp,
-                                                        int* __restrict__ npts, int* __restrict__ bbox, int* __restrict__ overflow) {
-  __shared__ uint8_t tile[BIG_T][BIG_T];
-  __shared__ int sh_cx, sh_cy, sh_done;
-  const int i = big[blockIdx.x];
-  const int root = roots[i];
-  const int x0 = root % W, y0 = root / W;
-  const long long cap = off_bound[i + 1] - off_bound[i];
-  int2* out = tmp + off_bound[i];
-  // walker state (thread 0)
-  int x1 = 0, y1 = 0, x3 = x0, y3 = y0, s = -1, n = 0, phase = 0;
-  int minx = x0, maxx = x0, miny = y0, maxy = y0;
-  long long steps = 0;
-  const long long limit = 8ll * H * W + 16;
-  if (threadIdx.x == 0) { sh_cx = x0; sh_cy = y0; sh_done = 0; }
-  __syncthreads();
-  while (true) {
-    const int ox = sh_cx - BIG_T / 2, oy = sh_cy - BIG_T / 2;  // window origin (may lie outside the image: zeros)
-    {  // 32 independent loads in flight per thread (a load -> store loop would pay one memory latency per row)
-      const int xx = ox + static_cast<int>(threadIdx.x);
-      const bool xok = xx >= 0 && xx < W;
-#pragma unroll 1
-      for (int r0 = 0; r0 < BIG_T; r0 += 32) {
-        uint8_t v[32];
-#pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          const int yy = oy + r0 + k;
-          v[k] = (xok && yy >= 0 && yy < H) ? __ldg(img + static_cast<size_t>(yy) * W + xx) : 0;
-        }
-#pragma unroll
-        for (int k = 0; k < 32; ++k) tile[r0 + k][threadIdx.x] = v[k];
-      }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      auto tmask = [&](int x, int y) -> unsigned {
-        const int lx = x - ox, ly = y - oy;  // 1 .. BIG_T-2
-        return (tile[ly][lx + 1] ? 1u : 0u) | (tile[ly - 1][lx + 1] ? 2u : 0u) | (tile[ly - 1][lx] ? 4u : 0u) |
-               (tile[ly - 1][lx - 1] ? 8u : 0u) | (tile[ly][lx - 1] ? 16u : 0u) | (tile[ly + 1][lx - 1] ? 32u : 0u) |
-               (tile[ly + 1][lx] ? 64u : 0u) | (tile[ly + 1][lx + 1] ? 128u : 0u);
-      };
-      unsigned m = tmask(x3, y3);  // the window is centred on (x3, y3)
-      if (phase == 0) {
-        // first neighbour clockwise from west (directions 3, 2, 1, 0, 7, 6, 5): the pixel the trace returns from
-#pragma unroll
-        for (int k = 0; k < 7; ++k) {
-          const int d = (3 - k) & 7;
-          if (s < 0 && (m >> d) & 1u) s = d;
-        }
-        if (s < 0) {
-          if (cap > 0) out[0] = make_int2(x0, y0);
-          n = 1;
-          phase = 2;
-        } else {
-          x1 = x0 + c_dx[s]; y1 = y0 + c_dy[s];
-          phase = 1;
-        }
-      }
-      while (phase == 1) {
-        const unsigned rot = ((m >> ((s + 1) & 7)) | (m << (8 - ((s + 1) & 7)))) & 0xFFu;
-        s = (s + __ffs(rot)) & 7;
-        const int x4 = x3 + c_dx[s], y4 = y3 + c_dy[s];
-        if (n < cap) out[n] = make_int2(x3, y3);
-        ++n;
-        minx = min(minx, x3); maxx = max(maxx, x3); miny = min(miny, y3); maxy = max(maxy, y3);
-        if ((x4 == x0 && y4 == y0 && x3 == x1 && y3 == y1) || ++steps >= limit) { phase = 2; break; }
-        x3 = x4; y3 = y4;
-        s = (s + 4) & 7;
-        const int lx = x3 - ox, ly = y3 - oy;
-        if (lx < 1 || lx > BIG_T - 2 || ly < 1 || ly > BIG_T - 2) break;  // re-centre the window
-        m = tmask(x3, y3);
-      }
-      sh_cx = x3; sh_cy = y3; sh_done = phase == 2;
-    }
-    __syncthreads();
-    if (sh_done) break;
-  }
-  if (threadIdx.x == 0) {
-    npts[i] = n;
-    bbox[4 * i] = minx; bbox[4 * i + 1] = miny; bbox[4 * i + 2] = maxx + 1; bbox[4 * i + 3] = maxy + 1;
-    if (n > cap) atomicExch(overflow, 1);
-  }
-}
-
-// pack: contour i occupies tmp[off_bound[i] ...) and goes to pts[off[i] ...); one block per contour
-static __global__ void __launch_bounds__(TPB) pack_points(const int2* __restrict__ tmp, const long long* __restrict__ off_bound,
-                                                   const long long* __restrict__ off, int2* __restrict__ pts) {
-  const int i = blockIdx.x;
-  const long long m = off[i + 1] - off[i];
-  const int2* src = tmp + off_bound[i];
-  int2* dst = pts + off[i];
-  for (long long k = threadIdx.x; k < m; k += TPB) dst[k] = src[k];
-}
-
 // edge_3.py:26-47 for every initial box against all eroded boxes: index of the first maximum IoU if any IoU
 // exceeds 0.5, else -1.  Boxes are (x0, y0, x1, y1); IoU in float64 exactly like numpy's int64 / int64.
 static __global__ void __launch_bounds__(TPB) match_boxes(const int* __restrict__ a, int na, const int* __restrict__ b, int nb,
@@ -438,14 +237,23 @@ struct HostSet {           // one traced contour list, in cv::findContours order
   int n = 0;
   std::vector<int> bbox;   // 4 per contour
   std::vector<long long> off;  // n + 1
-  std::vector<Pt> pts;
+  const Pt* pts = nullptr; // off[n] points in the context's pinned host buffer of this set (valid during the call)
   int* d_bbox = nullptr;   // device copy (matching kernel)
 };
 
-// trace every component of `img` (the u8 copy of rs.p) whose polygon area passes the threshold
-static int trace_set(bd_ctx* ctx, const uint8_t* img, const rle::RunSet& rs, const long long* a2, long long thr2, int strict, int H,
-                     int W, cudaStream_t s, HostSet* out, int slot0, int* n_launch) {
-  const size_t words = static_cast<size_t>(H) * rs.p.wp;
+static int grid_rows(bd_ctx* ctx, int H) {
+  return std::max(1, std::min((H + rle::TPB / 32 - 1) / (rle::TPB / 32), ctx->num_sms * 8));
+}
+
+// External contours (cv::findContours(RETR_EXTERNAL, CHAIN_APPROX_NONE)) of every component of rs whose polygon area
+// passes the threshold.  `p` is the plane that holds exactly those components (their runs are runs of rs.p).  The
+// borders are followed in parallel (rle.cuh: crack successors + pointer jumping), so a scene-sized contour costs the
+// same as twenty thousand small ones.  `which` (0..2): the set's pool slots and pinned host buffer.
+static int trace_set(bd_ctx* ctx, rle::Plane p, const rle::RunSet& rs, const long long* a2, long long thr2, int strict,
+                     cudaStream_t s, HostSet* out, int which, int* n_launch) {
+  const int slot0 = which * 8;
+  const int H = p.H;
+  const size_t words = static_cast<size_t>(H) * p.wp;
   post::DevPool& pool = ctx->pool;
   const bool timing = getenv("BD_POST_TIMING") != nullptr;  // per-step wall clock of this set (synchronises)
   auto t_last = std::chrono::steady_clock::now();
@@ -453,25 +261,42 @@ static int trace_set(bd_ctx* ctx, const uint8_t* img, const rle::RunSet& rs, con
     if (!timing) return;
     cudaStreamSynchronize(s);
     const auto t = std::chrono::steady_clock::now();
-    fprintf(stderr, "[trace_set %2d] %-28s %8.2f ms\n", slot0, what, std::chrono::duration<double, std::milli>(t - t_last).count());
+    fprintf(stderr, "[trace_set %d] %-28s %8.2f ms\n", which, what, std::chrono::duration<double, std::milli>(t - t_last).count());
     t_last = t;
   };
   out->n = 0;
   out->off.assign(1, 0);
   out->bbox.clear();
+  out->pts = nullptr;
   if (rs.nruns == 0) return 0;
-  int* d_count = nullptr;
-  if (pool.get(slot0 + 0, sizeof(int), reinterpret_cast<void**>(&d_count))) return 1;
-  BD_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int), s));
+  const int g = post::grid_words(ctx, words);
+  // roots + crack numbering, one synchronisation for both counts
+  int* d_count = nullptr;  // [0] components, [1] cracks
+  if (pool.get(slot0 + 0, 2 * sizeof(int), reinterpret_cast<void**>(&d_count))) return 1;
+  BD_CUDA(cudaMemsetAsync(d_count, 0, 2 * sizeof(int), s));
   const int cap = rs.nruns;  // a component has at least one run
   int* d_list = nullptr;     // [cap] first pixels, then [cap] root runs
   if (pool.get(slot0 + 1, sizeof(int) * 2 * static_cast<size_t>(cap), reinterpret_cast<void**>(&d_list))) return 1;
   int* d_rid = d_list + cap;
-  rle::collect_roots<<<post::grid_words(ctx, words), rle::TPB, 0, s>>>(rs, a2, thr2, strict, d_list, d_rid, d_count, cap);
-  ++*n_launch;
-  int cnt = 0;
-  BD_CUDA(cudaMemcpyAsync(&cnt, d_count, sizeof(int), cudaMemcpyDeviceToHost, s));
+  rle::collect_roots<<<g, rle::TPB, 0, s>>>(rs, a2, thr2, strict, d_list, d_rid, d_count, cap);
+  char* geo = nullptr;  // cbase [words] u32 | rows [H + 1] | bbmin [2 nruns] | bbmax [2 nruns]
+  const size_t geo_bytes = words * 4 + (static_cast<size_t>(H) + 1) * 4 + 16 * static_cast<size_t>(rs.nruns) + 64;
+  if (pool.get(slot0 + 7, geo_bytes, reinterpret_cast<void**>(&geo))) return 1;
+  uint32_t* cbase = reinterpret_cast<uint32_t*>(geo);
+  int* rows = reinterpret_cast<int*>(geo + words * 4);
+  int* bbmin = rows + H + 1;
+  int* bbmax = bbmin + 2 * static_cast<size_t>(rs.nruns);
+  rle::count_row_cracks<<<grid_rows(ctx, H), rle::TPB, 0, s>>>(p, rows);
+  rle::scan_rows<<<1, 1024, 0, s>>>(rows, H, d_count + 1);
+  rle::emit_crack_base<<<grid_rows(ctx, H), rle::TPB, 0, s>>>(p, rows, cbase);
+  BD_CUDA(cudaMemsetAsync(bbmin, 0x7f, 8 * static_cast<size_t>(rs.nruns), s));
+  BD_CUDA(cudaMemsetAsync(bbmax, 0xff, 8 * static_cast<size_t>(rs.nruns), s));
+  rle::run_bboxes<<<g, rle::TPB, 0, s>>>(rs, bbmin, bbmax);
+  *n_launch += 5;
+  int counts[2] = {0, 0};
+  BD_CUDA(cudaMemcpyAsync(counts, d_count, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
   BD_CUDA(cudaStreamSynchronize(s));
+  const int cnt = counts[0], nc = counts[1];
   BD_CHECK(cnt <= cap, "too many components for the contour stage");
   out->n = cnt;
   out->off.assign(cnt + 1, 0);
@@ -480,9 +305,8 @@ static int trace_set(bd_ctx* ctx, const uint8_t* img, const rle::RunSet& rs, con
   std::vector<int> roots(cnt), rids(cnt);
   BD_CUDA(cudaMemcpyAsync(roots.data(), d_list, sizeof(int) * cnt, cudaMemcpyDeviceToHost, s));
   BD_CUDA(cudaMemcpyAsync(rids.data(), d_rid, sizeof(int) * cnt, cudaMemcpyDeviceToHost, s));
-  BD_CUDA(cudaStreamSynchronize(s));  // (a synchronous cudaMemcpy would queue on the legacy default stream behind
-                                      // the other sets' single-thread walk kernels)
-  lap("collect roots");
+  BD_CUDA(cudaStreamSynchronize(s));
+  lap("roots + crack numbering");
   {  // findContours lists the last-found first: descending first pixel (== descending run number)
     std::vector<int> order(cnt);
     for (int i = 0; i < cnt; ++i) order[i] = i;
@@ -494,91 +318,56 @@ static int trace_set(bd_ctx* ctx, const uint8_t* img, const rle::RunSet& rs, con
   }
   BD_CUDA(cudaMemcpyAsync(d_list, roots.data(), sizeof(int) * cnt, cudaMemcpyHostToDevice, s));
   BD_CUDA(cudaMemcpyAsync(d_rid, rids.data(), sizeof(int) * cnt, cudaMemcpyHostToDevice, s));
-  int *d_npts = nullptr, *d_bbox = nullptr;
-  if (pool.get(slot0 + 2, sizeof(int) * cnt, reinterpret_cast<void**>(&d_npts))) return 1;
-  if (pool.get(slot0 + 3, sizeof(int) * 4 * cnt, reinterpret_cast<void**>(&d_bbox))) return 1;
-  static const bool one_walk = [] { const char* e = getenv("BD_CONTOUR_ONE_WALK"); return !(e && e[0] == '0'); }();
-  if (one_walk) {
-    // crack bound per component -> slots -> a single walk that writes and counts -> parallel pack
-    int *d_cracks = nullptr, *d_bound = nullptr, *d_ovf = nullptr;
-    if (pool.get(slot0 + 6, sizeof(int) * static_cast<size_t>(rs.nruns), reinterpret_cast<void**>(&d_cracks))) return 1;
-    if (pool.get(slot0 + 7, sizeof(int) * (cnt + 1), reinterpret_cast<void**>(&d_bound))) return 1;
-    d_ovf = d_bound + cnt;
-    BD_CUDA(cudaMemsetAsync(d_cracks, 0, sizeof(int) * static_cast<size_t>(rs.nruns), s));
-    BD_CUDA(cudaMemsetAsync(d_ovf, 0, sizeof(int), s));
-    rle::crack_count<<<post::grid_words(ctx, words), rle::TPB, 0, s>>>(rs, d_cracks);
-    gather_bounds<<<(cnt + 255) / 256, 256, 0, s>>>(d_cracks, d_rid, cnt, d_bound);
-    *n_launch += 2;
-    std::vector<int> bound(cnt + 1);
-    BD_CUDA(cudaMemcpyAsync(bound.data(), d_bound, sizeof(int) * cnt, cudaMemcpyDeviceToHost, s));
-    BD_CUDA(cudaStreamSynchronize(s));
-    lap("crack bounds");
-    std::vector<long long> off_bound(cnt + 1, 0);
-    for (int i = 0; i < cnt; ++i) off_bound[i + 1] = off_bound[i] + bound[i];
-    long long *d_offb = nullptr, *d_off = nullptr;
-    int2 *d_tmp = nullptr, *d_pts = nullptr;
-    // slot0+4 holds both offset arrays, slot0+5 the slots followed by the packed points
-    if (pool.get(slot0 + 4, sizeof(long long) * 2 * (cnt + 1), reinterpret_cast<void**>(&d_offb))) return 1;
-    d_off = d_offb + (cnt + 1);
-    if (pool.get(slot0 + 5, sizeof(int2) * 2 * std::max<long long>(off_bound[cnt], 1), reinterpret_cast<void**>(&d_tmp))) return 1;
-    d_pts = d_tmp + off_bound[cnt];
-    BD_CUDA(cudaMemcpyAsync(d_offb, off_bound.data(), sizeof(long long) * (cnt + 1), cudaMemcpyHostToDevice, s));
-    trace_both<<<(cnt + 63) / 64, 64, 0, s>>>(img, H, W, d_list, cnt, d_offb, d_tmp, d_npts, d_bbox, d_ovf);
-    ++*n_launch;
-    std::vector<int> big;
-    for (int i = 0; i < cnt; ++i)
-      if (bound[i] >= BIG_MIN) big.push_back(i);
-    if (!big.empty()) {
-      int* d_big = nullptr;
-      if (pool.get(slot0 + 0, sizeof(int) * (1 + big.size()), reinterpret_cast<void**>(&d_big))) return 1;
-      d_big += 1;  // (slot0+0 also holds the root counter, consumed above)
-      BD_CUDA(cudaMemcpyAsync(d_big, big.data(), sizeof(int) * big.size(), cudaMemcpyHostToDevice, s));
-      trace_big<<<static_cast<int>(big.size()), 128, 0, s>>>(img, H, W, d_list, d_big, static_cast<int>(big.size()), d_offb,
-                                                             d_tmp, d_npts, d_bbox, d_ovf);
-      ++*n_launch;
-    }
-    std::vector<int> npts1(cnt);
-    int ovf = 0;
-    BD_CUDA(cudaMemcpyAsync(npts1.data(), d_npts, sizeof(int) * cnt, cudaMemcpyDeviceToHost, s));
-    BD_CUDA(cudaMemcpyAsync(out->bbox.data(), d_bbox, sizeof(int) * 4 * cnt, cudaMemcpyDeviceToHost, s));
-    BD_CUDA(cudaMemcpyAsync(&ovf, d_ovf, sizeof(int), cudaMemcpyDeviceToHost, s));
-    BD_CUDA(cudaStreamSynchronize(s));
-    lap("walk");
-    if (timing) fprintf(stderr, "[trace_set %2d] %d contours, %lld crack slots\n", slot0, cnt, off_bound[cnt]);
-    if (!ovf) {
-      for (int i = 0; i < cnt; ++i) out->off[i + 1] = out->off[i] + npts1[i];
-      const long long total1 = out->off[cnt];
-      BD_CUDA(cudaMemcpyAsync(d_off, out->off.data(), sizeof(long long) * (cnt + 1), cudaMemcpyHostToDevice, s));
-      pack_points<<<cnt, TPB, 0, s>>>(d_tmp, d_offb, d_off, d_pts);
-      ++*n_launch;
-      out->pts.resize(total1);
-      BD_CUDA(cudaMemcpyAsync(out->pts.data(), d_pts, sizeof(int2) * total1, cudaMemcpyDeviceToHost, s));
-      BD_CUDA(cudaStreamSynchronize(s));
-      lap("pack + copy out");
-      if (timing) fprintf(stderr, "[trace_set %2d] %lld points\n", slot0, total1);
-      out->d_bbox = d_bbox;
-      return 0;
-    }
-    // a contour longer than its crack bound (not expected): the two-pass scheme below is always right
+  int *d_npts = nullptr, *d_bbox = nullptr, *d_cr = nullptr;
+  if (pool.get(slot0 + 2, sizeof(int) * 2 * static_cast<size_t>(cnt), reinterpret_cast<void**>(&d_npts))) return 1;
+  int* d_start = d_npts + cnt;
+  if (pool.get(slot0 + 3, sizeof(int) * 4 * static_cast<size_t>(cnt), reinterpret_cast<void**>(&d_bbox))) return 1;
+  // per crack: start_of | term_of | nxt | ws | nxt2 | ws2
+  const size_t ncp = static_cast<size_t>(nc) + 1;
+  if (pool.get(slot0 + 6, sizeof(int) * 6 * ncp, reinterpret_cast<void**>(&d_cr))) return 1;
+  int *start_of = d_cr, *term_of = d_cr + ncp, *nxt = d_cr + 2 * ncp, *ws = d_cr + 3 * ncp, *nxt2 = d_cr + 4 * ncp, *ws2 = d_cr + 5 * ncp;
+  BD_CUDA(cudaMemsetAsync(start_of, 0, sizeof(int) * ncp, s));
+  const int gc = post::grid_words(ctx, static_cast<size_t>(cnt));
+  rle::mark_starts<<<gc, rle::TPB, 0, s>>>(p, cbase, d_list, cnt, start_of, d_start, d_npts);
+  rle::init_cracks<<<g, rle::TPB, 0, s>>>(p, cbase, start_of, nxt, ws, term_of);
+  int rounds = 1;
+  while ((1ll << rounds) < static_cast<long long>(nc) + 1 && rounds < 31) ++rounds;
+  const int gk = post::grid_words(ctx, static_cast<size_t>(nc));
+  for (int r = 0; r < rounds; ++r) {
+    rle::jump_cracks<<<gk, rle::TPB, 0, s>>>(nxt, ws, nxt2, ws2, nc);
+    std::swap(nxt, nxt2);
+    std::swap(ws, ws2);
   }
-  trace_count<<<(cnt + 63) / 64, 64, 0, s>>>(img, H, W, d_list, cnt, d_npts, d_bbox);
-  ++*n_launch;
+  rle::contour_totals<<<gc, rle::TPB, 0, s>>>(d_start, ws, cnt, d_npts);
+  rle::gather_bboxes<<<gc, rle::TPB, 0, s>>>(bbmin, bbmax, d_rid, cnt, d_bbox);
+  *n_launch += 4 + rounds;
   std::vector<int> npts(cnt);
   BD_CUDA(cudaMemcpyAsync(npts.data(), d_npts, sizeof(int) * cnt, cudaMemcpyDeviceToHost, s));
   BD_CUDA(cudaMemcpyAsync(out->bbox.data(), d_bbox, sizeof(int) * 4 * cnt, cudaMemcpyDeviceToHost, s));
   BD_CUDA(cudaStreamSynchronize(s));
+  lap("successors + ranking");
   for (int i = 0; i < cnt; ++i) out->off[i + 1] = out->off[i] + npts[i];
   const long long total = out->off[cnt];
+  if (timing) fprintf(stderr, "[trace_set %d] %d contours, %d cracks, %d jump rounds, %lld points\n", which, cnt, nc, rounds, total);
   long long* d_off = nullptr;
   int2* d_pts = nullptr;
-  if (pool.get(slot0 + 4, sizeof(long long) * (cnt + 1), reinterpret_cast<void**>(&d_off))) return 1;
-  if (pool.get(slot0 + 5, sizeof(int2) * std::max<long long>(total, 1), reinterpret_cast<void**>(&d_pts))) return 1;
+  if (pool.get(slot0 + 4, sizeof(long long) * (static_cast<size_t>(cnt) + 1), reinterpret_cast<void**>(&d_off))) return 1;
+  if (pool.get(slot0 + 5, sizeof(int2) * static_cast<size_t>(std::max<long long>(total, 1)), reinterpret_cast<void**>(&d_pts))) return 1;
   BD_CUDA(cudaMemcpyAsync(d_off, out->off.data(), sizeof(long long) * (cnt + 1), cudaMemcpyHostToDevice, s));
-  trace_write<<<(cnt + 63) / 64, 64, 0, s>>>(img, H, W, d_list, cnt, d_off, d_pts);
+  rle::scatter_points<<<g, rle::TPB, 0, s>>>(p, cbase, nxt, ws, term_of, d_npts, d_off, d_list, cnt, d_pts);
   ++*n_launch;
-  out->pts.resize(total);
-  BD_CUDA(cudaMemcpyAsync(out->pts.data(), d_pts, sizeof(int2) * total, cudaMemcpyDeviceToHost, s));
+  // points -> pinned host memory (pageable vectors cost 10+ ms for the 30 MB of a 20 000^2 scene)
+  const size_t pbytes = sizeof(int2) * static_cast<size_t>(std::max<long long>(total, 1));
+  if (pbytes > ctx->h_pts_cap[which]) {
+    if (ctx->h_pts[which]) cudaFreeHost(ctx->h_pts[which]);
+    ctx->h_pts[which] = nullptr; ctx->h_pts_cap[which] = 0;
+    BD_CUDA(cudaMallocHost(&ctx->h_pts[which], pbytes + pbytes / 4));
+    ctx->h_pts_cap[which] = pbytes + pbytes / 4;
+  }
+  BD_CUDA(cudaMemcpyAsync(ctx->h_pts[which], d_pts, sizeof(int2) * static_cast<size_t>(total), cudaMemcpyDeviceToHost, s));
   BD_CUDA(cudaStreamSynchronize(s));
+  lap("scatter + copy out");
+  out->pts = static_cast<const Pt*>(ctx->h_pts[which]);
   out->d_bbox = d_bbox;
   return 0;
 }
@@ -652,7 +441,6 @@ int bd_contours(bd_ctx* ctx, const uint8_t* mask_dev, int h, int w, bd_polys* ou
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const post::PostConstants& K = ctx->consts;
   post::Arena& ar = ctx->arena;
-  const size_t n = static_cast<size_t>(h) * w;
   const size_t words = static_cast<size_t>(h) * rle::words_per_row(w);
   if (ar.reserve(post::cleanup_scratch_bytes(h, w))) return 1;
   const int g = post::grid_words(ctx, words);
@@ -683,13 +471,11 @@ int bd_contours(bd_ctx* ctx, const uint8_t* mask_dev, int h, int w, bd_polys* ou
   ctx->launches += 3;
   if (post::label_area(ctx, ar, eh, post::SLOT_EH, &EH, &a2h, s)) return 1;
   if (post::label_area(ctx, ar, ev, post::SLOT_EV, &EV, &a2v, s)) return 1;
-  // the border followers walk u8 images
-  uint8_t *img_keep = nullptr, *img_h = nullptr, *img_v = nullptr;
-  if (ctx->pool.get(post::SLOT_IMG, n, reinterpret_cast<void**>(&img_keep)) ||
-      ctx->pool.get(post::SLOT_IMG + 1, n, reinterpret_cast<void**>(&img_h)) ||
-      ctx->pool.get(post::SLOT_IMG + 2, n, reinterpret_cast<void**>(&img_v)))
-    return 1;
-  if (post::unpack(ctx, keep, img_keep, s) || post::unpack(ctx, eh, img_h, s) || post::unpack(ctx, ev, img_v, s)) return 1;
+  // the planes the borders are followed on hold exactly the traced components: eroded fragments of area < 50 are erased
+  rle::Plane ehk = post::take_plane(ar, h, w), evk = post::take_plane(ar, h, w);
+  rle::keep_large<<<g, rle::TPB, 0, s>>>(EH, a2h, 2LL * K.edge_min_fragment, 1, ehk);
+  rle::keep_large<<<g, rle::TPB, 0, s>>>(EV, a2v, 2LL * K.edge_min_fragment, 1, evk);
+  ctx->launches += 2;
   BD_CUDA(cudaGetLastError());
   lap("fill/label/area/erode passes");
 
@@ -711,15 +497,15 @@ int bd_contours(bd_ctx* ctx, const uint8_t* mask_dev, int h, int w, bd_polys* ou
     int rc[3] = {0, 0, 0}, nl[3] = {0, 0, 0};
     std::string err[3];
     const int device = ctx->device;
-    auto job = [&](int k, const uint8_t* img, const rle::RunSet* rs, const long long* ar2, long long thr2, int strict,
-                   cudaStream_t st, HostSet* out_set, int slot0) {
+    auto job = [&](int k, rle::Plane pl, const rle::RunSet* rs, const long long* ar2, long long thr2, int strict,
+                   cudaStream_t st, HostSet* out_set) {
       if (cudaSetDevice(device) != cudaSuccess) { rc[k] = 1; err[k] = "cudaSetDevice failed in a contour worker"; return; }
-      rc[k] = trace_set(ctx, img, *rs, ar2, thr2, strict, h, w, st, out_set, slot0, &nl[k]);
+      rc[k] = trace_set(ctx, pl, *rs, ar2, thr2, strict, st, out_set, k, &nl[k]);
       if (rc[k]) err[k] = bd::last_error();  // thread-local message of the worker
     };
-    std::thread t1(job, 1, img_h, &EH, a2h, 2LL * K.edge_min_fragment, 1, aux[0], &td, 8);
-    std::thread t2(job, 2, img_v, &EV, a2v, 2LL * K.edge_min_fragment, 1, aux[1], &rl, 16);
-    job(0, img_keep, &F, a2, 2LL * K.edge_min_area, 0, s, &ini, 0);
+    std::thread t1(job, 1, ehk, &EH, a2h, 2LL * K.edge_min_fragment, 1, aux[0], &td);
+    std::thread t2(job, 2, evk, &EV, a2v, 2LL * K.edge_min_fragment, 1, aux[1], &rl);
+    job(0, keep, &F, a2, 2LL * K.edge_min_area, 0, s, &ini);
     t1.join();
     t2.join();
     ctx->launches += nl[0] + nl[1] + nl[2];
@@ -776,7 +562,7 @@ int bd_contours(bd_ctx* ctx, const uint8_t* mask_dev, int h, int w, bd_polys* ou
       for (size_t i = t; i < nf; i += T) {
         const Ref& r = finals[i];
         if (!r.set) continue;
-        const Pt* c = r.set->pts.data() + r.set->off[r.idx];
+        const Pt* c = r.set->pts + r.set->off[r.idx];
         const int cn = static_cast<int>(r.set->off[r.idx + 1] - r.set->off[r.idx]);
         simp[i].kind = simplify(c, cn, simp[i].poly, K);
       }
@@ -802,7 +588,7 @@ int bd_contours(bd_ctx* ctx, const uint8_t* mask_dev, int h, int w, bd_polys* ou
       for (const Pt& p : poly) { xs.push_back(static_cast<float>(p.x)); ys.push_back(static_cast<float>(p.y)); }
       xs.push_back(static_cast<float>(poly[0].x)); ys.push_back(static_cast<float>(poly[0].y));  // closed (:379-384)
     } else {
-      const Pt* c = r.set->pts.data() + r.set->off[r.idx];
+      const Pt* c = r.set->pts + r.set->off[r.idx];
       const int cn = static_cast<int>(r.set->off[r.idx + 1] - r.set->off[r.idx]);
       for (int i = 0; i < cn; ++i) { xs.push_back(static_cast<float>(c[i].x)); ys.push_back(static_cast<float>(c[i].y)); }
     }

@@ -87,7 +87,7 @@ enum {
   SLOT_EH = 37,   // +1
   SLOT_EV = 39,   // +1
   SLOT_CNT = 41,  // fragment counters
-  SLOT_IMG = 42,  // +2: u8 images of the three traced planes
+  SLOT_TILEMASK = 42,  // argmax masks of one batch of tiles (bd_scene_run)
 };
 
 }  // namespace post
@@ -110,5 +110,7 @@ struct bd_ctx {
   bd::post::Arena arena;
   bd::post::DevPool pool;
   int* h_scalar = nullptr;    // pinned host word for device -> host counters
+  void* h_pts[3] = {nullptr, nullptr, nullptr};  // pinned host buffers of the three traced contour sets (grow-only)
+  size_t h_pts_cap[3] = {0, 0, 0};
   void* trace_buf = nullptr;  // BD_UMMA_TRACE debug buffer of the most recently built conv
 };

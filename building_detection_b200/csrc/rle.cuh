@@ -562,10 +562,208 @@ static __global__ void __launch_bounds__(TPB) collect_roots(RunSet r, const long
     }
   }
 }
-// Boundary cracks (pixel edges towards background or the frame) per component: an upper bound of the number of points
-// border following emits for it (every move of the follower passes at least one crack; tests/test_post_cpu.py).
-// cracks[] is indexed by root run and must be zero on entry.
-static __global__ void __launch_bounds__(TPB) crack_count(RunSet r, int* __restrict__ cracks) {
+// ---------------------------------------------------------------------------------------------- parallel border following
+// cv::findContours(RETR_EXTERNAL, CHAIN_APPROX_NONE) without a serial walk.  A *crack* is a pixel edge between a set
+// pixel and a clear one (or the frame), directed so that the set pixel lies on its left: left cracks run down, bottom
+// cracks right, right cracks up, top cracks left (counter-clockwise in image coordinates, the direction OpenCV's
+// border follower takes from the first raster pixel).  Every crack has exactly one successor, decided by the 2x2
+// pixels around its end vertex -- turn towards a diagonal neighbour first (8-connectivity), else go straight, else turn
+// around the own pixel's corner -- so the cracks of a component's outer border form one cycle.  The contour OpenCV
+// returns is the sequence of the cracks' pixels along that cycle, starting at the left crack of the component's first
+// raster pixel, with consecutive repetitions of a pixel collapsed (cyclically).  [tests/test_rle_emul.py walks this
+// rule against cv2.findContours; tests/test_post_gpu.py checks the device result point for point.]
+// The cycle is cut in front of the start crack and ranked by pointer jumping, carrying the number of points emitted
+// from a crack to the end of its list, so every crack knows where its point goes.
+//
+// Numbering: cbase[y][wd] = number of the first crack of word wd of row y; inside a word the left cracks come first
+// (by bit), then bottom, right, top.
+enum { CRACK_L = 0, CRACK_B = 1, CRACK_R = 2, CRACK_T = 3 };
+
+struct CrackMasks { uint32_t m[4]; };
+__device__ __forceinline__ uint32_t plane_word(const Plane& p, int y, int wd) {
+  return (y >= 0 && y < p.H && wd >= 0 && wd < p.wp) ? p.w[static_cast<size_t>(y) * p.wp + wd] : 0u;
+}
+__device__ __forceinline__ bool plane_bit(const Plane& p, int x, int y) {
+  return x >= 0 && x < p.W && y >= 0 && y < p.H && ((p.w[static_cast<size_t>(y) * p.wp + (x >> 5)] >> (x & 31)) & 1u);
+}
+__device__ __forceinline__ CrackMasks crack_masks(const Plane& p, int y, int wd) {
+  const uint32_t cur = plane_word(p, y, wd);
+  CrackMasks c;
+  c.m[CRACK_L] = cur & ~((cur << 1) | (plane_word(p, y, wd - 1) >> 31));
+  c.m[CRACK_B] = cur & ~plane_word(p, y + 1, wd);
+  c.m[CRACK_R] = cur & ~((cur >> 1) | (plane_word(p, y, wd + 1) << 31));
+  c.m[CRACK_T] = cur & ~plane_word(p, y - 1, wd);
+  return c;
+}
+__device__ __forceinline__ int crack_rank(const CrackMasks& c, int t, int j) {  // number inside the word
+  int r = __popc(c.m[t] & below(j));
+  if (t > CRACK_L) r += __popc(c.m[CRACK_L]);
+  if (t > CRACK_B) r += __popc(c.m[CRACK_B]);
+  if (t > CRACK_R) r += __popc(c.m[CRACK_R]);
+  return r;
+}
+__device__ __forceinline__ int crack_id(const Plane& p, const uint32_t* __restrict__ cbase, int x, int y, int t) {
+  const int wd = x >> 5;
+  return static_cast<int>(cbase[static_cast<size_t>(y) * p.wp + wd]) + crack_rank(crack_masks(p, y, wd), t, x & 31);
+}
+// successor of crack t of pixel (x, y): pixel and type
+__device__ __forceinline__ void crack_succ(const Plane& p, int x, int y, int t, int* nx, int* ny, int* nt) {
+  switch (t) {
+    case CRACK_L:
+      if (plane_bit(p, x - 1, y + 1)) { *nx = x - 1; *ny = y + 1; *nt = CRACK_T; }
+      else if (plane_bit(p, x, y + 1)) { *nx = x; *ny = y + 1; *nt = CRACK_L; }
+      else { *nx = x; *ny = y; *nt = CRACK_B; }
+      break;
+    case CRACK_B:
+      if (plane_bit(p, x + 1, y + 1)) { *nx = x + 1; *ny = y + 1; *nt = CRACK_L; }
+      else if (plane_bit(p, x + 1, y)) { *nx = x + 1; *ny = y; *nt = CRACK_B; }
+      else { *nx = x; *ny = y; *nt = CRACK_R; }
+      break;
+    case CRACK_R:
+      if (plane_bit(p, x + 1, y - 1)) { *nx = x + 1; *ny = y - 1; *nt = CRACK_B; }
+      else if (plane_bit(p, x, y - 1)) { *nx = x; *ny = y - 1; *nt = CRACK_R; }
+      else { *nx = x; *ny = y; *nt = CRACK_T; }
+      break;
+    default:
+      if (plane_bit(p, x - 1, y - 1)) { *nx = x - 1; *ny = y - 1; *nt = CRACK_R; }
+      else if (plane_bit(p, x - 1, y)) { *nx = x - 1; *ny = y; *nt = CRACK_T; }
+      else { *nx = x; *ny = y; *nt = CRACK_L; }
+      break;
+  }
+}
+#ifndef BD_HOST_EMUL
+static __global__ void __launch_bounds__(TPB) count_row_cracks(Plane p, int* __restrict__ rowcount) {
+  const int lane = threadIdx.x & 31;
+  const int nwarps = gridDim.x * (TPB / 32);
+  for (int y = blockIdx.x * (TPB / 32) + (threadIdx.x >> 5); y < p.H; y += nwarps) {
+    int c = 0;
+    for (int wd = lane; wd < p.wp; wd += 32) {
+      const CrackMasks k = crack_masks(p, y, wd);
+      c += __popc(k.m[0]) + __popc(k.m[1]) + __popc(k.m[2]) + __popc(k.m[3]);
+    }
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (lane == 0) rowcount[y] = c;
+  }
+}
+static __global__ void __launch_bounds__(TPB) emit_crack_base(Plane p, const int* __restrict__ rowbase, uint32_t* __restrict__ cbase) {
+  const int lane = threadIdx.x & 31;
+  const int nwarps = gridDim.x * (TPB / 32);
+  for (int y = blockIdx.x * (TPB / 32) + (threadIdx.x >> 5); y < p.H; y += nwarps) {
+    int base = rowbase[y];
+    for (int wd0 = 0; wd0 < p.wp; wd0 += 32) {
+      const int wd = wd0 + lane;
+      int c = 0;
+      if (wd < p.wp) {
+        const CrackMasks k = crack_masks(p, y, wd);
+        c = __popc(k.m[0]) + __popc(k.m[1]) + __popc(k.m[2]) + __popc(k.m[3]);
+      }
+      int incl = c;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += v;
+      }
+      if (wd < p.wp) cbase[static_cast<size_t>(y) * p.wp + wd] = static_cast<uint32_t>(base + incl - c);
+      base += __shfl_sync(0xffffffffu, incl, 31);
+    }
+  }
+}
+#endif  // BD_HOST_EMUL
+// For contour c (first pixel roots[c], in output order): isolated pixel -> npts[c] = 1 and its start crack stays
+// unmarked (its four cracks rank into a list nobody reads); otherwise start_of[crack id of the pixel's left crack] =
+// c + 1 and start_crack[c] = that id.
+static __global__ void __launch_bounds__(TPB) mark_starts(Plane p, const uint32_t* __restrict__ cbase, const int* __restrict__ roots,
+                                                   int n, int* __restrict__ start_of, int* __restrict__ start_crack,
+                                                   int* __restrict__ npts) {
+  for (int c = blockIdx.x * TPB + threadIdx.x; c < n; c += gridDim.x * TPB) {
+    const int x = roots[c] % p.W, y = roots[c] / p.W;
+    const int id = crack_id(p, cbase, x, y, CRACK_L);
+    start_crack[c] = id;
+    const bool isolated = !plane_bit(p, x + 1, y) && !plane_bit(p, x - 1, y + 1) && !plane_bit(p, x, y + 1) && !plane_bit(p, x + 1, y + 1);
+    if (isolated) npts[c] = 1;
+    else { npts[c] = 0; start_of[id] = c + 1; }
+  }
+}
+// per crack: successor (a crack whose successor is a marked start crack ends its list: nxt = itself, term_of = contour
+// + 1) and ws = 1 when the crack is the last one of its pixel's visit (the successor sits on another pixel)
+static __global__ void __launch_bounds__(TPB) init_cracks(Plane p, const uint32_t* __restrict__ cbase, const int* __restrict__ start_of,
+                                                   int* __restrict__ nxt, int* __restrict__ ws, int* __restrict__ term_of) {
+  const size_t total = static_cast<size_t>(p.H) * p.wp;
+  for (size_t i = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * TPB) {
+    if (!p.w[i]) continue;
+    const int y = static_cast<int>(i / p.wp), wd = static_cast<int>(i % p.wp);
+    const CrackMasks k = crack_masks(p, y, wd);
+    int id = static_cast<int>(cbase[i]);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      uint32_t m = k.m[t];
+      while (m) {
+        const int j = __ffs(m) - 1;
+        m &= m - 1;
+        const int x = wd * 32 + j;
+        int nx, ny, nt;
+        crack_succ(p, x, y, t, &nx, &ny, &nt);
+        const int sid = (ny == y && (nx >> 5) == wd) ? static_cast<int>(cbase[i]) + crack_rank(k, nt, nx & 31) : crack_id(p, cbase, nx, ny, nt);
+        const int st = start_of[sid];
+        if (st) { nxt[id] = id; ws[id] = 0; term_of[id] = st; }
+        else { nxt[id] = sid; ws[id] = (nx != x || ny != y) ? 1 : 0; term_of[id] = 0; }
+        ++id;
+      }
+    }
+  }
+}
+// one pointer-jumping round (double buffered): ws covers [crack, nxt) afterwards [crack, nxt[nxt])
+static __global__ void __launch_bounds__(TPB) jump_cracks(const int* __restrict__ nxt, const int* __restrict__ ws, int* __restrict__ nxt2,
+                                                   int* __restrict__ ws2, int n) {
+  for (int i = blockIdx.x * TPB + threadIdx.x; i < n; i += gridDim.x * TPB) {
+    const int s = nxt[i];
+    ws2[i] = ws[i] + ws[s];  // ws of a list end is 0
+    nxt2[i] = nxt[s];
+  }
+}
+static __global__ void __launch_bounds__(TPB) contour_totals(const int* __restrict__ start_crack, const int* __restrict__ ws, int n,
+                                                      int* __restrict__ npts) {
+  for (int c = blockIdx.x * TPB + threadIdx.x; c < n; c += gridDim.x * TPB)
+    if (npts[c] == 0) npts[c] = ws[start_crack[c]];  // (1: an isolated pixel, set by mark_starts)
+}
+// write the points: the crack that ends a pixel visit puts its pixel at off[contour] + (total - points from here on)
+static __global__ void __launch_bounds__(TPB) scatter_points(Plane p, const uint32_t* __restrict__ cbase, const int* __restrict__ nxt,
+                                                      const int* __restrict__ ws, const int* __restrict__ term_of,
+                                                      const int* __restrict__ npts, const long long* __restrict__ off,
+                                                      const int* __restrict__ roots, int ncontours, int2* __restrict__ pts) {
+  const size_t total = static_cast<size_t>(p.H) * p.wp;
+  for (size_t i = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * TPB) {
+    if (!p.w[i]) continue;
+    const int y = static_cast<int>(i / p.wp), wd = static_cast<int>(i % p.wp);
+    const CrackMasks k = crack_masks(p, y, wd);
+    int id = static_cast<int>(cbase[i]);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      uint32_t m = k.m[t];
+      while (m) {
+        const int j = __ffs(m) - 1;
+        m &= m - 1;
+        const int e = nxt[id];      // list end
+        const int c = term_of[e];   // contour + 1 (0: a list nobody reads -- isolated pixels, untraced components)
+        if (c && e != id) {
+          const int x = wd * 32 + j;
+          int nx, ny, nt;
+          crack_succ(p, x, y, t, &nx, &ny, &nt);
+          if (nx != x || ny != y) pts[off[c - 1] + (npts[c - 1] - ws[id])] = make_int2(x, y);
+        }
+        ++id;
+      }
+    }
+  }
+  // isolated pixels: one point
+  for (int c = blockIdx.x * TPB + threadIdx.x; c < ncontours; c += gridDim.x * TPB)
+    if (off[c + 1] - off[c] == 1 && npts[c] == 1) pts[off[c]] = make_int2(roots[c] % p.W, roots[c] / p.W);
+}
+// bounding boxes of components from their runs, indexed by root run: bbmin[2 r] = min x, min y (memset 0x7f),
+// bbmax[2 r] = max x + 1, max y + 1 (memset 0xff) -- cv::boundingRect's x, y, x + w, y + h
+static __global__ void __launch_bounds__(TPB) run_bboxes(RunSet r, int* __restrict__ bbmin, int* __restrict__ bbmax) {
+  // one update per RUN, issued where the run starts (x0, row) and where it ends (x1 + 1): a scene-sized component has
+  // 2 x H updates instead of one per word (12.5 M same-address atomics cost 30+ ms at 20 000^2)
   const Plane& p = r.p;
   const size_t total = static_cast<size_t>(p.H) * p.wp;
   for (size_t i = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * TPB) {
@@ -573,13 +771,24 @@ static __global__ void __launch_bounds__(TPB) crack_count(RunSet r, int* __restr
     if (!cur) continue;
     const int y = static_cast<int>(i / p.wp), wd = static_cast<int>(i % p.wp);
     const uint32_t prev = wd ? p.w[i - 1] : 0u, next = wd + 1 < p.wp ? p.w[i + 1] : 0u;
-    const uint32_t up = y ? p.w[i - p.wp] : 0u, dn = y + 1 < p.H ? p.w[i + p.wp] : 0u;
     const uint32_t st = starts_of(cur, prev);
     const uint32_t en = cur & ~((cur >> 1) | (next << 31));  // last pixels of runs
-    for_runs(cur, prev, r.wprefix[i], [&](int rid, uint32_t mask, int) {
-      const int c = __popc(mask & ~up) + __popc(mask & ~dn) + __popc(mask & st) + __popc(mask & en);
-      atomicAdd(cracks + r.P[rid], c);
+    for_runs(cur, prev, r.wprefix[i], [&](int rid, uint32_t mask, int j) {
+      const size_t o = 2 * static_cast<size_t>(r.P[rid]);
+      if (mask & st) {
+        atomicMin(bbmin + o, wd * 32 + j);
+        atomicMin(bbmin + o + 1, y);
+        atomicMax(bbmax + o + 1, y + 1);
+      }
+      if (mask & en) atomicMax(bbmax + o, wd * 32 + (32 - __clz(mask)));
     });
+  }
+}
+static __global__ void __launch_bounds__(TPB) gather_bboxes(const int* __restrict__ bbmin, const int* __restrict__ bbmax,
+                                                     const int* __restrict__ root_runs, int n, int* __restrict__ bbox4) {
+  for (int c = blockIdx.x * TPB + threadIdx.x; c < n; c += gridDim.x * TPB) {
+    const size_t o = 2 * static_cast<size_t>(root_runs[c]);
+    bbox4[4 * c] = bbmin[o]; bbox4[4 * c + 1] = bbmin[o + 1]; bbox4[4 * c + 2] = bbmax[o]; bbox4[4 * c + 3] = bbmax[o + 1];
   }
 }
 

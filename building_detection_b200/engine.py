@@ -23,6 +23,7 @@ class Model:
         net = G.Net(name, 1, None)
         build_fn(net)
         self.spec = net.spec
+        self.keras_layers = net.keras_layers  # (Keras class, weight keys) in this builder's construction order
         self.flops_per_tile = net.plan.flops
         # a fresh Keras model carries its random initialisation (predict.py:23-24 keeps it when the
         # checkpoint is missing); seeded per model so runs are reproducible
@@ -44,16 +45,28 @@ class Model:
         self._drop_native()
 
     def load_weights(self, path):
-        """Keras raises OSError for a missing file and the reference catches exactly that
-        (predict.py:23).  Accepted container here: ``.npz`` keyed by this package's layer names
-        (the Keras-h5 reader is SURVEY section 8f item 1)."""
+        """Keras raises OSError for a missing or unreadable file and the reference catches exactly that
+        (predict.py:23).  Containers: a Keras ``.h5`` weight file (what the reference's checkpoints are; matched by
+        topology like ``load_weights`` does, keras_h5.py) or an ``.npz`` keyed by this package's weight names."""
         if not os.path.exists(path):
             raise OSError(f"Unable to open file (name = '{path}')")
-        with np.load(path) as z:
+        from . import keras_h5
+        if keras_h5.is_hdf5(path):
+            keras_h5.load_into(self, path)
+            return
+        try:
+            z = np.load(path)
+        except ValueError as e:
+            raise OSError(f"Unable to open file (neither HDF5 nor npz): {path}: {e}") from e
+        with z:
             self.set_weights({k: z[k] for k in z.files})
 
     def save_weights(self, path):
-        np.savez(path, **self.weights)
+        if str(path).endswith((".h5", ".hdf5")):
+            from . import keras_h5
+            keras_h5.save(self, path)
+        else:
+            np.savez(path, **self.weights)
 
     def count_params(self):
         return G.count_params(self.spec)

@@ -125,14 +125,21 @@ class Net:
         self.split_weights = False  # see _conv_op
         self.w = weights
         self.spec = {}  # name -> (shape, init)
+        self.keras_layers = []  # (Keras class, [weight keys in Keras' get_weights() order]) in construction order
+        self._declared = set()
+        self._declared_layers = set()
         self.umma = umma
         self.keep_f32 = keep_f32  # tests only: also keep the unquantised conv weights in the op
 
     # ------------------------------------------------------------------ weights
     def _get(self, name, shape, init):
         shape = tuple(int(s) for s in shape)
-        assert name not in self.spec, f"duplicate weight {name}"
-        self.spec[name] = (shape, init)
+        if name in self._declared:  # registered ahead of use by declare_conv()
+            assert self.spec[name] == (shape, init), (name, self.spec[name], shape, init)
+            self._declared.discard(name)
+        else:
+            assert name not in self.spec, f"duplicate weight {name}"
+            self.spec[name] = (shape, init)
         if self.w is None:
             return np.zeros(shape, np.float32)
         a = np.asarray(self.w[name], dtype=np.float32)
@@ -145,8 +152,37 @@ class Net:
         b = self._get(name + "/beta", (c,), "bn_beta")
         m = self._get(name + "/mean", (c,), "bn_mean")
         v = self._get(name + "/var", (c,), "bn_var")
+        self._keras("BatchNormalization", [name + "/gamma", name + "/beta", name + "/mean", name + "/var"])
         scale = g / np.sqrt(v + BN_EPS)
         return scale.astype(np.float32), (b - m * scale).astype(np.float32)
+
+    def _keras(self, cls, keys):
+        """Record a Keras layer in construction order (unless declare_conv() already placed it)."""
+        if keys[0] in self._declared_layers:
+            self._declared_layers.discard(keys[0])
+        else:
+            self.keras_layers.append((cls, keys))
+
+    def declare_conv(self, cin, name, cout, k=1, bn=False, he=False):
+        """Register the weights of a Conv2D (+ BatchNormalization) NOW, although the fused op that uses them is
+        emitted later: the weight spec / Keras layer list then follow the order in which the reference's code constructs
+        its layers (tools/keras_trace.py), which is the order a Keras checkpoint is matched by.  Needed where a
+        convolution carries its residual input and therefore has to be emitted after the branch the reference builds
+        second (hrnet.py:28-38 shortcut, v3plus.py:185-194 block 1)."""
+        for key, shape, init in ((name + "/k", (k, k, cin, cout), "he_normal" if he else "glorot_uniform"),
+                                 (name + "/b", (cout,), "zeros")):
+            self._get(key, shape, init)
+            self._declared.add(key)
+        self.keras_layers.append(("Conv2D", [name + "/k", name + "/b"]))
+        self._declared_layers.add(name + "/k")
+        if bn:
+            bname = bn if isinstance(bn, str) else name + "_bn"
+            keys = [bname + "/gamma", bname + "/beta", bname + "/mean", bname + "/var"]
+            for key, init in zip(keys, ("bn_gamma", "bn_beta", "bn_mean", "bn_var")):
+                self._get(key, (cout,), init)
+                self._declared.add(key)
+            self.keras_layers.append(("BatchNormalization", keys))
+            self._declared_layers.add(keys[0])
 
     # ------------------------------------------------------------------ buffers
     def buf(self, H, W, C, dtype="f16", kind="map"):
@@ -187,6 +223,7 @@ class Net:
         H, W = self._input_hw
         kern = self._get(name + "/k", (3, 3, 3, cout), "he_normal" if he else "glorot_uniform")
         bias = self._get(name + "/b", (cout,), "zeros")
+        self._keras("Conv2D", [name + "/k", name + "/b"])
         w = kern.reshape(27, cout).T.copy()[None]  # (1, Cout, 27): column (kh*3+kw)*3+c
         if bn:
             sc, sh = self._bn(bn if isinstance(bn, str) else name + "_bn", cout)
@@ -262,6 +299,7 @@ class Net:
             return self._stem(x, name, cout, s, bn, act, out, he)
         kern = self._get(name + "/k", (k, k, x.cin, cout), "he_normal" if he else "glorot_uniform")
         bias = self._get(name + "/b", (cout,), "zeros")
+        self._keras("Conv2D", [name + "/k", name + "/b"])
         w = kern.reshape(k * k, x.cin, cout).transpose(0, 2, 1).copy()  # (taps, Cout, Cin)
         if bn:
             sc, sh = self._bn(bn if isinstance(bn, str) else name + "_bn", cout)
@@ -303,6 +341,7 @@ class Net:
         the nine-fold re-read of the 4x larger map (hrnet.py:198-199, v3plus.py:341-342)."""
         kern = self._get(name + "/k", (3, 3, x.cin, cout), "glorot_uniform")
         bias = self._get(name + "/b", (cout,), "zeros")
+        self._keras("Conv2D", [name + "/k", name + "/b"])
         w = kern.reshape(9, x.cin, cout).transpose(0, 2, 1).copy()  # (taps, Cout, Cin)
         if bn:
             sc, sh = self._bn(bn if isinstance(bn, str) else name + "_bn", cout)
@@ -335,6 +374,7 @@ class Net:
         y[2m+a] = sum over kh with kh = a (mod 2) of x[m - (kh-a)/2] W[kh]."""
         kern = self._get(name + "/k", (k, k, cout, x.C), "glorot_uniform")  # (kh,kw,Cout,Cin)
         bias = self._get(name + "/b", (cout,), "zeros")
+        self._keras("Conv2DTranspose", [name + "/k", name + "/b"])
         if out is None:
             out = self.new(2 * x.H, 2 * x.W, cout)
         a = ACT_RELU if act == "relu" else ACT_NONE
@@ -354,6 +394,7 @@ class Net:
         dw = self._get(name + "/dw", (3, 3, x.C, 1), "glorot_uniform")
         pw = self._get(name + "/pw", (1, 1, x.C, cout), "glorot_uniform")
         bias = self._get(name + "/b", (cout,), "zeros")
+        self._keras("SeparableConv2D", [name + "/dw", name + "/pw", name + "/b"])
         Ho, Wo = math.ceil(x.H / s), math.ceil(x.W / s)
         mid = self.new(Ho, Wo, x.C)
         pt, _ = same_pad(x.H, 3, s)
@@ -435,6 +476,7 @@ class Net:
         shape = (1, 1, cin, cout) if conv_kernel else (cin, cout)
         kern = self._get(name + "/k", shape, "glorot_uniform").reshape(cin, cout)
         bias = self._get(name + "/b", (cout,), "zeros")
+        self._keras("Conv2D" if conv_kernel else "Dense", [name + "/k", name + "/b"])
         w = kern.T.copy()  # (Cout, Cin)
         if bn:
             sc, sh = self._bn(bn, cout)
@@ -459,6 +501,7 @@ class Net:
         c = x.C
         ks = self._get(name + "_s/k", (1, 1, c, 1), "glorot_uniform").reshape(c)
         bs = self._get(name + "_s/b", (1,), "zeros")
+        self._keras("Conv2D", [name + "_s/k", name + "_s/b"])
         g = self.gap(x)
         h = self.dense([g], name + "_c1", c // 16, conv_kernel=True)
         cs = self.dense([h], name + "_c2", c, act="sigmoid", conv_kernel=True)

@@ -31,6 +31,7 @@ def backbone(g: Net, x, with_bam, c_out=None, c1_out=None, c2_out=None):
     c = t
 
     # block 1 (v3plus.py:185-194): sep+BN+ReLU, sep+BN, MaxPool(3,2,same), + strided 1x1 residual
+    g.declare_conv(t.C, "b1_res", 128, k=1, bn=True)  # the reference builds the residual conv + BN first
     m = g.sepconv(t, "b1_s1", 128, act="relu")
     m = g.sepconv(m, "b1_s2", 128)
     m = g.maxpool(m, 3, 2, same=True)

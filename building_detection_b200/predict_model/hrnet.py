@@ -12,6 +12,7 @@ def build(g: Net):
     def bottleneck(t, name, project):  # conv_block / identity_block, hrnet.py:28-49
         c = cb(t, name + "_a", 64, k=1)
         c = cb(c, name + "_b", 64, k=3)
+        g.declare_conv(64, name + "_c", 256, k=1, bn=True)  # the reference builds the third conv before the shortcut
         short = cb(t, name + "_s", 256, k=1, act=None) if project else t
         return cb(c, name + "_c", 256, k=1, act="relu", res=short)  # relu(bn(conv) + shortcut)
 
@@ -31,17 +32,19 @@ def build(g: Net):
         t = bottleneck(t, f"l1_{i}", False)
 
     # stage 1 (hrnet.py:172-178)
-    b10 = branch(cb(t, "t1_0", 32), "b1_0")
-    b11 = branch(cb(t, "t1_1", 64, s=2), "b1_1")
+    t10, t11 = cb(t, "t1_0", 32), cb(t, "t1_1", 64, s=2)  # transition_layer1 builds both before the branches
+    b10 = branch(t10, "b1_0")
+    b11 = branch(t11, "b1_1")
     # fuse_block_1 (hrnet.py:99-111): no activation after the sums
     u = cb(b11, "f1_up", 32, k=1, act=None)
     f1_0 = g.addn([(b10, 1), (u, 2)])
     f1_1 = cb(b10, "f1_down", 64, s=2, act=None, res=b11)
 
     # stage 2 (hrnet.py:180-187)
-    b20 = branch(cb(f1_0, "t2_0", 32), "b2_0")
-    b21 = branch(cb(f1_1, "t2_1", 64), "b2_1")
-    b22 = branch(cb(f1_1, "t2_2", 128, s=2), "b2_2")
+    t20, t21, t22 = cb(f1_0, "t2_0", 32), cb(f1_1, "t2_1", 64), cb(f1_1, "t2_2", 128, s=2)
+    b20 = branch(t20, "b2_0")
+    b21 = branch(t21, "b2_1")
+    b22 = branch(t22, "b2_2")
     # fuse_block_2 (hrnet.py:114-139)
     x12 = cb(b21, "f2_12", 32, k=1, act=None)
     x13 = cb(b22, "f2_13", 32, k=1, act=None)
@@ -55,10 +58,11 @@ def build(g: Net):
 
     # stage 3 (hrnet.py:189-196); fuse_block_3 concatenates, so branch 0 lands in its slice
     cat = g.buf(256, 256, 128)
-    branch(cb(f2_0, "t3_0", 32), "b3_0", out=T(cat, 0, 32))
-    b31 = branch(cb(f2_1, "t3_1", 64), "b3_1")
-    b32 = branch(cb(f2_2, "t3_2", 128), "b3_2")
-    b33 = branch(cb(f2_2, "t3_3", 256, s=2), "b3_3")
+    t30, t31, t32, t33 = cb(f2_0, "t3_0", 32), cb(f2_1, "t3_1", 64), cb(f2_2, "t3_2", 128), cb(f2_2, "t3_3", 256, s=2)
+    branch(t30, "b3_0", out=T(cat, 0, 32))
+    b31 = branch(t31, "b3_1")
+    b32 = branch(t32, "b3_2")
+    b33 = branch(t33, "b3_3")
     # fuse_block_3 (hrnet.py:142-162)
     g.upsample(cb(b31, "f3_1", 32, k=1, act=None), 2, out=T(cat, 32, 32))
     g.upsample(cb(b32, "f3_2", 32, k=1, act=None), 4, out=T(cat, 64, 32))

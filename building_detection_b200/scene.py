@@ -61,7 +61,6 @@ class SceneRunner:
         self.batch = batch
         self.ctx = R.context(self.device.index)
         self.lib = R.lib()
-        self.tile_masks = torch.empty((batch, TILE, TILE), dtype=torch.uint8, device=self.device)
 
     def upload(self, scene_bgr):
         """numpy (H,W,3) u8 BGR (what cv.imread returns) -> device tensor."""
@@ -84,21 +83,14 @@ class SceneRunner:
         L, C = self.lib, R.C
         if not len(origins):
             return out
-        # all tile origins go to the device once; the batches below are pure kernel launches
+        # One call for the whole scene (bd_scene_run: the batch loop, CUDA-graph replay of every plan).  A ragged last
+        # batch runs through the SAME batch-sized plan; scenes with fewer tiles than the batch use the next power of two
+        # (engine.Model.plan_batch_for), so at most five plan sizes per model ever exist.
         ys = np.ascontiguousarray([o[0] for o in origins], np.int32)
         xs = np.ascontiguousarray([o[1] for o in origins], np.int32)
-        R.check(L.bd_tiles_set_origins(self.ctx, R._ptr(ys), R._ptr(xs), len(origins), stream))
-        # A ragged last batch runs through the SAME batch-sized plan: only n tiles are gathered and stitched, the
-        # remaining slots of the input buffer keep stale tiles whose outputs are ignored (no per-n plan arenas).
-        # Scenes with fewer tiles than the batch use the next power of two (engine.Model.plan_batch_for).
         pb = self.batch if len(origins) >= self.batch else min(self.batch, self.models[0].plan_batch_for(len(origins)))
-        for b0 in range(0, len(origins), pb):
-            n = min(pb, len(origins) - b0)
-            for mi, m in enumerate(self.models):
-                plan = m.native_plan(pb, device=self.device.index)
-                x_ptr = plan.buffer_ptr(plan.plan.input)
-                R.check(L.bd_tiles_gather_at(self.ctx, scene_dev.data_ptr(), h, w, b0, n, x_ptr,
-                                             plan.plan.input_stride, stream))
-                plan.run_device(0, 0, self.tile_masks.data_ptr(), stream)
-                R.check(L.bd_stitch_or_at(self.ctx, self.tile_masks.data_ptr(), b0, n, out[mi].data_ptr(), h, w, stream))
+        plans = [m.native_plan(pb, device=self.device.index) for m in self.models]
+        handles = (C.c_void_p * len(plans))(*[p.h for p in plans])
+        R.check(L.bd_scene_run(self.ctx, handles, len(plans), scene_dev.data_ptr(), h, w, R._ptr(ys), R._ptr(xs),
+                               len(origins), out.data_ptr(), stream))
         return out

@@ -150,6 +150,16 @@ int bd_tiles_gather_at(bd_ctx* ctx, const uint8_t* scene_bgr_dev, int h, int w, 
 int bd_stitch_or_at(bd_ctx* ctx, const uint8_t* tile_masks_dev, int first, int n, uint8_t* scene_mask_dev, int h, int w,
                     void* stream);
 
+/* The whole tiled forward of a scene for n_plans models in ONE call (the loop of predict.py:98-114 per model; the
+ * reference's run_model, predict.py:75-87, calls it five times): tile origins (ys, xs) in the reference's order, plans
+ * of one common batch size, masks_dev = n_plans planes of (h, w) u8 that must be zeroed by the caller and receive
+ * 255 where any covering tile says "building".  A ragged last batch runs through the same plans.  Each plan's forward
+ * is replayed from a CUDA graph captured on first use (BD_GRAPHS=0: direct launches). */
+int bd_scene_run(bd_ctx* ctx, bd_plan* const* plans, int n_plans, const uint8_t* scene_bgr_dev, int h, int w,
+                 const int32_t* ys_host, const int32_t* xs_host, int n_tiles, uint8_t* masks_dev, void* stream);
+/* device bytes the context currently holds for the scene-level stages (fusion / contour scratch, tile masks) */
+size_t bd_workspace_bytes(bd_ctx* ctx);
+
 /* ---- fusion: replaces model_fuse.py:model_confuse (271-350) --------------------------------- */
 /* The literals of model_fuse.py / edge_3.py the library was built with (reference line in the comment). */
 typedef struct bd_post_constants_t {

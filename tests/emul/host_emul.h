@@ -28,6 +28,9 @@ template <class T> static inline T __ldg(const T* p) { return *p; }
 static inline int atomicMin(int* a, int v) { int o = *a; if (v < o) *a = v; return o; }
 static inline int atomicAdd(int* a, int v) { int o = *a; *a += v; return o; }
 static inline unsigned long long atomicAdd(unsigned long long* a, unsigned long long v) { unsigned long long o = *a; *a += v; return o; }
+static inline int atomicMax(int* a, int v) { int o = *a; if (v > o) *a = v; return o; }
+struct int2 { int x, y; };
+static inline int2 make_int2(int x, int y) { int2 r; r.x = x; r.y = y; return r; }
 static inline int atomicExch(int* a, int v) { int o = *a; *a = v; return o; }
 using std::max;
 using std::min;

@@ -115,9 +115,89 @@ void cleanup_plane(Plane in, Plane out, int stage, Plane* stage_out, int min_are
   emit(7, out);
 }
 
+// csrc/contours.cu: trace_set -- every component of the plane, in OpenCV's order (descending first pixel)
+void trace_all(Plane p, std::vector<int>* npts_out, std::vector<int2>* pts_out) {
+  RS R;
+  build_runs(p, true, &R);
+  std::vector<int> roots;
+  for (int y = 0; y < p.H; ++y)
+    for (int wd = 0; wd < p.wp; ++wd) {
+      const size_t i = static_cast<size_t>(y) * p.wp + wd;
+      uint32_t st = starts_of(p.w[i], wd ? p.w[i - 1] : 0u);
+      int rid = R.wprefix[i];
+      while (st) { const int j = __ffs(st) - 1; st &= st - 1; if (R.P[rid] == rid) roots.push_back(y * p.W + wd * 32 + j); ++rid; }
+    }
+  std::sort(roots.begin(), roots.end(), [](int a, int b) { return a > b; });
+  const int n = static_cast<int>(roots.size());
+  // count_row_cracks + scan_rows + emit_crack_base
+  std::vector<uint32_t> cbase(static_cast<size_t>(p.H) * p.wp);
+  int nc = 0;
+  for (int y = 0; y < p.H; ++y)
+    for (int wd = 0; wd < p.wp; ++wd) {
+      cbase[static_cast<size_t>(y) * p.wp + wd] = nc;
+      const CrackMasks k = crack_masks(p, y, wd);
+      nc += __popc(k.m[0]) + __popc(k.m[1]) + __popc(k.m[2]) + __popc(k.m[3]);
+    }
+  std::vector<int> start_of(nc + 1, 0), start_crack(n + 1), npts(n + 1, 0), nxt(nc + 1), ws(nc + 1), nxt2(nc + 1), ws2(nc + 1), term_of(nc + 1);
+  launch(mark_starts, p, static_cast<const uint32_t*>(cbase.data()), static_cast<const int*>(roots.data()), n, start_of.data(),
+         start_crack.data(), npts.data());
+  launch(init_cracks, p, static_cast<const uint32_t*>(cbase.data()), static_cast<const int*>(start_of.data()), nxt.data(), ws.data(),
+         term_of.data());
+  int rounds = 1;
+  while ((1ll << rounds) < nc + 1) ++rounds;
+  int *a = nxt.data(), *b = ws.data(), *a2 = nxt2.data(), *b2 = ws2.data();
+  for (int r = 0; r < rounds; ++r) {
+    launch(jump_cracks, static_cast<const int*>(a), static_cast<const int*>(b), a2, b2, nc);
+    std::swap(a, a2);
+    std::swap(b, b2);
+  }
+  launch(contour_totals, static_cast<const int*>(start_crack.data()), static_cast<const int*>(b), n, npts.data());
+  std::vector<long long> off(n + 1, 0);
+  for (int c = 0; c < n; ++c) off[c + 1] = off[c] + npts[c];
+  pts_out->assign(off[n] + 1, make_int2(-1, -1));
+  launch(scatter_points, p, static_cast<const uint32_t*>(cbase.data()), static_cast<const int*>(a), static_cast<const int*>(b),
+         static_cast<const int*>(term_of.data()), static_cast<const int*>(npts.data()), static_cast<const long long*>(off.data()),
+         static_cast<const int*>(roots.data()), n, pts_out->data());
+  pts_out->resize(off[n]);
+  npts.resize(n);
+  *npts_out = npts;
+}
+
 }  // namespace
 
 extern "C" {
+
+// external contours of every component of an (h, w) u8 mask, OpenCV order; returns the number of contours, fills
+// npts[contour] and xy[2 * point] (capacities given)
+int emul_contours(const uint8_t* mask, int h, int w, int* npts, int cap_contours, int* xy, int cap_points) {
+  Pl in(h, w);
+  pack(mask, in.p);
+  std::vector<int> n;
+  std::vector<int2> pts;
+  trace_all(in.p, &n, &pts);
+  if (static_cast<int>(n.size()) > cap_contours || static_cast<int>(pts.size()) > cap_points) return -1;
+  for (size_t i = 0; i < n.size(); ++i) npts[i] = n[i];
+  for (size_t i = 0; i < pts.size(); ++i) { xy[2 * i] = pts[i].x; xy[2 * i + 1] = pts[i].y; }
+  return static_cast<int>(n.size());
+}
+// bounding boxes per pixel's component (x0, y0, x1, y1 as cv::boundingRect gives x, y, x+w, y+h)
+void emul_bboxes(const uint8_t* mask, int h, int w, int* bb_px) {
+  Pl in(h, w);
+  pack(mask, in.p);
+  RS R;
+  build_runs(in.p, true, &R);
+  std::vector<int> bmin(2 * (R.r.nruns + 1), 0x7f7f7f7f), bmax(2 * (R.r.nruns + 1), -1), rr(R.r.nruns + 1), bb(4 * (R.r.nruns + 1));
+  for (int i = 0; i <= R.r.nruns; ++i) rr[i] = i;
+  launch(run_bboxes, R.r, bmin.data(), bmax.data());
+  launch(gather_bboxes, static_cast<const int*>(bmin.data()), static_cast<const int*>(bmax.data()), static_cast<const int*>(rr.data()),
+         R.r.nruns, bb.data());
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x) {
+      const size_t i = static_cast<size_t>(y) * in.p.wp + (x >> 5);
+      const bool on = (in.p.w[i] >> (x & 31)) & 1u;
+      for (int k = 0; k < 4; ++k) bb_px[(static_cast<size_t>(y) * w + x) * 4 + k] = on ? bb[4 * R.P[run_at(R.r, y, x)] + k] : 0;
+    }
+}
 
 // one clean-up pass (or an intermediate plane of it, stage 0..7; -1 / 7 = result) of an (h, w) u8 mask
 void emul_cleanup(const uint8_t* mask, int h, int w, int stage, uint8_t* out) {

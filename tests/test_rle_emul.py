@@ -129,3 +129,35 @@ def test_fuse_matches_reference_golden(emul, name, size, seed):
     out = np.empty((size, size), np.uint8)
     emul.emul_fuse(_p(masks), size, size, _p(out))
     assert (out != want).sum() == 0, f"{(out != want).sum()} px differ"
+
+
+@pytest.mark.parametrize("kind,size,seed", MASKS + [("noise1", 300, 11), ("base", 900, 12)])
+def test_parallel_border_following_matches_findcontours(emul, kind, size, seed):
+    """crack numbering + successor rule + pointer jumping + scatter == cv2.findContours(RETR_EXTERNAL, CHAIN_APPROX_NONE),
+    contour order and points, on hole-free masks (what the contour stage traces) and on raw ones (holes are skipped)"""
+    m0 = make(kind, size, seed)
+    if seed % 2:
+        m0 = np.ascontiguousarray(m0[:, :max(1, m0.shape[1] - 5)])
+    filled, _ = post_ref.fill_and_delete(m0, min_area=-1)
+    for m in (filled, m0):
+        h, w = m.shape
+        npts = np.zeros(h * w + 1, np.int32)
+        xy = np.zeros(2 * (4 * h * w + 4), np.int32)
+        n = emul.emul_contours(_p(np.ascontiguousarray(m)), h, w, _p(npts), npts.size, _p(xy), xy.size // 2)
+        want, _ = cv.findContours(m, cv.RETR_EXTERNAL, cv.CHAIN_APPROX_NONE)
+        offs = np.concatenate([[0], np.cumsum(npts[:n])])
+        mine = [xy[2 * offs[i]:2 * offs[i + 1]].reshape(-1, 2) for i in range(n)]
+        if m is filled:  # same contours in the same order
+            assert n == len(want)
+            for a, c in zip(mine, want):
+                np.testing.assert_array_equal(a, c[:, 0, :])
+        else:  # RETR_EXTERNAL skips islands inside holes; every contour it returns must be among ours, outer border only
+            by_start = {tuple(a[0]): a for a in mine}
+            assert n >= len(want)
+            for c in want:
+                np.testing.assert_array_equal(by_start[tuple(c[0, 0])], c[:, 0, :])
+        bb = np.zeros((h, w, 4), np.int32)
+        emul.emul_bboxes(_p(np.ascontiguousarray(m)), h, w, _p(bb))
+        for c in want:
+            x, y, bw, bh = cv.boundingRect(c)
+            assert tuple(bb[c[0, 0, 1], c[0, 0, 0]]) == (x, y, x + bw, y + bh)
