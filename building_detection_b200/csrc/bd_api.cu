@@ -159,6 +159,7 @@ void bd_destroy(bd_ctx* ctx) {
   if (ctx->h_scalar) cudaFreeHost(ctx->h_scalar);
   for (void* hp : ctx->h_pts)
     if (hp) cudaFreeHost(hp);
+  if (ctx->capture_stream) cudaStreamDestroy(ctx->capture_stream);
   delete ctx;
 }
 
@@ -877,16 +878,22 @@ static int plan_run_masks(bd_plan* p, uint8_t* mask_dev, cudaStream_t s) {
   if (graphs_on && !p->graph_failed && (!p->graph_exec || p->graph_mask != mask_dev)) {
     if (p->graph_exec) { cudaGraphExecDestroy(p->graph_exec); p->graph_exec = nullptr; }
     cudaGraph_t g = nullptr;
-    bool ok = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    // capture on an internal stream (the caller's may be the legacy default stream, which cannot capture); the
+    // instantiated graph is launched on the caller's stream
+    bd_ctx* ctx = p->ctx;
+    bool ok = true;
+    if (!ctx->capture_stream) ok = cudaStreamCreateWithFlags(&ctx->capture_stream, cudaStreamNonBlocking) == cudaSuccess;
+    cudaStream_t cs = ctx->capture_stream;
+    ok = ok && cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
     if (ok) {
       p->cur_probs = nullptr;
       p->cur_mask = mask_dev;
-      const int64_t launches0 = p->ctx->launches;
+      const int64_t launches0 = ctx->launches;
       int rc = 0;
       for (Op& op : p->ops)
-        if ((rc = op.run(s))) break;
-      p->ctx->launches = launches0;  // capturing is not launching
-      ok = cudaStreamEndCapture(s, &g) == cudaSuccess && rc == 0 && g != nullptr;
+        if ((rc = op.run(cs))) break;
+      ctx->launches = launches0;  // capturing is not launching
+      ok = cudaStreamEndCapture(cs, &g) == cudaSuccess && rc == 0 && g != nullptr;
     }
     if (ok) ok = cudaGraphInstantiate(&p->graph_exec, g, 0) == cudaSuccess;
     if (g) cudaGraphDestroy(g);
@@ -926,10 +933,12 @@ int bd_scene_run(bd_ctx* ctx, bd_plan* const* plans, int n_plans, const uint8_t*
   if (ctx->pool.get(bd::post::SLOT_TILEMASK, tm_bytes, &tm)) return 1;
   if (bd_tiles_set_origins(ctx, ys_host, xs_host, n_tiles, stream)) return 1;
   const size_t plane = static_cast<size_t>(h) * w;
+  NvtxRange nvtx("bd:scene_forward");
   for (int b0 = 0; b0 < n_tiles; b0 += B) {
     const int n = std::min(B, n_tiles - b0);  // a ragged last batch leaves stale tiles in the other slots: ignored
     for (int k = 0; k < n_plans; ++k) {
       bd_plan* p = plans[k];
+      NvtxRange nvtx_model(k == 0 ? "bd:model0" : k == 1 ? "bd:model1" : k == 2 ? "bd:model2" : k == 3 ? "bd:model3" : "bd:model4+");
       const BufInfo& ib = p->bufs[p->input_buf];
       if (bd_tiles_gather_at(ctx, scene_bgr_dev, h, w, b0, n, p->arena + ib.offset, ib.H == 512 ? 1 : 2, stream)) return 1;
       if (plan_run_masks(p, static_cast<uint8_t*>(tm), s)) return 1;
@@ -939,6 +948,9 @@ int bd_scene_run(bd_ctx* ctx, bd_plan* const* plans, int n_plans, const uint8_t*
   BD_CUDA(cudaGetLastError());
   return 0;
 }
+
+// 1 when the plan's forward is replayed from a captured CUDA graph (bd_scene_run), 0 when it is launched kernel by kernel
+int bd_plan_uses_graph(bd_plan* p) { return (p && p->graph_exec) ? 1 : 0; }
 
 // device bytes a context holds for the scene-level stages at (h, w): fusion / contour arena + pools (weights and
 // activation arenas belong to the plans: bd_plan_arena_bytes)

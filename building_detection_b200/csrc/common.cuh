@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include <string>
 #include <utility>
 
@@ -55,6 +57,14 @@ inline cudaError_t launch_k(bool pdl, void (*kern)(Params...), dim3 grid, dim3 b
   cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
+
+// NVTX range per stage / model: shows up in nsys / ncu timelines, costs nothing without a tool attached
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 // Every C-ABI entry point runs on its context's device and leaves the caller's current device as it found it.
 struct DeviceGuard {

@@ -65,6 +65,10 @@ static __global__ void __launch_bounds__(TPB) match_boxes(const int* __restrict_
         const int bx0 = sb[4 * j], by0 = sb[4 * j + 1], bx1 = sb[4 * j + 2], by1 = sb[4 * j + 3];
         const long long iw = max(min(ax1, bx1) - max(ax0, bx0), 0), ih = max(min(ay1, by1) - max(ay0, by0), 0);
         const long long inter = iw * ih;
+        if (inter == 0) {  // disjoint boxes (almost all pairs): IoU 0 without the float64 division
+          if (best < 0.0) { best = 0.0; besti = j0 + j; }
+          continue;
+        }
         const long long uni = aarea + static_cast<long long>(bx1 - bx0) * (by1 - by0) - inter;
         const double v = static_cast<double>(inter) / static_cast<double>(uni);
         if (v > best) { best = v; besti = j0 + j; }
@@ -437,6 +441,7 @@ int bd_contours(bd_ctx* ctx, const uint8_t* mask_dev, int h, int w, bd_polys* ou
   BD_CHECK(ctx && mask_dev && out && h >= 1 && w >= 1, "bad arguments");
   BD_CHECK(static_cast<size_t>(h) * w < (1ull << 31), "scene too large for int32 pixel labels");
   using namespace bd::cont;
+  NvtxRange nvtx("bd:contours");
   memset(out, 0, sizeof(*out));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const post::PostConstants& K = ctx->consts;

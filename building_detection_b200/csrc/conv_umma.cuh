@@ -506,7 +506,15 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
     const int num_kb_all = p.ntaps * p.kchunks;
     for (int tile = blockIdx.x; tile < p.total_tiles && (dual || issuer == 0); tile += gridDim.x, ++ti) {
       const uint32_t a = ti & 1u, aph = (ti >> 1) & 1u;
-      if (dual && a != issuer) {  // the other issuer's tile: step over its ring stages
+      if (dual && a != issuer) {
+        // The other issuer's tile: step over its ring stages WITHOUT touching their barriers.  An mbarrier parity wait
+        // is only sound when the waiter has seen the previous phase of that barrier complete, so the two issuers must
+        // never share a stage: the host enables two issuers only when a tile is ONE stage and the ring has an EVEN
+        // number of stages -- then issuer 0 owns the even stages and issuer 1 the odd ones, and each sees every phase
+        // of its own barriers in order.  (Round 1 ran odd rings, 5 or 3 stages for 64->64: a stage alternated between
+        // the issuers, an issuer that ran ahead could read "parity k done" from phase k-2 while the other's data was
+        // still landing -- the intermittent launch failures.  Making the skipping issuer wait on the skipped full
+        // barriers instead deadlocks when it falls a whole ring behind: tried, times out at batch 32.)
         if ((KSPEC == 3)) {
           for (int c = 0; c < p.kchunks; ++c) ring_advance(ring, p, HALO_STAGE, full0, empty0);
         } else if (KSPEC == 0 && p.spec == 1) {
@@ -1067,9 +1075,10 @@ inline int prepare(Launch* L, const TView& x, const TView& y, const TView* res, 
     // These are exactly the short-K tiles that lose the most to per-tile bookkeeping.
     static const int env_dbg = [] { const char* e = getenv("BD_UMMA_DBG"); return e ? atoi(e) : 0; }();
     p.dbg = env_dbg;
-    // OFF by default: with two issuers the per-op timing path failed intermittently at batch 32 (3 of 8 runs; 0 of 5
-    // with one issuer), so the scheme is not trusted yet although the scene loop stress-tested clean.
-    static const int env_issuers = [] { const char* e = getenv("BD_UMMA_ISSUERS"); return e ? atoi(e) : 1; }();
+    // ON by default since round 2: the intermittent failures of round 1 came from odd ring sizes (a stage shared by the
+    // two issuers -> mbarrier parity aliasing, see the issuer loop); with the even-ring rule below the scheme ran
+    // tools/stress2.py clean at batch 16 and 32 (result digests + the per-op timing path).  BD_UMMA_ISSUERS=1: one.
+    static const int env_issuers = [] { const char* e = getenv("BD_UMMA_ISSUERS"); return e ? atoi(e) : 2; }();
     const int stages_per_tile = p.spec == 3 ? p.kchunks : num_kb / p.group;
     // Only on the halo path: there one elected lane issues a whole tile (36 MMAs + both commits) in one go.  On the
     // grouped generic ring (several elect blocks per stage) two issuers showed an intermittent hang on B200 that
@@ -1079,6 +1088,11 @@ inline int prepare(Launch* L, const TView& x, const TView& y, const TView* res, 
     // chunks per tile) the two-issuer scheme faulted under tools/stress.py; single-issuer it is clean.
     p.issuers = (p.spec != 3 || p.halo_subset || p.kchunks != 1 || ntaps != 9 || env_issuers != 2 ||
                  stages_per_tile >= p.stages) ? 1 : 2;
+    if (p.issuers == 2 && (p.stages & 1)) {
+      // one stage per tile and an even ring: each issuer owns every other stage (see the issuer loop)
+      if (p.stages >= 3) { p.stages -= 1; L->smem_bytes -= HALO_STAGE; }
+      else p.issuers = 1;
+    }
   }
 
   // parity views of the input for stride 2 (a single plain view for stride 1)

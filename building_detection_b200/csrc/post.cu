@@ -126,6 +126,7 @@ int label_area(bd_ctx* ctx, Arena& a, Plane p, int slot, RunSet* rs, long long**
 // One clean-up pass (fill_and_delete + eroede_dilate_process + only_plt, model_fuse.py:9-218,265-268) on planes.
 // stage_out / stage: debugging hook (bd_debug_cleanup_stage) -- copies an intermediate plane out.
 int cleanup_plane(bd_ctx* ctx, Arena& a, Plane in, Plane out, cudaStream_t s, int stage, Plane* stage_out) {
+  NvtxRange nvtx("bd:cleanup");
   const PostConstants& K = ctx->consts;
   const int H = in.H, W = in.W;
   const size_t words = static_cast<size_t>(H) * in.wp;
@@ -287,6 +288,7 @@ int bd_fuse_planes(bd_ctx* ctx, const uint32_t* planes5_dev, int cleaned, int h,
                    uint32_t* fused_plane_dev, void* stream) {
   BD_ON_CTX(ctx);
   BD_CHECK(ctx && planes5_dev && (fused_dev || fused_plane_dev) && h >= 1 && w >= 1, "bad arguments");
+  NvtxRange nvtx("bd:fuse");
   BD_CHECK(static_cast<size_t>(h) * w < (1ull << 31), "scene too large for int32 pixel indices");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   post::Arena& a = ctx->arena;

@@ -112,5 +112,6 @@ struct bd_ctx {
   int* h_scalar = nullptr;    // pinned host word for device -> host counters
   void* h_pts[3] = {nullptr, nullptr, nullptr};  // pinned host buffers of the three traced contour sets (grow-only)
   size_t h_pts_cap[3] = {0, 0, 0};
+  cudaStream_t capture_stream = nullptr;  // CUDA-graph capture of the plans (bd_scene_run)
   void* trace_buf = nullptr;  // BD_UMMA_TRACE debug buffer of the most recently built conv
 };

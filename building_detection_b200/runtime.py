@@ -88,6 +88,7 @@ _SIGS = {
     "bd_scene_run": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                C.c_int, C.c_void_p, C.c_void_p]),
     "bd_workspace_bytes": (C.c_size_t, [C.c_void_p]),
+    "bd_plan_uses_graph": (C.c_int, [C.c_void_p]),
     "bd_fuse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "bd_fuse_cleaned": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "bd_mask_cleanup": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
@@ -331,6 +332,10 @@ class NativePlan:
                 dw = self.plan.ops[op["fused_dw"]]
                 flops[j] += 2.0 * self.plan.batch * op["Ho"] * op["Wo"] * dw["x"][2] * 9
         return ms, kinds, flops
+
+    @property
+    def uses_graph(self):
+        return bool(lib().bd_plan_uses_graph(self.h))
 
     @property
     def num_launches(self):

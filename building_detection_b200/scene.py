@@ -51,7 +51,7 @@ def shard_rows(origins, rank, world):
 class SceneRunner:
     """Runs models over one scene on one GPU.  ``models``: engine.Model objects."""
 
-    def __init__(self, models, batch=16, device=None):
+    def __init__(self, models, batch=32, device=None):
         import torch
         if not torch.cuda.is_available():
             raise R.NativeError("building_detection_b200 needs a CUDA device (B200); there is no CPU path")

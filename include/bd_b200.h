@@ -157,6 +157,8 @@ int bd_stitch_or_at(bd_ctx* ctx, const uint8_t* tile_masks_dev, int first, int n
  * is replayed from a CUDA graph captured on first use (BD_GRAPHS=0: direct launches). */
 int bd_scene_run(bd_ctx* ctx, bd_plan* const* plans, int n_plans, const uint8_t* scene_bgr_dev, int h, int w,
                  const int32_t* ys_host, const int32_t* xs_host, int n_tiles, uint8_t* masks_dev, void* stream);
+/* 1 when bd_scene_run replays this plan from a captured CUDA graph, 0 when capture was refused or is turned off */
+int bd_plan_uses_graph(bd_plan* plan);
 /* device bytes the context currently holds for the scene-level stages (fusion / contour scratch, tile masks) */
 size_t bd_workspace_bytes(bd_ctx* ctx);
 

@@ -35,7 +35,7 @@ def fill_and_delete(mask, min_area=1000):
         area = cv.contourArea(c)
         cv.fillPoly(g, [c], (255, 255, 255))
         if area <= min_area:
-            cv.drawContours(g, cs, i, 0, cv.FILLED)
+            cv.drawContours(g, [c], 0, 0, cv.FILLED)  # (= drawContours(g, cs, i, ...): O(1) instead of O(len(cs)) per call)
     return g, _contours(g)
 
 
@@ -54,7 +54,7 @@ def _split_one_direction(obj, kernel, iters=5, frag_area=500):
         cv.fillPoly(er, [c], (255, 255, 255))
         if area <= frag_area:
             erased = True
-            cv.drawContours(er, frags, i, 0, cv.FILLED)
+            cv.drawContours(er, [c], 0, 0, cv.FILLED)
     if erased:
         frags = _contours(er)
         if len(frags) == 0:

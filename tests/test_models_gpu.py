@@ -74,8 +74,13 @@ def test_forward_matches_fp16_interpreter(gpu, prepared, name):
     plan = m.build_plan(1)
     want = plan_interp.run_plan(plan, x[:1], emulate_h16=True)
     got, mask = m.native_plan(1).run_host(x[:1], want_probs=True, want_mask=True)
-    # summation order is the only difference
-    assert np.abs(got - want).max() < 5e-3, np.abs(got - want).max()
+    # Summation order is the only difference: 5e-3.  HRNet: 1e-2 -- its 40 stacked residual blocks amplify even on the
+    # damped parity recipe (flipping 1e-4 of the interpreter's own stored activations by one ulp moves its output by
+    # 3.8e-3, 1e-2 of them by more: tests/test_oracle_nets.py, profiles/r2_hrnet_chaos.txt), and the per-layer trace
+    # (profiles/r2a_layer_trace_hrnet_*.txt) shows the GPU differing from the interpreter by at most one or two ulp on a
+    # fraction of the elements that grows smoothly from 2.5e-5 (stem) to 0.4 (head): no kernel introduces a jump.
+    tol = 1e-2 if name == "hrnet" else 5e-3
+    assert np.abs(got - want).max() < tol, np.abs(got - want).max()
     np.testing.assert_array_equal(mask, (got[..., 1] > got[..., 0]).astype(np.uint8))
 
 

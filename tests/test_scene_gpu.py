@@ -53,12 +53,13 @@ def reference_loop(img_bgr, model):
     return np.where(label >= 1, 255, 0).astype(np.uint8)[:h, :w], tiles, probs
 
 
-@pytest.mark.parametrize("size,seed", [(1592, 41), (1000, 42), (1952, 43)])  # 16 tiles; 9 (ragged); 25 = 16 + 9
-def test_scene_runner_matches_reference_loop(gpu, parity_models, size, seed):
+# batch 16: 16 tiles; 9 (ragged); 25 = 16 + 9.  batch 32 (the default of the scene loop): 36 = 32 + 4
+@pytest.mark.parametrize("size,seed,batch", [(1592, 41, 16), (1000, 42, 16), (1952, 43, 16), (2312, 44, 32)])
+def test_scene_runner_matches_reference_loop(gpu, parity_models, size, seed, batch):
     import torch
     models = [parity_models(n) for n in MODEL_NAMES]
     img = blob_scene(size, size, seed)
-    r = S.SceneRunner(models, batch=16)
+    r = S.SceneRunner(models, batch=batch)
     got = r.run(r.upload(img)).cpu().numpy()
     torch.cuda.synchronize()
     assert got.shape == (5, size, size) and set(np.unique(got)) <= {0, 255}

@@ -94,6 +94,8 @@ for damp in (1.0, 0.5, 0.25):
     with torch.no_grad():
         ref = nets.FORWARD["hrnet"](w, x)
         got = plan_interp.run_plan(m.build_plan(1), x, emulate_h16=True)
-        pert = InterpPerturb(m.build_plan(1), 1e-4).run(x)
+        perts = {f: InterpPerturb(m.build_plan(1), f).run(x) for f in (1e-4, 1e-2)}
     print(f"x{damp:4.2f}: oracle p1 std {ref[..., 1].std():.3f}, class-1 {float((ref[..., 1] > 0.5).mean()):.3f} | fp16 vs fp32: "
-          f"{stats(got, ref)} | one-ulp flips f=1e-4: {stats(pert, got)}")
+          f"{stats(got, ref)}")
+    for f, pert in perts.items():
+        print(f"        one-ulp flips f={f:.0e} vs unperturbed: {stats(pert, got)}")
