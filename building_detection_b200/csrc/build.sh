@@ -7,5 +7,6 @@ FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompil
 $NVCC $FLAGS ${PTXAS_V:+-Xptxas -v} -c bd_api.cu -o bd_api.o
 $NVCC $FLAGS ${PTXAS_V:+-Xptxas -v} -c post.cu -o post.o
 $NVCC $FLAGS -fmad=false ${PTXAS_V:+-Xptxas -v} -c contours.cu -o contours.o
-$NVCC $FLAGS -shared bd_api.o post.o contours.o -o ../libbd_b200.so
+$NVCC $FLAGS -c png0.cpp -o png0.o
+$NVCC $FLAGS -shared bd_api.o post.o contours.o png0.o -o ../libbd_b200.so
 echo "built $(cd .. && pwd)/libbd_b200.so"

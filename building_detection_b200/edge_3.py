@@ -68,8 +68,21 @@ def detect(mask):
 
 def _detection(label_path):
     """edge_3.py:310-387: read the fused-mask PNG, return (all_coner, img_height)."""
+    import os
+
     import cv2 as cv
-    img = cv.imread(label_path)
-    if img is None:
+
+    from . import png0
+    if not os.path.isfile(label_path):
         raise AttributeError("'NoneType' object has no attribute 'copy'")  # what edge_3.py:313 raises for a bad path
-    return detect(cv.cvtColor(img, cv.COLOR_BGR2GRAY))
+    try:
+        with open(label_path, 'rb') as f:
+            img = png0.decode_gray(f.read())  # the fuse stage's level-0 grey PNG: no inflate, no colour conversion
+    except ValueError:
+        img = None
+    if img is None or img.ndim != 2 or img.dtype != np.uint8:
+        img = cv.imread(label_path)
+        if img is None:
+            raise AttributeError("'NoneType' object has no attribute 'copy'")
+        img = cv.cvtColor(img, cv.COLOR_BGR2GRAY)
+    return detect(img)

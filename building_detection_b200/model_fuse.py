@@ -128,5 +128,11 @@ def model_confuse(path, name=''):
     if len(all_path) != 5:
         print('no five images')
         return
-    masks = [cv.imread(p)[:, :, 0] for p in all_path]  # fill_and_delete reads channel 0 (:10)
-    cv.imwrite(path + r'\{}_result.png'.format(name), fuse(masks))
+    from . import png0
+    masks = []
+    for p in all_path:  # fill_and_delete reads channel 0 of cv.imread's BGR image (:10); a grey PNG has one
+        with open(p, 'rb') as f:
+            m = png0.decode_gray(f.read())
+        masks.append(m if m.ndim == 2 else cv.imread(p)[:, :, 0])
+    with open(path + r'\{}_result.png'.format(name), 'wb') as f:  # level-0 PNG like cv.imwrite(..., 0) (:350)
+        f.write(png0.encode_gray(fuse(masks)))

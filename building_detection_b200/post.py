@@ -57,7 +57,8 @@ def gather_packed(band_planes, bands, rank, world, h):
     m, _, wp = band_planes.shape
     if rank != 0:
         if band_planes.shape[1]:
-            dist.send(band_planes.contiguous(), dst=0)
+            for req in dist.batch_isend_irecv([dist.P2POp(dist.isend, band_planes.contiguous(), 0)]):
+                req.wait()
         return None
     planes = torch.zeros((m, h, wp), dtype=band_planes.dtype, device=band_planes.device)
     r0, r1 = bands[0]

@@ -69,7 +69,7 @@ def detection(img_path, user_path, model, save_name='model', bug_compatible=True
         raise TypeError("cv.imread returned None for {!r}".format(img_path))  # cvtColor(None) raises in the reference
     r = S.SceneRunner([model])
     mask = r.run(r.upload(img), bug_compatible=bug_compatible)[0]
-    cv.imwrite(user_path + '/{}.png'.format(save_name), mask.cpu().numpy(), [int(cv.IMWRITE_PNG_COMPRESSION), 0])
+    _write_png0(user_path + '/{}.png'.format(save_name), mask.cpu().numpy())
 
 
 def run_model(img_path, user_path, name='', bug_compatible=True):
@@ -82,7 +82,14 @@ def run_model(img_path, user_path, name='', bug_compatible=True):
     r = runner()
     masks = r.run(r.upload(img), bug_compatible=bug_compatible).cpu().numpy()
     for prefix, mask in zip(MODEL_PREFIXES, masks):
-        cv.imwrite(user_path + '/{}.png'.format(prefix + name), mask, [int(cv.IMWRITE_PNG_COMPRESSION), 0])
+        _write_png0(user_path + '/{}.png'.format(prefix + name), mask)
+
+
+def _write_png0(path, mask):
+    """cv.imwrite(path, mask, [IMWRITE_PNG_COMPRESSION, 0]) (predict.py:115) through the multi-threaded level-0 encoder"""
+    from . import png0
+    with open(path, 'wb') as f:
+        f.write(png0.encode_gray(mask))
 
 
 def write_points(points, path):

@@ -101,6 +101,8 @@ _SIGS = {
     "bd_debug_labels": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "bd_contours": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(Polys), C.c_void_p]),
     "bd_polys_free": (None, [C.POINTER(Polys)]),
+    "bd_png0_size": (C.c_size_t, [C.c_int, C.c_int]),
+    "bd_png0_encode": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_int]),
     "bd_host_contour_area": (C.c_double, [C.c_void_p, C.c_int]),
     "bd_host_arc_length": (C.c_double, [C.c_void_p, C.c_int]),
     "bd_host_approx_poly": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_void_p]),

@@ -219,6 +219,14 @@ typedef struct bd_polys {
 int bd_contours(bd_ctx* ctx, const uint8_t* mask_dev, int h, int w, bd_polys* out, void* stream);
 void bd_polys_free(bd_polys* p);
 
+/* ---- level-0 PNG of the stage hand-offs (host code: no GPU needed) ------------------------------------------- */
+/* The reference writes its masks with cv.imwrite(..., [IMWRITE_PNG_COMPRESSION, 0]) (predict.py:115, model_fuse.py:350)
+ * and base64-encodes the result file (buildAPI.py:122-123).  bd_png0_encode produces such a file for an (h, w) u8 mask
+ * in host memory: 8-bit grey, stored deflate blocks, filter 0 -- multi-threaded copy + CRC-32 / Adler-32 with
+ * checksum combination (threads <= 0: all cores, at most 32).  out_host needs bd_png0_size(h, w) bytes. */
+size_t bd_png0_size(int h, int w);
+int bd_png0_encode(const uint8_t* mask_host, int h, int w, uint8_t* out_host, size_t cap, size_t* out_len, int threads);
+
 /* host-side restatements of the OpenCV primitives edge_3.py applies per contour (integer (x,y) pairs, closed
  * curves), exposed so that they can be checked against cv2 without a GPU: cv::contourArea, cv::arcLength,
  * cv::approxPolyDP (returns the vertex count, writes out_xy[2*count]) and the area-tiered choice of

@@ -11,11 +11,12 @@ import pytest
 from building_detection_b200 import buildAPI, png0
 
 
-@pytest.mark.parametrize("shape", [(1, 1), (7, 5), (300, 217), (256, 256), (1000, 1311)])
+@pytest.mark.parametrize("shape", [(1, 1), (7, 5), (300, 217), (256, 256), (255, 256), (1, 65534), (65535, 1), (1000, 1311)])
 def test_png0_round_trip_and_opencv_interop(shape):
     rng = np.random.default_rng(shape[0] * 7 + shape[1])
     m = (rng.random(shape) < 0.4).astype(np.uint8) * 255
     data = png0.encode_gray(m)
+    assert data == png0.encode_gray_py(m) == png0.encode_gray(m, threads=3)  # native (all cores / 3 threads) == numpy twin
     np.testing.assert_array_equal(png0.decode_gray(data), m)
     np.testing.assert_array_equal(cv.imdecode(np.frombuffer(data, np.uint8), cv.IMREAD_UNCHANGED), m)   # libpng reads ours
     ok, theirs = cv.imencode(".png", m, [int(cv.IMWRITE_PNG_COMPRESSION), 0])                            # what the reference writes
