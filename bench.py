@@ -313,7 +313,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--scene", type=int, default=20000, help="scene edge in px (20000 = BASELINE configs[4])")
-    ap.add_argument("--batch", type=int, default=32, help="tiles per plan launch in the scene loop (configs 1-4 fix their own)")
+    ap.add_argument("--batch", type=int, default=0, help="tiles per plan launch in the scene loop; 0 = scene.best_batch of "
+                    "this rank's shard (32 for 3136 tiles, 28 for the 392 of one of 8 GPUs); configs 1-4 fix their own")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-post", action="store_true", help="skip fusion + contours (forward + stitch only)")
@@ -346,10 +347,12 @@ def main():
         torch.cuda.synchronize()
 
     models = [CTORS[n]() for n in MODEL_NAMES]  # seeded Keras-default random init (no checkpoints offline)
-    runner = S.SceneRunner(models, batch=args.batch, device=local)
     Ssz = args.scene
     origins = S.tile_origins(Ssz, Ssz)
     mine = S.shard_rows(origins, rank, world)
+    if not args.batch:
+        args.batch = S.best_batch(max(len(S.shard_rows(origins, r, world)) for r in range(world)))
+    runner = S.SceneRunner(models, batch=args.batch, device=local)
     job = post.SceneJob(runner, Ssz, Ssz, mine, rank, world, do_post=not args.no_post)
 
     scene_host = torch.from_numpy(synthetic_scene(Ssz)).pin_memory()

@@ -11,6 +11,7 @@ import numpy as np
 
 from . import graph as G
 
+MAX_LARGE_PLANS = 1  # per model and device
 MAX_PLAN_BATCH = 32  # largest plan batch (BASELINE configs 2-4 run 16; the scene loop runs 32: +3.6 % per tile on B200)
 
 
@@ -89,8 +90,16 @@ class Model:
         from .runtime import NativePlan, resolve_device
         device = resolve_device(device)
         key = (batch, umma, device)
-        if key not in self._native:
-            self._native[key] = NativePlan(self.build_plan(batch, umma=umma), device)
+        if key in self._native:
+            self._native[key] = self._native.pop(key)  # most recently used last
+            return self._native[key]
+        # bound the arenas a long-lived process holds: at most MAX_LARGE_PLANS plans of 16 or more tiles per device
+        # (0.45 GB of activations per tile and model: 14 GB for one batch-32 plan), least recently used first out;
+        # the small ones (1, 2, 4, 8 tiles) stay
+        large = [k for k in self._native if k[0] >= 16 and k[2] == device]
+        while batch >= 16 and len(large) >= MAX_LARGE_PLANS:
+            self._native.pop(large.pop(0)).close()
+        self._native[key] = NativePlan(self.build_plan(batch, umma=umma), device)
         return self._native[key]
 
     @staticmethod

@@ -53,7 +53,7 @@ def _models():
     return [res_model, hr_model, v3_model, unet_model, bam_model]
 
 
-def runner(batch=32):
+def runner(batch=None):
     global _runner
     if _runner is None or _runner.batch != batch or _runner.models != _models():
         _runner = S.SceneRunner(_models(), batch=batch)

@@ -48,10 +48,28 @@ def shard_rows(origins, rank, world):
     return [o for o in origins if o[0] in mine]
 
 
-class SceneRunner:
-    """Runs models over one scene on one GPU.  ``models``: engine.Model objects."""
+BATCH_CANDIDATES = (32, 28, 24, 20, 16)
 
-    def __init__(self, models, batch=32, device=None):
+
+def best_batch(n_tiles, max_batch=32):
+    """Tiles per plan launch for a shard of ``n_tiles``: the candidate that pads the shard the least (a ragged last
+    batch runs a whole plan), the largest on ties -- 3136 tiles -> 32 (98 launches), 392 tiles (one of 8 GPUs on a
+    20 000^2 scene) -> 28 (14 launches, no padding; 32 would pad 392 to 416).  Fewer than 16 tiles: the next power of
+    two (engine.Model.plan_batch_for)."""
+    cands = [b for b in BATCH_CANDIDATES if b <= max_batch]
+    if n_tiles < min(cands):
+        b = 1
+        while b < n_tiles:
+            b *= 2
+        return b
+    return min(cands, key=lambda b: (-(-n_tiles // b) * b, -b))
+
+
+class SceneRunner:
+    """Runs models over one scene on one GPU.  ``models``: engine.Model objects.  ``batch``: tiles per plan launch, or
+    None to choose per scene with ``best_batch``."""
+
+    def __init__(self, models, batch=None, device=None):
         import torch
         if not torch.cuda.is_available():
             raise R.NativeError("building_detection_b200 needs a CUDA device (B200); there is no CPU path")
@@ -88,7 +106,11 @@ class SceneRunner:
         # (engine.Model.plan_batch_for), so at most five plan sizes per model ever exist.
         ys = np.ascontiguousarray([o[0] for o in origins], np.int32)
         xs = np.ascontiguousarray([o[1] for o in origins], np.int32)
-        pb = self.batch if len(origins) >= self.batch else min(self.batch, self.models[0].plan_batch_for(len(origins)))
+        if self.batch is None:
+            pb = best_batch(len(origins))
+        else:
+            pb = self.batch if len(origins) >= self.batch else min(self.batch, self.models[0].plan_batch_for(len(origins)))
+        self.last_batch = pb
         plans = [m.native_plan(pb, device=self.device.index) for m in self.models]
         handles = (C.c_void_p * len(plans))(*[p.h for p in plans])
         R.check(L.bd_scene_run(self.ctx, handles, len(plans), scene_dev.data_ptr(), h, w, R._ptr(ys), R._ptr(xs),

@@ -33,6 +33,13 @@ def test_tile_origins_geometry():
     assert S.tile_origins(130, 130) == []
 
 
+def test_best_batch_pads_least():
+    assert S.best_batch(3136) == 32 and S.best_batch(1568) == 32      # 1 and 2 GPUs on the 20 000^2 scene: no padding
+    assert S.best_batch(784) == 28 and S.best_batch(392) == 28        # 4 and 8 GPUs: 28 divides, 32 would pad
+    assert S.best_batch(36) == 20 and S.best_batch(25) == 28 and S.best_batch(16) == 16
+    assert S.best_batch(9) == 16 and S.best_batch(4) == 4 and S.best_batch(1) == 1 and S.best_batch(3) == 4
+
+
 def test_row_band_shards_partition_the_tiles():
     o = S.tile_origins(20000, 20000)
     for world in (1, 2, 4, 8):
