@@ -244,6 +244,57 @@ int bd_plan_add_conv(bd_plan* p, const bd_conv_desc* dptr) {
     op.flops = 2.0 * pl->batch * d.ho * d.wo * (static_cast<double>(cout) * cin * d.ntaps + (dww ? 9.0 * cin : 0.0));
     op.launches = 1;
     bd_ctx* ctx = pl->ctx;
+    if (d.path == BD_CONV_SMALL) {
+      // CUDA-core path for <= 16 output channels (k::conv_small_kernel): fp32 weights [tap][ci][CO], only the channels
+      // that carry non-zero weights / bias
+      BD_CHECK(!has_res && d.stride == 1 && d.out_scale == 1 && d.ntaps <= 9 && d.act_post == BD_ACT_NONE,
+               "small conv: stride 1, no residual, at most 9 taps");
+      const BufInfo& xb = pl->bufs[d.x.buf];
+      const BufInfo& yb = pl->bufs[d.y.buf];
+      BD_CHECK(xb.dtype == BD_F16 && d.x.c % 8 == 0 && d.x.c0 % 8 == 0 && xb.C % 8 == 0, "small conv: fp16 input in 8-channel vectors");
+      BD_CHECK(yb.dtype == BD_F32 || (d.y.c % 8 == 0 && d.y.c0 % 8 == 0 && yb.C % 8 == 0), "small conv: output slice alignment");
+      int cin_used = 0, cout_used = 0;
+      auto h2f = [](uint16_t b) { return __half2float(__ushort_as_half(b)); };
+      for (int t = 0; t < d.ntaps; ++t)
+        for (int co = 0; co < cout; ++co)
+          for (int ci = 0; ci < cin; ++ci)
+            if ((*w)[(static_cast<size_t>(t) * cout + co) * cin + ci] & 0x7FFF) { cin_used = std::max(cin_used, ci + 1); cout_used = std::max(cout_used, co + 1); }
+      for (int co = 0; co < cout; ++co)
+        if ((*b)[co] != 0.0f) cout_used = std::max(cout_used, co + 1);
+      cin_used = std::max(cin_used, 1); cout_used = std::max(cout_used, 1);
+      BD_CHECK(cout_used <= 16, "small conv: more than 16 output channels in use");
+      const int CO = cout_used <= 2 ? 2 : cout_used <= 4 ? 4 : cout_used <= 8 ? 8 : 16;
+      std::vector<float> wf(static_cast<size_t>(d.ntaps) * cin_used * CO, 0.0f), bf(CO, 0.0f);
+      for (int t = 0; t < d.ntaps; ++t)
+        for (int ci = 0; ci < cin_used; ++ci)
+          for (int co = 0; co < cout_used; ++co)
+            wf[(static_cast<size_t>(t) * cin_used + ci) * CO + co] = h2f((*w)[(static_cast<size_t>(t) * cout + co) * cin + ci]);
+      for (int co = 0; co < cout_used; ++co) bf[co] = (*b)[co];
+      void *wfd = nullptr, *bfd = nullptr;
+      if (pl->upload(wf.data(), wf.size() * 4, &wfd) || pl->upload(bf.data(), bf.size() * 4, &bfd)) return 1;
+      k::SmallParams q;
+      memset(&q, 0, sizeof(q));
+      q.x = pl->kview(d.x); q.y = pl->kview(d.y);
+      q.N = pl->batch; q.Ho = d.ho; q.Wo = d.wo; q.ntaps = d.ntaps;
+      for (int t = 0; t < d.ntaps; ++t) { q.dy[t] = d.dy[t]; q.dx[t] = d.dx[t]; }
+      q.cin_used = cin_used; q.cout_used = cout_used; q.act = d.act_pre;
+      q.w = static_cast<const float*>(wfd); q.bias = static_cast<const float*>(bfd);
+      const size_t total = static_cast<size_t>(pl->batch) * d.ho * d.wo;
+      const int grid = grid_for(total, ctx->num_sms * 4);
+      const size_t smem = (wf.size() + CO) * sizeof(float);
+      BD_CHECK(smem <= 48 * 1024, "small conv: weights do not fit into shared memory");
+      op.kclass = 2;
+      op.flops = 2.0 * pl->batch * d.ho * d.wo * static_cast<double>(cout_used) * cin_used * d.ntaps;
+      op.run = [q, grid, smem, CO, ctx](cudaStream_t s) -> int {
+        ctx->launches++;
+        if (CO == 2) BD_LAUNCH(k::conv_small_kernel<2>, dim3(grid), dim3(k::TPB), smem, s, q);
+        else if (CO == 4) BD_LAUNCH(k::conv_small_kernel<4>, dim3(grid), dim3(k::TPB), smem, s, q);
+        else if (CO == 8) BD_LAUNCH(k::conv_small_kernel<8>, dim3(grid), dim3(k::TPB), smem, s, q);
+        else BD_LAUNCH(k::conv_small_kernel<16>, dim3(grid), dim3(k::TPB), smem, s, q);
+        BD_CUDA(cudaGetLastError());
+        return 0;
+      };
+    } else
     if (d.path == BD_CONV_UMMA) {
       std::shared_ptr<umma::Launch> L(new umma::Launch());
       TView x = pl->tview(d.x), y = pl->tview(d.y), r;

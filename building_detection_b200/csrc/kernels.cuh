@@ -88,6 +88,77 @@ __global__ void __launch_bounds__(TPB) conv_direct_kernel(const __grid_constant_
   }
 }
 
+// ---------------------------------------------------------------------------------- small-channel conv (CUDA cores)
+// Convolutions with at most 16 output channels and a few hundred multiply-adds per pixel: BAM's spatial-gate
+// convolutions on C/16 = 4 or 8 channels (3x3, dilation 4; stored padded to 16 channels), its 1-channel gate logits,
+// and the 1x1 two-channel heads.  On the tensor-core path these are 128-pixel tiles of N = 16 columns that spend their
+// time in per-k-block bookkeeping (bam 3x3 4->4 @256^2: 1.8 TFLOP/s, 17x its HBM time); here they are HBM-bound:
+// thread = output pixel, 128-bit loads of 8 input channels, the (tap, ci, co) weights as fp32 in shared memory
+// (warp-uniform broadcast reads), only the channels that carry non-zero weights are touched.
+struct SmallParams {
+  View x, y;
+  int N, Ho, Wo, ntaps;
+  int dy[9], dx[9];
+  int cin_used, cout_used, act;
+  const float* w;     // [ntaps][cin_used][CO] fp32
+  const float* bias;  // [CO]
+};
+template <int CO>
+__global__ void __launch_bounds__(TPB) conv_small_kernel(const __grid_constant__ SmallParams p) {
+  extern __shared__ float sw[];
+  pdl_trigger();
+  const int nw = p.ntaps * p.cin_used * CO;
+  for (int i = threadIdx.x; i < nw + CO; i += TPB) sw[i] = i < nw ? p.w[i] : p.bias[i - nw];  // constant data
+  __syncthreads();
+  pdl_wait();
+  const size_t total = static_cast<size_t>(p.N) * p.Ho * p.Wo;
+  const h16* xb = static_cast<const h16*>(p.x.base);
+  for (size_t pix = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; pix < total; pix += static_cast<size_t>(gridDim.x) * TPB) {
+    const int ow = static_cast<int>(pix % p.Wo), oh = static_cast<int>((pix / p.Wo) % p.Ho);
+    const int n = static_cast<int>(pix / (static_cast<size_t>(p.Wo) * p.Ho));
+    float acc[CO];
+#pragma unroll
+    for (int j = 0; j < CO; ++j) acc[j] = sw[nw + j];
+    for (int t = 0; t < p.ntaps; ++t) {
+      const int ih = oh + p.dy[t], iw = ow + p.dx[t];
+      if (ih < 0 || ih >= p.x.H || iw < 0 || iw >= p.x.W) continue;  // 'same' padding reads zero
+      const h16* xp = xb + ((static_cast<size_t>(n) * p.x.H + ih) * p.x.W + iw) * p.x.ctot + p.x.c0;
+      const float* wt = sw + t * p.cin_used * CO;
+      for (int c0 = 0; c0 < p.cin_used; c0 += 8) {
+        float f[8];
+        unpack8(*reinterpret_cast<const h16x8*>(xp + c0), f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          if (c0 + k < p.cin_used) {
+            const float* wr = wt + (c0 + k) * CO;
+#pragma unroll
+            for (int j = 0; j < CO; ++j) acc[j] = fmaf(f[k], wr[j], acc[j]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < CO; ++j) acc[j] = actf(acc[j], p.act);
+    if (p.y.f32) {
+      float* yp = static_cast<float*>(p.y.base) + pix * p.y.ctot + p.y.c0;
+#pragma unroll
+      for (int j = 0; j < CO; ++j)
+        if (j < p.y.c) yp[j] = acc[j];
+    } else {
+      // the whole (padded) slice is written: channels beyond cout_used carry zero weights and zero bias
+      for (int c0 = 0; c0 < p.y.c; c0 += 8) {
+        float f[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] = 0.0f;
+#pragma unroll
+        for (int j = 0; j < CO; ++j)
+          if (j >= c0 && j < c0 + 8) f[j - c0] = acc[j];
+        st8(p.y, pix, c0, f);
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------- depthwise 3x3
 struct DwParams {
   View x, y;

@@ -30,6 +30,7 @@ INPUT_SCALE = 255.0  # ... holding 255 * x (exact integers for 8-bit imagery)
 
 # op codes shared with csrc/bd_api.cu (enum bd_op_kind in include/bd_b200.h)
 MAX_TAPS = 18  # bd_b200.h BD_MAX_TAPS
+SMALL_MACS = 600  # multiply-adds per pixel up to which a <= 16-output-channel conv runs on CUDA cores (path "small")
 OP_CONV, OP_DWCONV, OP_MAXPOOL, OP_ADDN, OP_GAP, OP_DENSE, OP_GATE, OP_SKFUSE, OP_BCAST, OP_SOFTMAX2 = range(10)
 GATE_SE, GATE_SCSE, GATE_BAM = range(3)
 ACT_NONE, ACT_RELU, ACT_SIGMOID = range(3)
@@ -245,7 +246,7 @@ class Net:
 
     # ------------------------------------------------------------------ CONV
     def _conv_op(self, x, w_tco, bias, taps, stride, Ho, Wo, act_pre, res, act_post, out,
-                 out_scale=1, out_oy=0, out_ox=0, name="", macs_per_pixel=None):
+                 out_scale=1, out_oy=0, out_ox=0, name="", macs_per_pixel=None, cout_true=None):
         """w_tco: (ntaps, Cout, Cin) fp32 (BN already folded)."""
         nt, cout, cin = w_tco.shape
         assert cin == x.C and len(taps) == nt
@@ -277,6 +278,14 @@ class Net:
                     path = "umma"
             elif cout <= 16 and res is None and out_scale == 1:
                 path = "umma"  # fp32 logits / gate maps: one 16-column tile, direct stores
+        # <= 16 true output channels and at most SMALL_MACS multiply-adds per pixel (BAM's 4- / 8-channel gate
+        # convolutions, 1-channel gate logits, the 1x1 two-channel heads): HBM-bound CUDA-core kernel instead of
+        # 16-column tensor-core tiles that spend their time in per-k-block bookkeeping
+        if (self.umma and cout_true is not None and cout_true <= 16 and macs_per_pixel <= SMALL_MACS and stride == 1
+                and out_scale == 1 and res is None and nt <= 9 and x.buf.dtype == "f16" and cin % 8 == 0 and x.c0 % 8 == 0
+                and x.buf.C % 8 == 0 and (out.buf.dtype == "f32" or (cout % 8 == 0 and out.c0 % 8 == 0 and out.buf.C % 8 == 0))
+                and not self.split_weights):
+            path = "small"
         # algorithmic work: true (unpadded) channel counts
         self.plan.flops += 2 * self.plan.batch * Ho * Wo * macs_per_pixel
         self._emit(op=OP_CONV, name=name, path=path, x=x.ref(), y=out.ref(),
@@ -327,7 +336,7 @@ class Net:
         else:
             act_pre, act_post = ACT_NONE, a
         self._conv_op(x, w, bias, taps, s, Ho, Wo, act_pre, res, act_post, out, name=name,
-                      macs_per_pixel=cout_true * x.cin * k * k)
+                      macs_per_pixel=cout_true * x.cin * k * k, cout_true=cout_true)
         if cout != cout_true:
             out = T(out.buf, out.c0, out.C, ctrue=cout_true)
         return out

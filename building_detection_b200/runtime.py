@@ -201,7 +201,7 @@ class NativePlan:
                 d.stride, d.ho, d.wo = op["stride"], op["Ho"], op["Wo"]
                 d.act_pre, d.act_post = op["act_pre"], op["act_post"]
                 d.out_scale, d.out_oy, d.out_ox = op["out_scale"], op["out_oy"], op["out_ox"]
-                d.path = 1 if op["path"] == "umma" else 0
+                d.path = {"direct": 0, "umma": 1, "small": 2}[op["path"]]
                 w = np.ascontiguousarray(op["w"], np.uint16)
                 b = np.ascontiguousarray(op["b"], np.float32)
                 keep += [w, b]

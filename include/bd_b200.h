@@ -33,7 +33,8 @@ enum bd_dtype { BD_F16 = 0, BD_F32 = 1 };
 enum bd_buf_kind { BD_MAP = 0 /* (N,H,W,C) */, BD_VEC = 1 /* (N,C) fp32 */ };
 enum bd_act { BD_ACT_NONE = 0, BD_ACT_RELU = 1, BD_ACT_SIGMOID = 2 };
 enum bd_gate_mode { BD_GATE_SE = 0, BD_GATE_SCSE = 1, BD_GATE_BAM = 2 };
-enum bd_conv_path { BD_CONV_DIRECT = 0 /* CUDA cores */, BD_CONV_UMMA = 1 /* tcgen05 implicit GEMM */ };
+enum bd_conv_path { BD_CONV_DIRECT = 0 /* CUDA cores, generic */, BD_CONV_UMMA = 1 /* tcgen05 implicit GEMM */,
+                    BD_CONV_SMALL = 2 /* CUDA cores, <= 16 output channels, HBM-bound (heads, BAM gate convs) */ };
 
 typedef struct bd_tref { int32_t buf, c0, c; } bd_tref;
 

@@ -98,6 +98,19 @@ def test_conv_direct(gpu, case):
     conv_case(umma=False, expect="direct", **DIRECT_CASES[case])
 
 
+SMALL_CASES = {  # <= 16 output channels, <= 600 multiply-adds per pixel: the CUDA-core small-channel kernel
+    "1x1_64_8": dict(N=2, H=64, W=64, Cin=64, Cout=8, k=1),
+    "1x1_32_16_plain": dict(N=1, H=32, W=32, Cin=32, Cout=16, k=1, act=None, bn=False),
+    "3x3_d4_8_8": dict(N=2, H=40, W=24, Cin=8, Cout=8, d=4),
+    "1x1_16_8_slices": dict(N=1, H=32, W=32, Cin=16, Cout=8, k=1, in_slice=(16, 48), out_slice=(8, 24)),
+}
+
+
+@pytest.mark.parametrize("case", sorted(SMALL_CASES))
+def test_conv_small_channels(gpu, case):
+    conv_case(expect="small", **SMALL_CASES[case])
+
+
 def test_stem_conv(gpu):
     """3x3 stem on the RGB tile, lowered to a K=32 tensor-core 1x1 conv over the im2col'ed input buffer that
     bd_plan_run builds from the float tile (res34.py:50 stride 1, hrnet.py:168 stride 2)."""
@@ -130,7 +143,7 @@ def test_fp32_head_conv(gpu, cout, k):
         x = g.new(64, 64, 64)
         return x, g.conv(x, "head", cout, k=k, f32_out=True)
     plan, (x, y), _ = build_two_pass(builder, 2)
-    assert plan.ops[0]["path"] == "umma"
+    assert plan.ops[0]["path"] == ("small" if k == 1 else "umma")  # 64 x cout multiply-adds per pixel: CUDA cores
     rng = np.random.default_rng(4)
     inputs = {x.buf.id: rand_map(rng, plan, x.buf.id)}
     ref = run_interp(plan, inputs).get(y.buf.id)
