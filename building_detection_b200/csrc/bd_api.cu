@@ -279,18 +279,24 @@ int bd_plan_add_conv(bd_plan* p, const bd_conv_desc* dptr) {
       for (int t = 0; t < d.ntaps; ++t) { q.dy[t] = d.dy[t]; q.dx[t] = d.dx[t]; }
       q.cin_used = cin_used; q.cout_used = cout_used; q.act = d.act_pre;
       q.w = static_cast<const float*>(wfd); q.bias = static_cast<const float*>(bfd);
+      const int nvec = cdiv(cin_used, 8);
+      const int LPP = nvec <= 1 ? 1 : nvec <= 2 ? 2 : nvec <= 4 ? 4 : 8;  // lanes per pixel
       const size_t total = static_cast<size_t>(pl->batch) * d.ho * d.wo;
-      const int grid = grid_for(total, ctx->num_sms * 4);
+      const int grid = grid_for(total * LPP, ctx->num_sms * 4);
       const size_t smem = (wf.size() + CO) * sizeof(float);
       BD_CHECK(smem <= 48 * 1024, "small conv: weights do not fit into shared memory");
       op.kclass = 2;
       op.flops = 2.0 * pl->batch * d.ho * d.wo * static_cast<double>(cout_used) * cin_used * d.ntaps;
-      op.run = [q, grid, smem, CO, ctx](cudaStream_t s) -> int {
+      typedef void (*SmallKernel)(k::SmallParams);
+      static const SmallKernel table[4][4] = {
+          {k::conv_small_kernel<2, 1>, k::conv_small_kernel<2, 2>, k::conv_small_kernel<2, 4>, k::conv_small_kernel<2, 8>},
+          {k::conv_small_kernel<4, 1>, k::conv_small_kernel<4, 2>, k::conv_small_kernel<4, 4>, k::conv_small_kernel<4, 8>},
+          {k::conv_small_kernel<8, 1>, k::conv_small_kernel<8, 2>, k::conv_small_kernel<8, 4>, k::conv_small_kernel<8, 8>},
+          {k::conv_small_kernel<16, 1>, k::conv_small_kernel<16, 2>, k::conv_small_kernel<16, 4>, k::conv_small_kernel<16, 8>}};
+      const SmallKernel kern = table[CO == 2 ? 0 : CO == 4 ? 1 : CO == 8 ? 2 : 3][LPP == 1 ? 0 : LPP == 2 ? 1 : LPP == 4 ? 2 : 3];
+      op.run = [q, grid, smem, kern, ctx](cudaStream_t s) -> int {
         ctx->launches++;
-        if (CO == 2) BD_LAUNCH(k::conv_small_kernel<2>, dim3(grid), dim3(k::TPB), smem, s, q);
-        else if (CO == 4) BD_LAUNCH(k::conv_small_kernel<4>, dim3(grid), dim3(k::TPB), smem, s, q);
-        else if (CO == 8) BD_LAUNCH(k::conv_small_kernel<8>, dim3(grid), dim3(k::TPB), smem, s, q);
-        else BD_LAUNCH(k::conv_small_kernel<16>, dim3(grid), dim3(k::TPB), smem, s, q);
+        BD_LAUNCH(kern, dim3(grid), dim3(k::TPB), smem, s, q);
         BD_CUDA(cudaGetLastError());
         return 0;
       };

@@ -1004,24 +1004,12 @@ inline int prepare(Launch* L, const TView& x, const TView& y, const TView* res, 
   if (cout16 <= max_block_n) {
     p.block_n = cout16;  // a single N tile; staging chunks that overhang Cout are clipped by the output map
   } else {
-    // several N tiles: multiples of 64 so that no staging chunk spills into the next tile's channels.  The tile width
-    // is chosen per layer so that the tile count fills whole waves of the machine: a wave costs about
-    // (block_n + 64) column-equivalents (the MMA stream plus the per-tile fill / drain / epilogue tail), and
-    // 768->728 @32^2 at batch 32 is 256 pixel tiles -- 3 x 256 columns = 768 tiles = 5.2 waves (6 paid), 4 x 192 = 1024
-    // tiles = 6.9 waves (7 paid, each 20 % shorter).  BD_UMMA_MAX_N still caps the width.
-    static const bool wave_fit = [] { const char* e = getenv("BD_UMMA_WAVE_FIT"); return !(e && e[0] == '0'); }();
-    const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-    int best_bn = 0;
-    long long best_cost = 0;
-    for (int cap = std::max(64, max_block_n / 64 * 64); (wave_fit && cap >= 128) || best_bn == 0; cap -= 64) {
-      const int ntile = cdiv(cout16, cap);
-      const int bn_c = std::min(cap, cdiv(cdiv(cout16, ntile), 64) * 64);
-      const long long waves = cdiv64(static_cast<int64_t>(m_tiles) * cdiv(Cout, bn_c), num_sms);
-      const long long cost = waves * (bn_c + 64);
-      if (best_bn == 0 || cost < best_cost) { best_bn = bn_c; best_cost = cost; }
-      if (cap <= 64) break;
-    }
-    p.block_n = best_bn;
+    // several N tiles: multiples of 64 so that no staging chunk spills into the next tile's channels.  (A width chosen
+    // per layer to fill whole waves -- 4 x 192 instead of 3 x 256 for 768->728 @32^2 at batch 32 -- measured 2 % SLOWER:
+    // the per-tile costs outweigh the saved tail, profiles/README.md round 2.)
+    const int cap = std::max(64, max_block_n / 64 * 64);
+    const int ntile = cdiv(cout16, cap);
+    p.block_n = std::min(cap, cdiv(cdiv(cout16, ntile), 64) * 64);
   }
   p.n_tiles = cdiv(Cout, p.block_n);
   p.kchunks = cdiv(Cin, BLOCK_K);

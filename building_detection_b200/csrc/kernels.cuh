@@ -103,7 +103,11 @@ struct SmallParams {
   const float* w;     // [ntaps][cin_used][CO] fp32
   const float* bias;  // [CO]
 };
-template <int CO>
+// LPP lanes share a pixel: lane l of the group takes the 8-channel vectors l, l + LPP, ... so that the LPP loads of a
+// pixel are one contiguous 16 x LPP-byte segment (thread-per-pixel with 64 input channels touches 32 different
+// 128-byte lines per load instruction: measured 3x slower than the tensor-core tile it replaced), partial sums are
+// combined with shuffles.
+template <int CO, int LPP>
 __global__ void __launch_bounds__(TPB) conv_small_kernel(const __grid_constant__ SmallParams p) {
   extern __shared__ float sw[];
   pdl_trigger();
@@ -111,20 +115,27 @@ __global__ void __launch_bounds__(TPB) conv_small_kernel(const __grid_constant__
   for (int i = threadIdx.x; i < nw + CO; i += TPB) sw[i] = i < nw ? p.w[i] : p.bias[i - nw];  // constant data
   __syncthreads();
   pdl_wait();
+  constexpr int PPW = 32 / LPP;  // pixels per warp
   const size_t total = static_cast<size_t>(p.N) * p.Ho * p.Wo;
   const h16* xb = static_cast<const h16*>(p.x.base);
-  for (size_t pix = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; pix < total; pix += static_cast<size_t>(gridDim.x) * TPB) {
-    const int ow = static_cast<int>(pix % p.Wo), oh = static_cast<int>((pix / p.Wo) % p.Ho);
-    const int n = static_cast<int>(pix / (static_cast<size_t>(p.Wo) * p.Ho));
+  const int lane = threadIdx.x & 31, sub = lane % LPP;
+  const size_t warp0 = (blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x) >> 5;
+  const size_t nwarps = (static_cast<size_t>(gridDim.x) * TPB) >> 5;
+  for (size_t base = warp0 * PPW; base < total; base += nwarps * PPW) {  // warp-uniform trip count (shuffles below)
+    const size_t pix = base + lane / LPP;
+    const bool valid = pix < total;
+    const size_t pc = valid ? pix : total - 1;
+    const int ow = static_cast<int>(pc % p.Wo), oh = static_cast<int>((pc / p.Wo) % p.Ho);
+    const int n = static_cast<int>(pc / (static_cast<size_t>(p.Wo) * p.Ho));
     float acc[CO];
 #pragma unroll
-    for (int j = 0; j < CO; ++j) acc[j] = sw[nw + j];
+    for (int j = 0; j < CO; ++j) acc[j] = 0.0f;
     for (int t = 0; t < p.ntaps; ++t) {
       const int ih = oh + p.dy[t], iw = ow + p.dx[t];
       if (ih < 0 || ih >= p.x.H || iw < 0 || iw >= p.x.W) continue;  // 'same' padding reads zero
       const h16* xp = xb + ((static_cast<size_t>(n) * p.x.H + ih) * p.x.W + iw) * p.x.ctot + p.x.c0;
       const float* wt = sw + t * p.cin_used * CO;
-      for (int c0 = 0; c0 < p.cin_used; c0 += 8) {
+      for (int c0 = sub * 8; c0 < p.cin_used; c0 += 8 * LPP) {
         float f[8];
         unpack8(*reinterpret_cast<const h16x8*>(xp + c0), f);
 #pragma unroll
@@ -138,7 +149,13 @@ __global__ void __launch_bounds__(TPB) conv_small_kernel(const __grid_constant__
       }
     }
 #pragma unroll
-    for (int j = 0; j < CO; ++j) acc[j] = actf(acc[j], p.act);
+    for (int off = LPP / 2; off > 0; off >>= 1) {
+#pragma unroll
+      for (int j = 0; j < CO; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], off);
+    }
+    if (!valid || sub != 0) continue;
+#pragma unroll
+    for (int j = 0; j < CO; ++j) acc[j] = actf(acc[j] + sw[nw + j], p.act);
     if (p.y.f32) {
       float* yp = static_cast<float*>(p.y.base) + pix * p.y.ctot + p.y.c0;
 #pragma unroll
