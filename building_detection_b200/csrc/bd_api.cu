@@ -2,7 +2,9 @@
 // Fusion and contour entry points live in post.cu.
 #include "../../include/bd_b200.h"
 
+#include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <functional>
 #include <memory>
 #include <vector>
@@ -56,10 +58,48 @@ inline int grid_for(size_t total, int num_sms) {
 
 }  // namespace
 
+// Every bd_plan_add_* / finalize call is also appended to the plan's log (op code + plain arguments + weight arrays):
+// bd_plan_save writes the log, bd_plan_load replays it through the same entry points -- a host without the Python graph
+// builder loads pre-lowered plans (tools/export_plans.py) and runs the whole path through the C ABI.
+enum LogOp : uint32_t { LOG_BUFFER = 1, LOG_CONV, LOG_DWCONV, LOG_MAXPOOL, LOG_ADDN, LOG_GAP, LOG_DENSE, LOG_GATE, LOG_SKFUSE,
+                        LOG_BCAST, LOG_FINALIZE };
+struct LogWriter {
+  std::vector<uint8_t>& b;
+  template <class T> void pod(const T& v) { const uint8_t* p = reinterpret_cast<const uint8_t*>(&v); b.insert(b.end(), p, p + sizeof(T)); }
+  void arr(const void* p, size_t bytes) {
+    pod(static_cast<uint64_t>(bytes));
+    const uint8_t* q = static_cast<const uint8_t*>(p);
+    b.insert(b.end(), q, q + bytes);
+    b.insert(b.end(), (8 - bytes % 8) % 8, 0);
+  }
+};
+struct LogReader {
+  const uint8_t* p;
+  const uint8_t* end;
+  bool ok = true;
+  template <class T> T pod() {
+    T v{};
+    if (p + sizeof(T) > end) { ok = false; return v; }
+    memcpy(&v, p, sizeof(T));
+    p += sizeof(T);
+    return v;
+  }
+  const void* arr(size_t* bytes) {
+    const uint64_t n = pod<uint64_t>();
+    const size_t padded = n + (8 - n % 8) % 8;
+    if (!ok || p + padded > end) { ok = false; *bytes = 0; return nullptr; }
+    const void* q = p;
+    p += padded;
+    *bytes = n;
+    return q;
+  }
+};
+
 struct bd_plan {
   bd_ctx* ctx = nullptr;
   int batch = 0;
   bool finalized = false;
+  std::vector<uint8_t> log;
   std::vector<BufInfo> bufs;
   std::vector<std::function<int(bd_plan*)>> builders;  // run at finalize, append to ops
   std::vector<Op> ops;
@@ -200,6 +240,7 @@ int bd_plan_add_buffer(bd_plan* p, int h, int w, int c, int dtype, int kind) {
     fail("bd_plan_add_buffer: bad arguments");
     return -1;
   }
+  { LogWriter lw{p->log}; lw.pod(LOG_BUFFER); lw.pod(h); lw.pod(w); lw.pod(c); lw.pod(dtype); lw.pod(kind); }
   BufInfo b;
   b.H = h; b.W = w; b.C = c; b.dtype = dtype; b.kind = kind;
   if (kind == BD_VEC) b.bytes = static_cast<size_t>(p->batch) * c * 4;
@@ -235,6 +276,17 @@ int bd_plan_add_conv(bd_plan* p, const bd_conv_desc* dptr) {
     }
   }
   const int dw_relu = d.dw_relu_in;
+  {
+    LogWriter lw{p->log};
+    lw.pod(LOG_CONV);
+    bd_conv_desc plain = d;
+    plain.w_host = nullptr; plain.bias_host = nullptr; plain.dw_w_host = nullptr;
+    lw.pod(plain);
+    lw.arr(w->data(), w->size() * 2);
+    lw.arr(b->data(), b->size() * 4);
+    lw.pod(static_cast<int32_t>(d.dw_w_host ? 1 : 0));
+    if (d.dw_w_host) lw.arr(d.dw_w_host, static_cast<size_t>(9) * cin * 4);
+  }
   d.w_host = nullptr; d.bias_host = nullptr; d.dw_w_host = nullptr;
   p->builders.push_back([d, w, b, dww, dw_relu, has_res, cin, cout](bd_plan* pl) -> int {
     void *wd = nullptr, *bdv = nullptr, *dwd = nullptr;
@@ -282,6 +334,7 @@ int bd_plan_add_conv(bd_plan* p, const bd_conv_desc* dptr) {
       const int nvec = cdiv(cin_used, 8);
       const int LPP = nvec <= 1 ? 1 : nvec <= 2 ? 2 : nvec <= 4 ? 4 : 8;  // lanes per pixel
       const size_t total = static_cast<size_t>(pl->batch) * d.ho * d.wo;
+      BD_CHECK(total < (1ull << 31), "small conv: too many output pixels for 32-bit indices");
       const int grid = grid_for(total * LPP, ctx->num_sms * 4);
       const size_t smem = (wf.size() + CO) * sizeof(float);
       BD_CHECK(smem <= 48 * 1024, "small conv: weights do not fit into shared memory");
@@ -350,6 +403,8 @@ int bd_plan_add_dwconv(bd_plan* p, bd_tref x, bd_tref y, int stride, int pad_t, 
   BD_CHECK(p && !p->finalized && w_host, "bad arguments");
   if (p->check_ref(x, true) || p->check_ref(y, true)) return 1;
   BD_CHECK(x.c == y.c, "dwconv: channel mismatch");
+  { LogWriter lw{p->log}; lw.pod(LOG_DWCONV); lw.pod(x); lw.pod(y); lw.pod(stride); lw.pod(pad_t); lw.pod(pad_l); lw.pod(relu_in);
+    lw.arr(w_host, static_cast<size_t>(9) * x.c * 4); }
   // depthwise weights are stored as fp16 on the device (the host passes fp16-representable values)
   std::shared_ptr<std::vector<uint16_t>> w(new std::vector<uint16_t>(9 * static_cast<size_t>(x.c)));
   for (size_t i = 0; i < w->size(); ++i) {
@@ -413,6 +468,7 @@ int bd_plan_add_maxpool(bd_plan* p, bd_tref x, bd_tref y, int kk, int stride, in
   BD_CHECK(p && !p->finalized, "bad arguments");
   if (p->check_ref(x, true) || p->check_ref(y, true)) return 1;
   BD_CHECK(x.c == y.c && kk >= 1 && kk <= 3, "maxpool: bad arguments");
+  { LogWriter lw{p->log}; lw.pod(LOG_MAXPOOL); lw.pod(x); lw.pod(y); lw.pod(kk); lw.pod(stride); lw.pod(pad_t); lw.pod(pad_l); }
   p->builders.push_back([=](bd_plan* pl) -> int {
     k::PoolParams q;
     q.x = pl->kview(x); q.y = pl->kview(y);
@@ -439,6 +495,7 @@ int bd_plan_add_addn(bd_plan* p, int n, const bd_tref* xs, const int32_t* fs, bd
   if (p->check_ref(y, true)) return 1;
   std::vector<bd_tref> xv(xs, xs + n);
   std::vector<int> fv(fs, fs + n);
+  { LogWriter lw{p->log}; lw.pod(LOG_ADDN); lw.pod(n); for (int i = 0; i < n; ++i) { lw.pod(xs[i]); lw.pod(fs[i]); } lw.pod(y); lw.pod(act); }
   for (int i = 0; i < n; ++i) {
     if (p->check_ref(xv[i], true)) return 1;
     const BufInfo& b = p->bufs[xv[i].buf];
@@ -471,6 +528,7 @@ int bd_plan_add_gap(bd_plan* p, bd_tref x, int y_vec) {
   BD_CHECK(p && !p->finalized, "bad arguments");
   if (p->check_ref(x, true) || p->check_vec(y_vec, x.c)) return 1;
   BD_CHECK(x.c / 8 <= k::TPB, "gap: too many channels");
+  { LogWriter lw{p->log}; lw.pod(LOG_GAP); lw.pod(x); lw.pod(y_vec); }
   p->builders.push_back([=](bd_plan* pl) -> int {
     k::GapParams q;
     q.x = pl->kview(x); q.N = pl->batch;
@@ -513,6 +571,8 @@ int bd_plan_add_dense(bd_plan* p, int n_in, const int32_t* x_vecs, int y_vec, in
   if (p->check_vec(y_vec, cout)) return 1;
   std::shared_ptr<std::vector<float>> w(new std::vector<float>(w_host, w_host + static_cast<size_t>(cin) * cout));
   std::shared_ptr<std::vector<float>> b(new std::vector<float>(b_host, b_host + cout));
+  { LogWriter lw{p->log}; lw.pod(LOG_DENSE); lw.pod(n_in); for (int i = 0; i < n_in; ++i) lw.pod(x_vecs[i]); lw.pod(y_vec); lw.pod(cin);
+    lw.pod(cout); lw.pod(act); lw.arr(w_host, static_cast<size_t>(cin) * cout * 4); lw.arr(b_host, static_cast<size_t>(cout) * 4); }
   p->builders.push_back([=](bd_plan* pl) -> int {
     void *wd = nullptr, *bdv = nullptr;
     if (pl->upload(w->data(), w->size() * 4, &wd) || pl->upload(b->data(), b->size() * 4, &bdv)) return 1;
@@ -551,6 +611,8 @@ int bd_plan_add_gate(bd_plan* p, int mode, bd_tref x, bd_tref y, int v_vec, bd_t
     BD_CHECK(w_host != nullptr, "gate: scSE needs spatial weights");
     w.reset(new std::vector<float>(w_host, w_host + x.c));
   }
+  { LogWriter lw{p->log}; lw.pod(LOG_GATE); lw.pod(mode); lw.pod(x); lw.pod(y); lw.pod(v_vec); lw.pod(sref); lw.pod(bscalar);
+    lw.pod(static_cast<int32_t>(w ? 1 : 0)); if (w) lw.arr(w->data(), w->size() * 4); }
   p->builders.push_back([=](bd_plan* pl) -> int {
     k::GateParams q;
     memset(&q, 0, sizeof(q));
@@ -606,6 +668,8 @@ int bd_plan_add_skfuse(bd_plan* p, const bd_tref* xs4, int g_vec, const int32_t*
     if (p->check_vec(lv[i], y.c)) return 1;
   std::shared_ptr<std::vector<float>> sc(new std::vector<float>(scale_host, scale_host + y.c));
   std::shared_ptr<std::vector<float>> sh(new std::vector<float>(shift_host, shift_host + y.c));
+  { LogWriter lw{p->log}; lw.pod(LOG_SKFUSE); for (int i = 0; i < 4; ++i) lw.pod(xs4[i]); lw.pod(g_vec); for (int i = 0; i < 5; ++i) lw.pod(logit_vecs5[i]);
+    lw.pod(y); lw.arr(scale_host, static_cast<size_t>(y.c) * 4); lw.arr(shift_host, static_cast<size_t>(y.c) * 4); }
   p->builders.push_back([=](bd_plan* pl) -> int {
     void *scd = nullptr, *shd = nullptr;
     if (pl->upload(sc->data(), sc->size() * 4, &scd) || pl->upload(sh->data(), sh->size() * 4, &shd)) return 1;
@@ -635,6 +699,7 @@ int bd_plan_add_skfuse(bd_plan* p, const bd_tref* xs4, int g_vec, const int32_t*
 int bd_plan_add_bcast(bd_plan* p, int v_vec, bd_tref y) {
   BD_CHECK(p && !p->finalized, "bad arguments");
   if (p->check_ref(y, true) || p->check_vec(v_vec, y.c)) return 1;
+  { LogWriter lw{p->log}; lw.pod(LOG_BCAST); lw.pod(v_vec); lw.pod(y); }
   p->builders.push_back([=](bd_plan* pl) -> int {
     k::BcastParams q;
     q.y = pl->kview(y); q.v = pl->vecptr(v_vec); q.N = pl->batch;
@@ -658,6 +723,7 @@ int bd_plan_add_bcast(bd_plan* p, int v_vec, bd_tref y) {
 int bd_plan_finalize(bd_plan* p, int input_buf, int logits_buf, int logits_up) {
   BD_ON_PLAN(p);
   BD_CHECK(p && !p->finalized, "bad arguments");
+  { LogWriter lw{p->log}; lw.pod(LOG_FINALIZE); lw.pod(input_buf); lw.pod(logits_buf); lw.pod(logits_up); }
   const int nb = static_cast<int>(p->bufs.size());
   if (input_buf >= 0) {
     const BufInfo& ib = p->bufs[input_buf];
@@ -1004,6 +1070,92 @@ int bd_scene_run(bd_ctx* ctx, bd_plan* const* plans, int n_plans, const uint8_t*
   }
   BD_CUDA(cudaGetLastError());
   return 0;
+}
+
+// ---- plan files: the lowered network (buffers, fused ops, BN-folded fp16 weights) as the sequence of C-ABI calls that
+// built it.  Written once by the Python builder (tools/export_plans.py), loaded by any host language.
+static const char PLAN_MAGIC[8] = {'B', 'D', 'P', 'L', 'A', 'N', '0', '1'};
+int bd_plan_save(bd_plan* p, const char* path) {
+  BD_CHECK(p && p->finalized && path, "bd_plan_save: a finalized plan and a path");
+  FILE* f = fopen(path, "wb");
+  BD_CHECK(f != nullptr, "bd_plan_save: cannot open the file for writing");
+  const int32_t batch = p->batch;
+  const uint64_t n = p->log.size();
+  const bool ok = fwrite(PLAN_MAGIC, 1, 8, f) == 8 && fwrite(&batch, 4, 1, f) == 1 && fwrite(&n, 8, 1, f) == 1 &&
+                  fwrite(p->log.data(), 1, n, f) == n;
+  fclose(f);
+  BD_CHECK(ok, "bd_plan_save: short write");
+  return 0;
+}
+
+int bd_plan_load(bd_ctx* ctx, const char* path, bd_plan** out) {
+  BD_CHECK(ctx && path && out, "bad arguments");
+  FILE* f = fopen(path, "rb");
+  BD_CHECK(f != nullptr, "bd_plan_load: cannot open the file");
+  char magic[8];
+  int32_t batch = 0;
+  uint64_t n = 0;
+  bool ok = fread(magic, 1, 8, f) == 8 && memcmp(magic, PLAN_MAGIC, 8) == 0 && fread(&batch, 4, 1, f) == 1 && fread(&n, 8, 1, f) == 1 &&
+            n < (1ull << 34);
+  std::vector<uint8_t> log;
+  if (ok) { log.resize(n); ok = fread(log.data(), 1, n, f) == n; }
+  fclose(f);
+  BD_CHECK(ok, "bd_plan_load: not a plan file (or truncated)");
+  bd_plan* p = nullptr;
+  if (bd_plan_create(ctx, batch, &p)) return 1;
+  LogReader r{log.data(), log.data() + log.size()};
+  int rc = 0;
+  bool done = false;
+  while (!rc && r.ok && r.p < r.end && !done) {
+    const uint32_t op = r.pod<uint32_t>();
+    size_t nb = 0;
+    switch (op) {
+      case LOG_BUFFER: { const int h = r.pod<int>(), w = r.pod<int>(), c = r.pod<int>(), dt = r.pod<int>(), kd = r.pod<int>();
+        rc = bd_plan_add_buffer(p, h, w, c, dt, kd) < 0; break; }
+      case LOG_CONV: { bd_conv_desc d = r.pod<bd_conv_desc>();
+        d.w_host = static_cast<const uint16_t*>(r.arr(&nb)); d.bias_host = static_cast<const float*>(r.arr(&nb));
+        d.dw_w_host = r.pod<int32_t>() ? static_cast<const float*>(r.arr(&nb)) : nullptr;
+        if (r.ok) rc = bd_plan_add_conv(p, &d); break; }
+      case LOG_DWCONV: { const bd_tref x = r.pod<bd_tref>(), y = r.pod<bd_tref>(); const int st = r.pod<int>(), pt = r.pod<int>(), pl = r.pod<int>(), ri = r.pod<int>();
+        const float* w = static_cast<const float*>(r.arr(&nb)); if (r.ok) rc = bd_plan_add_dwconv(p, x, y, st, pt, pl, ri, w); break; }
+      case LOG_MAXPOOL: { const bd_tref x = r.pod<bd_tref>(), y = r.pod<bd_tref>(); const int kk = r.pod<int>(), st = r.pod<int>(), pt = r.pod<int>(), pl = r.pod<int>();
+        rc = bd_plan_add_maxpool(p, x, y, kk, st, pt, pl); break; }
+      case LOG_ADDN: { const int nn = r.pod<int>(); bd_tref xs[4]; int32_t fs[4];
+        if (nn < 1 || nn > 4) { r.ok = false; break; }
+        for (int i = 0; i < nn; ++i) { xs[i] = r.pod<bd_tref>(); fs[i] = r.pod<int32_t>(); }
+        const bd_tref y = r.pod<bd_tref>(); const int act = r.pod<int>(); rc = bd_plan_add_addn(p, nn, xs, fs, y, act); break; }
+      case LOG_GAP: { const bd_tref x = r.pod<bd_tref>(); const int yv = r.pod<int>(); rc = bd_plan_add_gap(p, x, yv); break; }
+      case LOG_DENSE: { const int ni = r.pod<int>(); int32_t xv[5];
+        if (ni < 1 || ni > 5) { r.ok = false; break; }
+        for (int i = 0; i < ni; ++i) xv[i] = r.pod<int32_t>();
+        const int yv = r.pod<int>(), cin = r.pod<int>(), cout = r.pod<int>(), act = r.pod<int>();
+        const float* w = static_cast<const float*>(r.arr(&nb)); const float* b = static_cast<const float*>(r.arr(&nb));
+        if (r.ok) rc = bd_plan_add_dense(p, ni, xv, yv, cin, cout, act, w, b); break; }
+      case LOG_GATE: { const int mode = r.pod<int>(); const bd_tref x = r.pod<bd_tref>(), y = r.pod<bd_tref>(); const int vv = r.pod<int>();
+        const bd_tref sr = r.pod<bd_tref>(); const float bs = r.pod<float>(); const float* w = r.pod<int32_t>() ? static_cast<const float*>(r.arr(&nb)) : nullptr;
+        if (r.ok) rc = bd_plan_add_gate(p, mode, x, y, vv, sr, w, bs); break; }
+      case LOG_SKFUSE: { bd_tref xs[4]; int32_t lv[5]; for (int i = 0; i < 4; ++i) xs[i] = r.pod<bd_tref>(); const int gv = r.pod<int>();
+        for (int i = 0; i < 5; ++i) lv[i] = r.pod<int32_t>(); const bd_tref y = r.pod<bd_tref>();
+        const float* sc = static_cast<const float*>(r.arr(&nb)); const float* sh = static_cast<const float*>(r.arr(&nb));
+        if (r.ok) rc = bd_plan_add_skfuse(p, xs, gv, lv, y, sc, sh); break; }
+      case LOG_BCAST: { const int vv = r.pod<int>(); const bd_tref y = r.pod<bd_tref>(); rc = bd_plan_add_bcast(p, vv, y); break; }
+      case LOG_FINALIZE: { const int ib = r.pod<int>(), lb = r.pod<int>(), up = r.pod<int>(); rc = bd_plan_finalize(p, ib, lb, up); done = true; break; }
+      default: r.ok = false;
+    }
+  }
+  if (rc || !r.ok || !done) {
+    const std::string why = rc ? bd::last_error() : std::string("bd_plan_load: corrupt plan file");
+    bd_plan_destroy(p);
+    return fail(why);
+  }
+  *out = p;
+  return 0;
+}
+
+// stride of the 3x3 stem the plan's input buffer is laid out for (1 or 2): what bd_tiles_gather needs
+int bd_plan_input_stride(bd_plan* p) {
+  if (!p || p->input_buf < 0) return 0;
+  return p->bufs[p->input_buf].H == 512 ? 1 : 2;
 }
 
 // 1 when the plan's forward is replayed from a captured CUDA graph (bd_scene_run), 0 when it is launched kernel by kernel

@@ -116,34 +116,53 @@ __global__ void __launch_bounds__(TPB) conv_small_kernel(const __grid_constant__
   __syncthreads();
   pdl_wait();
   constexpr int PPW = 32 / LPP;  // pixels per warp
-  const size_t total = static_cast<size_t>(p.N) * p.Ho * p.Wo;
-  const h16* xb = static_cast<const h16*>(p.x.base);
+  // 32-bit index arithmetic (the host checks N * Ho * Wo < 2^31): 64-bit divisions per pixel cost more than the loads
+  const unsigned total = static_cast<unsigned>(p.N) * p.Ho * p.Wo;
+  const h16* xb = static_cast<const h16*>(p.x.base) + p.x.c0;
   const int lane = threadIdx.x & 31, sub = lane % LPP;
-  const size_t warp0 = (blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x) >> 5;
-  const size_t nwarps = (static_cast<size_t>(gridDim.x) * TPB) >> 5;
-  for (size_t base = warp0 * PPW; base < total; base += nwarps * PPW) {  // warp-uniform trip count (shuffles below)
-    const size_t pix = base + lane / LPP;
+  const unsigned warp0 = (blockIdx.x * TPB + threadIdx.x) >> 5;
+  const unsigned nwarps = (gridDim.x * TPB) >> 5;
+  const bool pointwise = p.ntaps == 1 && p.dy[0] == 0 && p.dx[0] == 0;  // 1x1: input pixel == output pixel
+  const unsigned HW = static_cast<unsigned>(p.Ho) * p.Wo;
+  for (unsigned base = warp0 * PPW; base < total; base += nwarps * PPW) {  // warp-uniform trip count (shuffles below)
+    const unsigned pix = base + lane / LPP;
     const bool valid = pix < total;
-    const size_t pc = valid ? pix : total - 1;
-    const int ow = static_cast<int>(pc % p.Wo), oh = static_cast<int>((pc / p.Wo) % p.Ho);
-    const int n = static_cast<int>(pc / (static_cast<size_t>(p.Wo) * p.Ho));
+    const unsigned pc = valid ? pix : total - 1;
     float acc[CO];
 #pragma unroll
     for (int j = 0; j < CO; ++j) acc[j] = 0.0f;
-    for (int t = 0; t < p.ntaps; ++t) {
-      const int ih = oh + p.dy[t], iw = ow + p.dx[t];
-      if (ih < 0 || ih >= p.x.H || iw < 0 || iw >= p.x.W) continue;  // 'same' padding reads zero
-      const h16* xp = xb + ((static_cast<size_t>(n) * p.x.H + ih) * p.x.W + iw) * p.x.ctot + p.x.c0;
-      const float* wt = sw + t * p.cin_used * CO;
+    if (pointwise) {
+      const h16* xp = xb + static_cast<size_t>(pc) * p.x.ctot;
       for (int c0 = sub * 8; c0 < p.cin_used; c0 += 8 * LPP) {
         float f[8];
         unpack8(*reinterpret_cast<const h16x8*>(xp + c0), f);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           if (c0 + k < p.cin_used) {
-            const float* wr = wt + (c0 + k) * CO;
+            const float* wr = sw + (c0 + k) * CO;
 #pragma unroll
             for (int j = 0; j < CO; ++j) acc[j] = fmaf(f[k], wr[j], acc[j]);
+          }
+        }
+      }
+    } else {
+      const unsigned n = pc / HW, rem = pc - n * HW;
+      const int oh = static_cast<int>(rem / p.Wo), ow = static_cast<int>(rem - oh * p.Wo);
+      for (int t = 0; t < p.ntaps; ++t) {
+        const int ih = oh + p.dy[t], iw = ow + p.dx[t];
+        if (ih < 0 || ih >= p.x.H || iw < 0 || iw >= p.x.W) continue;  // 'same' padding reads zero
+        const h16* xp = xb + (static_cast<size_t>(n * p.x.H + ih) * p.x.W + iw) * p.x.ctot;
+        const float* wt = sw + t * p.cin_used * CO;
+        for (int c0 = sub * 8; c0 < p.cin_used; c0 += 8 * LPP) {
+          float f[8];
+          unpack8(*reinterpret_cast<const h16x8*>(xp + c0), f);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            if (c0 + k < p.cin_used) {
+              const float* wr = wt + (c0 + k) * CO;
+#pragma unroll
+              for (int j = 0; j < CO; ++j) acc[j] = fmaf(f[k], wr[j], acc[j]);
+            }
           }
         }
       }
@@ -157,7 +176,7 @@ __global__ void __launch_bounds__(TPB) conv_small_kernel(const __grid_constant__
 #pragma unroll
     for (int j = 0; j < CO; ++j) acc[j] = actf(acc[j] + sw[nw + j], p.act);
     if (p.y.f32) {
-      float* yp = static_cast<float*>(p.y.base) + pix * p.y.ctot + p.y.c0;
+      float* yp = static_cast<float*>(p.y.base) + static_cast<size_t>(pix) * p.y.ctot + p.y.c0;
 #pragma unroll
       for (int j = 0; j < CO; ++j)
         if (j < p.y.c) yp[j] = acc[j];

@@ -65,6 +65,9 @@ _SIGS = {
                                      C.c_void_p]),
     "bd_plan_add_bcast": (C.c_int, [C.c_void_p, C.c_int, TRef]),
     "bd_plan_finalize": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "bd_plan_save": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "bd_plan_load": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]),
+    "bd_plan_input_stride": (C.c_int, [C.c_void_p]),
     "bd_plan_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bd_plan_run_head": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bd_plan_run_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -334,6 +337,10 @@ class NativePlan:
                 dw = self.plan.ops[op["fused_dw"]]
                 flops[j] += 2.0 * self.plan.batch * op["Ho"] * op["Wo"] * dw["x"][2] * 9
         return ms, kinds, flops
+
+    def save(self, path):
+        """Write the plan file (bd_plan_save): what a non-Python host loads with bd_plan_load."""
+        check(lib().bd_plan_save(self.h, os.fsencode(path)))
 
     @property
     def uses_graph(self):

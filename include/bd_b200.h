@@ -132,6 +132,15 @@ int bd_plan_time_ops(bd_plan* plan, float* ms_out, void* stream);
 /* kind (0=conv umma, 1=conv direct, 2=other), and algorithmic flops of op i */
 int bd_plan_op_info(bd_plan* plan, int i, int* kind, double* flops);
 
+/* Plan files: a finalized plan as the sequence of bd_plan_add_* calls that built it (buffers, fused ops, BN-folded fp16
+ * weights).  The graph lowering of the five predict_model modules lives in the Python builder; tools/export_plans.py writes one
+ * file per (model, batch), and a host in ANY language loads them and runs the whole path -- bd_create, bd_plan_load x 5,
+ * bd_scene_run, bd_fuse, bd_contours (examples/host_scene.c).  Replaces predict.py:17-54 (load_model) for such hosts. */
+int bd_plan_save(bd_plan* plan, const char* path);
+int bd_plan_load(bd_ctx* ctx, const char* path, bd_plan** out);
+/* stride (1 or 2) of the 3x3 stem the plan's input buffer is laid out for: the stem_stride of bd_tiles_gather */
+int bd_plan_input_stride(bd_plan* plan);
+
 /* ---- tiler / stitcher: replace predict.py:detection (90-116) ------------------------------- */
 /* Gather n 512x512 tiles whose top-left corners are (ys[i], xs[i]) from a BGR u8 scene (h,w,3) into the plan
  * input layout for a stem of stride stem_stride (see bd_plan_finalize): values 2*pixel-255 = 255 * (pixel/127.5 - 1)

@@ -120,3 +120,27 @@ def test_keras_h5_checkpoint_round_trip(name, tmp_path):
     junk.write_bytes(b"\x00" * 64)
     with pytest.raises(OSError):
         m2.load_weights(str(junk))
+
+
+def test_load_model_with_keras_checkpoints(tmp_path, capsys):
+    """predict.load_model (predict.py:17-54): five constructors, `load_weights` per model, a missing / unreadable file
+    is reported and the model keeps its random initialisation (the reference catches OSError only)."""
+    from building_detection_b200 import predict as P
+    src = CTORS["hrnet"]()
+    w = G.init_weights(src.spec, seed=21, randomize_bn=True)
+    src.set_weights(w)
+    good = str(tmp_path / "hrnet.h5")
+    src.save_weights(good)
+    junk = tmp_path / "bad.h5"
+    junk.write_bytes(b"not a checkpoint")
+    models = P.load_model({"hrnet": good, "res34": str(tmp_path / "missing.h5"), "scse": str(junk)})
+    out = capsys.readouterr().out
+    assert len(models) == 5 and P.hr_model is models[1] and P.res_model is models[0]
+    for k in src.spec:
+        np.testing.assert_array_equal(P.hr_model.weights[k], w[k])
+    assert "load weights hrnet 2/5" in out and out.count("error while loading weights") == 2
+    fresh = CTORS["res34"]()
+    for k in fresh.spec:  # the failed loads left the seeded random initialisation in place
+        np.testing.assert_array_equal(P.res_model.weights[k], fresh.weights[k])
+    P.res_model = P.hr_model = P.v3_model = P.unet_model = P.bam_model = None
+    P._runner = None

@@ -341,3 +341,53 @@ def test_no_fp16_saturation_with_keras_default_init(gpu):
         print(f"{name}: max |activation| over all fp16 maps = {worst:.1f}")
         assert worst < G.H16_MAX, f"{name}: a stored activation saturated"
         m._drop_native()
+
+
+def test_plan_files_and_c_host(gpu, scene_1232, tmp_path):
+    """bd_plan_save / bd_plan_load and the whole path from a plain C host (examples/host_scene.c): plan files written
+    by the Python builder, then gcc-compiled C code alone produces the fused mask and the polygons the Python path does."""
+    import shutil
+    import subprocess
+    import ctypes as C
+    from building_detection_b200 import predict as P, runtime as R
+    img, masks, (fused_want, polys_want) = scene_1232
+    models = [P.res_model, P.hr_model, P.v3_model, P.unet_model, P.bam_model]
+    # round trip of one plan inside this process: identical logits
+    nat = models[1].native_plan(1)
+    path = str(tmp_path / "hrnet_b1.bdplan")
+    nat.save(path)
+    h2 = C.c_void_p()
+    R.check(R.lib().bd_plan_load(R.context(), os.fsencode(path), C.byref(h2)))
+    x = (np.random.default_rng(1).integers(0, 256, (1, 512, 512, 3), dtype=np.uint8) / 127.5 - 1).astype(np.float32)
+    want = nat.run_host(x)
+    got = np.empty_like(want)
+    R.check(R.lib().bd_plan_run_host(h2, R._ptr(x), R._ptr(got), None))
+    np.testing.assert_array_equal(got, want)
+    assert R.lib().bd_plan_input_stride(h2) == 2 and R.lib().bd_plan_load(R.context(), os.fsencode(str(tmp_path / "nope")), C.byref(h2)) != 0
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc on this box")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "host_scene")
+    libdir = os.path.join(root, "building_detection_b200")
+    subprocess.check_call(["gcc", "-O2", os.path.join(root, "examples", "host_scene.c"), "-I" + os.path.join(root, "include"),
+                           "-I/usr/local/cuda/include", "-L" + libdir, "-lbd_b200", "-L/usr/local/cuda/lib64", "-lcudart", "-lm",
+                           "-Wl,-rpath," + libdir, "-Wl,-rpath,/usr/local/cuda/lib64", "-o", exe])
+    plans = []
+    for name, m in zip(MODEL_NAMES, models):
+        p = str(tmp_path / f"{name}_b16.bdplan")
+        m.native_plan(16).save(p)
+        plans.append(p)
+    scene_path, mask_path, poly_path = str(tmp_path / "scene.bgr"), str(tmp_path / "mask.u8"), str(tmp_path / "polys.txt")
+    img.tofile(scene_path)
+    out = subprocess.run([exe, scene_path, "1232", "1232", mask_path, poly_path] + plans, capture_output=True, text=True, timeout=600)
+    print(out.stdout, out.stderr[-2000:])
+    assert out.returncode == 0
+    np.testing.assert_array_equal(np.fromfile(mask_path, np.uint8).reshape(1232, 1232), fused_want)
+    lines = open(poly_path).read().split("\n")[:-1]
+    if polys_want is IndexError:
+        assert lines and lines[0].startswith("ERROR IndexError")
+    else:
+        assert len(lines) == len(polys_want)
+        for line, (xs, ys) in zip(lines, polys_want):
+            if line != "RAW":
+                assert line == "".join("{},{} ".format(int(a), int(b)) for a, b in zip(xs, ys))
