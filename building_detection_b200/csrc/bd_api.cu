@@ -1161,6 +1161,44 @@ int bd_plan_input_stride(bd_plan* p) {
 // 1 when the plan's forward is replayed from a captured CUDA graph (bd_scene_run), 0 when it is launched kernel by kernel
 int bd_plan_uses_graph(bd_plan* p) { return (p && p->graph_exec) ? 1 : 0; }
 
+// Opt-in fusion by probability averaging (the reference votes on argmax masks): per tile pixel
+// the mean over the models of P(building) > 0.5, tiles OR-stitched into ONE scene mask.  The caller applies the
+// reference's final clean-up (bd_mask_cleanup) and bd_contours to it.
+int bd_scene_run_average(bd_ctx* ctx, bd_plan* const* plans, int n_plans, const uint8_t* scene_bgr_dev, int h, int w,
+                         const int32_t* ys_host, const int32_t* xs_host, int n_tiles, uint8_t* mask_dev, void* stream) {
+  BD_ON_CTX(ctx);
+  BD_CHECK(ctx && plans && n_plans >= 1 && scene_bgr_dev && mask_dev && h >= 1 && w >= 1 && n_tiles >= 0, "bad arguments");
+  if (n_tiles == 0) return 0;
+  BD_CHECK(ys_host && xs_host, "bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int B = plans[0]->batch;
+  for (int k = 0; k < n_plans; ++k)
+    BD_CHECK(plans[k] && plans[k]->finalized && plans[k]->ctx == ctx && plans[k]->batch == B && plans[k]->input_buf >= 0 &&
+                 plans[k]->logits_buf >= 0, "bd_scene_run_average: plans must be finalized on this context with one common batch size");
+  const size_t npx = static_cast<size_t>(B) * 512 * 512;
+  void *tm = nullptr, *probs = nullptr, *acc = nullptr;
+  if (ctx->pool.get(bd::post::SLOT_TILEMASK, npx, &tm) || ctx->pool.get(bd::post::SLOT_PROBS, npx * 2 * sizeof(float), &probs) ||
+      ctx->pool.get(bd::post::SLOT_PROBACC, npx * sizeof(float), &acc))
+    return 1;
+  if (bd_tiles_set_origins(ctx, ys_host, xs_host, n_tiles, stream)) return 1;
+  NvtxRange nvtx("bd:scene_forward_average");
+  for (int b0 = 0; b0 < n_tiles; b0 += B) {
+    const int n = std::min(B, n_tiles - b0);
+    for (int k = 0; k < n_plans; ++k) {
+      bd_plan* p = plans[k];
+      const BufInfo& ib = p->bufs[p->input_buf];
+      if (bd_tiles_gather_at(ctx, scene_bgr_dev, h, w, b0, n, p->arena + ib.offset, ib.H == 512 ? 1 : 2, stream)) return 1;
+      if (bd_plan_run(p, nullptr, static_cast<float*>(probs), nullptr, s)) return 1;
+      ctx->launches++;
+      BD_LAUNCH(k::prob_accum_kernel, dim3(grid_for(npx, ctx->num_sms * 4)), dim3(k::TPB), 0, s, static_cast<const float*>(probs),
+                static_cast<float*>(acc), npx, k == 0 ? 1 : 0, 0.5f * n_plans, k + 1 == n_plans ? static_cast<uint8_t*>(tm) : nullptr);
+    }
+    if (bd_stitch_or_at(ctx, static_cast<const uint8_t*>(tm), b0, n, mask_dev, h, w, stream)) return 1;
+  }
+  BD_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // device bytes a context holds for the scene-level stages at (h, w): fusion / contour arena + pools (weights and
 // activation arenas belong to the plans: bd_plan_arena_bytes)
 size_t bd_workspace_bytes(bd_ctx* ctx) {

@@ -615,6 +615,18 @@ __global__ void __launch_bounds__(TPB) softmax2_kernel(const float* __restrict__
   }
 }
 
+// ---------------------------------------------------------------------------------- probability-averaging fusion (opt-in)
+// acc[i] (+)= P(class 1) of one model; after the last model mask[i] = acc[i] > thr (thr = n_models / 2: mean > 0.5)
+__global__ void __launch_bounds__(TPB) prob_accum_kernel(const float* __restrict__ probs, float* __restrict__ acc, size_t n,
+                                                         int first, float thr, uint8_t* __restrict__ mask) {
+  pdl_prologue();
+  for (size_t i = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * TPB) {
+    const float v = (first ? 0.0f : acc[i]) + probs[2 * i + 1];
+    acc[i] = v;
+    if (mask) mask[i] = v > thr ? 1 : 0;
+  }
+}
+
 // ---------------------------------------------------------------------------------- tiler / stitcher
 // Network input layout (graph.Net.input): fp16, 32 channels per pixel of the STEM OUTPUT grid, channel
 // (kh*3+kw)*3+c = 255 * x[oy*S+kh-PAD, ox*S+kw-PAD, c] for the 3x3 stem conv of stride S with TF 'same' padding

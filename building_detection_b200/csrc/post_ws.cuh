@@ -88,6 +88,8 @@ enum {
   SLOT_EV = 39,   // +1
   SLOT_CNT = 41,  // fragment counters
   SLOT_TILEMASK = 42,  // argmax masks of one batch of tiles (bd_scene_run)
+  SLOT_PROBS = 43,     // probabilities of one batch of tiles, summed P(building) (bd_scene_run_average)
+  SLOT_PROBACC = 44,
 };
 
 }  // namespace post

@@ -100,11 +100,19 @@ def write_points(points, path):
             f.write('\n')
 
 
-def predict(image, bug_compatible=True):
+def predict(image, bug_compatible=True, fusion="vote"):
     """In-memory hot path: image (H,W,3) u8 BGR -> (mask (H,W) u8 {0,255}, points [[xs, ys], ...]).
-    = run_model -> model_confuse -> _detection (predict.py:148-152) without the PNG hand-offs."""
+    = run_model -> model_confuse -> _detection (predict.py:148-152) without the PNG hand-offs.
+    ``fusion="average"`` (opt-in, not the reference's behaviour): the five probability maps are averaged per pixel and
+    thresholded at 0.5 instead of cleaning and voting on the five argmax masks; the final clean-up stays."""
     from . import edge_3, model_fuse
     r = runner()
+    if fusion == "average":
+        fused = model_fuse.cleanup_device(r.run_average(r.upload(image), bug_compatible=bug_compatible))
+        points, _h = edge_3.contours_device(fused)
+        return fused.cpu().numpy(), points
+    if fusion != "vote":
+        raise ValueError("fusion must be 'vote' (the reference's 3-of-5) or 'average'")
     masks = r.run(r.upload(image), bug_compatible=bug_compatible)
     fused = model_fuse.fuse_device(masks)
     points, _h = edge_3.contours_device(fused)

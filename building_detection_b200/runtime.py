@@ -90,6 +90,8 @@ _SIGS = {
     "bd_stitch_or_at": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "bd_scene_run": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                C.c_int, C.c_void_p, C.c_void_p]),
+    "bd_scene_run_average": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                       C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "bd_workspace_bytes": (C.c_size_t, [C.c_void_p]),
     "bd_plan_uses_graph": (C.c_int, [C.c_void_p]),
     "bd_fuse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),

@@ -88,6 +88,28 @@ class SceneRunner:
             raise ValueError(f"expected (H,W,3) uint8 BGR, got {a.shape}")
         return t.from_numpy(a).to(self.device, non_blocking=True)
 
+    def run_average(self, scene_dev, origins=None, bug_compatible=True):
+        """Opt-in fusion by probability averaging (bd_scene_run_average): ONE (H,W) u8 mask, 255 where the mean over the
+        models of P(building) exceeds 0.5 in any covering tile.  Not the reference's behaviour (it votes 3 of 5 on
+        argmax masks, model_fuse.py:315-324); the caller applies the final clean-up and the contour stage."""
+        t = self.torch
+        h, w = int(scene_dev.shape[0]), int(scene_dev.shape[1])
+        if origins is None:
+            origins = tile_origins(h, w, bug_compatible)
+        out = t.zeros((h, w), dtype=t.uint8, device=self.device)
+        if not len(origins):
+            return out
+        ys = np.ascontiguousarray([o[0] for o in origins], np.int32)
+        xs = np.ascontiguousarray([o[1] for o in origins], np.int32)
+        pb = best_batch(len(origins)) if self.batch is None else (
+            self.batch if len(origins) >= self.batch else min(self.batch, self.models[0].plan_batch_for(len(origins))))
+        self.last_batch = pb
+        plans = [m.native_plan(pb, device=self.device.index) for m in self.models]
+        handles = (R.C.c_void_p * len(plans))(*[p.h for p in plans])
+        R.check(self.lib.bd_scene_run_average(self.ctx, handles, len(plans), scene_dev.data_ptr(), h, w, R._ptr(ys), R._ptr(xs),
+                                              len(origins), out.data_ptr(), t.cuda.current_stream(self.device).cuda_stream))
+        return out
+
     def run(self, scene_dev, origins=None, out=None, bug_compatible=True):
         """scene_dev: (H,W,3) u8 cuda tensor.  Returns masks (len(models),H,W) u8 {0,255} on the device
         (predict.py:113-114).  ``origins`` restricts the work to a shard of the tile list."""

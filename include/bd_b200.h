@@ -169,6 +169,12 @@ int bd_scene_run(bd_ctx* ctx, bd_plan* const* plans, int n_plans, const uint8_t*
                  const int32_t* ys_host, const int32_t* xs_host, int n_tiles, uint8_t* masks_dev, void* stream);
 /* 1 when bd_scene_run replays this plan from a captured CUDA graph, 0 when capture was refused or is turned off */
 int bd_plan_uses_graph(bd_plan* plan);
+/* Opt-in fusion by PROBABILITY AVERAGING instead of the reference's 3-of-5 vote on argmax masks (the north star's "per-pixel
+ * fusion of their probability maps"): mask_dev = ONE (h, w) u8 plane, zeroed by the caller, set to 255 where, in any
+ * covering tile, the mean over the n_plans models of P(building) exceeds 0.5.  Follow with bd_mask_cleanup (the
+ * reference's final clean-up, model_fuse.py:339-346) and bd_contours. */
+int bd_scene_run_average(bd_ctx* ctx, bd_plan* const* plans, int n_plans, const uint8_t* scene_bgr_dev, int h, int w,
+                         const int32_t* ys_host, const int32_t* xs_host, int n_tiles, uint8_t* mask_dev, void* stream);
 /* device bytes the context currently holds for the scene-level stages (fusion / contour scratch, tile masks) */
 size_t bd_workspace_bytes(bd_ctx* ctx);
 

@@ -391,3 +391,29 @@ def test_plan_files_and_c_host(gpu, scene_1232, tmp_path):
         for line, (xs, ys) in zip(lines, polys_want):
             if line != "RAW":
                 assert line == "".join("{},{} ".format(int(a), int(b)) for a, b in zip(xs, ys))
+
+
+def test_probability_averaging_fusion_opt_in(gpu, scene_1232):
+    """predict(image, fusion='average'): mean over the five models of P(building) > 0.5 per tile pixel, OR-stitched, then
+    the reference's final clean-up and contours -- against the same arithmetic in numpy around Model.predict."""
+    from building_detection_b200 import predict as P
+    img, _masks, _ = scene_1232
+    models = [P.res_model, P.hr_model, P.v3_model, P.unet_model, P.bam_model]
+    _, tiles, _ = reference_loop(img, models[0], 16)
+    acc = None
+    for m in models:
+        p1 = np.concatenate([m.predict(tiles[i:i + 16]) for i in range(0, len(tiles), 16)])[..., 1]
+        acc = p1.copy() if acc is None else acc + p1  # float32, model order: what prob_accum_kernel does
+    tile_mask = (acc > np.float32(2.5)).astype(np.uint8)
+    want = np.zeros((1232, 1232), np.uint8)
+    corners = [(i, j) for i in range(0, 1080, 360) for j in range(0, 1080, 360)]
+    for (i, j), tm in zip(corners, tile_mask):
+        want[i:i + 512, j:j + 512] |= tm[:1232 - i, :1232 - j] * 255
+    r = P.runner()
+    got = r.run_average(r.upload(img)).cpu().numpy()
+    assert 0.01 < (want > 0).mean() < 0.99
+    np.testing.assert_array_equal(got, want)
+    fused, points = P.predict(img, fusion="average")
+    np.testing.assert_array_equal(fused, post_ref.clean_mask(want))
+    with pytest.raises(ValueError):
+        P.predict(img, fusion="median")
