@@ -335,7 +335,8 @@ int bd_plan_add_conv(bd_plan* p, const bd_conv_desc* dptr) {
       const int LPP = nvec <= 1 ? 1 : nvec <= 2 ? 2 : nvec <= 4 ? 4 : 8;  // lanes per pixel
       const size_t total = static_cast<size_t>(pl->batch) * d.ho * d.wo;
       BD_CHECK(total < (1ull << 31), "small conv: too many output pixels for 32-bit indices");
-      const int grid = grid_for(total * LPP, ctx->num_sms * 4);
+      const bool fast1x1 = d.ntaps == 1 && d.dy[0] == 0 && d.dx[0] == 0 && cin_used <= 8 * LPP;  // 4 pixels per lane group
+      const int grid = grid_for(fast1x1 ? (total * LPP + 3) / 4 : total * LPP, ctx->num_sms * 4);
       const size_t smem = (wf.size() + CO) * sizeof(float);
       BD_CHECK(smem <= 48 * 1024, "small conv: weights do not fit into shared memory");
       op.kclass = 2;
@@ -474,13 +475,17 @@ int bd_plan_add_maxpool(bd_plan* p, bd_tref x, bd_tref y, int kk, int stride, in
     q.x = pl->kview(x); q.y = pl->kview(y);
     q.N = pl->batch; q.Ho = q.y.H; q.Wo = q.y.W; q.k = kk; q.stride = stride; q.pad_t = pad_t; q.pad_l = pad_l;
     const size_t total = static_cast<size_t>(pl->batch) * q.Ho * q.Wo * (x.c / 8);
+    BD_CHECK(total < (1ull << 31), "maxpool: too many vectors for 32-bit indices");
+    q.fd_cg = make_fastdiv(x.c / 8); q.fd_wo = make_fastdiv(q.Wo); q.fd_ho = make_fastdiv(q.Ho);
     bd_ctx* ctx = pl->ctx;
     const int grid = grid_for(total, ctx->num_sms * 4);
     Op op;
     op.kclass = 2; op.launches = 1; op.flops = 0;
-    op.run = [q, grid, ctx](cudaStream_t s) -> int {
+    op.run = [q, grid, ctx, kk](cudaStream_t s) -> int {
       ctx->launches++;
-      BD_LAUNCH(k::maxpool_kernel, dim3(grid), dim3(k::TPB), 0, s, q);
+      if (kk == 1) BD_LAUNCH(k::maxpool_kernel<1>, dim3(grid), dim3(k::TPB), 0, s, q);
+      else if (kk == 2) BD_LAUNCH(k::maxpool_kernel<2>, dim3(grid), dim3(k::TPB), 0, s, q);
+      else BD_LAUNCH(k::maxpool_kernel<3>, dim3(grid), dim3(k::TPB), 0, s, q);
       BD_CUDA(cudaGetLastError());
       return 0;
     };
@@ -505,11 +510,19 @@ int bd_plan_add_addn(bd_plan* p, int n, const bd_tref* xs, const int32_t* fs, bd
   p->builders.push_back([=](bd_plan* pl) -> int {
     k::AddnParams q;
     memset(&q, 0, sizeof(q));
-    for (int i = 0; i < n; ++i) { q.x[i] = pl->kview(xv[i]); q.f[i] = fv[i]; }
+    for (int i = 0; i < n; ++i) {
+      q.x[i] = pl->kview(xv[i]);
+      int sh = 0;
+      while ((1 << sh) < fv[i]) ++sh;
+      BD_CHECK((1 << sh) == fv[i], "addn: up-sampling factors must be powers of two");
+      q.sh[i] = sh;
+    }
     q.y = pl->kview(y); q.n_in = n; q.N = pl->batch; q.act = act;
     const size_t total = static_cast<size_t>(pl->batch) * q.y.H * q.y.W * (y.c / 8);
+    BD_CHECK(total < (1ull << 31), "addn: too many vectors for 32-bit indices");
+    q.fd_cg = make_fastdiv(y.c / 8); q.fd_w = make_fastdiv(q.y.W); q.fd_h = make_fastdiv(q.y.H);
     bd_ctx* ctx = pl->ctx;
-    const int grid = grid_for(total, ctx->num_sms * 4);
+    const int grid = grid_for((total + 1) / 2, ctx->num_sms * 4);
     Op op;
     op.kclass = 2; op.launches = 1; op.flops = 0;
     op.run = [q, grid, ctx](cudaStream_t s) -> int {
@@ -624,6 +637,8 @@ int bd_plan_add_gate(bd_plan* p, int mode, bd_tref x, bd_tref y, int v_vec, bd_t
       q.w = static_cast<const float*>(wd);
     }
     const size_t npix = static_cast<size_t>(pl->batch) * q.x.H * q.x.W;
+    BD_CHECK(npix * (x.c / 8) < (1ull << 31), "gate: too many vectors for 32-bit indices");
+    q.fd_cg = make_fastdiv(x.c / 8); q.fd_hw = make_fastdiv(static_cast<uint32_t>(q.x.H) * q.x.W);
     bd_ctx* ctx = pl->ctx;
     Op op;
     op.kclass = 2; op.launches = 1;
@@ -631,16 +646,22 @@ int bd_plan_add_gate(bd_plan* p, int mode, bd_tref x, bd_tref y, int v_vec, bd_t
     if (mode == BD_GATE_SCSE) {
       int lanes = 1;
       while (lanes < 32 && lanes * 2 <= x.c / 8) lanes *= 2;
-      const size_t warps = (npix + (32 / lanes) - 1) / (32 / lanes);
+      const int vpl = (x.c / 8) / lanes;  // vectors per lane
+      BD_CHECK(vpl * lanes == x.c / 8 && (vpl == 1 || vpl == 2 || vpl == 4),
+               "gate: scSE needs a channel count of 8 * 2^k up to 1024");
+      const int U = 4 / vpl;  // pixels in flight per lane group
+      const size_t warps = (npix + (32 / lanes) * U - 1) / ((32 / lanes) * U);
       const int grid = grid_for(warps * 32, ctx->num_sms * 4);
-      op.run = [q, grid, lanes, ctx](cudaStream_t s) -> int {
+      op.run = [q, grid, lanes, vpl, ctx](cudaStream_t s) -> int {
         ctx->launches++;
-        BD_LAUNCH(k::gate_scse_kernel, dim3(grid), dim3(k::TPB), 0, s, q, lanes);
+        if (vpl == 1) BD_LAUNCH((k::gate_scse_kernel<1, 4>), dim3(grid), dim3(k::TPB), 0, s, q, lanes);
+        else if (vpl == 2) BD_LAUNCH((k::gate_scse_kernel<2, 2>), dim3(grid), dim3(k::TPB), 0, s, q, lanes);
+        else BD_LAUNCH((k::gate_scse_kernel<4, 1>), dim3(grid), dim3(k::TPB), 0, s, q, lanes);
         BD_CUDA(cudaGetLastError());
         return 0;
       };
     } else {
-      const int grid = grid_for(npix * (x.c / 8), ctx->num_sms * 4);
+      const int grid = grid_for((npix * (x.c / 8) + 3) / 4, ctx->num_sms * 4);
       op.run = [q, grid, ctx](cudaStream_t s) -> int {
         ctx->launches++;
         BD_LAUNCH(k::gate_kernel, dim3(grid), dim3(k::TPB), 0, s, q);
@@ -752,11 +773,14 @@ int bd_plan_finalize(bd_plan* p, int input_buf, int logits_buf, int logits_up) {
     const float* lg = reinterpret_cast<const float*>(p->arena + lb.offset);
     const int H = lb.H * logits_up, W = lb.W * logits_up, N = p->batch, up = logits_up;
     bd_ctx* ctx = p->ctx;
-    const int grid = grid_for(static_cast<size_t>(N) * H * W, ctx->num_sms * 4);
+    BD_CHECK(W % 4 == 0, "softmax head: the output width must be a multiple of 4");
+    const int grid = grid_for(static_cast<size_t>(N) * H * W / 4, ctx->num_sms * 4);
     Op op;
     op.kclass = 2; op.launches = 1; op.flops = 0;
     op.run = [p, lg, N, H, W, up, grid, ctx](cudaStream_t s) -> int {
       if (!p->cur_probs && !p->cur_mask) return 0;
+      BD_CHECK((reinterpret_cast<uintptr_t>(p->cur_probs) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->cur_mask) & 3) == 0,
+               "bd_plan_run: probs must be 16-byte aligned and mask 4-byte aligned");
       ctx->launches++;
       BD_LAUNCH(k::softmax2_kernel, dim3(grid), dim3(k::TPB), 0, s, lg, N, H, W, up, p->cur_probs, p->cur_mask);
       BD_CUDA(cudaGetLastError());

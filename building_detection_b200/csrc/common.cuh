@@ -87,6 +87,15 @@ struct DeviceGuard {
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// division by a launch constant: q = (umulhi(mul, n) + n) >> shr, exact for n < 2^31 (Granlund-Montgomery)
+struct FastDiv { uint32_t mul, shr; };
+inline FastDiv make_fastdiv(uint32_t d) {
+  uint32_t l = 0;
+  while ((1ull << l) < d) ++l;
+  return FastDiv{static_cast<uint32_t>(((1ull << 32) * ((1ull << l) - d)) / d + 1), l};
+}
+__device__ __forceinline__ uint32_t fd_div(uint32_t n, FastDiv f) { return (__umulhi(f.mul, n) + n) >> f.shr; }
+
 // A channel-slice view of an NHWC feature map resident in the plan arena.
 struct TView {
   void* base;      // buffer base (element 0 of channel 0)

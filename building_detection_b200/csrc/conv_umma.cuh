@@ -49,14 +49,9 @@ constexpr int EPI_WARPS = 8;                 // two warps per TMEM lane quadrant
 constexpr int MMA2_WARP = 2 + EPI_WARPS;       // second MMA issuer (tiles of odd index), see the kernel
 constexpr int THREADS = 64 + 32 * EPI_WARPS + 32;
 
-// division by a launch constant: q = (umulhi(mul, n) + n) >> shr, exact for n < 2^31 (Granlund-Montgomery)
-struct FastDiv { uint32_t mul, shr; };
-inline FastDiv make_fastdiv(uint32_t d) {
-  uint32_t l = 0;
-  while ((1ull << l) < d) ++l;
-  return FastDiv{static_cast<uint32_t>(((1ull << 32) * ((1ull << l) - d)) / d + 1), l};
-}
-__device__ __forceinline__ uint32_t fd_div(uint32_t n, FastDiv f) { return (__umulhi(f.mul, n) + n) >> f.shr; }
+using ::bd::FastDiv;  // division by a launch constant (common.cuh)
+using ::bd::make_fastdiv;
+using ::bd::fd_div;
 
 struct Params {
   int N, Ho, Wo, Cout, Cin;

@@ -124,6 +124,84 @@ __global__ void __launch_bounds__(TPB) conv_small_kernel(const __grid_constant__
   const unsigned nwarps = (gridDim.x * TPB) >> 5;
   const bool pointwise = p.ntaps == 1 && p.dy[0] == 0 && p.dx[0] == 0;  // 1x1: input pixel == output pixel
   const unsigned HW = static_cast<unsigned>(p.Ho) * p.Wo;
+  auto finish = [&](float* acc, unsigned pix) {  // bias, activation, store (one lane per pixel)
+#pragma unroll
+    for (int j = 0; j < CO; ++j) acc[j] = actf(acc[j] + sw[nw + j], p.act);
+    if (p.y.f32) {
+      float* yp = static_cast<float*>(p.y.base) + static_cast<size_t>(pix) * p.y.ctot + p.y.c0;
+      if (CO == 2 && p.y.c == 2 && ((p.y.ctot | p.y.c0) & 1) == 0) {
+        *reinterpret_cast<float2*>(yp) = make_float2(acc[0], acc[1]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < CO; ++j)
+          if (j < p.y.c) yp[j] = acc[j];
+      }
+    } else {
+      // the whole (padded) slice is written: channels beyond cout_used carry zero weights and zero bias
+      for (int c0 = 0; c0 < p.y.c; c0 += 8) {
+        float f[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] = 0.0f;
+#pragma unroll
+        for (int j = 0; j < CO; ++j)
+          if (j >= c0 && j < c0 + 8) f[j - c0] = acc[j];
+        st8(p.y, pix, c0, f);
+      }
+    }
+  };
+  if (pointwise && p.cin_used <= 8 * LPP) {
+    // 1x1 with one 16-byte vector per lane (the two-channel heads on 32 / 64 channels, BAM's 64 -> 4 reduce): U pixels
+    // per lane group in flight -- one load per thread and iteration left the kernel at a quarter of the HBM rate
+    constexpr int U = 4;
+    const bool has_vec = sub * 8 < p.cin_used;
+    constexpr bool WREG = CO <= 4;         // the lane's weight rows in registers (shared memory for wider outputs)
+    float wr[WREG ? 8 : 1][WREG ? CO : 1];
+    if (WREG) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int j = 0; j < CO; ++j) wr[WREG ? k : 0][WREG ? j : 0] = (has_vec && sub * 8 + k < p.cin_used) ? sw[(sub * 8 + k) * CO + j] : 0.0f;
+    }
+    for (unsigned base = warp0 * PPW; base < total; base += nwarps * PPW * U) {  // warp-uniform trip count
+      h16x8 xr[U];
+      unsigned pixs[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        pixs[u] = base + u * nwarps * PPW + lane / LPP;
+        if (pixs[u] < total && has_vec)
+          xr[u] = *reinterpret_cast<const h16x8*>(xb + static_cast<size_t>(pixs[u]) * p.x.ctot + sub * 8);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const bool valid = pixs[u] < total;
+        float acc[CO];
+#pragma unroll
+        for (int j = 0; j < CO; ++j) acc[j] = 0.0f;
+        if (valid && has_vec) {
+          float f[8];
+          unpack8(xr[u], f);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            if (WREG) {
+#pragma unroll
+              for (int j = 0; j < CO; ++j) acc[j] = fmaf(f[k], wr[WREG ? k : 0][WREG ? j : 0], acc[j]);
+            } else if (sub * 8 + k < p.cin_used) {
+              const float* wrow = sw + (sub * 8 + k) * CO;
+#pragma unroll
+              for (int j = 0; j < CO; ++j) acc[j] = fmaf(f[k], wrow[j], acc[j]);
+            }
+          }
+        }
+#pragma unroll
+        for (int off = LPP / 2; off > 0; off >>= 1) {
+#pragma unroll
+          for (int j = 0; j < CO; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], off);
+        }
+        if (valid && sub == 0) finish(acc, pixs[u]);
+      }
+    }
+    return;
+  }
   for (unsigned base = warp0 * PPW; base < total; base += nwarps * PPW) {  // warp-uniform trip count (shuffles below)
     const unsigned pix = base + lane / LPP;
     const bool valid = pix < total;
@@ -173,25 +251,7 @@ __global__ void __launch_bounds__(TPB) conv_small_kernel(const __grid_constant__
       for (int j = 0; j < CO; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], off);
     }
     if (!valid || sub != 0) continue;
-#pragma unroll
-    for (int j = 0; j < CO; ++j) acc[j] = actf(acc[j] + sw[nw + j], p.act);
-    if (p.y.f32) {
-      float* yp = static_cast<float*>(p.y.base) + static_cast<size_t>(pix) * p.y.ctot + p.y.c0;
-#pragma unroll
-      for (int j = 0; j < CO; ++j)
-        if (j < p.y.c) yp[j] = acc[j];
-    } else {
-      // the whole (padded) slice is written: channels beyond cout_used carry zero weights and zero bias
-      for (int c0 = 0; c0 < p.y.c; c0 += 8) {
-        float f[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) f[k] = 0.0f;
-#pragma unroll
-        for (int j = 0; j < CO; ++j)
-          if (j >= c0 && j < c0 + 8) f[j - c0] = acc[j];
-        st8(p.y, pix, c0, f);
-      }
-    }
+    finish(acc, pix);
   }
 }
 
@@ -290,65 +350,97 @@ __global__ void __launch_bounds__(TPB) dwconv3x3_kernel(const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------------------------- max pool
+// The element-wise kernels below share one shape: a grid-stride loop over 16-byte vectors with 32-bit indices
+// (multiply-shift division by launch constants; the host checks that the vector count stays below 2^31) that issues
+// every load of an iteration before the first use.  The first versions took three 64-bit divisions per vector
+// (~200 instructions for one 16-byte load and store) and were bound by instruction issue at 0.3-0.6 of the HBM peak.
 struct PoolParams {
   View x, y;
   int N, Ho, Wo, k, stride, pad_t, pad_l;
+  FastDiv fd_cg, fd_wo, fd_ho;
 };
+// max is exact in any precision: it runs on packed fp16 (stored maps never hold inf: stores saturate)
+template <int K>
 __global__ void __launch_bounds__(TPB) maxpool_kernel(const __grid_constant__ PoolParams p) {
   pdl_prologue();
-  const int cg = p.x.c >> 3;
-  const size_t total = static_cast<size_t>(p.N) * p.Ho * p.Wo * cg;
-  for (size_t idx = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; idx < total;
-       idx += static_cast<size_t>(gridDim.x) * TPB) {
-    const int g = static_cast<int>(idx % cg);
-    const size_t pix = idx / cg;
-    const int ow = static_cast<int>(pix % p.Wo), oh = static_cast<int>((pix / p.Wo) % p.Ho);
-    const int n = static_cast<int>(pix / (static_cast<size_t>(p.Wo) * p.Ho));
-    float m[8];
+  const unsigned cg = static_cast<unsigned>(p.x.c) >> 3;
+  const unsigned total = static_cast<unsigned>(p.N) * p.Ho * p.Wo * cg;
+  const h16* xb = static_cast<const h16*>(p.x.base) + p.x.c0;
+  h16* yb = static_cast<h16*>(p.y.base) + p.y.c0;
+  const __half2 ninf = __float2half2_rn(-INFINITY);
+  for (unsigned idx = blockIdx.x * TPB + threadIdx.x; idx < total; idx += gridDim.x * TPB) {
+    const unsigned pix = fd_div(idx, p.fd_cg), g = idx - pix * cg;
+    const unsigned t = fd_div(pix, p.fd_wo), ow = pix - t * p.Wo;
+    const unsigned n = fd_div(t, p.fd_ho), oh = t - n * p.Ho;
+    const int ih0 = static_cast<int>(oh) * p.stride - p.pad_t, iw0 = static_cast<int>(ow) * p.stride - p.pad_l;
+    const h16* xn = xb + static_cast<size_t>(n) * p.x.H * p.x.W * p.x.ctot + g * 8;
+    h16x8 v[K * K];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
-    for (int kh = 0; kh < p.k; ++kh) {
-      const int ih = oh * p.stride + kh - p.pad_t;
-      if (ih < 0 || ih >= p.x.H) continue;
-      for (int kw = 0; kw < p.k; ++kw) {
-        const int iw = ow * p.stride + kw - p.pad_l;
-        if (iw < 0 || iw >= p.x.W) continue;
-        float xv[8];
-        ld8(p.x, (static_cast<size_t>(n) * p.x.H + ih) * p.x.W + iw, g * 8, xv);
+    for (int kh = 0; kh < K; ++kh)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], xv[j]);
+      for (int kw = 0; kw < K; ++kw) {
+        const int ih = ih0 + kh, iw = iw0 + kw;
+        if (ih >= 0 && ih < p.x.H && iw >= 0 && iw < p.x.W)
+          v[kh * K + kw] = *reinterpret_cast<const h16x8*>(xn + (static_cast<size_t>(ih) * p.x.W + iw) * p.x.ctot);
+        else
+          v[kh * K + kw].v[0] = v[kh * K + kw].v[1] = v[kh * K + kw].v[2] = v[kh * K + kw].v[3] = ninf;
       }
-    }
-    st8(p.y, pix, g * 8, m);
+    h16x8 m = v[0];
+#pragma unroll
+    for (int i = 1; i < K * K; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) m.v[j] = __hmax2(m.v[j], v[i].v[j]);
+    *reinterpret_cast<h16x8*>(yb + static_cast<size_t>(pix) * p.y.ctot + g * 8) = m;
   }
 }
 
 // ---------------------------------------------------------------------------------- add-N with nearest upsample
 struct AddnParams {
   View x[4], y;
-  int f[4];
+  int sh[4];  // log2 of the nearest-upsampling factor of input i
   int n_in, N, act;
+  FastDiv fd_cg, fd_w, fd_h;
 };
 __global__ void __launch_bounds__(TPB) addn_kernel(const __grid_constant__ AddnParams p) {
   pdl_prologue();
-  const int cg = p.y.c >> 3;
-  const size_t total = static_cast<size_t>(p.N) * p.y.H * p.y.W * cg;
-  for (size_t idx = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; idx < total;
-       idx += static_cast<size_t>(gridDim.x) * TPB) {
-    const int g = static_cast<int>(idx % cg);
-    const size_t pix = idx / cg;
-    const int ow = static_cast<int>(pix % p.y.W), oh = static_cast<int>((pix / p.y.W) % p.y.H);
-    const int n = static_cast<int>(pix / (static_cast<size_t>(p.y.W) * p.y.H));
-    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int i = 0; i < p.n_in; ++i) {
-      float xv[8];
-      ld8(p.x[i], (static_cast<size_t>(n) * p.x[i].H + oh / p.f[i]) * p.x[i].W + ow / p.f[i], g * 8, xv);
+  constexpr int U = 2;
+  const unsigned cg = static_cast<unsigned>(p.y.c) >> 3;
+  const unsigned total = static_cast<unsigned>(p.N) * p.y.H * p.y.W * cg;
+  const unsigned stride = gridDim.x * TPB;
+  for (unsigned i0 = blockIdx.x * TPB + threadIdx.x; i0 < total; i0 += U * stride) {
+    h16x8 v[U][4];
+    unsigned pixs[U], gs[U];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] += xv[j];
+    for (int u = 0; u < U; ++u) {
+      const unsigned idx = i0 + u * stride;
+      if (idx >= total) continue;
+      const unsigned pix = fd_div(idx, p.fd_cg), g = idx - pix * cg;
+      const unsigned t = fd_div(pix, p.fd_w), ow = pix - t * p.y.W;
+      const unsigned n = fd_div(t, p.fd_h), oh = t - n * p.y.H;
+      pixs[u] = pix; gs[u] = g;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (i < p.n_in)
+          v[u][i] = *reinterpret_cast<const h16x8*>(
+              static_cast<const h16*>(p.x[i].base) + p.x[i].c0 + g * 8 +
+              ((static_cast<size_t>(n) * p.x[i].H + (oh >> p.sh[i])) * p.x[i].W + (ow >> p.sh[i])) * p.x[i].ctot);
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = actf(acc[j], p.act);
-    st8(p.y, pix, g * 8, acc);
+    for (int u = 0; u < U; ++u) {
+      if (i0 + u * stride >= total) continue;
+      float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (i < p.n_in) {
+          float xv[8];
+          unpack8(v[u][i], xv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] += xv[j];
+        }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = actf(acc[j], p.act);
+      st8(p.y, pixs[u], gs[u] * 8, acc);
+    }
   }
 }
 
@@ -451,77 +543,109 @@ struct GateParams {
   const float* w;  // [C] spatial-squeeze weights (scSE)
   float b;
   int mode, N;
+  FastDiv fd_cg, fd_hw;
 };
 // SE: y = x*v ; BAM: y = x*(1+sigmoid(v+s))
 __global__ void __launch_bounds__(TPB) gate_kernel(const __grid_constant__ GateParams p) {
   pdl_prologue();
-  const int C = p.x.c, cg = C >> 3;
-  const size_t HW = static_cast<size_t>(p.x.H) * p.x.W;
-  const size_t total = static_cast<size_t>(p.N) * HW * cg;
-  for (size_t idx = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; idx < total;
-       idx += static_cast<size_t>(gridDim.x) * TPB) {
-    const int g = static_cast<int>(idx % cg);
-    const size_t pix = idx / cg;
-    const int n = static_cast<int>(pix / HW);
-    float xv[8];
-    ld8(p.x, pix, g * 8, xv);
-    const float* vv = p.v + static_cast<size_t>(n) * C + g * 8;
-    if (p.mode == 0) {
+  constexpr int U = 4;
+  const unsigned C = p.x.c, cg = C >> 3;
+  const unsigned HW = static_cast<unsigned>(p.x.H) * p.x.W;
+  const unsigned total = static_cast<unsigned>(p.N) * HW * cg;
+  const unsigned stride = gridDim.x * TPB;
+  const h16* xb = static_cast<const h16*>(p.x.base) + p.x.c0;
+  for (unsigned i0 = blockIdx.x * TPB + threadIdx.x; i0 < total; i0 += U * stride) {
+    h16x8 xr[U];
+    float sg[U];
+    unsigned pixs[U], gs[U];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) xv[j] *= vv[j];
-    } else {
-      const float sg = ld1(p.s, pix, 0);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) xv[j] *= 1.0f + sigmoidf_(vv[j] + sg);
+    for (int u = 0; u < U; ++u) {
+      const unsigned idx = i0 + u * stride;
+      if (idx >= total) continue;
+      const unsigned pix = fd_div(idx, p.fd_cg), g = idx - pix * cg;
+      pixs[u] = pix; gs[u] = g;
+      xr[u] = *reinterpret_cast<const h16x8*>(xb + static_cast<size_t>(pix) * p.x.ctot + g * 8);
+      if (p.mode != 0) sg[u] = ld1(p.s, pix, 0);
     }
-    st8(p.y, pix, g * 8, xv);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (i0 + u * stride >= total) continue;
+      const unsigned n = fd_div(pixs[u], p.fd_hw);
+      const float4* vv = reinterpret_cast<const float4*>(p.v + static_cast<size_t>(n) * C + gs[u] * 8);
+      const float4 va = __ldg(vv), vb = __ldg(vv + 1);
+      const float vf[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+      float xv[8];
+      unpack8(xr[u], xv);
+      if (p.mode == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) xv[j] *= vf[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) xv[j] *= 1.0f + sigmoidf_(vf[j] + sg[u]);
+      }
+      st8(p.y, pixs[u], gs[u] * 8, xv);
+    }
   }
 }
-// scSE: y = x*(sigmoid(w.x + b) + v): a group of min(32, C/8) lanes owns one pixel; the per-pixel dot
-// product over channels is a shuffle reduction inside the group.
+// scSE: y = x*(sigmoid(w.x + b) + v): a group of LPP = min(32, C/8) lanes owns one pixel and VPL = C/8/LPP vectors per
+// lane; the per-pixel dot product over channels is a shuffle reduction inside the group.  U pixels per group and
+// iteration, all U x VPL loads issued before the first reduction; x stays in registers between the dot product and
+// the gated store (read once, written once).
+template <int VPL, int U>
 __global__ void __launch_bounds__(TPB) gate_scse_kernel(const __grid_constant__ GateParams p, int lanes_per_pix) {
   pdl_prologue();
-  const int C = p.x.c, cg = C >> 3;
-  const size_t HW = static_cast<size_t>(p.x.H) * p.x.W;
-  const size_t npix = static_cast<size_t>(p.N) * HW;
-  const int lane = threadIdx.x & 31;
-  const int sub = lane % lanes_per_pix;
-  const int pix_per_warp = 32 / lanes_per_pix;
-  const size_t warp_global = (blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x) >> 5;
-  const size_t nwarps = (static_cast<size_t>(gridDim.x) * TPB) >> 5;
-  for (size_t base = warp_global * pix_per_warp; base < npix; base += nwarps * pix_per_warp) {
-    const size_t pix = base + lane / lanes_per_pix;
-    const bool ok = pix < npix;
-    float dot = 0.0f;
-    float x0[8];  // the lane's first vector stays in registers (the only one for C <= 256)
-    if (ok) {
-      for (int g = sub; g < cg; g += lanes_per_pix) {
-        float xv[8];
-        ld8(p.x, pix, g * 8, xv);
+  const unsigned C = p.x.c;
+  const unsigned HW = static_cast<unsigned>(p.x.H) * p.x.W;
+  const unsigned npix = static_cast<unsigned>(p.N) * HW;
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned sub = lane % lanes_per_pix;
+  const unsigned ppw = 32 / lanes_per_pix;  // pixels per warp and step
+  const unsigned warp_global = (blockIdx.x * TPB + threadIdx.x) >> 5;
+  const unsigned nwarps = (gridDim.x * TPB) >> 5;
+  const h16* xb = static_cast<const h16*>(p.x.base) + p.x.c0;
+  float wv[VPL][8];  // the lane's spatial-squeeze weights
 #pragma unroll
-        for (int j = 0; j < 8; ++j) dot = fmaf(xv[j], p.w[g * 8 + j], dot);
-        if (g == sub) {
+  for (int k = 0; k < VPL; ++k)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) x0[j] = xv[j];
-        }
+    for (int j = 0; j < 8; ++j) wv[k][j] = p.w[(sub + k * lanes_per_pix) * 8 + j];
+  for (unsigned base = warp_global * ppw; base < npix; base += nwarps * ppw * U) {  // warp-uniform trip count
+    h16x8 xr[U][VPL];
+    unsigned pixs[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      pixs[u] = base + u * nwarps * ppw + lane / lanes_per_pix;
+      if (pixs[u] < npix) {
+        const h16* xp = xb + static_cast<size_t>(pixs[u]) * p.x.ctot + sub * 8;
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) xr[u][k] = *reinterpret_cast<const h16x8*>(xp + k * lanes_per_pix * 8);
       }
     }
-    for (int o = lanes_per_pix >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-    if (ok) {
-      const float sp = sigmoidf_(dot + p.b);
-      const int n = static_cast<int>(pix / HW);
-      for (int g = sub; g < cg; g += lanes_per_pix) {
-        float xv[8];
-        if (g == sub) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) xv[j] = x0[j];
-        } else {
-          ld8(p.x, pix, g * 8, xv);
+    for (int u = 0; u < U; ++u) {
+      const bool ok = pixs[u] < npix;
+      float xv[VPL][8];
+      float dot = 0.0f;
+      if (ok) {
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+          unpack8(xr[u][k], xv[k]);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dot = fmaf(xv[k][j], wv[k][j], dot);
         }
-        const float* vv = p.v + static_cast<size_t>(n) * C + g * 8;
+      }
+      for (int o = lanes_per_pix >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+      if (!ok) continue;
+      const float sp = sigmoidf_(dot + p.b);
+      const unsigned n = fd_div(pixs[u], p.fd_hw);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) xv[j] = xv[j] * sp + xv[j] * vv[j];
-        st8(p.y, pix, g * 8, xv);
+      for (int k = 0; k < VPL; ++k) {
+        const unsigned g = sub + k * lanes_per_pix;
+        const float4* vv = reinterpret_cast<const float4*>(p.v + static_cast<size_t>(n) * C + g * 8);
+        const float4 va = __ldg(vv), vb = __ldg(vv + 1);
+        const float vf[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) xv[k][j] = xv[k][j] * sp + xv[k][j] * vf[j];
+        st8(p.y, pixs[u], g * 8, xv[k]);
       }
     }
   }
@@ -597,21 +721,38 @@ __global__ void __launch_bounds__(TPB) bcast_kernel(const __grid_constant__ Bcas
 __global__ void __launch_bounds__(TPB) softmax2_kernel(const float* __restrict__ logits, int N, int H, int W, int up,
                                                        float* __restrict__ probs, uint8_t* __restrict__ mask) {
   pdl_prologue();
-  const size_t total = static_cast<size_t>(N) * H * W;
+  // thread = 4 consecutive output pixels of a row (W % 4 == 0: W is 512): one 4-byte mask store, two float4 prob stores
+  const unsigned w4 = static_cast<unsigned>(W) >> 2;
+  const unsigned total = static_cast<unsigned>(N) * H * w4;
   const int h2 = H / up, w2 = W / up;
-  for (size_t idx = blockIdx.x * static_cast<size_t>(TPB) + threadIdx.x; idx < total;
-       idx += static_cast<size_t>(gridDim.x) * TPB) {
-    const int ow = static_cast<int>(idx % W), oh = static_cast<int>((idx / W) % H);
-    const int n = static_cast<int>(idx / (static_cast<size_t>(W) * H));
-    const float2 l = *reinterpret_cast<const float2*>(logits + ((static_cast<size_t>(n) * h2 + oh / up) * w2 + ow / up) * 2);
+  const int sh = up == 1 ? 0 : up == 2 ? 1 : up == 4 ? 2 : -1;
+  for (unsigned idx = blockIdx.x * TPB + threadIdx.x; idx < total; idx += gridDim.x * TPB) {
+    const unsigned row = idx / w4, q = idx - row * w4;     // row = n * H + oh
+    const unsigned n = row / H, oh = row - n * H;
+    const unsigned ow = q * 4;
+    const unsigned sy = sh >= 0 ? oh >> sh : oh / up;
+    const float* lrow = logits + (static_cast<size_t>(n) * h2 + sy) * w2 * 2;
+    float2 l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) l[j] = *reinterpret_cast<const float2*>(lrow + 2 * (sh >= 0 ? (ow + j) >> sh : (ow + j) / up));
     // The mask is the argmax of the float32 PROBABILITIES (predict.py:109-110: tf.argmax of the softmax output, first
     // maximum on ties), not of the logits: logits closer than one float32 ulp of 0.5 tie after the softmax.
-    const float m = fmaxf(l.x, l.y);
-    const float e0 = expf(l.x - m), e1 = expf(l.y - m);
-    const float inv = 1.0f / (e0 + e1);
-    const float p0 = e0 * inv, p1 = e1 * inv;
-    if (probs) *reinterpret_cast<float2*>(probs + idx * 2) = make_float2(p0, p1);
-    if (mask) mask[idx] = p1 > p0 ? 1 : 0;
+    float pr[8];
+    uint32_t mk = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float m = fmaxf(l[j].x, l[j].y);
+      const float e0 = expf(l[j].x - m), e1 = expf(l[j].y - m);
+      const float inv = 1.0f / (e0 + e1);
+      pr[2 * j] = e0 * inv; pr[2 * j + 1] = e1 * inv;
+      mk |= (pr[2 * j + 1] > pr[2 * j] ? 1u : 0u) << (8 * j);
+    }
+    const size_t o = static_cast<size_t>(row) * W + ow;
+    if (probs) {
+      *reinterpret_cast<float4*>(probs + o * 2) = make_float4(pr[0], pr[1], pr[2], pr[3]);
+      *reinterpret_cast<float4*>(probs + o * 2 + 4) = make_float4(pr[4], pr[5], pr[6], pr[7]);
+    }
+    if (mask) *reinterpret_cast<uint32_t*>(mask + o) = mk;
   }
 }
 
