@@ -2,6 +2,7 @@
 // Fusion and contour entry points live in post.cu.
 #include "../../include/bd_b200.h"
 
+#include <climits>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -34,6 +35,11 @@ namespace {
 struct BufInfo {
   int H, W, C, dtype, kind;
   size_t bytes, offset;
+  int first = INT32_MAX, last = -1;  // first / last plan step (bd_plan_add_* call) that touches the buffer
+  bool shared = false;               // its arena range is reused by buffers with disjoint lifetimes
+  std::vector<std::pair<int, int>> written;  // channel intervals some op writes
+  int hard_read_end = 0;             // highest channel (+1) read by a kernel that cannot clip its reads
+  int valid_c = -1;                  // shared buffers: channels [valid_c, C) are never written (TMA reads clip there)
 };
 
 struct Op {
@@ -106,7 +112,34 @@ struct bd_plan {
   std::vector<void*> dev_allocs;
   char* arena = nullptr;
   size_t arena_bytes = 0;
+  // Arena reuse: map buffers whose lifetimes (first .. last step touching them) are disjoint share address ranges.
+  // On by default; bd_plan_set_arena_reuse(plan, 0) gives every buffer a range of its own (readable after a forward).
+  bool reuse = true;
+  size_t arena_bytes_flat = 0;  // what the arena would take without reuse
   int input_buf = -1, logits_buf = -1, logits_up = 1;
+  void touch(int buf) {  // called by bd_plan_add_* for every map buffer the op reads or writes
+    if (buf < 0 || buf >= static_cast<int>(bufs.size())) return;
+    const int step = static_cast<int>(builders.size());
+    bufs[buf].first = std::min(bufs[buf].first, step);
+    bufs[buf].last = std::max(bufs[buf].last, step);
+  }
+  void touch_w(const bd_tref& r) {
+    touch(r.buf);
+    if (r.buf >= 0 && r.buf < static_cast<int>(bufs.size())) bufs[r.buf].written.emplace_back(r.c0, r.c0 + r.c);
+  }
+  // clip_ok: the reader goes through a TMA tensor map whose channel extent can be cut at the written channels (reads
+  // beyond it return zero); every other kernel reads its whole slice from memory
+  void touch_r(const bd_tref& r, bool clip_ok = false) {
+    touch(r.buf);
+    if (!clip_ok && r.buf >= 0 && r.buf < static_cast<int>(bufs.size()))
+      bufs[r.buf].hard_read_end = std::max(bufs[r.buf].hard_read_end, r.c0 + r.c);
+  }
+  // channels of a read slice that hold written data (the rest of a shared buffer is another tenant's garbage)
+  int valid_channels(const bd_tref& r) const {
+    const BufInfo& b = bufs[r.buf];
+    if (b.valid_c < 0) return r.c;
+    return std::max(0, std::min(r.c, b.valid_c - r.c0));
+  }
   float* cur_probs = nullptr;
   uint8_t* cur_mask = nullptr;
   // CUDA graph of one forward writing the argmax masks to graph_mask (bd_scene_run): captured on first use
@@ -222,6 +255,10 @@ int bd_plan_create(bd_ctx* ctx, int batch, bd_plan** out) {
   bd_plan* p = new bd_plan();
   p->ctx = ctx;
   p->batch = batch;
+  {  // arena reuse is the default (BD_ARENA_REUSE=0 or bd_plan_set_arena_reuse(plan, 0) keep every buffer apart)
+    const char* e = getenv("BD_ARENA_REUSE");
+    p->reuse = !(e && e[0] == '0');
+  }
   *out = p;
   return 0;
 }
@@ -288,6 +325,7 @@ int bd_plan_add_conv(bd_plan* p, const bd_conv_desc* dptr) {
     if (d.dw_w_host) lw.arr(d.dw_w_host, static_cast<size_t>(9) * cin * 4);
   }
   d.w_host = nullptr; d.bias_host = nullptr; d.dw_w_host = nullptr;
+  p->touch_r(d.x, d.path == BD_CONV_UMMA); p->touch_w(d.y); if (has_res) p->touch_r(d.res);
   p->builders.push_back([d, w, b, dww, dw_relu, has_res, cin, cout](bd_plan* pl) -> int {
     void *wd = nullptr, *bdv = nullptr, *dwd = nullptr;
     if (pl->upload(w->data(), w->size() * 2, &wd) || pl->upload(b->data(), b->size() * 4, &bdv)) return 1;
@@ -362,7 +400,7 @@ int bd_plan_add_conv(bd_plan* p, const bd_conv_desc* dptr) {
       if (umma::prepare(L.get(), x, y, has_res ? &r : nullptr, d.ntaps, d.dy, d.dx, d.stride, d.ho, d.wo, d.act_pre,
                         d.act_post, d.out_scale, d.out_oy, d.out_ox, static_cast<const h16*>(wd),
                         static_cast<const float*>(bdv), ctx->umma_smem_kb, ctx->umma_max_block_n, ctx->num_sms, ctx->umma_group,
-                        static_cast<const h16*>(dwd), dw_relu))
+                        static_cast<const h16*>(dwd), dw_relu, pl->valid_channels(d.x)))
         return 1;
       if (const char* tr = getenv("BD_UMMA_TRACE")) {  // debug: event trace of CTA 0 (tools/umma_trace.py)
         void* tbuf = nullptr;
@@ -412,6 +450,7 @@ int bd_plan_add_dwconv(bd_plan* p, bd_tref x, bd_tref y, int stride, int pad_t, 
     const __half hv = __float2half_rn(std::max(-65504.0f, std::min(65504.0f, w_host[i])));
     memcpy(&(*w)[i], &hv, 2);
   }
+  p->touch_r(x); p->touch_w(y);
   p->builders.push_back([=](bd_plan* pl) -> int {
     void* wd = nullptr;
     if (pl->upload(w->data(), w->size() * 2, &wd)) return 1;
@@ -470,6 +509,7 @@ int bd_plan_add_maxpool(bd_plan* p, bd_tref x, bd_tref y, int kk, int stride, in
   if (p->check_ref(x, true) || p->check_ref(y, true)) return 1;
   BD_CHECK(x.c == y.c && kk >= 1 && kk <= 3, "maxpool: bad arguments");
   { LogWriter lw{p->log}; lw.pod(LOG_MAXPOOL); lw.pod(x); lw.pod(y); lw.pod(kk); lw.pod(stride); lw.pod(pad_t); lw.pod(pad_l); }
+  p->touch_r(x); p->touch_w(y);
   p->builders.push_back([=](bd_plan* pl) -> int {
     k::PoolParams q;
     q.x = pl->kview(x); q.y = pl->kview(y);
@@ -507,6 +547,8 @@ int bd_plan_add_addn(bd_plan* p, int n, const bd_tref* xs, const int32_t* fs, bd
     BD_CHECK(xv[i].c == y.c && b.H * fv[i] == p->bufs[y.buf].H && b.W * fv[i] == p->bufs[y.buf].W,
              "addn: geometry mismatch");
   }
+  for (int i = 0; i < n; ++i) p->touch_r(xv[i]);
+  p->touch_w(y);
   p->builders.push_back([=](bd_plan* pl) -> int {
     k::AddnParams q;
     memset(&q, 0, sizeof(q));
@@ -542,6 +584,7 @@ int bd_plan_add_gap(bd_plan* p, bd_tref x, int y_vec) {
   if (p->check_ref(x, true) || p->check_vec(y_vec, x.c)) return 1;
   BD_CHECK(x.c / 8 <= k::TPB, "gap: too many channels");
   { LogWriter lw{p->log}; lw.pod(LOG_GAP); lw.pod(x); lw.pod(y_vec); }
+  p->touch_r(x);
   p->builders.push_back([=](bd_plan* pl) -> int {
     k::GapParams q;
     q.x = pl->kview(x); q.N = pl->batch;
@@ -626,6 +669,7 @@ int bd_plan_add_gate(bd_plan* p, int mode, bd_tref x, bd_tref y, int v_vec, bd_t
   }
   { LogWriter lw{p->log}; lw.pod(LOG_GATE); lw.pod(mode); lw.pod(x); lw.pod(y); lw.pod(v_vec); lw.pod(sref); lw.pod(bscalar);
     lw.pod(static_cast<int32_t>(w ? 1 : 0)); if (w) lw.arr(w->data(), w->size() * 4); }
+  p->touch_r(x); p->touch_w(y); if (mode == BD_GATE_BAM) p->touch_r(sref);
   p->builders.push_back([=](bd_plan* pl) -> int {
     k::GateParams q;
     memset(&q, 0, sizeof(q));
@@ -691,6 +735,8 @@ int bd_plan_add_skfuse(bd_plan* p, const bd_tref* xs4, int g_vec, const int32_t*
   std::shared_ptr<std::vector<float>> sh(new std::vector<float>(shift_host, shift_host + y.c));
   { LogWriter lw{p->log}; lw.pod(LOG_SKFUSE); for (int i = 0; i < 4; ++i) lw.pod(xs4[i]); lw.pod(g_vec); for (int i = 0; i < 5; ++i) lw.pod(logit_vecs5[i]);
     lw.pod(y); lw.arr(scale_host, static_cast<size_t>(y.c) * 4); lw.arr(shift_host, static_cast<size_t>(y.c) * 4); }
+  for (int i = 0; i < 4; ++i) p->touch_r(xv[i]);
+  p->touch_w(y);
   p->builders.push_back([=](bd_plan* pl) -> int {
     void *scd = nullptr, *shd = nullptr;
     if (pl->upload(sc->data(), sc->size() * 4, &scd) || pl->upload(sh->data(), sh->size() * 4, &shd)) return 1;
@@ -721,6 +767,7 @@ int bd_plan_add_bcast(bd_plan* p, int v_vec, bd_tref y) {
   BD_CHECK(p && !p->finalized, "bad arguments");
   if (p->check_ref(y, true) || p->check_vec(v_vec, y.c)) return 1;
   { LogWriter lw{p->log}; lw.pod(LOG_BCAST); lw.pod(v_vec); lw.pod(y); }
+  p->touch_w(y);
   p->builders.push_back([=](bd_plan* pl) -> int {
     k::BcastParams q;
     q.y = pl->kview(y); q.v = pl->vecptr(v_vec); q.N = pl->batch;
@@ -760,6 +807,67 @@ int bd_plan_finalize(bd_plan* p, int input_buf, int logits_buf, int logits_up) {
   for (BufInfo& b : p->bufs) {
     b.offset = off;
     off += (b.bytes + 1023) / 1024 * 1024;
+  }
+  p->arena_bytes_flat = std::max<size_t>(off, 1024);
+  if (p->reuse) {
+    // Lifetime of a map buffer = first .. last step that reads or writes it (the input is written before step 0, the
+    // logits are read by the softmax head after the last).  Buffers are placed in order of first use at the lowest
+    // offset that is free of every already placed buffer with an intersecting lifetime (an op's outputs therefore
+    // never alias its inputs).  Every kernel waits for the complete previous kernel before it touches data
+    // (griddepcontrol.wait), so step order is execution order.  Pooled vectors and untouched buffers keep ranges of
+    // their own.  Nothing may rely on the zero fill of the arena: channel padding is never read (TMA boxes are clipped
+    // by the tensor map, the CUDA-core kernels loop over the slice) and padded slices are written whole.
+    const int NB = static_cast<int>(p->bufs.size());
+    if (input_buf >= 0) p->bufs[input_buf].first = -1;
+    if (logits_buf >= 0) p->bufs[logits_buf].last = INT32_MAX;
+    std::vector<int> order;
+    size_t fixed_end = 0;
+    for (int i = 0; i < NB; ++i) {
+      BufInfo& b = p->bufs[i];
+      bool movable = b.kind == BD_MAP && b.last >= 0 && b.first != INT32_MAX;
+      if (movable && i != input_buf) {
+        // Channels no op writes (728-channel maps are stored with a 768-channel pitch and read at that width with zero
+        // weights) hold zeros only in a range of the buffer's own.  In a shared range they are garbage: the buffer may
+        // share only if the written channels are one run [0, valid_c) and every reader beyond valid_c is a TMA map
+        // that can be cut there (out-of-range elements read as zero).
+        std::sort(b.written.begin(), b.written.end());
+        int run_end = 0;
+        bool holes = false;
+        for (const auto& iv : b.written) {
+          if (iv.first > run_end) { holes = true; break; }
+          run_end = std::max(run_end, iv.second);
+        }
+        if (holes || run_end == 0 || b.hard_read_end > run_end) movable = false;
+        else b.valid_c = run_end;
+      }
+      if (movable) { order.push_back(i); b.shared = !(i == input_buf || i == logits_buf); }
+      else { b.offset = fixed_end; fixed_end += (b.bytes + 1023) / 1024 * 1024; }
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int a, int c) {
+      const BufInfo &x = p->bufs[a], &y = p->bufs[c];
+      return x.first != y.first ? x.first < y.first : x.bytes > y.bytes;
+    });
+    std::vector<int> placed;
+    size_t end = fixed_end;
+    for (int i : order) {
+      BufInfo& b = p->bufs[i];
+      const size_t need = (b.bytes + 1023) / 1024 * 1024;
+      std::vector<std::pair<size_t, size_t>> busy;  // ranges of placed buffers alive during b's lifetime
+      for (int j : placed) {
+        const BufInfo& o = p->bufs[j];
+        if (o.first <= b.last && b.first <= o.last) busy.emplace_back(o.offset, o.offset + (o.bytes + 1023) / 1024 * 1024);
+      }
+      std::sort(busy.begin(), busy.end());
+      size_t at = fixed_end;
+      for (const auto& r : busy) {
+        if (at + need <= r.first) break;
+        at = std::max(at, r.second);
+      }
+      b.offset = at;
+      end = std::max(end, at + need);
+      placed.push_back(i);
+    }
+    off = end;
   }
   p->arena_bytes = std::max<size_t>(off, 1024);
   BD_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->arena), p->arena_bytes));
@@ -865,6 +973,8 @@ int bd_plan_read_buffer(bd_plan* p, int buf, void* host_dst, size_t bytes) {
   BD_ON_PLAN(p);
   BD_CHECK(p && p->finalized && buf >= 0 && buf < static_cast<int>(p->bufs.size()) && bytes <= p->bufs[buf].bytes,
            "bad arguments");
+  BD_CHECK(!p->bufs[buf].shared, "this buffer shares its arena range with others (arena reuse): build the plan with "
+                                 "bd_plan_set_arena_reuse(plan, 0) to read intermediates");
   BD_CUDA(cudaDeviceSynchronize());
   BD_CUDA(cudaMemcpy(host_dst, p->arena + p->bufs[buf].offset, bytes, cudaMemcpyDeviceToHost));
   return 0;
@@ -877,6 +987,19 @@ int bd_plan_write_buffer(bd_plan* p, int buf, const void* host_src, size_t bytes
   return 0;
 }
 size_t bd_plan_arena_bytes(bd_plan* p) { return p ? p->arena_bytes : 0; }
+size_t bd_plan_arena_bytes_flat(bd_plan* p) { return p ? p->arena_bytes_flat : 0; }
+int bd_plan_buffer_lifetime(bd_plan* p, int buf, int* first, int* last, int* shared) {
+  BD_CHECK(p && p->finalized && buf >= 0 && buf < static_cast<int>(p->bufs.size()), "bad arguments");
+  if (first) *first = p->bufs[buf].first;
+  if (last) *last = p->bufs[buf].last;
+  if (shared) *shared = p->bufs[buf].shared ? 1 : 0;
+  return 0;
+}
+int bd_plan_set_arena_reuse(bd_plan* p, int on) {
+  BD_CHECK(p && !p->finalized, "bd_plan_set_arena_reuse: call before bd_plan_finalize");
+  p->reuse = on != 0;
+  return 0;
+}
 int bd_plan_num_launches(bd_plan* p) {
   int n = 0;
   if (p) for (const Op& op : p->ops) n += op.launches;

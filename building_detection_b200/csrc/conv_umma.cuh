@@ -969,7 +969,9 @@ inline int floor_pow2(int v) {
 inline int prepare(Launch* L, const TView& x, const TView& y, const TView* res, int ntaps, const int* dy,
                    const int* dx, int stride, int Ho, int Wo, int act_pre, int act_post, int out_scale, int out_oy,
                    int out_ox, const h16* w_dev, const float* bias_dev, int smem_budget_kb, int max_block_n,
-                   int num_sms, int group_hint = 0, const h16* dw_w_dev = nullptr, int dw_relu = 0) {
+                   int num_sms, int group_hint = 0, const h16* dw_w_dev = nullptr, int dw_relu = 0, int cin_valid = -1) {
+  // cin_valid < Cin: only the first cin_valid channels of the input slice hold data (the rest of a buffer that shares
+  // its arena range is garbage): the A tensor maps end there and the TMA zero-fills the tail of the last k-block
   const int Cin = x.c, Cout = y.c;
   BD_CHECK(!x.f32, "umma conv needs an fp16 input map");
   BD_CHECK(Cin % 8 == 0 && x.c0 % 8 == 0 && x.ctot % 8 == 0, "umma conv needs 16-byte aligned input channel slices");
@@ -1108,7 +1110,8 @@ inline int prepare(Launch* L, const TView& x, const TView& y, const TView* res, 
   for (int m = 0; m < 4; ++m) {
     if (!used[m]) continue;
     const int py = m / 2, px = m % 2;
-    uint64_t dims[4] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>((x.W - px + stride - 1) / stride),
+    uint64_t dims[4] = {static_cast<uint64_t>(cin_valid >= 0 && cin_valid < Cin ? std::max(cin_valid, 8) : Cin),
+                        static_cast<uint64_t>((x.W - px + stride - 1) / stride),
                         static_cast<uint64_t>((x.H - py + stride - 1) / stride), static_cast<uint64_t>(x.N)};
     uint64_t strides[3] = {pitch * stride, pitch * x.W * stride, pitch * x.W * x.H};
     uint32_t box[4] = {BLOCK_K, static_cast<uint32_t>(p.bw), static_cast<uint32_t>(p.bh), static_cast<uint32_t>(p.bn)};

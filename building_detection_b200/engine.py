@@ -83,13 +83,13 @@ class Model:
             p.close()
         self._native = {}
 
-    def native_plan(self, batch, umma=True, device=None):
+    def native_plan(self, batch, umma=True, device=None, keep_buffers=False):
         """The native plan of this model for ``batch`` tiles on ``device`` (None: the device the C ABI context
         resolves from LOCAL_RANK / BD_DEVICE).  One arena per (batch, device): callers that see ragged batch
         sizes go through ``plan_batch_for`` so that the cache stays bounded."""
         from .runtime import NativePlan, resolve_device
         device = resolve_device(device)
-        key = (batch, umma, device)
+        key = (batch, umma, device, bool(keep_buffers))
         if key in self._native:
             self._native[key] = self._native.pop(key)  # most recently used last
             return self._native[key]
@@ -99,7 +99,9 @@ class Model:
         large = [k for k in self._native if k[0] >= 16 and k[2] == device]
         while batch >= 16 and len(large) >= MAX_LARGE_PLANS:
             self._native.pop(large.pop(0)).close()
-        self._native[key] = NativePlan(self.build_plan(batch, umma=umma), device)
+        # keep_buffers: every buffer in a range of its own so that intermediates can be read back (tests, tools);
+        # the product path shares ranges between buffers with disjoint lifetimes (5-10x smaller arenas)
+        self._native[key] = NativePlan(self.build_plan(batch, umma=umma), device, reuse=not keep_buffers)
         return self._native[key]
 
     @staticmethod

@@ -76,6 +76,9 @@ _SIGS = {
     "bd_plan_read_buffer": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
     "bd_plan_write_buffer": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
     "bd_plan_arena_bytes": (C.c_size_t, [C.c_void_p]),
+    "bd_plan_arena_bytes_flat": (C.c_size_t, [C.c_void_p]),
+    "bd_plan_set_arena_reuse": (C.c_int, [C.c_void_p, C.c_int]),
+    "bd_plan_buffer_lifetime": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "bd_plan_num_launches": (C.c_int, [C.c_void_p]),
     "bd_plan_num_ops": (C.c_int, [C.c_void_p]),
     "bd_plan_time_ops": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -173,12 +176,16 @@ def _tref(r):
 class NativePlan:
     """A graph.Plan uploaded through the C ABI: arena + weights + launch list on one GPU."""
 
-    def __init__(self, plan: G.Plan, device=None):
+    def __init__(self, plan: G.Plan, device=None, reuse=False):
+        """``reuse``: map buffers with disjoint lifetimes share arena ranges (bd_plan_set_arena_reuse; what
+        Model.native_plan asks for).  Off here by default: tests and tools read intermediates back."""
         L = lib()
         self.plan = plan
         self.ctx = context(device)
         self.h = C.c_void_p()
         check(L.bd_plan_create(self.ctx, plan.batch, C.byref(self.h)))
+        check(L.bd_plan_set_arena_reuse(self.h, 1 if reuse else 0))
+        self.reuse = bool(reuse)
         try:
             self._upload(L, plan)
         except Exception:
@@ -355,6 +362,17 @@ class NativePlan:
     @property
     def arena_bytes(self):
         return lib().bd_plan_arena_bytes(self.h)
+
+    def buffer_lifetime(self, buf):
+        """(first step, last step, shared) of a buffer as the arena allocator saw it."""
+        f, l, sh = C.c_int(), C.c_int(), C.c_int()
+        check(lib().bd_plan_buffer_lifetime(self.h, buf, C.byref(f), C.byref(l), C.byref(sh)))
+        return f.value, l.value, bool(sh.value)
+
+    @property
+    def arena_bytes_flat(self):
+        """Arena size without buffer reuse (one range per buffer)."""
+        return lib().bd_plan_arena_bytes_flat(self.h)
 
     def close(self):
         if self.h:

@@ -125,6 +125,17 @@ size_t bd_plan_buffer_bytes(bd_plan* plan, int buf);
 int bd_plan_read_buffer(bd_plan* plan, int buf, void* host_dst, size_t bytes);
 int bd_plan_write_buffer(bd_plan* plan, int buf, const void* host_src, size_t bytes);
 size_t bd_plan_arena_bytes(bd_plan* plan);
+/* Arena reuse (default on; BD_ARENA_REUSE=0 in the environment turns the default off): map buffers whose lifetimes --
+ * first to last plan step touching them -- are disjoint share address ranges, which cuts the activation arena of the
+ * five networks 5-10x (what makes batch 64 fit next to a 20 000^2 scene).  With reuse on only the input, the logits and
+ * the pooled vectors can be read back (bd_plan_read_buffer refuses the others); call with on = 0 BEFORE
+ * bd_plan_finalize for debugging plans whose intermediates are inspected.  bd_plan_arena_bytes_flat = the arena size
+ * without reuse. */
+int bd_plan_set_arena_reuse(bd_plan* plan, int on);
+size_t bd_plan_arena_bytes_flat(bd_plan* plan);
+/* first / last plan step (index of the bd_plan_add_* call) touching a buffer (INT32_MAX / -1: never; the input starts at
+ * -1, the logits end at INT32_MAX) and whether its range is shared -- what the arena allocator worked from (tests) */
+int bd_plan_buffer_lifetime(bd_plan* plan, int buf, int* first, int* last, int* shared);
 int bd_plan_num_launches(bd_plan* plan);
 /* per-op device times of one run (CUDA events around every op; for profiling only): ms_out[num_ops] */
 int bd_plan_num_ops(bd_plan* plan);

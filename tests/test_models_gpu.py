@@ -19,6 +19,7 @@ import pytest
 import torch
 
 from building_detection_b200.predict_model import CTORS, MODEL_NAMES
+from building_detection_b200 import runtime as R
 from oracle import nets, plan_interp
 
 pytestmark = pytest.mark.gpu
@@ -115,4 +116,44 @@ def test_hrnet_undamped_recipe_stays_within_its_conditioning(gpu):
     agree = got.argmax(-1) == ref.argmax(-1)
     print(f"hrnet undamped: max|dp|={err:.3e} p99.99={np.quantile(np.abs(got - ref), 0.9999):.3e} sure-agree={agree[sure].mean():.5f}")
     assert err < 4e-2 and agree[sure].mean() >= MASK_AGREE
+    m._drop_native()
+
+
+@pytest.mark.parametrize("name", MODEL_NAMES)
+def test_arena_reuse_is_invisible(gpu, prepared, name):
+    """The product plans share arena ranges between buffers with disjoint lifetimes (bd_plan_set_arena_reuse).  The
+    allocator's own invariant -- two buffers whose lifetimes intersect never overlap in memory -- is checked from the
+    lifetimes and addresses it reports, and the probabilities of a forward are bit-identical to the plan that keeps
+    every buffer apart, also on a second forward over the dirty arena (nothing relies on the arena's zero fill)."""
+    m, x, _ = prepared(name)
+    xb = np.concatenate([x[:1], tiles(11, 1)], axis=0)
+    shared = m.native_plan(2)
+    flat = m.native_plan(2, keep_buffers=True)
+    assert shared.reuse and not flat.reuse
+    assert flat.arena_bytes == flat.arena_bytes_flat == shared.arena_bytes_flat
+    ratio = shared.arena_bytes / shared.arena_bytes_flat
+    print(f"{name}: arena {shared.arena_bytes / 2**20:.0f} MiB with reuse, {shared.arena_bytes_flat / 2**20:.0f} MiB without ({ratio:.2f})")
+    assert ratio < 0.5
+    spans = []
+    for b in shared.plan.bufs:
+        first, last, is_shared = shared.buffer_lifetime(b.id)
+        if b.kind != "map" or last < 0:
+            assert not is_shared
+            continue
+        p0 = shared.buffer_ptr(b.id)
+        spans.append((first, last, p0, p0 + R.lib().bd_plan_buffer_bytes(shared.h, b.id), b.id))
+        if b.id in (shared.plan.input, shared.plan.logits):
+            assert not is_shared
+    assert len(spans) > 10
+    for i, (f0, l0, a0, e0, id0) in enumerate(spans):
+        for f1, l1, a1, e1, id1 in spans[i + 1:]:
+            if f0 <= l1 and f1 <= l0:
+                assert e0 <= a1 or e1 <= a0, f"buffers {id0} and {id1} are alive together and overlap"
+    want = flat.run_host(xb)
+    np.testing.assert_array_equal(shared.run_host(xb), want)
+    np.testing.assert_array_equal(shared.run_host(xb[::-1].copy()), flat.run_host(xb[::-1].copy()))
+    np.testing.assert_array_equal(shared.run_host(xb), want)
+    with pytest.raises(R.NativeError):
+        some = next(b.id for b in shared.plan.bufs if shared.buffer_lifetime(b.id)[2])
+        shared.read_buffer(some)
     m._drop_native()

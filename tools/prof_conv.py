@@ -1,5 +1,5 @@
-"""One tcgen05 conv layer at batch 16, launched a few times: the short command ncu --set full replays.
-usage: python tools/prof_conv.py [H Cin Cout k]"""
+"""One tcgen05 conv layer at batch 16 (BATCH=n in the environment: another batch), launched a few times: the short
+command ncu --set full replays.  usage: python tools/prof_conv.py [H Cin Cout k]"""
 import os
 import sys
 
@@ -11,6 +11,7 @@ from util import build_two_pass  # noqa: E402
 from building_detection_b200.runtime import NativePlan  # noqa: E402
 
 H, Cin, Cout, k = (int(a) for a in sys.argv[1:5]) if len(sys.argv) >= 5 else (128, 256, 256, 3)
+B = int(os.environ.get("BATCH", "16"))
 
 
 def builder(g):
@@ -18,12 +19,12 @@ def builder(g):
     return x, g.conv(x, "c", Cout, k=k, bn=True, act="relu")
 
 
-plan, (x, y), _ = build_two_pass(builder, 16)
+plan, (x, y), _ = build_two_pass(builder, B)
 nat = NativePlan(plan)
-nat.write_buffer(x.buf.id, np.random.default_rng(0).standard_normal((16, H, H, Cin)).astype(np.float32))
+nat.write_buffer(x.buf.id, np.random.default_rng(0).standard_normal((B, H, H, Cin)).astype(np.float32))
 best = 1e9
 for _ in range(5):
     ms, kinds, flops = nat.time_ops()
     best = min(best, ms[0])
-print(f"conv {k}x{k} {Cin}->{Cout} @{H}^2 batch 16: {best:.3f} ms, {flops[0] / best / 1e9:.1f} TFLOP/s")
+print(f"conv {k}x{k} {Cin}->{Cout} @{H}^2 batch {B}: {best:.3f} ms, {flops[0] / best / 1e9:.1f} TFLOP/s")
 nat.close()
