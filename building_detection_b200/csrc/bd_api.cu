@@ -589,11 +589,13 @@ int bd_plan_add_gap(bd_plan* p, bd_tref x, int y_vec) {
     k::GapParams q;
     q.x = pl->kview(x); q.N = pl->batch;
     const int HW = q.x.H * q.x.W;
-    // enough blocks to fill the machine four times over, at least 32 pixels and (for the large maps) about 512
+    // enough blocks to fill the machine four times over, at least 32 pixels and (for the large maps) about 2048
     // pixels per block
     bd_ctx* ctx = pl->ctx;
     // (sized for batch 16, and NOT a function of the batch: a tile's result must not depend on its batch neighbours)
-    const int want = std::max(cdiv(HW, 512), cdiv(4 * 148, 16));
+    // (about 2048 pixels per block on the large maps: with 512 the per-block reduction, fence and ticket were ~20 % of a
+    // block's life; 37 x batch blocks still fill the machine)
+    const int want = std::max(cdiv(HW, 2048), cdiv(4 * 148, 16));
     q.splits = std::max(1, std::min(std::min(want, 1024), std::max(1, HW / 32)));
     void *part = nullptr, *tick = nullptr;
     if (pl->scratch(static_cast<size_t>(pl->batch) * q.splits * x.c * 4, &part)) return 1;

@@ -1061,7 +1061,9 @@ inline int prepare(Launch* L, const TView& x, const TView& y, const TView* res, 
   if (p.spec != 3 && p.spec != 4) {
     const int stage_bytes = sub_bytes * p.group;
     p.stages = std::max(2, std::min(12, avail / stage_bytes));
-    p.stages = std::min(p.stages, std::max(2, 2 * num_kb / p.group));
+    // the ring covers two tiles, and at least ~190 KB / 8 stages of loads in flight: the short-K 1x1 layers (the K = 32
+    // stems: one 24 KB stage per tile) are bound by load latency, not by shared memory
+    p.stages = std::min(p.stages, std::max({2, 2 * num_kb / p.group, std::min(8, 192 * 1024 / stage_bytes)}));
     L->smem_bytes = p.stages * stage_bytes + fixed;
   }
   BD_CHECK(L->smem_bytes <= 227 * 1024, "umma conv smem budget exceeded");

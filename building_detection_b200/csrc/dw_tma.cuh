@@ -21,6 +21,7 @@ constexpr int OUT_TILE_BYTES = 128 * 128;  // 128 pixels x 64 channels fp16
 struct Params {
   int N, H, W, C;          // map geometry, channels of the slice
   int kchunks, tiles_w, tiles_h, total_items, stages, relu_in;
+  int out_tiles;           // output staging tiles (2, or 1 when that buys a third halo stage)
   int w_bytes;             // staged weights [9][kchunks*64] fp16
   umma::FastDiv fd_kc, fd_tw, fd_th;
   const h16* w;            // [9][C] fp16
@@ -49,7 +50,7 @@ __global__ void __launch_bounds__(THREADS, 2) dwconv_tma_kernel(const __grid_con
   uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t out0 = smem_base + static_cast<uint32_t>(p.stages) * HALO_STAGE;  // two output tiles
-  const uint32_t w0 = out0 + 2u * OUT_TILE_BYTES;                                   // staged weights
+  const uint32_t w0 = out0 + static_cast<uint32_t>(p.out_tiles) * OUT_TILE_BYTES;   // staged weights
   const uint32_t full0 = w0 + static_cast<uint32_t>(p.w_bytes), empty0 = full0 + 8u * p.stages;
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -125,9 +126,14 @@ __global__ void __launch_bounds__(THREADS, 2) dwconv_tma_kernel(const __grid_con
       __syncwarp();
       if (lane == 0) mbar_arrive(empty0 + 8u * s);
       if (++s == static_cast<uint32_t>(p.stages)) { s = 0; ph ^= 1u; }
-      // the TMA store that last read this output tile (two items ago) must have finished reading it
-      if (dt == 0) tma_store_wait_read<1>();
+      // the TMA store that last read this output tile (two items ago; the previous item with a single tile) must have
+      // finished reading it
+      if (dt == 0) {
+        if (p.out_tiles == 2) tma_store_wait_read<1>();
+        else tma_store_wait_read<0>();
+      }
       asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (p.out_tiles == 1) ob = 0u;
       uint8_t* otile = gen_base + (out0 - smem_base) + ob * OUT_TILE_BYTES;
 #pragma unroll
       for (int oy = 0; oy < 4; ++oy)
@@ -180,11 +186,19 @@ inline int prepare(Launch* L, const TView& x, const TView& y, const h16* w_dev, 
   p.w = w_dev;
   p.w_bytes = (9 * p.kchunks * 64 * 2 + 127) / 128 * 128;
   p.fd_kc = umma::make_fastdiv(p.kchunks); p.fd_tw = umma::make_fastdiv(p.tiles_w); p.fd_th = umma::make_fastdiv(p.tiles_h);
-  // two CTAs per SM when two halo stages + everything else fit into half the shared memory
-  const int fixed = 2 * OUT_TILE_BYTES + p.w_bytes + 1024 + 256;
+  // two CTAs per SM when two halo stages + everything else fit into half the shared memory.  The kernel is bound by the
+  // latency of the halo loads (ncu: long-scoreboard stalls, 20 % of the DRAM rate), i.e. by the bytes in flight: when two
+  // output tiles leave room for only two halo stages (728 channels: 13.8 KB of weights) a single output tile buys a third
+  p.out_tiles = 2;
+  int fixed = 2 * OUT_TILE_BYTES + p.w_bytes + 1024 + 256;
   const int half_sm = 113 * 1024;
   int ctas_per_sm = 2;
   p.stages = (half_sm - fixed) / umma::HALO_STAGE;
+  if (p.stages < 3 && (half_sm - (fixed - OUT_TILE_BYTES)) / umma::HALO_STAGE >= 3) {
+    p.out_tiles = 1;
+    fixed -= OUT_TILE_BYTES;
+    p.stages = (half_sm - fixed) / umma::HALO_STAGE;
+  }
   if (p.stages < 2) { ctas_per_sm = 1; p.stages = std::min(4, (226 * 1024 - fixed) / umma::HALO_STAGE); }
   p.stages = std::min(p.stages, 4);
   BD_CHECK(p.stages >= 2, "dwconv_tma: shared memory budget too small");
