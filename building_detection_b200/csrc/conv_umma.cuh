@@ -61,6 +61,7 @@ struct Params {
   int block_n, kchunks, ntaps, stages, group, tmem_cols;  // group: k-blocks per shared-memory stage
   int dbg;      // debug switches (BD_UMMA_DBG): 1 = every thread waits for the previous grid before the role split, 2 = no early launch_dependents
   int halo_subset;  // spec 3 with a runtime tap list (kernel instance <3, 0>)
+  int prefetch; // 1: the producer prefetches the next tile's activation boxes into L2 (BD_UMMA_PREFETCH=0: off)
   int issuers;  // MMA-issuing warps: 2 = warp 1 takes the even tiles of a CTA, warp MMA2_WARP the odd ones
   int spec;  // 0 generic loops; 1 = 9 taps x 1 chunk, group 3; 2 = 9 taps x 2 chunks, group 2 (fully unrolled loops);
              // 3 = halo path: 3x3 stride 1, one halo box per chunk, weights resident in shared memory;
@@ -149,6 +150,14 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm,
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
+}
+// L2 prefetch of a tensor-map box (no shared-memory destination, no barrier): the producer asks for the boxes of its
+// NEXT tile while it loads the current one, so that the loads which would miss to DRAM (the first touch of an
+// activation region) find their lines in L2 -- the ring holds ~2000 clk of work, a DRAM round trip under load is longer
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* tm, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
 }
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
@@ -284,7 +293,7 @@ __device__ __forceinline__ uint32_t ring_test_next_full(const Ring& r, const Par
 template <int NTAPS, int KCH, int G>
 __device__ __forceinline__ void produce_tile(const Maps& maps, const Params& p, Ring& r, uint32_t smem_base, uint32_t sub_bytes,
                                              uint32_t full0, uint32_t empty0, int w0, int h0, int n0, int n_base, int& tr_i,
-                                             int tile) {
+                                             int tile, bool pf, int pw0, int ph0, int pn0) {
   static_assert((NTAPS * KCH) % G == 0, "group must divide the k-block count");
   const char* maps_a = reinterpret_cast<const char*>(&maps.a[0]);
 #pragma unroll
@@ -300,6 +309,7 @@ __device__ __forceinline__ void produce_tile(const Maps& maps, const Params& p, 
         const uint32_t dst = smem_base + r.off + g * sub_bytes;
         tma_load_4d(dst, tm, r.fb, kc * BLOCK_K, w0 + p.tap_dx[tap], h0 + p.tap_dy[tap], n0);
         tma_load_3d(dst + A_STAGE_BYTES, &maps.b, r.fb, kc * BLOCK_K, n_base, tap);
+        if (tap == NTAPS / 2 && pf) tma_prefetch_4d(tm, kc * BLOCK_K, pw0 + p.tap_dx[tap], ph0 + p.tap_dy[tap], pn0);
       }
     }
     __syncwarp();
@@ -431,6 +441,14 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
       int nt, tw, th, tn;
       tile_coords(p, tile, nt, tw, th, tn);
       const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn, n_base = nt * p.block_n;
+      // the next tile of this CTA: its activation boxes are prefetched into L2 while this tile loads
+      int pw0 = 0, ph0 = 0, pn0 = 0;
+      const bool pf = p.prefetch && tile + static_cast<int>(gridDim.x) < p.total_tiles;
+      if (pf) {
+        int nt2, tw2, th2, tn2;
+        tile_coords(p, tile + gridDim.x, nt2, tw2, th2, tn2);
+        pw0 = tw2 * p.bw; ph0 = th2 * p.bh; pn0 = tn2 * p.bn;
+      }
       if ((KSPEC == 3)) {  // one halo box per 64-channel chunk
         for (int c = 0; c < p.Cin; c += BLOCK_K) {
           mbar_wait(ring.eb, ring.ph ^ 1u);
@@ -438,6 +456,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
             trace_ev(p, 0, tr_i, tile, c);
             mbar_expect_tx(ring.fb, HALO_BYTES);
             tma_load_4d(smem_base + ring.off, &maps.a[0], ring.fb, c, w0 - 1, h0 - 1, n0);
+            if (pf) tma_prefetch_4d(&maps.a[0], c, pw0 - 1, ph0 - 1, pn0);
           }
           __syncwarp();
           ring_advance(ring, p, HALO_STAGE, full0, empty0);
@@ -452,14 +471,16 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
             mbar_expect_tx(ring.fb, HALO_BYTES + b_bytes);
             tma_load_4d(smem_base + ring.off, &maps.a[0], ring.fb, c, w0 - 1, h0 - 1, n0);
             tma_load_3d(smem_base + ring.off + HALO_STAGE, &maps.b, ring.fb, c, n_base, 0);
+            if (pf) tma_prefetch_4d(&maps.a[0], c, pw0 - 1, ph0 - 1, pn0);
           }
           __syncwarp();
           ring_advance(ring, p, stage_bytes, full0, empty0);
         }
         continue;
       }
-      if (KSPEC == 0 && p.spec == 1) { produce_tile<9, 1, 3>(maps, p, ring, smem_base, sub_bytes, full0, empty0, w0, h0, n0, n_base, tr_i, tile); continue; }
-      if (KSPEC == 0 && p.spec == 2) { produce_tile<9, 2, 2>(maps, p, ring, smem_base, sub_bytes, full0, empty0, w0, h0, n0, n_base, tr_i, tile); continue; }
+      if (KSPEC == 0 && p.spec == 1) { produce_tile<9, 1, 3>(maps, p, ring, smem_base, sub_bytes, full0, empty0, w0, h0, n0, n_base, tr_i, tile, pf, pw0, ph0, pn0); continue; }
+      if (KSPEC == 0 && p.spec == 2) { produce_tile<9, 2, 2>(maps, p, ring, smem_base, sub_bytes, full0, empty0, w0, h0, n0, n_base, tr_i, tile, pf, pw0, ph0, pn0); continue; }
+      const int pf_tap = p.ntaps >> 1;  // the centre tap of a 3x3: its box covers the region all taps read (+- 1 pixel)
       for (int tap = 0; tap < p.ntaps; ++tap) {
         const CUtensorMap* tm = reinterpret_cast<const CUtensorMap*>(maps_a + p.tap_map[tap] * sizeof(CUtensorMap));
         const int cx = w0 + p.tap_dx[tap], cy = h0 + p.tap_dy[tap];
@@ -470,6 +491,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
             if (sub == 0) mbar_expect_tx(fb, stage_bytes);
             tma_load_4d(a_s, tm, fb, c, cx, cy, n0);
             tma_load_3d(a_s + A_STAGE_BYTES, &maps.b, fb, c, n_base, tap);
+            if (pf && tap == pf_tap) tma_prefetch_4d(tm, c, pw0 + p.tap_dx[tap], ph0 + p.tap_dy[tap], pn0);
           }
           __syncwarp();
           a_s += sub_bytes;
@@ -1076,6 +1098,8 @@ inline int prepare(Launch* L, const TView& x, const TView& y, const TView* res, 
     // These are exactly the short-K tiles that lose the most to per-tile bookkeeping.
     static const int env_dbg = [] { const char* e = getenv("BD_UMMA_DBG"); return e ? atoi(e) : 0; }();
     p.dbg = env_dbg;
+    static const int env_pf = [] { const char* e = getenv("BD_UMMA_PREFETCH"); return e ? atoi(e) : 1; }();
+    p.prefetch = env_pf;
     // ON by default since round 2: the intermittent failures of round 1 came from odd ring sizes (a stage shared by the
     // two issuers -> mbarrier parity aliasing, see the issuer loop); with the even-ring rule below the scheme ran
     // tools/stress2.py clean at batch 16 and 32 (result digests + the per-op timing path).  BD_UMMA_ISSUERS=1: one.
