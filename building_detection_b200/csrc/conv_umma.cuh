@@ -56,6 +56,8 @@ using ::bd::fd_div;
 struct Params {
   int N, Ho, Wo, Cout, Cin;
   FastDiv fd_nt, fd_tw, fd_th;  // dividers by n_tiles, tiles_w, tiles_h
+  FastDiv fd_mt;                // divider by the number of pixel tiles (m_fast order)
+  int m_total, m_fast;          // m_fast: pixel tiles run fastest in the tile index (all CTAs on one N tile at a time)
   int bw, bh, bn;
   int tiles_w, tiles_h, tiles_n, n_tiles, total_tiles;
   int block_n, kchunks, ntaps, stages, group, tmem_cols;  // group: k-blocks per shared-memory stage
@@ -65,6 +67,7 @@ struct Params {
   int issuers;  // MMA-issuing warps: 2 = warp 1 takes the even tiles of a CTA, warp MMA2_WARP the odd ones
   int spec;  // 0 generic loops; 1 = 9 taps x 1 chunk, group 3; 2 = 9 taps x 2 chunks, group 2 (fully unrolled loops);
              // 3 = halo path: 3x3 stride 1, one halo box per chunk, weights resident in shared memory;
+             // 5 = halo path with streamed weights: halo box per chunk in two slots, the ring holds weight tiles;
              // 4 = fused separable convolution: warps 2-5 compute the depthwise 3x3 of a halo box into the A tile of
              //     the pointwise 1x1 GEMM, warps 6-9 are the epilogue
   int wres_bytes;  // bytes of resident weights (spec 3), 0 otherwise
@@ -264,8 +267,15 @@ struct alignas(64) Maps {
 // tile index -> (N tile, column tile, row tile, image tile); the N tile runs fastest
 __device__ __forceinline__ void tile_coords(const Params& p, int tile, int& nt, int& tw, int& th, int& tn) {
   const uint32_t t = static_cast<uint32_t>(tile);
-  const uint32_t mt = fd_div(t, p.fd_nt);
-  nt = static_cast<int>(t - mt * p.n_tiles);
+  uint32_t mt;
+  if (p.m_fast) {
+    const uint32_t q = fd_div(t, p.fd_mt);
+    nt = static_cast<int>(q);
+    mt = t - q * p.m_total;
+  } else {
+    mt = fd_div(t, p.fd_nt);
+    nt = static_cast<int>(t - mt * p.n_tiles);
+  }
   const uint32_t t2 = fd_div(mt, p.fd_tw);
   tw = static_cast<int>(mt - t2 * p.tiles_w);
   const uint32_t t3 = fd_div(t2, p.fd_th);
@@ -370,6 +380,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
   const uint32_t b_bytes = static_cast<uint32_t>(p.block_n) * 128u;
   const uint32_t sub_bytes = A_STAGE_BYTES + b_bytes;                       // one k-block: A box + W tile
   const uint32_t stage_bytes = (KSPEC == 3) ? static_cast<uint32_t>(HALO_STAGE)
+                               : (KSPEC == 5) ? b_bytes * static_cast<uint32_t>(p.group)   // `group` weight tiles (taps)
                                : (KSPEC == 4) ? static_cast<uint32_t>(HALO_STAGE) + b_bytes  // halo box + pointwise W tile
                                              : sub_bytes * static_cast<uint32_t>(p.group);  // a stage holds `group` k-blocks
   const uint32_t wres0 = smem_base + static_cast<uint32_t>(p.stages) * stage_bytes;      // resident weights (spec 3)
@@ -393,7 +404,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
       mbar_init(empty0 + 8u * s, (KSPEC == 4) ? 5 : 1);  // spec 4: four depthwise warps + the MMA commit free a stage
     }
     for (int a = 0; a < 2; ++a) {
-      mbar_init(afull0 + 8u * a, 4);   // one arrival per depthwise warp
+      mbar_init(afull0 + 8u * a, (KSPEC == 5) ? 1 : 4);   // one arrival per depthwise warp (spec 5: the producer's expect_tx)
       mbar_init(aempty0 + 8u * a, 1);  // MMA commit
     }
     for (int a = 0; a < 2; ++a) {
@@ -429,6 +440,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
     uint32_t s = 0, sub = 0, ph = 0, a_s = smem_base, fb = full0, eb = empty0;  // ring position, kept incrementally
     const char* maps_a = reinterpret_cast<const char*>(&maps.a[0]);
     Ring ring{0u, 0u, 0u, full0, empty0};
+    uint32_t hcount = 0;  // spec 5: running chunk counter (halo slot / parity)
     if ((KSPEC == 3) && elect_one()) {  // all weight tiles once: [chunk][tap] blocks of block_n x 128 B
       mbar_expect_tx(wbar, static_cast<uint32_t>(p.wres_bytes));
       uint32_t dst = wres0;
@@ -460,6 +472,33 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
           }
           __syncwarp();
           ring_advance(ring, p, HALO_STAGE, full0, empty0);
+        }
+        continue;
+      }
+      if ((KSPEC == 5)) {
+        // halo path with STREAMED weights (3x3 layers whose weights do not fit into shared memory): per 64-channel
+        // chunk one halo box into one of two slots (it feeds all nine taps), then the nine weight tiles through the
+        // ring, `group` taps per stage
+        for (int c = 0; c < p.Cin; c += BLOCK_K, ++hcount) {
+          const uint32_t slot = hcount & 1u;
+          mbar_wait(aempty0 + 8u * slot, ((hcount >> 1) & 1u) ^ 1u);
+          if (elect_one()) {
+            trace_ev(p, 0, tr_i, tile, c);
+            mbar_expect_tx(afull0 + 8u * slot, HALO_BYTES);
+            tma_load_4d(wres0 + slot * HALO_STAGE, &maps.a[0], afull0 + 8u * slot, c, w0 - 1, h0 - 1, n0);
+            if (pf) tma_prefetch_4d(&maps.a[0], c, pw0 - 1, ph0 - 1, pn0);
+          }
+          __syncwarp();
+          for (int t0 = 0; t0 < 9; t0 += p.group) {
+            mbar_wait(ring.eb, ring.ph ^ 1u);
+            if (elect_one()) {
+              mbar_expect_tx(ring.fb, stage_bytes);
+              for (int g = 0; g < p.group; ++g)
+                tma_load_3d(smem_base + ring.off + g * b_bytes, &maps.b, ring.fb, c, n_base, t0 + g);
+            }
+            __syncwarp();
+            ring_advance(ring, p, stage_bytes, full0, empty0);
+          }
         }
         continue;
       }
@@ -587,6 +626,41 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
       const uint32_t tacc = tmem_base + a * static_cast<uint32_t>(p.block_n);
       // the NEXT tile's accumulator stage / phase, tested early during this tile's last k-block
       const uint32_t te_bar = tempty0 + 16u * (a ^ 1u), te_par = (((ti + 1u) >> 1) & 1u) ^ 1u;
+      if ((KSPEC == 5)) {
+        for (int c = p.Cin; c > 0; c -= BLOCK_K, ++it4) {  // c = channels left; it4 = running chunk counter
+          const uint32_t slot = it4 & 1u;
+          mbar_wait(afull0 + 8u * slot, (it4 >> 1) & 1u);  // halo box of this chunk
+          const uint64_t hdesc = make_sdesc_sbo(wres0 + slot * HALO_STAGE, HALO_W * 128);
+          for (int t0 = 0; t0 < 9; t0 += p.group) {
+            if (!f_ready) mbar_wait(ring.fb, ring.ph);
+            tc_fence_after();
+            if (elect_one()) {
+              if (t0 == 0) trace_ev(p, 1, tr_i, tile, c);
+              const uint64_t bdesc0 = make_sdesc(smem_base + ring.off);
+              for (int g = 0; g < p.group; ++g) {
+                const int tap = t0 + g;
+                const uint64_t adesc = hdesc + static_cast<uint32_t>(((tap / 3) * HALO_W + tap % 3) * 8);
+                const uint64_t bd = bdesc0 + static_cast<uint32_t>(g) * (b_bytes >> 4);
+                tc_mma_f16(tacc, adesc, bd, idesc, (tap > 0 || c < p.Cin) ? 1u : 0u);
+                if (c > 16) tc_mma_f16(tacc, adesc + 2u, bd + 2u, idesc, 1u);
+                if (c > 32) tc_mma_f16(tacc, adesc + 4u, bd + 4u, idesc, 1u);
+                if (c > 48) tc_mma_f16(tacc, adesc + 6u, bd + 6u, idesc, 1u);
+              }
+              tc_commit(ring.eb);                                   // weight stage free once these MMAs have read it
+              if (t0 + p.group >= 9) {
+                tc_commit(aempty0 + 8u * slot);                     // ... and the halo slot after the ninth tap
+                if (c <= BLOCK_K) tc_commit(tfull0 + 8u * a);       // accumulator complete
+              }
+            }
+            __syncwarp();
+            // these MMAs are queued: test what the next round will wait for
+            f_ready = ring_test_next_full(ring, p, full0);
+            ring_advance(ring, p, stage_bytes, full0, empty0);
+          }
+        }
+        te_ready = 0u;
+        continue;
+      }
       if ((KSPEC == 3)) {
         if (ti < 2) mbar_wait(wbar, 0);  // (each issuer before its first tile; completes once, parity 0)
         const uint32_t dkb = b_bytes >> 4;   // descriptor units per weight tile
@@ -988,6 +1062,12 @@ inline int floor_pow2(int v) {
 }
 
 // x: input view (fp16), y: output view (fp16, or fp32 with at most 16 channels).  w_dev: [ntaps][Cout][Cin] fp16.
+// BD_HALO_STREAM: 0 = off, 1 = N tiles of at most 128 columns, 2 = every width (default: measured faster on every
+// 3x3 layer of the five networks, profiles/r2r_op_table_*)
+inline bool halo_stream_mode(int block_n) {
+  static const int mode = [] { const char* e = getenv("BD_HALO_STREAM"); return e ? atoi(e) : 2; }();
+  return mode >= 2 || (mode == 1 && block_n <= 128);
+}
 inline int prepare(Launch* L, const TView& x, const TView& y, const TView* res, int ntaps, const int* dy,
                    const int* dx, int stride, int Ho, int Wo, int act_pre, int act_post, int out_scale, int out_oy,
                    int out_ox, const h16* w_dev, const float* bias_dev, int smem_budget_kb, int max_block_n,
@@ -1078,9 +1158,22 @@ inline int prepare(Launch* L, const TView& x, const TView& y, const TView* res, 
     p.stages = std::max(2, std::min(12, (avail - wbytes) / HALO_STAGE));
     L->smem_bytes = p.stages * HALO_STAGE + wbytes + fixed;
   } else
+  if (halo && full3x3 && ntaps == 9 && halo_stream_mode(p.block_n) &&
+      2 * HALO_STAGE + 2 * (p.block_n <= 128 ? 3 : 1) * p.block_n * 128 <= avail) {
+    // halo path with streamed weights: the weights do not fit, but the activations still arrive as ONE halo box per
+    // 64-channel chunk (two slots) instead of nine shifted boxes; the ring holds weight tiles only, `group` taps per
+    // stage (three 16 KB tiles for N <= 128, where a single tile's four MMAs are shorter than a barrier round trip)
+    p.spec = 5; p.group = p.block_n <= 128 ? 3 : 1;
+    p.wres_bytes = 2 * HALO_STAGE;
+    p.bw = 8; p.bh = 16; p.bn = 1;
+    p.tiles_w = cdiv(Wo, p.bw); p.tiles_h = cdiv(Ho, p.bh); p.tiles_n = x.N;
+    const int stage5 = p.group * p.block_n * 128;
+    p.stages = std::max(2, std::min(12, (avail - p.wres_bytes) / stage5));
+    L->smem_bytes = p.stages * stage5 + p.wres_bytes + fixed;
+  } else
   if (group_hint == 0 && ntaps == 9 && p.kchunks == 1 && 2 * 3 * sub_bytes <= avail) { p.spec = 1; p.group = 3; }
   else if (group_hint == 0 && ntaps == 9 && p.kchunks == 2 && 2 * 2 * sub_bytes <= avail) { p.spec = 2; p.group = 2; }
-  if (p.spec != 3 && p.spec != 4) {
+  if (p.spec != 3 && p.spec != 4 && p.spec != 5) {
     const int stage_bytes = sub_bytes * p.group;
     p.stages = std::max(2, std::min(12, avail / stage_bytes));
     // the ring covers two tiles, and at least ~190 KB / 8 stages of loads in flight: the short-K 1x1 layers (the K = 32
@@ -1141,7 +1234,7 @@ inline int prepare(Launch* L, const TView& x, const TView& y, const TView* res, 
                         static_cast<uint64_t>((x.H - py + stride - 1) / stride), static_cast<uint64_t>(x.N)};
     uint64_t strides[3] = {pitch * stride, pitch * x.W * stride, pitch * x.W * x.H};
     uint32_t box[4] = {BLOCK_K, static_cast<uint32_t>(p.bw), static_cast<uint32_t>(p.bh), static_cast<uint32_t>(p.bn)};
-    if (p.spec == 3 || p.spec == 4) { box[1] = HALO_W; box[2] = HALO_H; box[3] = 1; }
+    if (p.spec == 3 || p.spec == 4 || p.spec == 5) { box[1] = HALO_W; box[2] = HALO_H; box[3] = 1; }
     char* base = static_cast<char*>(x.base) + (static_cast<size_t>(py) * x.W + px) * pitch + static_cast<size_t>(x.c0) * 2;
     if (encode_h16(&L->maps.a[m], base, 4, dims, strides, box)) return 1;
     if (first < 0) first = m;
@@ -1158,6 +1251,14 @@ inline int prepare(Launch* L, const TView& x, const TView& y, const TView* res, 
   // a (bw x qbh x qbn) sub-box of the (bw x bh x bn) tile box
   const int qbh = std::min(p.bh, 32 / p.bw), qbn = 32 / (p.bw * qbh);
   p.fd_nt = make_fastdiv(p.n_tiles); p.fd_tw = make_fastdiv(p.tiles_w); p.fd_th = make_fastdiv(p.tiles_h);
+  p.m_total = p.tiles_w * p.tiles_h * p.tiles_n;
+  p.fd_mt = make_fastdiv(p.m_total);
+  {
+    // BD_UMMA_TILE_ORDER: 0 = N tile fastest (CTAs that run together share pixel tiles), 1 = pixel tile fastest (they
+    // share one weight tile)
+    static const int env_order = [] { const char* e = getenv("BD_UMMA_TILE_ORDER"); return e ? atoi(e) : 0; }();
+    p.m_fast = (env_order == 1 && p.n_tiles > 1) ? 1 : 0;
+  }
   p.y_ctot = y.ctot; p.y_c0 = y.c0; p.y_H = y.H; p.y_W = y.W;
   p.out_scale = out_scale; p.out_oy = out_oy; p.out_ox = out_ox;
   if (y.f32) {
@@ -1204,11 +1305,13 @@ inline int launch(const Launch& L, cudaStream_t stream, bool pdl = false) {
     BD_CUDA(cudaFuncSetAttribute(conv_umma_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     BD_CUDA(cudaFuncSetAttribute(conv_umma_kernel<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     BD_CUDA(cudaFuncSetAttribute(conv_umma_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    BD_CUDA(cudaFuncSetAttribute(conv_umma_kernel<5, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   void (*kern)(Maps, Params) = conv_umma_kernel<0, 1>;
   if (L.p.spec == 3) kern = L.p.halo_subset ? conv_umma_kernel<3, 0> : L.p.ntaps == 18 ? conv_umma_kernel<3, 2> : conv_umma_kernel<3, 1>;
   else if (L.p.spec == 4) kern = conv_umma_kernel<4, 1>;
+  else if (L.p.spec == 5) kern = conv_umma_kernel<5, 1>;
   BD_CUDA(launch_k(pdl, kern, L.grid, dim3(THREADS), static_cast<size_t>(L.smem_bytes), stream, L.maps, L.p));
   return 0;
 }
