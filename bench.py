@@ -56,14 +56,15 @@ def peaks():
 
 
 def conv_traffic():
-    """DRAM bytes (read + write) per conv_umma launch, averaged over the launches of one batch-16 pass of the five
-    plans, from the committed ncu capture (tools/traffic_batch.py); None when no capture is committed."""
+    """DRAM bytes (read + write) per conv_umma launch, averaged over the launches of one pass of the five plans at the
+    batch the capture names (32 = the scene loop's), from the committed ncu capture (tools/traffic_batch.py); None
+    when no capture is committed."""
     import glob
     files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_conv_umma_traffic.json")))
     if not files:
         return None, None
     d = json.load(open(files[-1]))
-    return d["dram_bytes_per_launch"], f"{os.path.relpath(files[-1], ROOT)} ({d['launches']} launches)"
+    return d["dram_bytes_per_launch"], f"{os.path.relpath(files[-1], ROOT)} ({d['launches']} launches, batch {d.get('batch', 16)})"
 
 
 class ClockSampler:
