@@ -61,6 +61,7 @@ struct Params {
   int bw, bh, bn;
   int tiles_w, tiles_h, tiles_n, n_tiles, total_tiles;
   int block_n, kchunks, ntaps, stages, group, tmem_cols;  // group: k-blocks per shared-memory stage
+  int nacc, nacc_sh;  // TMEM accumulator stages (2, or 4 when four N tiles fit into the 512 columns) and log2 of it
   int dbg;      // debug switches (BD_UMMA_DBG): 1 = every thread waits for the previous grid before the role split, 2 = no early launch_dependents
   int halo_subset;  // spec 3 with a runtime tap list (kernel instance <3, 0>)
   int prefetch; // 1: the producer prefetches the next tile's activation boxes into L2 (BD_UMMA_PREFETCH=0: off)
@@ -391,8 +392,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
   const uint32_t aux0 = bias0 + static_cast<uint32_t>(p.bias_bytes);                 // depthwise weights (spec 4)
   const uint32_t bar_base = aux0 + static_cast<uint32_t>(p.aux_bytes);               // 8-byte slots
   const uint32_t full0 = bar_base, empty0 = bar_base + 8u * p.stages;
-  const uint32_t tfull0 = bar_base + 16u * p.stages, tempty0 = tfull0 + 16u;  // tempty: [stage][epilogue group]
-  const uint32_t rbar0 = tempty0 + 32u;  // one per epilogue warp
+  const uint32_t tfull0 = bar_base + 16u * p.stages, tempty0 = tfull0 + 32u;  // up to 4 accumulator stages; tempty: [stage][epilogue group]
+  const uint32_t rbar0 = tempty0 + 64u;  // one per epilogue warp
   const uint32_t wbar = rbar0 + 8u * EPI_WARPS;
   const uint32_t afull0 = wbar + 16u, aempty0 = afull0 + 16u;  // spec 4: two depthwise-output (A tile) slots
   const uint32_t holder = aempty0 + 16u;
@@ -407,7 +408,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
       mbar_init(afull0 + 8u * a, (KSPEC == 5) ? 1 : 4);   // one arrival per depthwise warp (spec 5: the producer's expect_tx)
       mbar_init(aempty0 + 8u * a, 1);  // MMA commit
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < 4; ++a) {
       mbar_init(tfull0 + 8u * a, 1);
       mbar_init(tempty0 + 16u * a, EPI_WARPS / 2);       // one arrival per warp of epilogue group 0
       mbar_init(tempty0 + 16u * a + 8u, EPI_WARPS / 2);  // ... of group 1
@@ -561,8 +562,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
     const bool single_unit = p.block_n <= OUT_CHUNK;  // one epilogue unit per tile
     const int num_kb_all = p.ntaps * p.kchunks;
     for (int tile = blockIdx.x; tile < p.total_tiles && (dual || issuer == 0); tile += gridDim.x, ++ti) {
-      const uint32_t a = ti & 1u, aph = (ti >> 1) & 1u;
-      if (dual && a != issuer) {
+      // accumulator stage of this tile and the phase of its barriers (two stages; four with BD_UMMA_NACC=4 and N <= 128:
+      // an issuer that owns every other tile then alternates between two stages of its own)
+      const uint32_t a = ti & static_cast<uint32_t>(p.nacc - 1), aph = (ti >> p.nacc_sh) & 1u;
+      if (dual && (ti & 1u) != issuer) {
         // The other issuer's tile: step over its ring stages WITHOUT touching their barriers.  An mbarrier parity wait
         // is only sound when the waiter has seen the previous phase of that barrier complete, so the two issuers must
         // never share a stage: the host enables two issuers only when a tile is ONE stage and the ring has an EVEN
@@ -619,13 +622,14 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
       // chunk belongs to ONE group (group = tile parity = a), wider tiles to both; each (stage, group) barrier
       // completes one phase per tile on that stage, so the parity is the same for all of them.
       if (!te_ready) {
-        if (single_unit) mbar_wait(tempty0 + 16u * a + 8u * a, aph ^ 1u);
+        if (single_unit) mbar_wait(tempty0 + 16u * a + 8u * (ti & 1u), aph ^ 1u);
         else { mbar_wait(tempty0 + 16u * a, aph ^ 1u); mbar_wait(tempty0 + 16u * a + 8u, aph ^ 1u); }
       }
       tc_fence_after();
       const uint32_t tacc = tmem_base + a * static_cast<uint32_t>(p.block_n);
       // the NEXT tile's accumulator stage / phase, tested early during this tile's last k-block
-      const uint32_t te_bar = tempty0 + 16u * (a ^ 1u), te_par = (((ti + 1u) >> 1) & 1u) ^ 1u;
+      const uint32_t te_bar = tempty0 + 16u * ((ti + 1u) & static_cast<uint32_t>(p.nacc - 1)),
+                     te_par = (((ti + 1u) >> p.nacc_sh) & 1u) ^ 1u;
       if ((KSPEC == 5)) {
         for (int c = p.Cin; c > 0; c -= BLOCK_K, ++it4) {  // c = channels left; it4 = running chunk counter
           const uint32_t slot = it4 & 1u;
@@ -711,7 +715,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
               // most of this chunk's MMAs are queued: test what the next chunk / tile will wait for
               f_ready = ring_test_next_full(ring, p, full0);
               if (c <= BLOCK_K)
-                te_ready = single_unit ? mbar_test(te_bar + 8u * (a ^ 1u), te_par)
+                te_ready = single_unit ? mbar_test(te_bar + 8u * ((ti + 1u) & 1u), te_par)
                                        : (mbar_test(te_bar, te_par) & mbar_test(te_bar + 8u, te_par));
             }
             if (elect_one()) {
@@ -893,7 +897,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
     }
     uint32_t ti = 0, u = 0, rcount = 0;  // tiles done, units before this tile, residual tiles consumed
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti, u += nch) {
-      const uint32_t a = ti & 1u, aph = (ti >> 1) & 1u;
+      const uint32_t a = ti & static_cast<uint32_t>(p.nacc - 1), aph = (ti >> p.nacc_sh) & 1u;
       int nt, tw, th, tn;
       tile_coords(p, tile, nt, tw, th, tn);
       const int n_base = nt * p.block_n;
@@ -1113,8 +1117,16 @@ inline int prepare(Launch* L, const TView& x, const TView& y, const TView* res, 
   p.n_tiles = cdiv(Cout, p.block_n);
   p.kchunks = cdiv(Cin, BLOCK_K);
   p.ntaps = ntaps;
+  {
+    // Four accumulator stages (BD_UMMA_NACC=4) measured no different from two on every layer (profiles/r2v_*): the
+    // small-N tiles are bound by the ~70 clk a tcgen05.mma costs whatever its N (18 MMAs = 1270 clk per 32->32 tile,
+    // two issuers alternating), not by the accumulator hand-off.  Two stays the default.
+    static const int env_nacc = [] { const char* e = getenv("BD_UMMA_NACC"); return e ? atoi(e) : 2; }();
+    p.nacc = (env_nacc == 4 && 4 * p.block_n <= 512) ? 4 : 2;
+    p.nacc_sh = p.nacc == 4 ? 2 : 1;
+  }
   p.tmem_cols = 32;
-  while (p.tmem_cols < 2 * p.block_n) p.tmem_cols *= 2;
+  while (p.tmem_cols < p.nacc * p.block_n) p.tmem_cols *= 2;
   const int sub_bytes = A_STAGE_BYTES + p.block_n * 128;
   p.bias_bytes = (p.n_tiles * p.block_n * 4 + 127) / 128 * 128;
   // per-warp staging (+ residual) tiles, staged bias, alignment slack, barriers
