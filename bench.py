@@ -506,6 +506,10 @@ def main():
             "gpu_launches": int(launches),
             "cuda_graphs": all(m.native_plan(args.batch, device=local).uses_graph for m in models),
             "clocks": clocks,
+            "memory": {"plan_arenas_gib": sum(m.native_plan(args.batch, device=local).arena_bytes for m in models) / 2**30,
+                       "plan_arenas_without_reuse_gib":
+                           sum(m.native_plan(args.batch, device=local).arena_bytes_flat for m in models) / 2**30,
+                       "torch_peak_gib": torch.cuda.max_memory_allocated() / 2**30},
             "stages": stages,
             "roofline": roof,
             "roofline_post": post_roof,
