@@ -73,6 +73,14 @@ UMMA_CASES = {
     "3x3_64_64_split_weights_halo18": dict(N=2, H=32, W=32, Cin=64, Cout=64, split=True),
     "3x3_256_256_split_weights": dict(N=1, H=32, W=32, Cin=256, Cout=256, split=True),
     "1x1_64_256_split_weights": dict(N=1, H=32, W=32, Cin=64, Cout=256, k=1, split=True),
+    # halo path with streamed weights (conv_umma_kernel<5,1>): three taps per ring stage for N <= 128, one for wider
+    # tiles; ragged maps, a partial last channel chunk, residual, channel slices, several N tiles
+    "3x3_128_128_stream_ragged": dict(N=2, H=40, W=24, Cin=128, Cout=128),
+    "3x3_128_128_stream_res": dict(N=3, H=32, W=32, Cin=128, Cout=128, res=True, res_after_act=True),
+    "3x3_96_128_stream_partial_chunk": dict(N=2, H=32, W=16, Cin=96, Cout=128, in_slice=(64, 256)),
+    "3x3_256_128_stream_slices": dict(N=1, H=32, W=32, Cin=256, Cout=128, in_slice=(64, 384), out_slice=(128, 256)),
+    "3x3_128_320_stream_two_n_tiles": dict(N=2, H=16, W=24, Cin=128, Cout=320),
+    "3x3_512_256_stream_batch5": dict(N=5, H=16, W=8, Cin=512, Cout=256, res=True),
 }
 
 
