@@ -61,6 +61,7 @@ struct Params {
   int bw, bh, bn;
   int tiles_w, tiles_h, tiles_n, n_tiles, total_tiles;
   int block_n, kchunks, ntaps, stages, group, tmem_cols;  // group: k-blocks per shared-memory stage
+  int pair;           // spec 6: CTA pairs (cluster of 2): tile index t -> pair tile t >> 1, the CTA's M tile by t & 1
   int nacc, nacc_sh;  // TMEM accumulator stages (2, or 4 when four N tiles fit into the 512 columns) and log2 of it
   int dbg;      // debug switches (BD_UMMA_DBG): 1 = every thread waits for the previous grid before the role split, 2 = no early launch_dependents
   int halo_subset;  // spec 3 with a runtime tap list (kernel instance <3, 0>)
@@ -198,6 +199,49 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// ---- CTA pair (cta_group::2): two CTAs of a cluster on one TPC run ONE M = 256 MMA per instruction; each holds its own
+// 128 pixel rows of A and HALF of the weight tile, so a CTA pulls 16 KB less per k-block through L2.  The leader (rank
+// 0) issues the MMAs; both producers' TMA bytes complete on the LEADER's full barrier (address with the rank bit
+// cleared), the leader's commits arrive on both CTAs' barriers by multicast.
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;  // shared::cluster address of the same offset in the even (leader) CTA
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap* tm, uint32_t leader_bar, int c0, int c1,
+                                                int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap* tm, uint32_t leader_bar, int c0, int c1,
+                                                int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint32_t bar) {  // arrives on `bar` in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(static_cast<uint16_t>(3)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {  // remote arrive on the leader CTA's barrier
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & PEER_BIT_MASK) : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
@@ -245,8 +289,8 @@ __device__ __forceinline__ uint64_t make_sdesc_sbo(uint32_t saddr, uint32_t sbo_
 }
 // kind::f16 instruction descriptor: D=f32 (bit 4), A and B formats at [7,10) / [10,13) = 0 (fp16; 1 would be
 // bf16), both K-major, N>>3 at [17,23), M>>4 at [24,29)
-__device__ __forceinline__ uint32_t make_idesc(int n) {
-  return (1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(BLOCK_M >> 4) << 24);
+__device__ __forceinline__ uint32_t make_idesc(int n, int m = BLOCK_M) {
+  return (1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 
 // two fp32 -> packed fp16x2 (lo = first argument), round to nearest, saturating at +-65504 (one F2FP instruction)
@@ -269,7 +313,12 @@ struct alignas(64) Maps {
 __device__ __forceinline__ void tile_coords(const Params& p, int tile, int& nt, int& tw, int& th, int& tn) {
   const uint32_t t = static_cast<uint32_t>(tile);
   uint32_t mt;
-  if (p.m_fast) {
+  if (p.pair) {
+    // CTAs 2P and 2P+1 walk tiles t and t+1 (t even): the same N tile, adjacent pixel tiles
+    const uint32_t q = t >> 1, mp = fd_div(q, p.fd_nt);
+    nt = static_cast<int>(q - mp * p.n_tiles);
+    mt = 2u * mp + (t & 1u);
+  } else if (p.m_fast) {
     const uint32_t q = fd_div(t, p.fd_mt);
     nt = static_cast<int>(q);
     mt = t - q * p.m_total;
@@ -378,7 +427,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t b_bytes = static_cast<uint32_t>(p.block_n) * 128u;
+  constexpr bool PAIR = KSPEC == 6;
+  const uint32_t pair_rank = PAIR ? cluster_ctarank() : 0u;
+  const uint32_t b_bytes = static_cast<uint32_t>(PAIR ? p.block_n / 2 : p.block_n) * 128u;  // pair: half of the weight tile
   const uint32_t sub_bytes = A_STAGE_BYTES + b_bytes;                       // one k-block: A box + W tile
   const uint32_t stage_bytes = (KSPEC == 3) ? static_cast<uint32_t>(HALO_STAGE)
                                : (KSPEC == 5) ? b_bytes * static_cast<uint32_t>(p.group)   // `group` weight tiles (taps)
@@ -410,8 +461,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
     }
     for (int a = 0; a < 4; ++a) {
       mbar_init(tfull0 + 8u * a, 1);
-      mbar_init(tempty0 + 16u * a, EPI_WARPS / 2);       // one arrival per warp of epilogue group 0
-      mbar_init(tempty0 + 16u * a + 8u, EPI_WARPS / 2);  // ... of group 1
+      // one arrival per warp of epilogue group 0 / group 1 (pair: the warps of BOTH CTAs arrive on the leader's barrier)
+      mbar_init(tempty0 + 16u * a, (PAIR ? 2 : 1) * EPI_WARPS / 2);
+      mbar_init(tempty0 + 16u * a + 8u, (PAIR ? 2 : 1) * EPI_WARPS / 2);
     }
     for (int w = 0; w < EPI_WARPS; ++w) mbar_init(rbar0 + 8u * w, 1);
     mbar_init(wbar, 1);
@@ -419,12 +471,19 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
     fence_async_smem();
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(holder), "r"(p.tmem_cols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {  // the same warp of both CTAs allocates the pair's columns
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(holder), "r"(p.tmem_cols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(holder), "r"(p.tmem_cols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them remotely
   tc_fence_after();
   const uint32_t tmem_base = *holder_ptr;
   // Barrier set-up and TMEM allocation above overlap the previous kernel's tail.  Each role calls pdl_wait() itself,
@@ -528,9 +587,17 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
           if (sub == 0) mbar_wait(eb, ph ^ 1u);
           if (elect_one()) {
             trace_ev(p, 0, tr_i, tile, tap);
-            if (sub == 0) mbar_expect_tx(fb, stage_bytes);
-            tma_load_4d(a_s, tm, fb, c, cx, cy, n0);
-            tma_load_3d(a_s + A_STAGE_BYTES, &maps.b, fb, c, n_base, tap);
+            if (PAIR) {
+              // both CTAs' bytes (own pixel tile + own half of the weight tile) complete on the LEADER's full barrier
+              if (sub == 0 && pair_rank == 0) mbar_expect_tx(fb, 2u * stage_bytes);
+              tma_load_4d_2sm(a_s, tm, fb & PEER_BIT_MASK, c, cx, cy, n0);
+              tma_load_3d_2sm(a_s + A_STAGE_BYTES, &maps.b, fb & PEER_BIT_MASK, c,
+                              n_base + static_cast<int>(pair_rank) * (p.block_n / 2), tap);
+            } else {
+              if (sub == 0) mbar_expect_tx(fb, stage_bytes);
+              tma_load_4d(a_s, tm, fb, c, cx, cy, n0);
+              tma_load_3d(a_s + A_STAGE_BYTES, &maps.b, fb, c, n_base, tap);
+            }
             if (pf && tap == pf_tap) tma_prefetch_4d(tm, c, pw0 + p.tap_dx[tap], ph0 + p.tap_dy[tap], pn0);
           }
           __syncwarp();
@@ -552,7 +619,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
     const uint32_t issuer = warp == 1 ? 0u : 1u;
     const bool dual = p.issuers == 2;
     if (issuer == 1) tr_i = 1 << 20;  // (debug trace: issuer 0 only)
-    const uint32_t idesc = make_idesc(p.block_n);
+    const uint32_t idesc = PAIR ? make_idesc(p.block_n, 2 * BLOCK_M) : make_idesc(p.block_n);
     const uint64_t desc0 = make_sdesc(smem_base);
     const uint32_t dsub = sub_bytes >> 4;  // descriptor start-address field counts 16-byte units
     uint32_t s = 0, sub = 0, ph = 0, doff = 0, fb = full0, eb = empty0, ti = 0;
@@ -561,7 +628,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
     uint32_t it4 = 0;                    // spec 4: running k-block counter (A slot / parity)
     const bool single_unit = p.block_n <= OUT_CHUNK;  // one epilogue unit per tile
     const int num_kb_all = p.ntaps * p.kchunks;
-    for (int tile = blockIdx.x; tile < p.total_tiles && (dual || issuer == 0); tile += gridDim.x, ++ti) {
+    // (pair: the leader CTA issues for both; the peer's MMA warp only allocated its half of the tensor memory)
+    for (int tile = blockIdx.x; tile < p.total_tiles && (dual || issuer == 0) && !(PAIR && pair_rank != 0);
+         tile += gridDim.x, ++ti) {
       // accumulator stage of this tile and the phase of its barriers (two stages; four with BD_UMMA_NACC=4 and N <= 128:
       // an issuer that owns every other tile then alternates between two stages of its own)
       const uint32_t a = ti & static_cast<uint32_t>(p.nacc - 1), aph = (ti >> p.nacc_sh) & 1u;
@@ -754,11 +823,19 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
             trace_ev(p, 1, tr_i, tile, tap);
             const uint64_t adesc = desc0 + doff, bdesc = adesc + (A_STAGE_BYTES >> 4);
             // 16 fp16 = 32 bytes inside the swizzle atom per MMA: +2 in the (addr >> 4) field
-            tc_mma_f16(tacc, adesc, bdesc, idesc, accum);
-            if (c > 16) tc_mma_f16(tacc, adesc + 2u, bdesc + 2u, idesc, 1u);
-            if (c > 32) tc_mma_f16(tacc, adesc + 4u, bdesc + 4u, idesc, 1u);
-            if (c > 48) tc_mma_f16(tacc, adesc + 6u, bdesc + 6u, idesc, 1u);
-            if (sub + 1 == static_cast<uint32_t>(p.group)) tc_commit(eb);  // frees the stage once these MMAs have read it
+            if (PAIR) {
+              tc_mma_f16_2sm(tacc, adesc, bdesc, idesc, accum);
+              if (c > 16) tc_mma_f16_2sm(tacc, adesc + 2u, bdesc + 2u, idesc, 1u);
+              if (c > 32) tc_mma_f16_2sm(tacc, adesc + 4u, bdesc + 4u, idesc, 1u);
+              if (c > 48) tc_mma_f16_2sm(tacc, adesc + 6u, bdesc + 6u, idesc, 1u);
+              if (sub + 1 == static_cast<uint32_t>(p.group)) tc_commit_2sm(eb);  // frees the stage in both CTAs
+            } else {
+              tc_mma_f16(tacc, adesc, bdesc, idesc, accum);
+              if (c > 16) tc_mma_f16(tacc, adesc + 2u, bdesc + 2u, idesc, 1u);
+              if (c > 32) tc_mma_f16(tacc, adesc + 4u, bdesc + 4u, idesc, 1u);
+              if (c > 48) tc_mma_f16(tacc, adesc + 6u, bdesc + 6u, idesc, 1u);
+              if (sub + 1 == static_cast<uint32_t>(p.group)) tc_commit(eb);  // frees the stage once these MMAs have read it
+            }
           }
           __syncwarp();
           accum = 1u;
@@ -770,7 +847,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
           }
         }
       }
-      if (elect_one()) tc_commit(tfull0 + 8u * a);  // accumulator complete
+      if (elect_one()) {  // accumulator complete (pair: in both CTAs)
+        if (PAIR) tc_commit_2sm(tfull0 + 8u * a);
+        else tc_commit(tfull0 + 8u * a);
+      }
       __syncwarp();
     }
   } else if ((KSPEC == 4) && warp < 6) {
@@ -916,7 +996,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty);
+        if (lane == 0) { if (PAIR) mbar_arrive_leader(tempty); else mbar_arrive(tempty); }
         const int ow = tw * p.bw + wl, oh = th * p.bh + hl, on = tn * p.bn + nl;
         if ((ow < p.Wo) && (oh < p.Ho) && (on < p.N)) {
           const size_t ypix = (static_cast<size_t>(on) * p.y_H + (oh * p.out_scale + p.out_oy)) * p.y_W +
@@ -946,7 +1026,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
         if (ci == last) {  // the accumulator now lives in registers: hand the TMEM stage back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tempty);
+          if (lane == 0) { if (PAIR) mbar_arrive_leader(tempty); else mbar_arrive(tempty); }
         }
         // bias + activation in place (columns beyond cw hold garbage that the output map clips)
 #pragma unroll
@@ -1010,8 +1090,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
   if (p.dbg & 4) __nanosleep(5000);
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // no remote arrive / multicast may target a CTA that has left
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
   }
 }
 
@@ -1185,8 +1267,22 @@ inline int prepare(Launch* L, const TView& x, const TView& y, const TView* res, 
   } else
   if (group_hint == 0 && ntaps == 9 && p.kchunks == 1 && 2 * 3 * sub_bytes <= avail) { p.spec = 1; p.group = 3; }
   else if (group_hint == 0 && ntaps == 9 && p.kchunks == 2 && 2 * 2 * sub_bytes <= avail) { p.spec = 2; p.group = 2; }
+  {
+    // CTA pairs (BD_UMMA_PAIR=1) for the generic ring: 1x1 / dilated layers with N tiles of at least 128 columns and an
+    // even number of pixel tiles -- M = 256 MMAs issued by the even CTA of a 2-CTA cluster, each CTA loads its own pixel
+    // tile and half of the weight tile (the generic ring is bound by L2->SM traffic: 48 -> 32 KB per k-block)
+    // Measured per layer (profiles/r2z_op_table_b32_pair.txt): +8 ... +20 % on the compute-heavy layers (K = taps x Cin
+    // >= 512: 768->728 684 -> 750, dilated 2048->256 1173 -> 1418, 1536->2048 1274 -> 1459 TFLOP/s), -5 ... -10 % on
+    // the HBM-bound short-K 1x1 layers (128->128 @256^2), which therefore stay single.  BD_UMMA_PAIR=0 turns it off.
+    static const int env_pair = [] { const char* e = getenv("BD_UMMA_PAIR"); return e ? atoi(e) : 1; }();
+    const int m_total = p.tiles_w * p.tiles_h * p.tiles_n;
+    if (env_pair && p.spec == 0 && !dw_w_dev && stride == 1 && !y.f32 && p.block_n >= 128 && p.block_n % 32 == 0 &&
+        m_total % 2 == 0 && num_sms >= 2 && group_hint == 0 && ntaps * Cin >= 512) {
+      p.spec = 6; p.pair = 1;
+    }
+  }
   if (p.spec != 3 && p.spec != 4 && p.spec != 5) {
-    const int stage_bytes = sub_bytes * p.group;
+    const int stage_bytes = (p.pair ? A_STAGE_BYTES + p.block_n / 2 * 128 : sub_bytes) * p.group;
     p.stages = std::max(2, std::min(12, avail / stage_bytes));
     // the ring covers two tiles, and at least ~190 KB / 8 stages of loads in flight: the short-K 1x1 layers (the K = 32
     // stems: one 24 KB stage per tile) are bound by load latency, not by shared memory
@@ -1256,7 +1352,7 @@ inline int prepare(Launch* L, const TView& x, const TView& y, const TView* res, 
   {
     uint64_t dims[3] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(Cout), static_cast<uint64_t>(ntaps)};
     uint64_t strides[2] = {static_cast<uint64_t>(Cin) * 2, static_cast<uint64_t>(Cin) * Cout * 2};
-    uint32_t box[3] = {BLOCK_K, static_cast<uint32_t>(p.block_n), 1};
+    uint32_t box[3] = {BLOCK_K, static_cast<uint32_t>(p.pair ? p.block_n / 2 : p.block_n), 1};  // pair: half a tile per CTA
     if (encode_h16(&L->maps.b, const_cast<h16*>(w_dev), 3, dims, strides, box)) return 1;
   }
   // an epilogue warp stores (and fetches residuals for) its TMEM lane quadrant: 32 consecutive tile rows =
@@ -1302,6 +1398,7 @@ inline int prepare(Launch* L, const TView& x, const TView& y, const TView* res, 
   p.bias = bias_dev; p.act_pre = act_pre; p.act_post = act_post;
   p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
   L->grid = dim3(static_cast<unsigned>(std::min(p.total_tiles, num_sms)));
+  if (p.pair) L->grid = dim3(L->grid.x & ~1u);  // whole clusters of two (total_tiles is even)
   return 0;
 }
 
@@ -1318,12 +1415,25 @@ inline int launch(const Launch& L, cudaStream_t stream, bool pdl = false) {
     BD_CUDA(cudaFuncSetAttribute(conv_umma_kernel<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     BD_CUDA(cudaFuncSetAttribute(conv_umma_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     BD_CUDA(cudaFuncSetAttribute(conv_umma_kernel<5, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    BD_CUDA(cudaFuncSetAttribute(conv_umma_kernel<6, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   void (*kern)(Maps, Params) = conv_umma_kernel<0, 1>;
   if (L.p.spec == 3) kern = L.p.halo_subset ? conv_umma_kernel<3, 0> : L.p.ntaps == 18 ? conv_umma_kernel<3, 2> : conv_umma_kernel<3, 1>;
   else if (L.p.spec == 4) kern = conv_umma_kernel<4, 1>;
   else if (L.p.spec == 5) kern = conv_umma_kernel<5, 1>;
+  if (L.p.spec == 6) {  // CTA pairs: clusters of two
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = L.grid; cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = static_cast<size_t>(L.smem_bytes); cfg.stream = stream;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 2 : 1;
+    BD_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<6, 1>, L.maps, L.p));
+    return 0;
+  }
   BD_CUDA(launch_k(pdl, kern, L.grid, dim3(THREADS), static_cast<size_t>(L.smem_bytes), stream, L.maps, L.p));
   return 0;
 }
