@@ -427,12 +427,13 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr bool PAIR = KSPEC == 6;
+  constexpr bool PAIR = KSPEC == 6 || KSPEC == 7;    // CTA pairs: generic ring (6), streamed-weight halo path (7)
+  constexpr bool HSTREAM = KSPEC == 5 || KSPEC == 7; // halo path with streamed weights
   const uint32_t pair_rank = PAIR ? cluster_ctarank() : 0u;
   const uint32_t b_bytes = static_cast<uint32_t>(PAIR ? p.block_n / 2 : p.block_n) * 128u;  // pair: half of the weight tile
   const uint32_t sub_bytes = A_STAGE_BYTES + b_bytes;                       // one k-block: A box + W tile
   const uint32_t stage_bytes = (KSPEC == 3) ? static_cast<uint32_t>(HALO_STAGE)
-                               : (KSPEC == 5) ? b_bytes * static_cast<uint32_t>(p.group)   // `group` weight tiles (taps)
+                               : HSTREAM ? b_bytes * static_cast<uint32_t>(p.group)   // `group` weight tiles (taps)
                                : (KSPEC == 4) ? static_cast<uint32_t>(HALO_STAGE) + b_bytes  // halo box + pointwise W tile
                                              : sub_bytes * static_cast<uint32_t>(p.group);  // a stage holds `group` k-blocks
   const uint32_t wres0 = smem_base + static_cast<uint32_t>(p.stages) * stage_bytes;      // resident weights (spec 3)
@@ -456,7 +457,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
       mbar_init(empty0 + 8u * s, (KSPEC == 4) ? 5 : 1);  // spec 4: four depthwise warps + the MMA commit free a stage
     }
     for (int a = 0; a < 2; ++a) {
-      mbar_init(afull0 + 8u * a, (KSPEC == 5) ? 1 : 4);   // one arrival per depthwise warp (spec 5: the producer's expect_tx)
+      mbar_init(afull0 + 8u * a, HSTREAM ? 1 : 4);   // one arrival per depthwise warp (spec 5: the producer's expect_tx)
       mbar_init(aempty0 + 8u * a, 1);  // MMA commit
     }
     for (int a = 0; a < 4; ++a) {
@@ -535,7 +536,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
         }
         continue;
       }
-      if ((KSPEC == 5)) {
+      if (HSTREAM) {
         // halo path with STREAMED weights (3x3 layers whose weights do not fit into shared memory): per 64-channel
         // chunk one halo box into one of two slots (it feeds all nine taps), then the nine weight tiles through the
         // ring, `group` taps per stage
@@ -544,17 +545,29 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
           mbar_wait(aempty0 + 8u * slot, ((hcount >> 1) & 1u) ^ 1u);
           if (elect_one()) {
             trace_ev(p, 0, tr_i, tile, c);
-            mbar_expect_tx(afull0 + 8u * slot, HALO_BYTES);
-            tma_load_4d(wres0 + slot * HALO_STAGE, &maps.a[0], afull0 + 8u * slot, c, w0 - 1, h0 - 1, n0);
+            if (PAIR) {  // both halo boxes complete on the leader's barrier
+              if (pair_rank == 0) mbar_expect_tx(afull0 + 8u * slot, 2u * HALO_BYTES);
+              tma_load_4d_2sm(wres0 + slot * HALO_STAGE, &maps.a[0], (afull0 + 8u * slot) & PEER_BIT_MASK, c, w0 - 1, h0 - 1, n0);
+            } else {
+              mbar_expect_tx(afull0 + 8u * slot, HALO_BYTES);
+              tma_load_4d(wres0 + slot * HALO_STAGE, &maps.a[0], afull0 + 8u * slot, c, w0 - 1, h0 - 1, n0);
+            }
             if (pf) tma_prefetch_4d(&maps.a[0], c, pw0 - 1, ph0 - 1, pn0);
           }
           __syncwarp();
           for (int t0 = 0; t0 < 9; t0 += p.group) {
             mbar_wait(ring.eb, ring.ph ^ 1u);
             if (elect_one()) {
-              mbar_expect_tx(ring.fb, stage_bytes);
-              for (int g = 0; g < p.group; ++g)
-                tma_load_3d(smem_base + ring.off + g * b_bytes, &maps.b, ring.fb, c, n_base, t0 + g);
+              if (PAIR) {  // each CTA streams its half of every weight tile
+                if (pair_rank == 0) mbar_expect_tx(ring.fb, 2u * stage_bytes);
+                for (int g = 0; g < p.group; ++g)
+                  tma_load_3d_2sm(smem_base + ring.off + g * b_bytes, &maps.b, ring.fb & PEER_BIT_MASK, c,
+                                  n_base + static_cast<int>(pair_rank) * (p.block_n / 2), t0 + g);
+              } else {
+                mbar_expect_tx(ring.fb, stage_bytes);
+                for (int g = 0; g < p.group; ++g)
+                  tma_load_3d(smem_base + ring.off + g * b_bytes, &maps.b, ring.fb, c, n_base, t0 + g);
+              }
             }
             __syncwarp();
             ring_advance(ring, p, stage_bytes, full0, empty0);
@@ -699,7 +712,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
       // the NEXT tile's accumulator stage / phase, tested early during this tile's last k-block
       const uint32_t te_bar = tempty0 + 16u * ((ti + 1u) & static_cast<uint32_t>(p.nacc - 1)),
                      te_par = (((ti + 1u) >> p.nacc_sh) & 1u) ^ 1u;
-      if ((KSPEC == 5)) {
+      if (HSTREAM) {
         for (int c = p.Cin; c > 0; c -= BLOCK_K, ++it4) {  // c = channels left; it4 = running chunk counter
           const uint32_t slot = it4 & 1u;
           mbar_wait(afull0 + 8u * slot, (it4 >> 1) & 1u);  // halo box of this chunk
@@ -714,15 +727,30 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
                 const int tap = t0 + g;
                 const uint64_t adesc = hdesc + static_cast<uint32_t>(((tap / 3) * HALO_W + tap % 3) * 8);
                 const uint64_t bd = bdesc0 + static_cast<uint32_t>(g) * (b_bytes >> 4);
-                tc_mma_f16(tacc, adesc, bd, idesc, (tap > 0 || c < p.Cin) ? 1u : 0u);
-                if (c > 16) tc_mma_f16(tacc, adesc + 2u, bd + 2u, idesc, 1u);
-                if (c > 32) tc_mma_f16(tacc, adesc + 4u, bd + 4u, idesc, 1u);
-                if (c > 48) tc_mma_f16(tacc, adesc + 6u, bd + 6u, idesc, 1u);
+                if (PAIR) {
+                  tc_mma_f16_2sm(tacc, adesc, bd, idesc, (tap > 0 || c < p.Cin) ? 1u : 0u);
+                  if (c > 16) tc_mma_f16_2sm(tacc, adesc + 2u, bd + 2u, idesc, 1u);
+                  if (c > 32) tc_mma_f16_2sm(tacc, adesc + 4u, bd + 4u, idesc, 1u);
+                  if (c > 48) tc_mma_f16_2sm(tacc, adesc + 6u, bd + 6u, idesc, 1u);
+                } else {
+                  tc_mma_f16(tacc, adesc, bd, idesc, (tap > 0 || c < p.Cin) ? 1u : 0u);
+                  if (c > 16) tc_mma_f16(tacc, adesc + 2u, bd + 2u, idesc, 1u);
+                  if (c > 32) tc_mma_f16(tacc, adesc + 4u, bd + 4u, idesc, 1u);
+                  if (c > 48) tc_mma_f16(tacc, adesc + 6u, bd + 6u, idesc, 1u);
+                }
               }
-              tc_commit(ring.eb);                                   // weight stage free once these MMAs have read it
-              if (t0 + p.group >= 9) {
-                tc_commit(aempty0 + 8u * slot);                     // ... and the halo slot after the ninth tap
-                if (c <= BLOCK_K) tc_commit(tfull0 + 8u * a);       // accumulator complete
+              if (PAIR) {  // multicast: the stage / slot / accumulator barriers of BOTH CTAs
+                tc_commit_2sm(ring.eb);
+                if (t0 + p.group >= 9) {
+                  tc_commit_2sm(aempty0 + 8u * slot);
+                  if (c <= BLOCK_K) tc_commit_2sm(tfull0 + 8u * a);
+                }
+              } else {
+                tc_commit(ring.eb);                                   // weight stage free once these MMAs have read it
+                if (t0 + p.group >= 9) {
+                  tc_commit(aempty0 + 8u * slot);                     // ... and the halo slot after the ninth tap
+                  if (c <= BLOCK_K) tc_commit(tfull0 + 8u * a);       // accumulator complete
+                }
               }
             }
             __syncwarp();
@@ -1261,7 +1289,14 @@ inline int prepare(Launch* L, const TView& x, const TView& y, const TView* res, 
     p.wres_bytes = 2 * HALO_STAGE;
     p.bw = 8; p.bh = 16; p.bn = 1;
     p.tiles_w = cdiv(Wo, p.bw); p.tiles_h = cdiv(Ho, p.bh); p.tiles_n = x.N;
-    const int stage5 = p.group * p.block_n * 128;
+    {  // CTA pairs (BD_UMMA_PAIR_HALO=0: off): each CTA its own halo box and half of every weight tile
+      static const int env_pair5 = [] { const char* e = getenv("BD_UMMA_PAIR_HALO"); return e ? atoi(e) : 1; }();
+      if (env_pair5 && !y.f32 && p.block_n >= 128 && p.block_n % 32 == 0 && (p.tiles_w * p.tiles_h * p.tiles_n) % 2 == 0 &&
+          num_sms >= 2) {
+        p.spec = 7; p.pair = 1;
+      }
+    }
+    const int stage5 = p.group * (p.pair ? p.block_n / 2 : p.block_n) * 128;
     p.stages = std::max(2, std::min(12, (avail - p.wres_bytes) / stage5));
     L->smem_bytes = p.stages * stage5 + p.wres_bytes + fixed;
   } else
@@ -1281,7 +1316,7 @@ inline int prepare(Launch* L, const TView& x, const TView& y, const TView* res, 
       p.spec = 6; p.pair = 1;
     }
   }
-  if (p.spec != 3 && p.spec != 4 && p.spec != 5) {
+  if (p.spec != 3 && p.spec != 4 && p.spec != 5 && p.spec != 7) {
     const int stage_bytes = (p.pair ? A_STAGE_BYTES + p.block_n / 2 * 128 : sub_bytes) * p.group;
     p.stages = std::max(2, std::min(12, avail / stage_bytes));
     // the ring covers two tiles, and at least ~190 KB / 8 stages of loads in flight: the short-K 1x1 layers (the K = 32
@@ -1342,7 +1377,7 @@ inline int prepare(Launch* L, const TView& x, const TView& y, const TView* res, 
                         static_cast<uint64_t>((x.H - py + stride - 1) / stride), static_cast<uint64_t>(x.N)};
     uint64_t strides[3] = {pitch * stride, pitch * x.W * stride, pitch * x.W * x.H};
     uint32_t box[4] = {BLOCK_K, static_cast<uint32_t>(p.bw), static_cast<uint32_t>(p.bh), static_cast<uint32_t>(p.bn)};
-    if (p.spec == 3 || p.spec == 4 || p.spec == 5) { box[1] = HALO_W; box[2] = HALO_H; box[3] = 1; }
+    if (p.spec == 3 || p.spec == 4 || p.spec == 5 || p.spec == 7) { box[1] = HALO_W; box[2] = HALO_H; box[3] = 1; }
     char* base = static_cast<char*>(x.base) + (static_cast<size_t>(py) * x.W + px) * pitch + static_cast<size_t>(x.c0) * 2;
     if (encode_h16(&L->maps.a[m], base, 4, dims, strides, box)) return 1;
     if (first < 0) first = m;
@@ -1416,13 +1451,14 @@ inline int launch(const Launch& L, cudaStream_t stream, bool pdl = false) {
     BD_CUDA(cudaFuncSetAttribute(conv_umma_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     BD_CUDA(cudaFuncSetAttribute(conv_umma_kernel<5, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     BD_CUDA(cudaFuncSetAttribute(conv_umma_kernel<6, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    BD_CUDA(cudaFuncSetAttribute(conv_umma_kernel<7, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   void (*kern)(Maps, Params) = conv_umma_kernel<0, 1>;
   if (L.p.spec == 3) kern = L.p.halo_subset ? conv_umma_kernel<3, 0> : L.p.ntaps == 18 ? conv_umma_kernel<3, 2> : conv_umma_kernel<3, 1>;
   else if (L.p.spec == 4) kern = conv_umma_kernel<4, 1>;
   else if (L.p.spec == 5) kern = conv_umma_kernel<5, 1>;
-  if (L.p.spec == 6) {  // CTA pairs: clusters of two
+  if (L.p.spec == 6 || L.p.spec == 7) {  // CTA pairs: clusters of two
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = L.grid; cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = static_cast<size_t>(L.smem_bytes); cfg.stream = stream;
     cudaLaunchAttribute at[2];
@@ -1431,7 +1467,8 @@ inline int launch(const Launch& L, cudaStream_t stream, bool pdl = false) {
     at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = pdl ? 2 : 1;
-    BD_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<6, 1>, L.maps, L.p));
+    if (L.p.spec == 6) BD_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<6, 1>, L.maps, L.p));
+    else BD_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<7, 1>, L.maps, L.p));
     return 0;
   }
   BD_CUDA(launch_k(pdl, kern, L.grid, dim3(THREADS), static_cast<size_t>(L.smem_bytes), stream, L.maps, L.p));
