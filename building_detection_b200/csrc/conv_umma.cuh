@@ -427,12 +427,22 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr bool PAIR = KSPEC == 6 || KSPEC == 7;    // CTA pairs: generic ring (6), streamed-weight halo path (7)
+  constexpr bool PAIR = KSPEC == 6 || KSPEC == 7 || KSPEC == 8;  // CTA pairs: generic ring (6), streamed-weight halo path (7),
+                                                                 // resident-weight halo path (8)
   constexpr bool HSTREAM = KSPEC == 5 || KSPEC == 7; // halo path with streamed weights
+  constexpr bool HALO3 = KSPEC == 3 || KSPEC == 8;   // halo path with resident weights
+  auto mma = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t id, uint32_t acc) {
+    if (PAIR) tc_mma_f16_2sm(d, ad, bd, id, acc);
+    else tc_mma_f16(d, ad, bd, id, acc);
+  };
+  auto commit = [&](uint32_t bar) {  // pair: arrives on the barrier at this offset in BOTH CTAs
+    if (PAIR) tc_commit_2sm(bar);
+    else tc_commit(bar);
+  };
   const uint32_t pair_rank = PAIR ? cluster_ctarank() : 0u;
   const uint32_t b_bytes = static_cast<uint32_t>(PAIR ? p.block_n / 2 : p.block_n) * 128u;  // pair: half of the weight tile
   const uint32_t sub_bytes = A_STAGE_BYTES + b_bytes;                       // one k-block: A box + W tile
-  const uint32_t stage_bytes = (KSPEC == 3) ? static_cast<uint32_t>(HALO_STAGE)
+  const uint32_t stage_bytes = HALO3 ? static_cast<uint32_t>(HALO_STAGE)
                                : HSTREAM ? b_bytes * static_cast<uint32_t>(p.group)   // `group` weight tiles (taps)
                                : (KSPEC == 4) ? static_cast<uint32_t>(HALO_STAGE) + b_bytes  // halo box + pointwise W tile
                                              : sub_bytes * static_cast<uint32_t>(p.group);  // a stage holds `group` k-blocks
@@ -502,11 +512,18 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
     const char* maps_a = reinterpret_cast<const char*>(&maps.a[0]);
     Ring ring{0u, 0u, 0u, full0, empty0};
     uint32_t hcount = 0;  // spec 5: running chunk counter (halo slot / parity)
-    if ((KSPEC == 3) && elect_one()) {  // all weight tiles once: [chunk][tap] blocks of block_n x 128 B
-      mbar_expect_tx(wbar, static_cast<uint32_t>(p.wres_bytes));
+    if (HALO3 && elect_one()) {  // all weight tiles once: [chunk][tap] blocks of block_n x 128 B
       uint32_t dst = wres0;
-      for (int c = 0; c < p.Cin; c += BLOCK_K)
-        for (int tap = 0; tap < p.ntaps; ++tap, dst += b_bytes) tma_load_3d(dst, &maps.b, wbar, c, 0, tap);
+      if (PAIR) {  // each CTA keeps its half of the columns; both halves complete on the leader's barrier
+        if (pair_rank == 0) mbar_expect_tx(wbar, 2u * static_cast<uint32_t>(p.wres_bytes));
+        for (int c = 0; c < p.Cin; c += BLOCK_K)
+          for (int tap = 0; tap < p.ntaps; ++tap, dst += b_bytes)
+            tma_load_3d_2sm(dst, &maps.b, wbar & PEER_BIT_MASK, c, static_cast<int>(pair_rank) * (p.block_n / 2), tap);
+      } else {
+        mbar_expect_tx(wbar, static_cast<uint32_t>(p.wres_bytes));
+        for (int c = 0; c < p.Cin; c += BLOCK_K)
+          for (int tap = 0; tap < p.ntaps; ++tap, dst += b_bytes) tma_load_3d(dst, &maps.b, wbar, c, 0, tap);
+      }
     }
     __syncwarp();
     pdl_wait();  // activations of the previous kernel from here on
@@ -522,13 +539,18 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
         tile_coords(p, tile + gridDim.x, nt2, tw2, th2, tn2);
         pw0 = tw2 * p.bw; ph0 = th2 * p.bh; pn0 = tn2 * p.bn;
       }
-      if ((KSPEC == 3)) {  // one halo box per 64-channel chunk
+      if (HALO3) {  // one halo box per 64-channel chunk
         for (int c = 0; c < p.Cin; c += BLOCK_K) {
           mbar_wait(ring.eb, ring.ph ^ 1u);
           if (elect_one()) {
             trace_ev(p, 0, tr_i, tile, c);
-            mbar_expect_tx(ring.fb, HALO_BYTES);
-            tma_load_4d(smem_base + ring.off, &maps.a[0], ring.fb, c, w0 - 1, h0 - 1, n0);
+            if (PAIR) {
+              if (pair_rank == 0) mbar_expect_tx(ring.fb, 2u * HALO_BYTES);
+              tma_load_4d_2sm(smem_base + ring.off, &maps.a[0], ring.fb & PEER_BIT_MASK, c, w0 - 1, h0 - 1, n0);
+            } else {
+              mbar_expect_tx(ring.fb, HALO_BYTES);
+              tma_load_4d(smem_base + ring.off, &maps.a[0], ring.fb, c, w0 - 1, h0 - 1, n0);
+            }
             if (pf) tma_prefetch_4d(&maps.a[0], c, pw0 - 1, ph0 - 1, pn0);
           }
           __syncwarp();
@@ -656,7 +678,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
         // the issuers, an issuer that ran ahead could read "parity k done" from phase k-2 while the other's data was
         // still landing -- the intermittent launch failures.  Making the skipping issuer wait on the skipped full
         // barriers instead deadlocks when it falls a whole ring behind: tried, times out at batch 32.)
-        if ((KSPEC == 3)) {
+        if (HALO3) {
           for (int c = 0; c < p.kchunks; ++c) ring_advance(ring, p, HALO_STAGE, full0, empty0);
         } else if (KSPEC == 0 && p.spec == 1) {
           for (int g2 = 0; g2 < 3; ++g2) ring_advance(ring, p, sub_bytes * 3, full0, empty0);
@@ -762,7 +784,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
         te_ready = 0u;
         continue;
       }
-      if ((KSPEC == 3)) {
+      if (HALO3) {
         if (ti < 2) mbar_wait(wbar, 0);  // (each issuer before its first tile; completes once, parity 0)
         const uint32_t dkb = b_bytes >> 4;   // descriptor units per weight tile
         uint64_t bdesc = make_sdesc(wres0);  // weights are laid out [chunk][tap]: a running descriptor
@@ -778,13 +800,13 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
               for (int t = 0; t < p.ntaps; ++t) {
                 const uint64_t adesc = hdesc + static_cast<uint32_t>(((p.tap_dy[t] + 1) * HALO_W + p.tap_dx[t] + 1) * 8);
                 const uint64_t bd = bdesc + static_cast<uint32_t>(t) * dkb;
-                tc_mma_f16(tacc, adesc, bd, idesc, (t > 0 || c < p.Cin) ? 1u : 0u);
-                if (c > 16) tc_mma_f16(tacc, adesc + 2u, bd + 2u, idesc, 1u);
-                if (c > 32) tc_mma_f16(tacc, adesc + 4u, bd + 4u, idesc, 1u);
-                if (c > 48) tc_mma_f16(tacc, adesc + 6u, bd + 6u, idesc, 1u);
+                mma(tacc, adesc, bd, idesc, (t > 0 || c < p.Cin) ? 1u : 0u);
+                if (c > 16) mma(tacc, adesc + 2u, bd + 2u, idesc, 1u);
+                if (c > 32) mma(tacc, adesc + 4u, bd + 4u, idesc, 1u);
+                if (c > 48) mma(tacc, adesc + 6u, bd + 6u, idesc, 1u);
               }
-              tc_commit(ring.eb);
-              if (c <= BLOCK_K) tc_commit(tfull0 + 8u * a);
+              commit(ring.eb);
+              if (c <= BLOCK_K) commit(tfull0 + 8u * a);
               trace_ev(p, 1, tr_i, tile, -1);
             }
             __syncwarp();
@@ -801,10 +823,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
                 // tap (kh, kw) reads the halo rows shifted by kh halo rows and kw pixels
                 const uint64_t adesc = hdesc + (((tap / 3) * HALO_W + tap % 3) * 128 >> 4);
                 const uint64_t bd = bdesc + static_cast<uint32_t>(tap) * dkb;
-                tc_mma_f16(tacc, adesc, bd, idesc, (tap > 0 || rep > 0 || c < p.Cin) ? 1u : 0u);
-                if (c > 16) tc_mma_f16(tacc, adesc + 2u, bd + 2u, idesc, 1u);
-                if (c > 32) tc_mma_f16(tacc, adesc + 4u, bd + 4u, idesc, 1u);
-                if (c > 48) tc_mma_f16(tacc, adesc + 6u, bd + 6u, idesc, 1u);
+                mma(tacc, adesc, bd, idesc, (tap > 0 || rep > 0 || c < p.Cin) ? 1u : 0u);
+                if (c > 16) mma(tacc, adesc + 2u, bd + 2u, idesc, 1u);
+                if (c > 32) mma(tacc, adesc + 4u, bd + 4u, idesc, 1u);
+                if (c > 48) mma(tacc, adesc + 6u, bd + 6u, idesc, 1u);
               }
             }
             __syncwarp();
@@ -820,14 +842,14 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
               for (int tap = 6; tap < 9; ++tap) {
                 const uint64_t adesc = hdesc + (((tap / 3) * HALO_W + tap % 3) * 128 >> 4);
                 const uint64_t bd = bdesc + static_cast<uint32_t>(tap) * dkb;
-                tc_mma_f16(tacc, adesc, bd, idesc, 1u);
-                if (c > 16) tc_mma_f16(tacc, adesc + 2u, bd + 2u, idesc, 1u);
-                if (c > 32) tc_mma_f16(tacc, adesc + 4u, bd + 4u, idesc, 1u);
-                if (c > 48) tc_mma_f16(tacc, adesc + 6u, bd + 6u, idesc, 1u);
+                mma(tacc, adesc, bd, idesc, 1u);
+                if (c > 16) mma(tacc, adesc + 2u, bd + 2u, idesc, 1u);
+                if (c > 32) mma(tacc, adesc + 4u, bd + 4u, idesc, 1u);
+                if (c > 48) mma(tacc, adesc + 6u, bd + 6u, idesc, 1u);
               }
               if (last_rep) {
-                tc_commit(ring.eb);
-                if (c <= BLOCK_K) tc_commit(tfull0 + 8u * a);
+                commit(ring.eb);
+                if (c <= BLOCK_K) commit(tfull0 + 8u * a);
                 trace_ev(p, 1, tr_i, tile, -1);
               }
             }
@@ -1277,8 +1299,16 @@ inline int prepare(Launch* L, const TView& x, const TView& y, const TView* res, 
     p.spec = 3; p.group = 1; p.wres_bytes = wbytes;
     p.bw = 8; p.bh = 16; p.bn = 1;
     p.tiles_w = cdiv(Wo, p.bw); p.tiles_h = cdiv(Ho, p.bh); p.tiles_n = x.N;
-    p.stages = std::max(2, std::min(12, (avail - wbytes) / HALO_STAGE));
-    L->smem_bytes = p.stages * HALO_STAGE + wbytes + fixed;
+    {  // CTA pairs (BD_UMMA_PAIR_RES=0: off): each CTA keeps half of the columns of the resident weights.  Measured at
+       // batch 32: 64->64 @512^2 915 -> 1188, 128->64 @512^2 1012 -> 1219, 32->32 @256^2 366 -> 388 TFLOP/s
+      static const int env_pair3 = [] { const char* e = getenv("BD_UMMA_PAIR_RES"); return e ? atoi(e) : 1; }();
+      if (env_pair3 && full3x3 && ntaps == 9 && !y.f32 && p.block_n >= 32 && p.block_n % 32 == 0 &&
+          (p.tiles_w * p.tiles_h * p.tiles_n) % 2 == 0 && num_sms >= 2) {
+        p.spec = 8; p.pair = 1; p.wres_bytes = wbytes / 2;
+      }
+    }
+    p.stages = std::max(2, std::min(12, (avail - p.wres_bytes) / HALO_STAGE));
+    L->smem_bytes = p.stages * HALO_STAGE + p.wres_bytes + fixed;
   } else
   if (halo && full3x3 && ntaps == 9 && halo_stream_mode(p.block_n) &&
       2 * HALO_STAGE + 2 * (p.block_n <= 128 ? 3 : 1) * p.block_n * 128 <= avail) {
@@ -1316,7 +1346,7 @@ inline int prepare(Launch* L, const TView& x, const TView& y, const TView* res, 
       p.spec = 6; p.pair = 1;
     }
   }
-  if (p.spec != 3 && p.spec != 4 && p.spec != 5 && p.spec != 7) {
+  if (p.spec != 3 && p.spec != 4 && p.spec != 5 && p.spec != 7 && p.spec != 8) {
     const int stage_bytes = (p.pair ? A_STAGE_BYTES + p.block_n / 2 * 128 : sub_bytes) * p.group;
     p.stages = std::max(2, std::min(12, avail / stage_bytes));
     // the ring covers two tiles, and at least ~190 KB / 8 stages of loads in flight: the short-K 1x1 layers (the K = 32
@@ -1340,14 +1370,15 @@ inline int prepare(Launch* L, const TView& x, const TView& y, const TView* res, 
     // two issuers -> mbarrier parity aliasing, see the issuer loop); with the even-ring rule below the scheme ran
     // tools/stress2.py clean at batch 16 and 32 (result digests + the per-op timing path).  BD_UMMA_ISSUERS=1: one.
     static const int env_issuers = [] { const char* e = getenv("BD_UMMA_ISSUERS"); return e ? atoi(e) : 2; }();
-    const int stages_per_tile = p.spec == 3 ? p.kchunks : num_kb / p.group;
+    const bool halo3 = p.spec == 3 || p.spec == 8;
+    const int stages_per_tile = halo3 ? p.kchunks : num_kb / p.group;
     // Only on the halo path: there one elected lane issues a whole tile (36 MMAs + both commits) in one go.  On the
     // grouped generic ring (several elect blocks per stage) two issuers showed an intermittent hang on B200 that
     // is not understood yet, so those layers keep the single issuer.
     // ... and there only for the configuration that has been stress-tested: the full 3x3 with one 64-channel chunk
     // per tile (the 64->64 and 32->32 layers, which are the ones that gain).  With the tap-subset variant (two
     // chunks per tile) the two-issuer scheme faulted under tools/stress.py; single-issuer it is clean.
-    p.issuers = (p.spec != 3 || p.halo_subset || p.kchunks != 1 || ntaps != 9 || env_issuers != 2 ||
+    p.issuers = (!halo3 || p.halo_subset || p.kchunks != 1 || ntaps != 9 || env_issuers != 2 ||
                  stages_per_tile >= p.stages) ? 1 : 2;
     if (p.issuers == 2 && (p.stages & 1)) {
       // one stage per tile and an even ring: each issuer owns every other stage (see the issuer loop)
@@ -1377,7 +1408,7 @@ inline int prepare(Launch* L, const TView& x, const TView& y, const TView* res, 
                         static_cast<uint64_t>((x.H - py + stride - 1) / stride), static_cast<uint64_t>(x.N)};
     uint64_t strides[3] = {pitch * stride, pitch * x.W * stride, pitch * x.W * x.H};
     uint32_t box[4] = {BLOCK_K, static_cast<uint32_t>(p.bw), static_cast<uint32_t>(p.bh), static_cast<uint32_t>(p.bn)};
-    if (p.spec == 3 || p.spec == 4 || p.spec == 5 || p.spec == 7) { box[1] = HALO_W; box[2] = HALO_H; box[3] = 1; }
+    if (p.spec == 3 || p.spec == 4 || p.spec == 5 || p.spec == 7 || p.spec == 8) { box[1] = HALO_W; box[2] = HALO_H; box[3] = 1; }
     char* base = static_cast<char*>(x.base) + (static_cast<size_t>(py) * x.W + px) * pitch + static_cast<size_t>(x.c0) * 2;
     if (encode_h16(&L->maps.a[m], base, 4, dims, strides, box)) return 1;
     if (first < 0) first = m;
@@ -1452,13 +1483,14 @@ inline int launch(const Launch& L, cudaStream_t stream, bool pdl = false) {
     BD_CUDA(cudaFuncSetAttribute(conv_umma_kernel<5, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     BD_CUDA(cudaFuncSetAttribute(conv_umma_kernel<6, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     BD_CUDA(cudaFuncSetAttribute(conv_umma_kernel<7, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    BD_CUDA(cudaFuncSetAttribute(conv_umma_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   void (*kern)(Maps, Params) = conv_umma_kernel<0, 1>;
   if (L.p.spec == 3) kern = L.p.halo_subset ? conv_umma_kernel<3, 0> : L.p.ntaps == 18 ? conv_umma_kernel<3, 2> : conv_umma_kernel<3, 1>;
   else if (L.p.spec == 4) kern = conv_umma_kernel<4, 1>;
   else if (L.p.spec == 5) kern = conv_umma_kernel<5, 1>;
-  if (L.p.spec == 6 || L.p.spec == 7) {  // CTA pairs: clusters of two
+  if (L.p.spec == 6 || L.p.spec == 7 || L.p.spec == 8) {  // CTA pairs: clusters of two
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = L.grid; cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = static_cast<size_t>(L.smem_bytes); cfg.stream = stream;
     cudaLaunchAttribute at[2];
@@ -1468,7 +1500,8 @@ inline int launch(const Launch& L, cudaStream_t stream, bool pdl = false) {
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = pdl ? 2 : 1;
     if (L.p.spec == 6) BD_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<6, 1>, L.maps, L.p));
-    else BD_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<7, 1>, L.maps, L.p));
+    else if (L.p.spec == 7) BD_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<7, 1>, L.maps, L.p));
+    else BD_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<8, 1>, L.maps, L.p));
     return 0;
   }
   BD_CUDA(launch_k(pdl, kern, L.grid, dim3(THREADS), static_cast<size_t>(L.smem_bytes), stream, L.maps, L.p));
