@@ -8,13 +8,16 @@
 // padding (and the channel padding when Cin is not a multiple of 64).  Stride-2 convolutions use up to four
 // parity views of the input (one tensor map per (row parity, column parity)), each again a plain tiled map.
 //
-// Persistent kernel, one CTA per SM, 352 threads, warp-specialised (four template instances: generic ring, halo
-// path, halo path with a tap subset / split weights, fused separable convolution):
+// Persistent kernel, one CTA per SM, 352 threads, warp-specialised.  Template instances: <0,1> generic ring, <3,1> halo
+// path with resident weights (<3,2> split weights, <3,0> tap subset), <5,1> halo path with streamed weights, <4,1> fused
+// separable convolution, and the CTA-pair variants (clusters of two, tcgen05.mma.cta_group::2 with M = 256, each CTA
+// loads its own pixel tile and half of every weight tile): <6,1> generic ring, <7,1> streamed-weight halo path, <8,1>
+// resident-weight halo path.
 //   warp 0 (one lane)  TMA producer: A box + W tile per k-block into a ring of shared-memory stages (halo path: one
 //                      (16+2) x (8+2) halo box per 64-channel chunk, the weights of all taps resident)
 //   warp 1 (one lane)  MMA issuer: tcgen05.mma kind::f16 (fp16 x fp16 -> fp32) into one of TWO TMEM accumulator
 //                      stages; tcgen05.commit releases the smem stage / publishes the accumulator
-//   warp 10            optional second MMA issuer for the odd tiles (BD_UMMA_ISSUERS=2, off by default)
+//   warp 10            second MMA issuer for the odd tiles on the 3x3 one-chunk halo path (BD_UMMA_ISSUERS=1: off)
 //   warps 2-5          in the fused separable instance: depthwise warps that compute the A tile from a halo box
 //   warps 2-9          epilogue, two warps per TMEM lane quadrant (warp w may read TMEM lanes 32*(w%4)..+31 = tile
 //                      rows).  The work units are (tile, 64-column chunk) pairs; the two warps of a quadrant take
