@@ -113,7 +113,10 @@ int bd_plan_finalize(bd_plan* plan, int input_buf, int logits_buf, int logits_up
 /* One forward of the whole network.  x_dev: fp32 (N,512,512,3) NHWC in [-1,1] as handed to model.predict
  * (converted on the device into the input buffer), or NULL to use what is already in the input buffer (e.g.
  * written by bd_tiles_gather).  probs_dev: fp32 (N,512,512,2) or NULL;
- * mask_dev: u8 (N,512,512), 1 where class 1 wins (argmax, ties -> class 0, predict.py:110) or NULL. */
+ * mask_dev: u8 (N,512,512), 1 where class 1 wins (argmax, ties -> class 0, predict.py:110) or NULL.
+ * probs_dev must be 16-byte aligned and mask_dev 4-byte aligned (the head kernel stores four pixels per thread; any
+ * cudaMalloc'ed or torch-allocated buffer is); with arena reuse (the default) the input buffer does not survive a
+ * forward -- pass x_dev, or refill it (bd_tiles_gather_at), before every run. */
 int bd_plan_run(bd_plan* plan, const float* x_dev, float* probs_dev, uint8_t* mask_dev, void* stream);
 /* only the softmax / argmax head (last op) on whatever the logits buffer currently holds */
 int bd_plan_run_head(bd_plan* plan, float* probs_dev, uint8_t* mask_dev, void* stream);
