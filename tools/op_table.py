@@ -9,8 +9,9 @@ import numpy as np  # noqa: E402
 from building_detection_b200 import graph as G  # noqa: E402
 from building_detection_b200.predict_model import CTORS, MODEL_NAMES  # noqa: E402
 
-batch = int(sys.argv[1]) if len(sys.argv) > 1 else 16
-top = int(sys.argv[2]) if len(sys.argv) > 2 else 14
+_args = [a for a in sys.argv[1:] if a not in ("--batch", "--top")]  # "32 30" and "--batch 32 --top 30" both work
+batch = int(_args[0]) if len(_args) > 0 else 16
+top = int(_args[1]) if len(_args) > 1 else 14
 KIND = {G.OP_CONV: "conv", G.OP_DWCONV: "dwconv", G.OP_MAXPOOL: "maxpool", G.OP_ADDN: "addn", G.OP_GAP: "gap",
         G.OP_DENSE: "dense", G.OP_GATE: "gate", G.OP_SKFUSE: "skfuse", G.OP_BCAST: "bcast", G.OP_SOFTMAX2: "softmax"}
 grand = {}
